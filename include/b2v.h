@@ -1,0 +1,129 @@
+/* b2v.h — C ABI of the B200-native volumetric integrator (libb2v.so).
+ *
+ * Drop-in boundary for pySLAM's dense-mapping plugin path.  Plain pointers and sizes only; no
+ * torch / pybind types; status codes instead of exceptions.  Every entry point names the
+ * reference interface it replaces (paths relative to the pySLAM tree).
+ *
+ * Conventions (same as the reference front-end):
+ *   - depth  : float32 [H*W], metres, row-major           (pyslam/dense/volumetric_integrator_base.py:713)
+ *   - color  : uint8   [H*W*3], RGB interleaved, row-major (base.py:1054)
+ *   - K      : float64 [4] = {fx, fy, cx, cy}              (volumetric_integrator_tsdf.py:110-119)
+ *   - Tcw    : float64 [16] row-major world->camera pose   (base.py:116; tsdf.py:223 `pose`)
+ *   - image / point pointers may be HOST or DEVICE memory; the library detects which.
+ *     Pinned host memory makes the host->device copies asynchronous.
+ *   - all calls on one volume must come from one thread at a time (the reference's integrator
+ *     process is single-consumer, base.py:789-967).
+ */
+#ifndef B2V_H
+#define B2V_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2V_OK 0
+#define B2V_ERR_INVALID_ARGUMENT 1
+#define B2V_ERR_CUDA 2
+#define B2V_ERR_CAPACITY 3 /* block pool or hash table full: raise capacity_blocks */
+#define B2V_ERR_UNSUPPORTED 4
+
+#define B2V_BLOCK_SIZE 8                 /* voxels per block side (config_parameters.py:313) */
+#define B2V_BLOCK_VOXELS 512
+#define B2V_VOXEL_PLANES 5               /* tsdf, weight, r, g, b : float32 planes per block */
+
+typedef struct b2v_volume b2v_volume;    /* TSDF volume (Open3D-like duck type A)           */
+typedef struct b2v_grid b2v_grid;        /* point-average voxel block grid (duck type B)    */
+
+typedef struct b2v_config {
+    float voxel_size;        /* kVolumetricIntegrationVoxelLength   (config_parameters.py:311) */
+    int32_t block_size;      /* must be 8                            (config_parameters.py:313) */
+    float sdf_trunc;         /* kVolumetricIntegrationTSdfTrunc      (config_parameters.py:349) */
+    float depth_trunc;       /* ...TsdfDepthTruncIndoor/Outdoor      (config_parameters.py:350-351) */
+    int32_t depth_stride;    /* Open3D depth_sampling_stride, default 4 (tsdf.py:104-108)      */
+    uint32_t capacity_blocks;/* block-pool capacity (10 KiB per block)                          */
+    int32_t device;          /* CUDA device ordinal                                             */
+    int32_t shard_rank;      /* this GPU's shard; a block is owned iff                          */
+    int32_t shard_count;     /*   BlockKeyHash(key) % shard_count == shard_rank (1 = own all)   */
+} b2v_config;
+
+/* ---- lifetime: replaces o3d.pipelines.integration.ScalableTSDFVolume(...) (tsdf.py:104-108) ---- */
+int b2v_create(const b2v_config *cfg, b2v_volume **out);
+int b2v_destroy(b2v_volume *v);
+/* replaces self.volume.reset() (tsdf.py:156; base.py:642) */
+int b2v_reset(b2v_volume *v);
+const char *b2v_last_error(const b2v_volume *v);
+
+/* ---- integrate: replaces self.volume.integrate(rgbd, intrinsic, pose) (tsdf.py:215-223) ----
+ * Asynchronous: returns once the work is enqueued.  `stream` (a cudaStream_t) may be non-NULL only
+ * with DEVICE image pointers; NULL uses the library's own streams. */
+int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
+                  int32_t width, const double K[4], const double Tcw[16], void *stream);
+/* n frames back to back (the rebuild(map) bulk path, base.py:1242-1318): depth [n*H*W],
+ * color [n*H*W*3], Tcw [n*16]; same K for all. */
+int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float *depth, const uint8_t *color,
+                        int32_t height, int32_t width, const double K[4], const double *Tcw);
+/* wait for all enqueued work; returns B2V_ERR_CAPACITY if a frame overflowed the pool */
+int b2v_synchronize(b2v_volume *v);
+
+/* ---- inspection / parity hooks ---- */
+int64_t b2v_num_blocks(b2v_volume *v);                 /* synchronises */
+/* blocks touched / newly allocated by the most recent frame (synchronises) */
+int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int64_t *new_blocks);
+/* total (block,frame) updates and kernel launches since create/reset: bench accounting */
+int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches);
+/* keys int32[nb*3], hashes uint64[nb] (= reference BlockKeyHash, cpp/volumetric/voxel_hashing.h:106-113),
+ * voxels float32[nb*5*512] (planes tsdf, weight, r, g, b; voxel index lx + 8*ly + 64*lz,
+ * cpp/volumetric/voxel_block.h:67-70).  HOST outputs, any may be NULL; returns nb or <0. */
+int64_t b2v_dump_blocks(b2v_volume *v, int32_t *keys, uint64_t *hashes, float *voxels);
+/* Restore / seed blocks from HOST arrays keys int32[n*3] (unique), voxels float32[n*5*512]; existing
+ * blocks are overwritten.  The reference's load() is a stub (base.py:595-604); this is the restore
+ * half of b2v_dump_blocks, also used to gather shards onto one GPU and by the tests. */
+int b2v_upload_blocks(b2v_volume *v, int64_t n_blocks, const int32_t *keys, const float *voxels);
+/* keys int32[n*3] of the blocks touched by the most recent frame; returns n or <0 */
+int64_t b2v_last_touched_keys(b2v_volume *v, int32_t *keys, int64_t max_keys);
+
+/* ---- mesh: replaces self.volume.extract_triangle_mesh() (tsdf.py:239,260) ----
+ * Two-call pattern: b2v_extract_mesh runs the kernels and returns the sizes; b2v_copy_mesh copies
+ * the result of the last extraction into HOST arrays vertices f32[nv*3], colors f32[nv*3] in [0,1],
+ * edge_ids int32[nv*4] (canonical weld key: voxel x,y,z + axis), triangles int32[nt*3]. */
+int b2v_extract_mesh(b2v_volume *v, int64_t *n_vertices, int64_t *n_triangles);
+int b2v_copy_mesh(b2v_volume *v, float *vertices, float *colors, int32_t *edge_ids,
+                  int32_t *triangles);
+/* replaces self.volume.extract_point_cloud() (tsdf.py:246,267): zero crossings along +x,+y,+z */
+int b2v_extract_points(b2v_volume *v, int64_t *n_points);
+int b2v_copy_points(b2v_volume *v, float *points, float *colors);
+
+/* ---- duck type B: pySLAM's own volumetric.VoxelBlockGrid (point-average grid) ----
+ * replaces VoxelBlockGridT<VoxelData> (cpp/volumetric/voxel_block_grid.h:61-233) behind the pybind
+ * class registered at cpp/volumetric/volumetric_grid_module.h:732-935. */
+int b2v_grid_create(float voxel_size, int32_t block_size, uint32_t capacity_blocks, int32_t device,
+                    b2v_grid **out);
+int b2v_grid_destroy(b2v_grid *g);
+int b2v_grid_clear(b2v_grid *g);                       /* clear()/reset() */
+const char *b2v_grid_last_error(const b2v_grid *g);
+/* integrate(points f32[n*3], colors f32[n*3] | NULL)  (volumetric_grid_module.h:131-467 ->
+ * voxel_block_grid.hpp:115-136) */
+int b2v_grid_integrate(b2v_grid *g, const float *points, const float *colors, int64_t n_points);
+int b2v_grid_synchronize(b2v_grid *g);
+int64_t b2v_grid_num_blocks(b2v_grid *g);              /* num_blocks() */
+int64_t b2v_grid_size(b2v_grid *g);                    /* size(): voxels with count > 0 */
+/* get_voxels(min_count) (voxel_block_grid.hpp:717-819): returns n; then copy */
+int64_t b2v_grid_get_voxels(b2v_grid *g, int32_t min_count);
+int b2v_grid_copy_voxels(b2v_grid *g, float *points, float *colors);
+/* remove_low_count_voxels(min_count) (voxel_block_grid.hpp:625-647) */
+int b2v_grid_remove_low_count_voxels(b2v_grid *g, int32_t min_count);
+/* parity hook: keys int32[nb*3], hashes u64[nb], count int32[nb*512], pos_sum f32[nb*512*3],
+ * col_sum f32[nb*512*3]  (same layout as the reference's VoxelData, voxel_data.h:118-133) */
+int64_t b2v_grid_dump_blocks(b2v_grid *g, int32_t *keys, uint64_t *hashes, int32_t *count,
+                             float *pos_sum, float *col_sum);
+
+/* library / device info */
+int b2v_version(void);
+int b2v_device_sm_count(int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2V_H */

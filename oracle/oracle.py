@@ -1,0 +1,360 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes front-ends for the oracle libraries + numpy cross-checks."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_TSDF_SO = os.path.join(_DIR, "liboracle_tsdf.so")
+_REF_SO = os.path.join(_DIR, "_ref", "libref_grid.so")
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+
+
+def build(quiet: bool = True) -> None:
+    """Compile the oracle libraries (the C restatement always; `_ref` when /root/reference exists)."""
+    subprocess.run(["make", "-C", _DIR, "all"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def have_ref() -> bool:
+    return os.path.exists(_REF_SO)
+
+
+_tsdf_lib = None
+_ref_lib = None
+
+
+def _tsdf():
+    global _tsdf_lib
+    if _tsdf_lib is None:
+        if not os.path.exists(_TSDF_SO):
+            build()
+        L = C.CDLL(_TSDF_SO)
+        L.tsdf_oracle_create.restype = C.c_void_p
+        L.tsdf_oracle_create.argtypes = [C.c_float, C.c_int, C.c_float, C.c_float, C.c_int]
+        L.tsdf_oracle_destroy.argtypes = [C.c_void_p]
+        L.tsdf_oracle_reset.argtypes = [C.c_void_p]
+        L.tsdf_oracle_num_blocks.restype = C.c_int64
+        L.tsdf_oracle_num_blocks.argtypes = [C.c_void_p]
+        L.tsdf_oracle_num_touched.restype = C.c_int64
+        L.tsdf_oracle_num_touched.argtypes = [C.c_void_p]
+        L.tsdf_oracle_integrate.restype = C.c_int64
+        L.tsdf_oracle_integrate.argtypes = [C.c_void_p, _f32p, _u8p, C.c_int, C.c_int, _f64p, _f64p,
+                                            C.c_int]
+        L.tsdf_oracle_last_touched.restype = C.c_int64
+        L.tsdf_oracle_last_touched.argtypes = [C.c_void_p, _i32p]
+        L.tsdf_oracle_dump.restype = C.c_int64
+        L.tsdf_oracle_dump.argtypes = [C.c_void_p, _i32p, _u64p, _f32p]
+        L.tsdf_oracle_extract_mesh.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.tsdf_oracle_mesh_copy.argtypes = [_f32p, _f64p, _f32p, _i32p, _i32p]
+        L.tsdf_oracle_block_key_hash.restype = C.c_uint64
+        L.tsdf_oracle_block_key_hash.argtypes = [C.c_int32] * 3
+        L.tsdf_oracle_floor_div.restype = C.c_int64
+        L.tsdf_oracle_floor_div.argtypes = [C.c_int64, C.c_int64]
+        L.tsdf_oracle_voxel_coord.restype = C.c_int32
+        L.tsdf_oracle_voxel_coord.argtypes = [C.c_float, C.c_float]
+        L.tsdf_oracle_max_threads.restype = C.c_int
+        L.tsdf_oracle_set_block.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _f32p]
+        _tsdf_lib = L
+    return _tsdf_lib
+
+
+def _ref():
+    global _ref_lib
+    if _ref_lib is None:
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libref_grid.so missing (needs /root/reference to build)")
+        L = C.CDLL(_REF_SO)
+        L.refgrid_create.restype = C.c_void_p
+        L.refgrid_create.argtypes = [C.c_float, C.c_int]
+        L.refgrid_destroy.argtypes = [C.c_void_p]
+        L.refgrid_clear.argtypes = [C.c_void_p]
+        L.refgrid_integrate.restype = C.c_double
+        L.refgrid_integrate.argtypes = [C.c_void_p, _f32p, C.c_void_p, C.c_int64]
+        L.refgrid_num_blocks.restype = C.c_int64
+        L.refgrid_num_blocks.argtypes = [C.c_void_p]
+        L.refgrid_block_size.argtypes = [C.c_void_p]
+        L.refgrid_inv_voxel_size.restype = C.c_float
+        L.refgrid_inv_voxel_size.argtypes = [C.c_void_p]
+        L.refgrid_dump_blocks.restype = C.c_int64
+        L.refgrid_dump_blocks.argtypes = [C.c_void_p] * 6
+        L.refgrid_get_voxels.restype = C.c_int64
+        L.refgrid_get_voxels.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_double)]
+        L.refgrid_remove_low_count_voxels.argtypes = [C.c_void_p, C.c_int]
+        L.refgrid_carve.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                    C.c_int, _f64p, C.c_float, C.c_float, _f32p, C.c_float]
+        L.ref_voxel_key_inv.argtypes = [C.c_float] * 4 + [_i32p]
+        L.ref_floor_div.restype = C.c_int64
+        L.ref_floor_div.argtypes = [C.c_int64, C.c_int64]
+        L.ref_block_and_local_key.argtypes = [_i32p, C.c_int, _i32p, _i32p]
+        L.ref_block_key_hash.restype = C.c_uint64
+        L.ref_block_key_hash.argtypes = [C.c_int32] * 3
+        L.ref_sizeof_voxel_data.restype = C.c_int
+        _ref_lib = L
+    return _ref_lib
+
+
+# ---------------------------------------------------------------------------------------------
+# compiled reference
+# ---------------------------------------------------------------------------------------------
+
+def ref_block_key_hash(x, y, z) -> int:
+    return int(_ref().ref_block_key_hash(int(x), int(y), int(z)))
+
+
+def ref_floor_div(a, b) -> int:
+    return int(_ref().ref_floor_div(int(a), int(b)))
+
+
+def ref_keys(point, voxel_size, block_size=8):
+    """(voxel key, block key, local key) of one point exactly as the reference computes them."""
+    L = _ref()
+    inv = np.float32(1.0) / np.float32(voxel_size)
+    vk = np.zeros(3, np.int32)
+    L.ref_voxel_key_inv(float(np.float32(point[0])), float(np.float32(point[1])),
+                        float(np.float32(point[2])), float(inv), vk)
+    bk, lk = np.zeros(3, np.int32), np.zeros(3, np.int32)
+    L.ref_block_and_local_key(vk, int(block_size), bk, lk)
+    return vk, bk, lk
+
+
+class RefGrid:
+    """The unmodified reference `volumetric::VoxelBlockGrid` (sequential branch)."""
+
+    def __init__(self, voxel_size: float, block_size: int = 8):
+        self._L = _ref()
+        self._h = self._L.refgrid_create(float(voxel_size), int(block_size))
+        self.block_size = block_size
+        self.last_elapsed_s = 0.0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.refgrid_destroy(self._h)
+            self._h = None
+
+    def integrate(self, points, colors=None) -> float:
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        assert pts.ndim == 2 and pts.shape[1] == 3
+        cp = None
+        if colors is not None:
+            cols = np.ascontiguousarray(colors, dtype=np.float32)
+            assert cols.shape == pts.shape
+            cp = cols.ctypes.data
+        self.last_elapsed_s = self._L.refgrid_integrate(self._h, pts, cp, pts.shape[0])
+        return self.last_elapsed_s
+
+    def num_blocks(self) -> int:
+        return int(self._L.refgrid_num_blocks(self._h))
+
+    def clear(self):
+        self._L.refgrid_clear(self._h)
+
+    def dump_blocks(self):
+        nb = self.num_blocks()
+        nv = self.block_size ** 3
+        keys = np.zeros((nb, 3), np.int32)
+        hashes = np.zeros(nb, np.uint64)
+        count = np.zeros((nb, nv), np.int32)
+        pos = np.zeros((nb, nv, 3), np.float32)
+        col = np.zeros((nb, nv, 3), np.float32)
+        self._L.refgrid_dump_blocks(self._h, keys.ctypes.data, hashes.ctypes.data, count.ctypes.data,
+                                    pos.ctypes.data, col.ctypes.data)
+        return dict(keys=keys, hashes=hashes, count=count, pos_sum=pos, col_sum=col)
+
+    def get_voxels(self, min_count=1):
+        el = C.c_double(0.0)
+        n = self._L.refgrid_get_voxels(self._h, int(min_count), None, None, C.byref(el))
+        pts = np.zeros((n, 3), np.float32)
+        cols = np.zeros((n, 3), np.float32)
+        if n:
+            self._L.refgrid_get_voxels(self._h, int(min_count), pts.ctypes.data, cols.ctypes.data,
+                                       C.byref(el))
+        self.last_elapsed_s = el.value
+        return pts, cols
+
+    def remove_low_count_voxels(self, min_count):
+        self._L.refgrid_remove_low_count_voxels(self._h, int(min_count))
+
+    def carve(self, K, width, height, Tcw, depth, depth_threshold=1e-2, depth_max=10.0,
+              depth_min=1e-2):
+        d = np.ascontiguousarray(depth, np.float32)
+        T = np.ascontiguousarray(Tcw, np.float64).reshape(16)
+        self._L.refgrid_carve(self._h, K[0], K[1], K[2], K[3], int(width), int(height), T,
+                              depth_max, depth_min, d, depth_threshold)
+
+
+# ---------------------------------------------------------------------------------------------
+# C restatement of the TSDF path
+# ---------------------------------------------------------------------------------------------
+
+class TsdfOracle:
+    def __init__(self, voxel_size, sdf_trunc, depth_trunc, block_size=8, stride=4):
+        self._L = _tsdf()
+        self.block_size = block_size
+        self.nvox = block_size ** 3
+        self._h = self._L.tsdf_oracle_create(float(np.float32(voxel_size)), int(block_size),
+                                             float(np.float32(sdf_trunc)),
+                                             float(np.float32(depth_trunc)), int(stride))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.tsdf_oracle_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def max_threads() -> int:
+        return int(_tsdf().tsdf_oracle_max_threads())
+
+    def reset(self):
+        self._L.tsdf_oracle_reset(self._h)
+
+    def integrate(self, depth, color, K, Tcw, nthreads=1) -> int:
+        d = np.ascontiguousarray(depth, np.float32)
+        c = np.ascontiguousarray(color, np.uint8)
+        H, W = d.shape
+        assert c.shape == (H, W, 3)
+        return int(self._L.tsdf_oracle_integrate(self._h, d, c, H, W,
+                                                 np.ascontiguousarray(K, np.float64).reshape(4),
+                                                 np.ascontiguousarray(Tcw, np.float64).reshape(16),
+                                                 int(nthreads)))
+
+    def num_blocks(self) -> int:
+        return int(self._L.tsdf_oracle_num_blocks(self._h))
+
+    def set_block(self, key, vox):
+        """test hook: overwrite / create one block with vox f32 [5, B^3]"""
+        v = np.ascontiguousarray(vox, np.float32).reshape(5 * self.nvox)
+        self._L.tsdf_oracle_set_block(self._h, int(key[0]), int(key[1]), int(key[2]), v)
+
+    def last_touched(self):
+        n = int(self._L.tsdf_oracle_num_touched(self._h))
+        keys = np.zeros((n, 3), np.int32)
+        self._L.tsdf_oracle_last_touched(self._h, keys)
+        return keys
+
+    def dump_blocks(self):
+        nb = self.num_blocks()
+        keys = np.zeros((nb, 3), np.int32)
+        hashes = np.zeros(nb, np.uint64)
+        vox = np.zeros((nb, 5, self.nvox), np.float32)
+        self._L.tsdf_oracle_dump(self._h, keys, hashes, vox)
+        return dict(keys=keys, hashes=hashes, vox=vox)
+
+    def extract_mesh(self):
+        nv, nt = C.c_int64(0), C.c_int64(0)
+        self._L.tsdf_oracle_extract_mesh(self._h, C.byref(nv), C.byref(nt))
+        V = np.zeros((nv.value, 3), np.float32)
+        V64 = np.zeros((nv.value, 3), np.float64)
+        Cc = np.zeros((nv.value, 3), np.float32)
+        E = np.zeros((nv.value, 4), np.int32)
+        T = np.zeros((nt.value, 3), np.int32)
+        self._L.tsdf_oracle_mesh_copy(V, V64, Cc, E, T)
+        return dict(vertices=V, vertices64=V64, colors=Cc, edges=E, triangles=T)
+
+
+def canonical_mesh(vertices, colors, edges, triangles):
+    """Order-independent form of a welded mesh: vertices sorted by canonical edge id
+    (gx,gy,gz,axis); triangles re-indexed, each rotated so its smallest index leads (winding kept),
+    then sorted.  Two extractions of the same volume are equal iff these arrays are equal."""
+    edges = np.asarray(edges)
+    order = np.lexsort((edges[:, 3], edges[:, 2], edges[:, 1], edges[:, 0]))
+    inv = np.empty_like(order)
+    inv[order] = np.arange(order.size)
+    tri = inv[np.asarray(triangles)] if len(triangles) else np.zeros((0, 3), np.int64)
+    if len(tri):
+        k = np.argmin(tri, axis=1)
+        idx = (k[:, None] + np.arange(3)[None, :]) % 3
+        tri = np.take_along_axis(tri, idx, axis=1)
+        tri = tri[np.lexsort((tri[:, 2], tri[:, 1], tri[:, 0]))]
+    return dict(vertices=np.asarray(vertices)[order], colors=np.asarray(colors)[order],
+                edges=edges[order], triangles=tri.astype(np.int64))
+
+
+# ---------------------------------------------------------------------------------------------
+# independent numpy restatement (pins the C oracle; float32 numpy, no FMA -> tolerance compare)
+# ---------------------------------------------------------------------------------------------
+
+def numpy_touched_blocks(depth, K, Tcw, voxel_size, sdf_trunc, depth_trunc, block_size=8, stride=4):
+    """A.2 touched-block set of one frame as a sorted int32 [n,3] array (numpy, vectorised)."""
+    fx, fy, cx, cy = [float(v) for v in K]
+    d = np.asarray(depth, np.float32)[::stride, ::stride]
+    H, W = d.shape
+    jj, ii = np.meshgrid(np.arange(W) * stride, np.arange(H) * stride)
+    valid = (d > 0) & (d < np.float32(depth_trunc))
+    z = d[valid].astype(np.float64)
+    x = (jj[valid].astype(np.float64) - cx) * z / fx
+    y = (ii[valid].astype(np.float64) - cy) * z / fy
+    Tcw = np.asarray(Tcw, np.float64).reshape(4, 4)
+    R = Tcw[:3, :3].T
+    t = -np.stack([(R[a, 0] * Tcw[0, 3] + R[a, 1] * Tcw[1, 3]) + R[a, 2] * Tcw[2, 3]
+                   for a in range(3)])
+    pw = np.stack([((R[a, 0] * x + R[a, 1] * y) + R[a, 2] * z) + t[a] for a in range(3)], axis=1)
+    tau = float(np.float32(sdf_trunc))
+    inv_vs = np.float32(1.0) / np.float32(voxel_size)
+    lo = np.floor((pw - tau).astype(np.float32) * inv_vs).astype(np.int64) // block_size
+    hi = np.floor((pw + tau).astype(np.float32) * inv_vs).astype(np.int64) // block_size
+    keys = set()
+    span = (hi - lo).max(axis=0) + 1 if len(lo) else np.zeros(3, np.int64)
+    for dx in range(int(span[0])):
+        for dy in range(int(span[1])):
+            for dz in range(int(span[2])):
+                k = lo + np.array([dx, dy, dz])
+                ok = np.all(k <= hi, axis=1)
+                keys.update(map(tuple, k[ok]))
+    out = np.array(sorted(keys), dtype=np.int32).reshape(-1, 3)
+    return out
+
+
+def numpy_integrate_block(vox, key, depth, color, K, Tcw, voxel_size, sdf_trunc, depth_trunc,
+                          block_size=8):
+    """A.3 update of one block in float32 numpy (no FMA, true divisions): an independent second
+    restatement.  vox: f32 [5, B^3] -> new f32 [5, B^3]."""
+    B = block_size
+    f32 = np.float32
+    vs, tau = f32(voxel_size), f32(sdf_trunc)
+    fx, fy, cx, cy = [f32(v) for v in K]
+    E = np.asarray(Tcw, np.float64).reshape(4, 4).astype(np.float32)
+    H, W = depth.shape
+    l = np.arange(B ** 3)
+    lx, ly, lz = l % B, (l // B) % B, l // (B * B)
+    c = np.stack([(f32(key[0] * B) + lx.astype(np.float32) + f32(0.5)) * vs,
+                  (f32(key[1] * B) + ly.astype(np.float32) + f32(0.5)) * vs,
+                  (f32(key[2] * B) + lz.astype(np.float32) + f32(0.5)) * vs], axis=1)
+    p = (c.astype(np.float64) @ E[:3, :3].astype(np.float64).T + E[:3, 3].astype(np.float64))
+    p = p.astype(np.float32)
+    out = np.array(vox, dtype=np.float32, copy=True)
+    pz = p[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u_f = p[:, 0] * fx / pz + cx + f32(0.5)
+        v_f = p[:, 1] * fy / pz + cy + f32(0.5)
+    ok = (pz > 0) & (u_f >= f32(0.0001)) & (u_f < f32(W) - f32(0.0001)) & \
+         (v_f >= f32(0.0001)) & (v_f < f32(H) - f32(0.0001))
+    u = np.where(ok, u_f, 0).astype(np.int64)
+    v = np.where(ok, v_f, 0).astype(np.int64)
+    d = depth[v, u].astype(np.float32)
+    ok &= (d > 0) & (d < f32(depth_trunc))
+    xx = (u.astype(np.float32) - cx) / fx
+    yy = (v.astype(np.float32) - cy) / fy
+    lam = np.sqrt(xx * xx + yy * yy + f32(1.0))
+    sdf = (d - pz) * lam
+    ok &= sdf > -tau
+    t = np.minimum(f32(1.0), sdf / tau)
+    w = out[1]
+    wn = w + f32(1.0)
+    rgb = color[v, u].astype(np.float32)
+    new_t = (out[0] * w + t) / wn
+    out[0] = np.where(ok, new_t, out[0])
+    for k in range(3):
+        out[2 + k] = np.where(ok, (out[2 + k] * w + rgb[:, k]) / wn, out[2 + k])
+    out[1] = np.where(ok, wn, w)
+    return out, ok

@@ -1,0 +1,131 @@
+"""ctypes binding of libb2v.so (the C ABI declared in include/b2v.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or fails to load, every
+entry point raises.  (`pyslam_b200.build.build()` compiles it in-tree with nvcc.)
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libb2v.so")
+
+B2V_OK = 0
+B2V_ERR_INVALID_ARGUMENT = 1
+B2V_ERR_CUDA = 2
+B2V_ERR_CAPACITY = 3
+B2V_ERR_UNSUPPORTED = 4
+
+BLOCK_SIZE = 8
+BLOCK_VOXELS = 512
+VOXEL_PLANES = 5
+
+#: every symbol include/b2v.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "b2v_create", "b2v_destroy", "b2v_reset", "b2v_last_error", "b2v_integrate",
+    "b2v_integrate_batch", "b2v_synchronize", "b2v_num_blocks", "b2v_last_frame_stats",
+    "b2v_counters", "b2v_dump_blocks", "b2v_upload_blocks", "b2v_last_touched_keys", "b2v_extract_mesh", "b2v_copy_mesh",
+    "b2v_extract_points", "b2v_copy_points", "b2v_grid_create", "b2v_grid_destroy", "b2v_grid_clear",
+    "b2v_grid_last_error", "b2v_grid_integrate", "b2v_grid_synchronize", "b2v_grid_num_blocks",
+    "b2v_grid_size", "b2v_grid_get_voxels", "b2v_grid_copy_voxels",
+    "b2v_grid_remove_low_count_voxels", "b2v_grid_dump_blocks", "b2v_version", "b2v_device_sm_count",
+]
+
+
+class B2VConfig(C.Structure):
+    _fields_ = [
+        ("voxel_size", C.c_float),
+        ("block_size", C.c_int32),
+        ("sdf_trunc", C.c_float),
+        ("depth_trunc", C.c_float),
+        ("depth_stride", C.c_int32),
+        ("capacity_blocks", C.c_uint32),
+        ("device", C.c_int32),
+        ("shard_rank", C.c_int32),
+        ("shard_count", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libb2v.so and declare the prototypes.  Raises RuntimeError when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension was not built "
+            "(run `python -m pyslam_b200.build`); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+    p_i64 = C.POINTER(C.c_int64)
+
+    L.b2v_version.restype = C.c_int
+    L.b2v_device_sm_count.restype = C.c_int
+    L.b2v_device_sm_count.argtypes = [i32]
+
+    L.b2v_create.restype = C.c_int
+    L.b2v_create.argtypes = [C.POINTER(B2VConfig), C.POINTER(vp)]
+    L.b2v_destroy.restype = C.c_int
+    L.b2v_destroy.argtypes = [vp]
+    L.b2v_reset.restype = C.c_int
+    L.b2v_reset.argtypes = [vp]
+    L.b2v_last_error.restype = C.c_char_p
+    L.b2v_last_error.argtypes = [vp]
+    L.b2v_integrate.restype = C.c_int
+    L.b2v_integrate.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.b2v_integrate_batch.restype = C.c_int
+    L.b2v_integrate_batch.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp]
+    L.b2v_synchronize.restype = C.c_int
+    L.b2v_synchronize.argtypes = [vp]
+    L.b2v_num_blocks.restype = i64
+    L.b2v_num_blocks.argtypes = [vp]
+    L.b2v_last_frame_stats.restype = C.c_int
+    L.b2v_last_frame_stats.argtypes = [vp, p_i64, p_i64]
+    L.b2v_counters.restype = C.c_int
+    L.b2v_counters.argtypes = [vp, p_i64, p_i64]
+    L.b2v_dump_blocks.restype = i64
+    L.b2v_dump_blocks.argtypes = [vp, vp, vp, vp]
+    L.b2v_upload_blocks.restype = C.c_int
+    L.b2v_upload_blocks.argtypes = [vp, i64, vp, vp]
+    L.b2v_last_touched_keys.restype = i64
+    L.b2v_last_touched_keys.argtypes = [vp, vp, i64]
+    L.b2v_extract_mesh.restype = C.c_int
+    L.b2v_extract_mesh.argtypes = [vp, p_i64, p_i64]
+    L.b2v_copy_mesh.restype = C.c_int
+    L.b2v_copy_mesh.argtypes = [vp, vp, vp, vp, vp]
+    L.b2v_extract_points.restype = C.c_int
+    L.b2v_extract_points.argtypes = [vp, p_i64]
+    L.b2v_copy_points.restype = C.c_int
+    L.b2v_copy_points.argtypes = [vp, vp, vp]
+
+    L.b2v_grid_create.restype = C.c_int
+    L.b2v_grid_create.argtypes = [C.c_float, i32, u32, i32, C.POINTER(vp)]
+    L.b2v_grid_destroy.restype = C.c_int
+    L.b2v_grid_destroy.argtypes = [vp]
+    L.b2v_grid_clear.restype = C.c_int
+    L.b2v_grid_clear.argtypes = [vp]
+    L.b2v_grid_last_error.restype = C.c_char_p
+    L.b2v_grid_last_error.argtypes = [vp]
+    L.b2v_grid_integrate.restype = C.c_int
+    L.b2v_grid_integrate.argtypes = [vp, vp, vp, i64]
+    L.b2v_grid_synchronize.restype = C.c_int
+    L.b2v_grid_synchronize.argtypes = [vp]
+    L.b2v_grid_num_blocks.restype = i64
+    L.b2v_grid_num_blocks.argtypes = [vp]
+    L.b2v_grid_size.restype = i64
+    L.b2v_grid_size.argtypes = [vp]
+    L.b2v_grid_get_voxels.restype = i64
+    L.b2v_grid_get_voxels.argtypes = [vp, i32]
+    L.b2v_grid_copy_voxels.restype = C.c_int
+    L.b2v_grid_copy_voxels.argtypes = [vp, vp, vp]
+    L.b2v_grid_remove_low_count_voxels.restype = C.c_int
+    L.b2v_grid_remove_low_count_voxels.argtypes = [vp, i32]
+    L.b2v_grid_dump_blocks.restype = i64
+    L.b2v_grid_dump_blocks.argtypes = [vp, vp, vp, vp, vp, vp]
+    _lib = L
+    return L

@@ -1,0 +1,797 @@
+// b2v_api.cu — the C ABI (include/b2v.h): volume / grid lifetime, frame staging and stream
+// pipelining, parity hooks.  Host code only; kernels live in b2v_tsdf.cu, b2v_mesh.cu, b2v_grid.cu.
+//
+// Per frame (b2v_integrate):   copy stream:    H2D depth, colour  -> event ready[s]
+//                              compute stream: wait ready[s]; allocate_kernel; integrate_kernel;
+//                                              event free[s]
+// with a ring of kStage device staging slots, so the upload of frame f+1 overlaps the kernels of
+// frame f.  Nothing synchronises with the host until b2v_synchronize / an inspection call.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b2v.h"
+#include "b2v_internal.h"
+
+using namespace b2v;
+
+namespace b2v {
+
+// Host-side pose algebra, same operation order as the oracle (and -ffp-contract=off on the host
+// compiler), so allocation keys agree bit for bit.
+void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], int H, int W,
+                       int stride, float vs, float tau, float depth_trunc, uint32_t frame_id,
+                       int shard_rank, int shard_count) {
+    p->fx = K[0];
+    p->fy = K[1];
+    p->cx = K[2];
+    p->cy = K[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) p->Rwc[3 * i + j] = Tcw[4 * j + i];
+    for (int i = 0; i < 3; ++i)
+        p->twc[i] = -((p->Rwc[3 * i + 0] * Tcw[3] + p->Rwc[3 * i + 1] * Tcw[7]) +
+                      p->Rwc[3 * i + 2] * Tcw[11]);
+    p->tau_d = static_cast<double>(tau);
+    for (int i = 0; i < 12; ++i) p->E[i] = static_cast<float>(Tcw[i]);
+    p->fxf = static_cast<float>(K[0]);
+    p->fyf = static_cast<float>(K[1]);
+    p->cxf = static_cast<float>(K[2]);
+    p->cyf = static_cast<float>(K[3]);
+    p->inv_fx = 1.0f / p->fxf;
+    p->inv_fy = 1.0f / p->fyf;
+    p->cxh = p->cxf + 0.5f;
+    p->cyh = p->cyf + 0.5f;
+    p->safe_w = static_cast<float>(W) - 0.0001f;
+    p->safe_h = static_cast<float>(H) - 0.0001f;
+    p->vs = vs;
+    p->inv_vs = 1.0f / vs;  // voxel_block_grid.hpp:6
+    p->tau = tau;
+    p->inv_tau = 1.0f / tau;
+    p->depth_trunc = depth_trunc;
+    p->H = H;
+    p->W = W;
+    p->stride = stride;
+    p->frame_id = frame_id;
+    p->shard_rank = shard_rank;
+    p->shard_count = shard_count;
+}
+
+}  // namespace b2v
+
+namespace {
+
+constexpr int kStage = 4;
+
+uint32_t next_pow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return static_cast<uint32_t>(p);
+}
+
+bool is_device_pointer(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct b2v_volume {
+    b2v_config cfg{};
+    cudaStream_t compute = nullptr, copy = nullptr;
+    float *d_depth[kStage] = {};
+    uint8_t *d_color[kStage] = {};
+    size_t stage_pixels = 0;
+    cudaEvent_t ev_ready[kStage] = {}, ev_free[kStage] = {};
+    HashTable table{};
+    PoolMeta meta{};
+    uint32_t frame_id = 0;  // frames integrated since reset (stamp = frame_id + 1)
+    int grid_ctas = 0;
+    int64_t launches = 0;
+    uint32_t *h_counters = nullptr;  // pinned mirror
+    std::string err;
+    // mesh / point-cloud extraction
+    MeshBuffers mb{};
+    uint32_t mesh_blocks_cap = 0;
+    size_t mesh_v_cap = 0, mesh_t_cap = 0;
+    int64_t last_nv = 0, last_nt = 0;
+    uint32_t *h_totals = nullptr;
+};
+
+#define B2V_CUDA(v, call)                                                                  \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            (v)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+            return B2V_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+static int volume_clear_device(b2v_volume *v) {
+    const size_t tcap = static_cast<size_t>(v->table.mask) + 1;
+    B2V_CUDA(v, cudaMemsetAsync(v->table.entries, 0xFF, tcap * sizeof(uint4), v->compute));
+    B2V_CUDA(v, cudaMemsetAsync(v->table.stamp, 0, tcap * sizeof(uint32_t), v->compute));
+    B2V_CUDA(v, cudaMemsetAsync(v->meta.counters, 0, kNumCounters * sizeof(uint32_t), v->compute));
+    return B2V_OK;
+}
+
+extern "C" int b2v_version(void) { return 100; }
+
+extern "C" int b2v_device_sm_count(int32_t device) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+    return n;
+}
+
+extern "C" const char *b2v_last_error(const b2v_volume *v) { return v ? v->err.c_str() : "null volume"; }
+
+extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
+    if (!cfg || !out) return B2V_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (cfg->block_size != B2V_BLOCK_SIZE || !(cfg->voxel_size > 0.0f) || !(cfg->sdf_trunc > 0.0f) ||
+        !(cfg->depth_trunc > 0.0f) || cfg->capacity_blocks == 0 || cfg->shard_count < 1 ||
+        cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count)
+        return B2V_ERR_INVALID_ARGUMENT;
+    // allocate_kernel packs 21 bits per axis inside one frustum
+    if (static_cast<double>(cfg->depth_trunc) / (static_cast<double>(cfg->voxel_size) * kB) > 5.0e5)
+        return B2V_ERR_UNSUPPORTED;
+    b2v_volume *v = new (std::nothrow) b2v_volume();
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    v->cfg = *cfg;
+    if (v->cfg.depth_stride < 1) v->cfg.depth_stride = 4;
+    *out = v;  // returned even on CUDA failure so the caller can read b2v_last_error and destroy
+    B2V_CUDA(v, cudaSetDevice(cfg->device));
+    B2V_CUDA(v, cudaStreamCreateWithFlags(&v->compute, cudaStreamNonBlocking));
+    B2V_CUDA(v, cudaStreamCreateWithFlags(&v->copy, cudaStreamNonBlocking));
+    for (int s = 0; s < kStage; ++s) {
+        B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_ready[s], cudaEventDisableTiming));
+        B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_free[s], cudaEventDisableTiming));
+    }
+    const uint32_t cap = cfg->capacity_blocks;
+    const uint32_t tcap = next_pow2(static_cast<uint64_t>(cap) * 2);
+    v->table.mask = tcap - 1;
+    v->meta.capacity = cap;
+    B2V_CUDA(v, cudaMalloc(&v->table.entries, static_cast<size_t>(tcap) * sizeof(uint4)));
+    B2V_CUDA(v, cudaMalloc(&v->table.stamp, static_cast<size_t>(tcap) * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMalloc(&v->meta.pool, static_cast<size_t>(cap) * kBlockFloats * sizeof(float)));
+    B2V_CUDA(v, cudaMalloc(&v->meta.block_keys, static_cast<size_t>(cap) * sizeof(int4)));
+    B2V_CUDA(v, cudaMalloc(&v->meta.counters, kNumCounters * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMalloc(&v->meta.active_slots, static_cast<size_t>(cap) * kActiveRing * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMallocHost(&v->h_counters, kNumCounters * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMallocHost(&v->h_totals, 2 * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMemsetAsync(v->meta.pool, 0, static_cast<size_t>(cap) * kBlockFloats * sizeof(float),
+                                v->compute));
+    int rc = volume_clear_device(v);
+    if (rc != B2V_OK) return rc;
+    const int sms = b2v_device_sm_count(cfg->device);
+    v->grid_ctas = (sms > 0 ? sms : 148) * 16;  // persistent: 16 resident 128-thread CTAs per SM
+    B2V_CUDA(v, cudaStreamSynchronize(v->compute));
+    return B2V_OK;
+}
+
+extern "C" int b2v_destroy(b2v_volume *v) {
+    if (!v) return B2V_OK;
+    cudaSetDevice(v->cfg.device);
+    if (v->compute) cudaStreamSynchronize(v->compute);
+    if (v->copy) cudaStreamSynchronize(v->copy);
+    for (int s = 0; s < kStage; ++s) {
+        cudaFree(v->d_depth[s]);
+        cudaFree(v->d_color[s]);
+        if (v->ev_ready[s]) cudaEventDestroy(v->ev_ready[s]);
+        if (v->ev_free[s]) cudaEventDestroy(v->ev_free[s]);
+    }
+    cudaFree(v->table.entries);
+    cudaFree(v->table.stamp);
+    cudaFree(v->meta.pool);
+    cudaFree(v->meta.block_keys);
+    cudaFree(v->meta.counters);
+    cudaFree(v->meta.active_slots);
+    cudaFree(v->mb.nbr);
+    cudaFree(v->mb.cube);
+    cudaFree(v->mb.edge_mask);
+    cudaFree(v->mb.vert_base);
+    cudaFree(v->mb.sums);
+    cudaFree(v->mb.offs);
+    cudaFree(v->mb.totals);
+    cudaFree(v->mb.vertices);
+    cudaFree(v->mb.colors);
+    cudaFree(v->mb.edge_ids);
+    cudaFree(v->mb.triangles);
+    cudaFreeHost(v->h_counters);
+    cudaFreeHost(v->h_totals);
+    if (v->compute) cudaStreamDestroy(v->compute);
+    if (v->copy) cudaStreamDestroy(v->copy);
+    delete v;
+    return B2V_OK;
+}
+
+static int read_counters(b2v_volume *v) {
+    B2V_CUDA(v, cudaSetDevice(v->cfg.device));
+    B2V_CUDA(v, cudaStreamSynchronize(v->copy));
+    B2V_CUDA(v, cudaMemcpyAsync(v->h_counters, v->meta.counters, kNumCounters * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, v->compute));
+    B2V_CUDA(v, cudaStreamSynchronize(v->compute));
+    if (v->h_counters[kCtrError]) {
+        v->err = (v->h_counters[kCtrError] & 2u) ? "hash table full: raise capacity_blocks"
+                                                 : "block pool full: raise capacity_blocks";
+        return B2V_ERR_CAPACITY;
+    }
+    return B2V_OK;
+}
+
+static uint32_t block_count(const b2v_volume *v) {
+    const uint32_t n = v->h_counters[kCtrPool];
+    return n < v->meta.capacity ? n : v->meta.capacity;
+}
+
+extern "C" int b2v_reset(b2v_volume *v) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    int rc = read_counters(v);
+    if (rc == B2V_ERR_CUDA) return rc;
+    const uint32_t nb = block_count(v);
+    B2V_CUDA(v, cudaMemsetAsync(v->meta.pool, 0, static_cast<size_t>(nb) * kBlockFloats * sizeof(float),
+                                v->compute));
+    rc = volume_clear_device(v);
+    if (rc != B2V_OK) return rc;
+    v->frame_id = 0;
+    v->err.clear();
+    B2V_CUDA(v, cudaStreamSynchronize(v->compute));
+    return B2V_OK;
+}
+
+static int ensure_staging(b2v_volume *v, size_t pixels) {
+    if (pixels <= v->stage_pixels) return B2V_OK;
+    B2V_CUDA(v, cudaStreamSynchronize(v->compute));
+    B2V_CUDA(v, cudaStreamSynchronize(v->copy));
+    for (int s = 0; s < kStage; ++s) {
+        cudaFree(v->d_depth[s]);
+        cudaFree(v->d_color[s]);
+        v->d_depth[s] = nullptr;
+        v->d_color[s] = nullptr;
+        B2V_CUDA(v, cudaMalloc(&v->d_depth[s], pixels * sizeof(float)));
+        B2V_CUDA(v, cudaMalloc(&v->d_color[s], pixels * 3));
+    }
+    v->stage_pixels = pixels;
+    return B2V_OK;
+}
+
+extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
+                             int32_t width, const double K[4], const double Tcw[16], void *stream) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    if (!depth || !color || !K || !Tcw || height <= 0 || width <= 0) {
+        v->err = "b2v_integrate: null pointer or non-positive image size";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    if (!(K[0] > 0.0) || !(K[1] > 0.0)) {
+        v->err = "b2v_integrate: focal lengths must be positive";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    B2V_CUDA(v, cudaSetDevice(v->cfg.device));
+    const size_t pixels = static_cast<size_t>(height) * width;
+    const bool dev_depth = is_device_pointer(depth), dev_color = is_device_pointer(color);
+    if (stream != nullptr && !(dev_depth && dev_color)) {
+        v->err = "b2v_integrate: a caller stream requires device image pointers";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t cs = stream ? static_cast<cudaStream_t>(stream) : v->compute;
+    const int s = static_cast<int>(v->frame_id % kStage);
+    const float *d_depth = depth;
+    const uint8_t *d_color = color;
+    const bool staged = !(dev_depth && dev_color);
+    if (staged) {
+        int rc = ensure_staging(v, pixels);
+        if (rc != B2V_OK) return rc;
+        B2V_CUDA(v, cudaStreamWaitEvent(v->copy, v->ev_free[s], 0));
+        if (!dev_depth) {
+            B2V_CUDA(v, cudaMemcpyAsync(v->d_depth[s], depth, pixels * sizeof(float),
+                                        cudaMemcpyHostToDevice, v->copy));
+            d_depth = v->d_depth[s];
+        }
+        if (!dev_color) {
+            B2V_CUDA(v, cudaMemcpyAsync(v->d_color[s], color, pixels * 3, cudaMemcpyHostToDevice, v->copy));
+            d_color = v->d_color[s];
+        }
+        B2V_CUDA(v, cudaEventRecord(v->ev_ready[s], v->copy));
+        B2V_CUDA(v, cudaStreamWaitEvent(cs, v->ev_ready[s], 0));
+    }
+    FrameParams P;
+    fill_frame_params(&P, K, Tcw, height, width, v->cfg.depth_stride, v->cfg.voxel_size, v->cfg.sdf_trunc,
+                      v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank, v->cfg.shard_count);
+    const int ring = static_cast<int>(v->frame_id % kActiveRing);
+    B2V_CUDA(v, launch_allocate(P, d_depth, v->table, v->meta, ring, cs));
+    B2V_CUDA(v, launch_integrate(P, d_depth, d_color, v->table, v->meta, ring, v->grid_ctas, cs));
+    if (staged) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], cs));
+    v->launches += 2;
+    v->frame_id += 1;
+    return B2V_OK;
+}
+
+extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float *depth,
+                                   const uint8_t *color, int32_t height, int32_t width,
+                                   const double K[4], const double *Tcw) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    if (n_frames < 0 || (n_frames > 0 && (!depth || !color || !Tcw))) {
+        v->err = "b2v_integrate_batch: bad arguments";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    const size_t pixels = static_cast<size_t>(height) * width;
+    for (int32_t f = 0; f < n_frames; ++f) {
+        const int rc = b2v_integrate(v, depth + pixels * f, color + pixels * 3 * f, height, width, K,
+                                     Tcw + 16 * static_cast<size_t>(f), nullptr);
+        if (rc != B2V_OK) return rc;
+    }
+    return B2V_OK;
+}
+
+extern "C" int b2v_synchronize(b2v_volume *v) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    return read_counters(v);
+}
+
+extern "C" int64_t b2v_num_blocks(b2v_volume *v) {
+    if (!v) return -1;
+    const int rc = read_counters(v);
+    if (rc == B2V_ERR_CUDA) return -1;
+    return block_count(v);
+}
+
+extern "C" int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int64_t *new_blocks) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    const int rc = read_counters(v);
+    if (rc == B2V_ERR_CUDA) return rc;
+    const int ring = v->frame_id ? static_cast<int>((v->frame_id - 1) % kActiveRing) : 0;
+    if (touched_blocks) *touched_blocks = v->frame_id ? v->h_counters[kCtrActive0 + ring] : 0;
+    if (new_blocks) *new_blocks = v->frame_id ? v->h_counters[kCtrNew0 + ring] : 0;
+    return rc;
+}
+
+extern "C" int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    const int rc = read_counters(v);
+    if (rc == B2V_ERR_CUDA) return rc;
+    if (block_updates)
+        *block_updates = static_cast<int64_t>(static_cast<uint64_t>(v->h_counters[kCtrUpdatesLo]) |
+                                              (static_cast<uint64_t>(v->h_counters[kCtrUpdatesHi]) << 32));
+    if (kernel_launches) *kernel_launches = v->launches;
+    return rc;
+}
+
+extern "C" int64_t b2v_dump_blocks(b2v_volume *v, int32_t *keys, uint64_t *hashes, float *voxels) {
+    if (!v) return -1;
+    if (read_counters(v) == B2V_ERR_CUDA) return -1;
+    const uint32_t nb = block_count(v);
+    if (nb == 0) return 0;
+    if (keys) {
+        std::vector<int4> tmp(nb);
+        if (cudaMemcpy(tmp.data(), v->meta.block_keys, nb * sizeof(int4), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -1;
+        for (uint32_t i = 0; i < nb; ++i) {
+            keys[3 * i + 0] = tmp[i].x;
+            keys[3 * i + 1] = tmp[i].y;
+            keys[3 * i + 2] = tmp[i].z;
+        }
+    }
+    if (hashes) {
+        uint64_t *d_h = nullptr;
+        if (cudaMalloc(&d_h, nb * sizeof(uint64_t)) != cudaSuccess) return -1;
+        cudaError_t e = launch_block_hashes(v->meta.block_keys, d_h, nb, v->compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(v->compute);
+        if (e == cudaSuccess) e = cudaMemcpy(hashes, d_h, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+        cudaFree(d_h);
+        v->launches += 1;
+        if (e != cudaSuccess) return -1;
+    }
+    if (voxels) {
+        if (cudaMemcpy(voxels, v->meta.pool, static_cast<size_t>(nb) * kBlockFloats * sizeof(float),
+                       cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -1;
+    }
+    return nb;
+}
+
+extern "C" int b2v_upload_blocks(b2v_volume *v, int64_t n_blocks, const int32_t *keys, const float *voxels) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    if (n_blocks < 0 || (n_blocks > 0 && (!keys || !voxels))) {
+        v->err = "b2v_upload_blocks: bad arguments";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    if (n_blocks == 0) return B2V_OK;
+    B2V_CUDA(v, cudaSetDevice(v->cfg.device));
+    const size_t n = static_cast<size_t>(n_blocks);
+    std::vector<int4> k4(n);
+    for (size_t i = 0; i < n; ++i) k4[i] = make_int4(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2], 0);
+    int4 *d_k = nullptr;
+    float *d_v = nullptr;
+    uint32_t *d_i = nullptr;
+    cudaError_t e = cudaMalloc(&d_k, n * sizeof(int4));
+    if (e == cudaSuccess) e = cudaMalloc(&d_v, n * kBlockFloats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_i, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_k, k4.data(), n * sizeof(int4), cudaMemcpyHostToDevice, v->compute);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_v, voxels, n * kBlockFloats * sizeof(float), cudaMemcpyHostToDevice, v->compute);
+    if (e == cudaSuccess)
+        e = launch_upload_blocks(d_k, d_v, static_cast<uint32_t>(n), d_i, v->table, v->meta, v->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->compute);
+    cudaFree(d_k);
+    cudaFree(d_v);
+    cudaFree(d_i);
+    v->launches += 2;
+    if (e != cudaSuccess) {
+        v->err = std::string("b2v_upload_blocks: ") + cudaGetErrorString(e);
+        return B2V_ERR_CUDA;
+    }
+    return read_counters(v);
+}
+
+extern "C" int64_t b2v_last_touched_keys(b2v_volume *v, int32_t *keys, int64_t max_keys) {
+    if (!v) return -1;
+    if (read_counters(v) == B2V_ERR_CUDA) return -1;
+    if (v->frame_id == 0) return 0;
+    const int ring = static_cast<int>((v->frame_id - 1) % kActiveRing);
+    uint32_t n = v->h_counters[kCtrActive0 + ring];
+    if (n > v->meta.capacity) n = v->meta.capacity;
+    if (!keys) return n;
+    if (static_cast<int64_t>(n) > max_keys) n = static_cast<uint32_t>(max_keys);
+    if (n == 0) return 0;
+    int4 *d_k = nullptr;
+    if (cudaMalloc(&d_k, n * sizeof(int4)) != cudaSuccess) return -1;
+    std::vector<int4> tmp(n);
+    cudaError_t e = launch_gather_active_keys(
+        v->table, v->meta.active_slots + static_cast<size_t>(ring) * v->meta.capacity, n, d_k, v->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->compute);
+    if (e == cudaSuccess) e = cudaMemcpy(tmp.data(), d_k, n * sizeof(int4), cudaMemcpyDeviceToHost);
+    cudaFree(d_k);
+    v->launches += 1;
+    if (e != cudaSuccess) return -1;
+    for (uint32_t i = 0; i < n; ++i) {
+        keys[3 * i + 0] = tmp[i].x;
+        keys[3 * i + 1] = tmp[i].y;
+        keys[3 * i + 2] = tmp[i].z;
+    }
+    return n;
+}
+
+// ---- mesh / point cloud ---------------------------------------------------------------------
+
+template <typename T> static cudaError_t regrow(T **p, size_t n) {
+    cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc(p, (n ? n : 1) * sizeof(T));
+}
+
+static int ensure_mesh_scratch(b2v_volume *v, uint32_t nb) {
+    if (!v->mb.totals) B2V_CUDA(v, cudaMalloc(&v->mb.totals, 2 * sizeof(uint32_t)));
+    if (nb <= v->mesh_blocks_cap) return B2V_OK;
+    const size_t n = nb;
+    B2V_CUDA(v, regrow(&v->mb.nbr, n * 8));
+    B2V_CUDA(v, regrow(&v->mb.cube, n * kVox));
+    B2V_CUDA(v, regrow(&v->mb.edge_mask, n * (kVox / 4)));
+    B2V_CUDA(v, regrow(&v->mb.vert_base, n * kVox));
+    B2V_CUDA(v, regrow(&v->mb.sums, n * 2));
+    B2V_CUDA(v, regrow(&v->mb.offs, n * 2));
+    v->mesh_blocks_cap = nb;
+    return B2V_OK;
+}
+
+static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t *n_triangles) {
+    int rc = read_counters(v);
+    if (rc == B2V_ERR_CUDA) return rc;
+    const uint32_t nb = block_count(v);
+    rc = ensure_mesh_scratch(v, nb);
+    if (rc != B2V_OK) return rc;
+    v->mb.n_blocks = nb;
+    cudaStream_t cs = v->compute;
+    B2V_CUDA(v, launch_mesh_neighbors(v->table, v->meta, v->mb, cs));
+    if (mesh) {
+        B2V_CUDA(v, launch_mesh_classify(v->meta, v->mb, cs));
+    } else {
+        B2V_CUDA(v, launch_point_masks(v->meta, v->mb, cs));
+    }
+    B2V_CUDA(v, launch_mesh_scan(v->mb, cs));
+    B2V_CUDA(v, cudaMemcpyAsync(v->h_totals, v->mb.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+    B2V_CUDA(v, cudaStreamSynchronize(cs));
+    const size_t nv = v->h_totals[0], nt = v->h_totals[1];
+    if (nv > v->mesh_v_cap) {
+        B2V_CUDA(v, regrow(&v->mb.vertices, nv * 3));
+        B2V_CUDA(v, regrow(&v->mb.colors, nv * 3));
+        B2V_CUDA(v, regrow(&v->mb.edge_ids, nv * 4));
+        v->mesh_v_cap = nv;
+    }
+    if (nt > v->mesh_t_cap) {
+        B2V_CUDA(v, regrow(&v->mb.triangles, nt * 3));
+        v->mesh_t_cap = nt;
+    }
+    B2V_CUDA(v, launch_mesh_vertices(v->meta, v->mb, v->cfg.voxel_size, cs));
+    if (mesh) B2V_CUDA(v, launch_mesh_triangles(v->mb, cs));
+    B2V_CUDA(v, cudaStreamSynchronize(cs));
+    v->launches += mesh ? 6 : 5;
+    v->last_nv = static_cast<int64_t>(nv);
+    v->last_nt = mesh ? static_cast<int64_t>(nt) : 0;
+    if (n_vertices) *n_vertices = v->last_nv;
+    if (n_triangles) *n_triangles = v->last_nt;
+    return rc;
+}
+
+extern "C" int b2v_extract_mesh(b2v_volume *v, int64_t *n_vertices, int64_t *n_triangles) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    return extract_common(v, true, n_vertices, n_triangles);
+}
+
+extern "C" int b2v_copy_mesh(b2v_volume *v, float *vertices, float *colors, int32_t *edge_ids,
+                             int32_t *triangles) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    const size_t nv = static_cast<size_t>(v->last_nv), nt = static_cast<size_t>(v->last_nt);
+    if (vertices && nv) B2V_CUDA(v, cudaMemcpy(vertices, v->mb.vertices, nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (colors && nv) B2V_CUDA(v, cudaMemcpy(colors, v->mb.colors, nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (edge_ids && nv) B2V_CUDA(v, cudaMemcpy(edge_ids, v->mb.edge_ids, nv * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (triangles && nt) B2V_CUDA(v, cudaMemcpy(triangles, v->mb.triangles, nt * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return B2V_OK;
+}
+
+extern "C" int b2v_extract_points(b2v_volume *v, int64_t *n_points) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    return extract_common(v, false, n_points, nullptr);
+}
+
+extern "C" int b2v_copy_points(b2v_volume *v, float *points, float *colors) {
+    return b2v_copy_mesh(v, points, colors, nullptr, nullptr);
+}
+
+// ---- point-average grid (duck type B) ---------------------------------------------------------
+
+struct b2v_grid {
+    float voxel_size = 0.0f, inv_voxel_size = 0.0f;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    HashTable table{};
+    GridMeta meta{};
+    uint32_t *h_counters = nullptr;
+    float *d_pts = nullptr, *d_cols = nullptr;
+    size_t stage_points = 0;
+    uint32_t *d_sums = nullptr, *d_offs = nullptr, *d_total = nullptr;
+    uint32_t scan_cap = 0;
+    float *d_out_pts = nullptr, *d_out_cols = nullptr;
+    size_t out_cap = 0;
+    int64_t last_n = 0;
+    std::string err;
+};
+
+constexpr int kGridBlockWordsHost = 7 * kVox;
+
+extern "C" const char *b2v_grid_last_error(const b2v_grid *g) { return g ? g->err.c_str() : "null grid"; }
+
+static int grid_clear_device(b2v_grid *g, uint32_t used_blocks) {
+    const size_t tcap = static_cast<size_t>(g->table.mask) + 1;
+    B2V_CUDA(g, cudaMemsetAsync(g->table.entries, 0xFF, tcap * sizeof(uint4), g->stream));
+    B2V_CUDA(g, cudaMemsetAsync(g->meta.counters, 0, kNumCounters * sizeof(uint32_t), g->stream));
+    B2V_CUDA(g, cudaMemsetAsync(g->meta.pool, 0,
+                                static_cast<size_t>(used_blocks) * kGridBlockWordsHost * sizeof(uint32_t),
+                                g->stream));
+    return B2V_OK;
+}
+
+extern "C" int b2v_grid_create(float voxel_size, int32_t block_size, uint32_t capacity_blocks,
+                               int32_t device, b2v_grid **out) {
+    if (!out) return B2V_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (block_size != B2V_BLOCK_SIZE || !(voxel_size > 0.0f) || capacity_blocks == 0)
+        return B2V_ERR_INVALID_ARGUMENT;
+    b2v_grid *g = new (std::nothrow) b2v_grid();
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    g->voxel_size = voxel_size;
+    g->inv_voxel_size = 1.0f / voxel_size;  // voxel_block_grid.hpp:6
+    g->device = device;
+    *out = g;
+    B2V_CUDA(g, cudaSetDevice(device));
+    B2V_CUDA(g, cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    const uint32_t tcap = next_pow2(static_cast<uint64_t>(capacity_blocks) * 2);
+    g->table.mask = tcap - 1;
+    g->table.stamp = nullptr;
+    g->meta.capacity = capacity_blocks;
+    B2V_CUDA(g, cudaMalloc(&g->table.entries, static_cast<size_t>(tcap) * sizeof(uint4)));
+    B2V_CUDA(g, cudaMalloc(&g->meta.pool, static_cast<size_t>(capacity_blocks) * kGridBlockWordsHost * sizeof(uint32_t)));
+    B2V_CUDA(g, cudaMalloc(&g->meta.block_keys, static_cast<size_t>(capacity_blocks) * sizeof(int4)));
+    B2V_CUDA(g, cudaMalloc(&g->meta.counters, kNumCounters * sizeof(uint32_t)));
+    B2V_CUDA(g, cudaMalloc(&g->d_total, sizeof(uint32_t)));
+    B2V_CUDA(g, cudaMallocHost(&g->h_counters, kNumCounters * sizeof(uint32_t)));
+    int rc = grid_clear_device(g, capacity_blocks);
+    if (rc != B2V_OK) return rc;
+    B2V_CUDA(g, cudaStreamSynchronize(g->stream));
+    return B2V_OK;
+}
+
+extern "C" int b2v_grid_destroy(b2v_grid *g) {
+    if (!g) return B2V_OK;
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    cudaFree(g->table.entries);
+    cudaFree(g->meta.pool);
+    cudaFree(g->meta.block_keys);
+    cudaFree(g->meta.counters);
+    cudaFree(g->d_pts);
+    cudaFree(g->d_cols);
+    cudaFree(g->d_sums);
+    cudaFree(g->d_offs);
+    cudaFree(g->d_total);
+    cudaFree(g->d_out_pts);
+    cudaFree(g->d_out_cols);
+    cudaFreeHost(g->h_counters);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+    return B2V_OK;
+}
+
+static int grid_read_counters(b2v_grid *g) {
+    B2V_CUDA(g, cudaSetDevice(g->device));
+    B2V_CUDA(g, cudaMemcpyAsync(g->h_counters, g->meta.counters, kNumCounters * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, g->stream));
+    B2V_CUDA(g, cudaStreamSynchronize(g->stream));
+    if (g->h_counters[kCtrError]) {
+        g->err = (g->h_counters[kCtrError] & 2u) ? "hash table full: raise capacity_blocks"
+                                                 : "block pool full: raise capacity_blocks";
+        return B2V_ERR_CAPACITY;
+    }
+    return B2V_OK;
+}
+
+static uint32_t grid_block_count(const b2v_grid *g) {
+    const uint32_t n = g->h_counters[kCtrPool];
+    return n < g->meta.capacity ? n : g->meta.capacity;
+}
+
+extern "C" int b2v_grid_clear(b2v_grid *g) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    int rc = grid_read_counters(g);
+    if (rc == B2V_ERR_CUDA) return rc;
+    rc = grid_clear_device(g, grid_block_count(g));
+    if (rc != B2V_OK) return rc;
+    g->err.clear();
+    B2V_CUDA(g, cudaStreamSynchronize(g->stream));
+    return B2V_OK;
+}
+
+extern "C" int b2v_grid_integrate(b2v_grid *g, const float *points, const float *colors, int64_t n_points) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    if (n_points < 0 || (n_points > 0 && !points)) {
+        g->err = "b2v_grid_integrate: bad arguments";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    if (n_points == 0) return B2V_OK;  // voxel_block_grid.hpp:22-24,121-123
+    B2V_CUDA(g, cudaSetDevice(g->device));
+    const float *d_p = points, *d_c = colors;
+    const bool dev_p = is_device_pointer(points);
+    const bool dev_c = colors ? is_device_pointer(colors) : true;
+    if (!dev_p || !dev_c) {
+        if (static_cast<size_t>(n_points) > g->stage_points) {
+            B2V_CUDA(g, cudaStreamSynchronize(g->stream));
+            B2V_CUDA(g, regrow(&g->d_pts, static_cast<size_t>(n_points) * 3));
+            B2V_CUDA(g, regrow(&g->d_cols, static_cast<size_t>(n_points) * 3));
+            g->stage_points = static_cast<size_t>(n_points);
+        }
+        if (!dev_p) {
+            B2V_CUDA(g, cudaMemcpyAsync(g->d_pts, points, static_cast<size_t>(n_points) * 3 * sizeof(float),
+                                        cudaMemcpyHostToDevice, g->stream));
+            d_p = g->d_pts;
+        }
+        if (colors && !dev_c) {
+            B2V_CUDA(g, cudaMemcpyAsync(g->d_cols, colors, static_cast<size_t>(n_points) * 3 * sizeof(float),
+                                        cudaMemcpyHostToDevice, g->stream));
+            d_c = g->d_cols;
+        }
+    }
+    B2V_CUDA(g, launch_grid_integrate(d_p, d_c, n_points, g->inv_voxel_size, g->table, g->meta, g->stream));
+    return B2V_OK;
+}
+
+extern "C" int b2v_grid_synchronize(b2v_grid *g) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    return grid_read_counters(g);
+}
+
+extern "C" int64_t b2v_grid_num_blocks(b2v_grid *g) {
+    if (!g) return -1;
+    if (grid_read_counters(g) == B2V_ERR_CUDA) return -1;
+    return grid_block_count(g);
+}
+
+static int grid_ensure_scan(b2v_grid *g, uint32_t nb) {
+    if (nb <= g->scan_cap) return B2V_OK;
+    B2V_CUDA(g, regrow(&g->d_sums, static_cast<size_t>(nb)));
+    B2V_CUDA(g, regrow(&g->d_offs, static_cast<size_t>(nb)));
+    g->scan_cap = nb;
+    return B2V_OK;
+}
+
+static int64_t grid_count(b2v_grid *g, int32_t min_count, uint32_t *nb_out) {
+    if (grid_read_counters(g) == B2V_ERR_CUDA) return -1;
+    const uint32_t nb = grid_block_count(g);
+    if (nb_out) *nb_out = nb;
+    if (grid_ensure_scan(g, nb) != B2V_OK) return -1;
+    if (launch_grid_count(g->meta, nb, min_count, g->d_sums, g->d_offs, g->d_total, g->stream) != cudaSuccess)
+        return -1;
+    uint32_t total = 0;
+    if (cudaMemcpyAsync(&total, g->d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream) != cudaSuccess)
+        return -1;
+    if (cudaStreamSynchronize(g->stream) != cudaSuccess) return -1;
+    return total;
+}
+
+extern "C" int64_t b2v_grid_size(b2v_grid *g) {
+    if (!g) return -1;
+    return grid_count(g, 1, nullptr);
+}
+
+extern "C" int64_t b2v_grid_get_voxels(b2v_grid *g, int32_t min_count) {
+    if (!g) return -1;
+    uint32_t nb = 0;
+    const int64_t n = grid_count(g, min_count, &nb);
+    if (n < 0) return -1;
+    if (static_cast<size_t>(n) > g->out_cap) {
+        if (regrow(&g->d_out_pts, static_cast<size_t>(n) * 3) != cudaSuccess) return -1;
+        if (regrow(&g->d_out_cols, static_cast<size_t>(n) * 3) != cudaSuccess) return -1;
+        g->out_cap = static_cast<size_t>(n);
+    }
+    if (launch_grid_emit(g->meta, nb, min_count, g->d_offs, g->d_out_pts, g->d_out_cols, g->stream) != cudaSuccess)
+        return -1;
+    if (cudaStreamSynchronize(g->stream) != cudaSuccess) return -1;
+    g->last_n = n;
+    return n;
+}
+
+extern "C" int b2v_grid_copy_voxels(b2v_grid *g, float *points, float *colors) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    const size_t n = static_cast<size_t>(g->last_n);
+    if (points && n) B2V_CUDA(g, cudaMemcpy(points, g->d_out_pts, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (colors && n) B2V_CUDA(g, cudaMemcpy(colors, g->d_out_cols, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2V_OK;
+}
+
+extern "C" int b2v_grid_remove_low_count_voxels(b2v_grid *g, int32_t min_count) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    const int rc = grid_read_counters(g);
+    if (rc == B2V_ERR_CUDA) return rc;
+    B2V_CUDA(g, launch_grid_remove_low_count(g->meta, grid_block_count(g), min_count, g->stream));
+    return B2V_OK;
+}
+
+extern "C" int64_t b2v_grid_dump_blocks(b2v_grid *g, int32_t *keys, uint64_t *hashes, int32_t *count,
+                                        float *pos_sum, float *col_sum) {
+    if (!g) return -1;
+    if (grid_read_counters(g) == B2V_ERR_CUDA) return -1;
+    const uint32_t nb = grid_block_count(g);
+    if (nb == 0) return 0;
+    std::vector<int4> k(nb);
+    if (cudaMemcpy(k.data(), g->meta.block_keys, nb * sizeof(int4), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    for (uint32_t i = 0; i < nb; ++i) {
+        if (keys) {
+            keys[3 * i + 0] = k[i].x;
+            keys[3 * i + 1] = k[i].y;
+            keys[3 * i + 2] = k[i].z;
+        }
+        if (hashes) hashes[i] = block_key_hash(k[i].x, k[i].y, k[i].z);
+    }
+    if (count || pos_sum || col_sum) {
+        std::vector<uint32_t> raw(static_cast<size_t>(nb) * kGridBlockWordsHost);
+        if (cudaMemcpy(raw.data(), g->meta.pool, raw.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -1;
+        for (size_t b = 0; b < nb; ++b) {
+            const uint32_t *blk = raw.data() + b * kGridBlockWordsHost;
+            const float *fb = reinterpret_cast<const float *>(blk);
+            for (int l = 0; l < kVox; ++l) {
+                if (count) count[b * kVox + l] = static_cast<int32_t>(blk[l]);
+                for (int c = 0; c < 3; ++c) {
+                    if (pos_sum) pos_sum[(b * kVox + l) * 3 + c] = fb[(1 + c) * kVox + l];
+                    if (col_sum) col_sum[(b * kVox + l) * 3 + c] = fb[(4 + c) * kVox + l];
+                }
+            }
+        }
+    }
+    return nb;
+}

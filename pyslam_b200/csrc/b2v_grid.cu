@@ -1,0 +1,167 @@
+// b2v_grid.cu — point-average voxel block grid (pySLAM's own `volumetric.VoxelBlockGrid`), sm_100a.
+//
+// Replaces VoxelBlockGridT<VoxelData>::integrate_raw / get_voxels / remove_low_count_voxels
+// (cpp/volumetric/voxel_block_grid.hpp:115-136, 524-614, 625-647, 717-819).  Per voxel the
+// reference keeps {count, position_sum[3], color_sum[3]} (cpp/volumetric/voxel_data.h:118-133);
+// here each block stores the same seven fields as 512-wide planes so a warp's accesses coalesce.
+//   keys: voxel = floor(p * inv_vs) (voxel_hashing.h:69-75), block = floor_div(voxel, 8),
+//         local index lx + 8 ly + 64 lz (voxel_block.h:67-70) -- bit exact.
+//   sums: float atomics => same values as the reference up to summation order.
+#include "b2v_internal.h"
+#include "b2v_scan.cuh"
+
+namespace b2v {
+
+constexpr int kGridPlanes = 7;  // count(int32), px, py, pz, cr, cg, cb
+constexpr int kGridBlockWords = kGridPlanes * kVox;
+
+// ---- pass 1: make sure every point's block exists -------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_insert_kernel(const float *__restrict__ pts, const int64_t n, const float inv_vs,
+                   const HashTable T, const GridMeta G) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool have = i < n;
+    int bx = 0, by = 0, bz = 0;
+    if (have) {
+        bx = block_coord(voxel_coord(pts[3 * i + 0], inv_vs));
+        by = block_coord(voxel_coord(pts[3 * i + 1], inv_vs));
+        bz = block_coord(voxel_coord(pts[3 * i + 2], inv_vs));
+    }
+    // one probe per distinct block per warp (neighbouring pixels share blocks)
+    const unsigned long long pk = have ? (static_cast<unsigned long long>(slot_hash(bx, by, bz)) << 32 |
+                                          static_cast<uint32_t>(bx * 73856093 ^ by * 19349663 ^ bz * 83492791))
+                                       : ((1ull << 63) | static_cast<unsigned long long>(lane) << 40 | 0xFFFFFFull);
+    const unsigned grp = __match_any_sync(0xffffffffu, pk);
+    // hash equality is not key equality: only skip when the leader's key really matches
+    const int leader = __ffs(grp) - 1;
+    const int lbx = __shfl_sync(0xffffffffu, bx, leader), lby = __shfl_sync(0xffffffffu, by, leader),
+              lbz = __shfl_sync(0xffffffffu, bz, leader);
+    if (!have) return;
+    if (leader != lane && lbx == bx && lby == by && lbz == bz) return;
+    bool is_new;
+    const uint32_t slot = table_insert(T, bx, by, bz, &is_new);
+    if (slot == kEmpty) {
+        atomicOr(G.counters + kCtrError, 2u);
+        return;
+    }
+    if (is_new) {
+        const uint32_t idx = atomicAdd(G.counters + kCtrPool, 1u);
+        uint32_t *w = reinterpret_cast<uint32_t *>(T.entries + slot) + 3;
+        if (idx < G.capacity) {
+            G.block_keys[idx] = make_int4(bx, by, bz, 0);
+            *w = idx;
+        } else {
+            *w = kNoBlock;
+            atomicOr(G.counters + kCtrError, 1u);
+        }
+    }
+}
+
+// ---- pass 2: accumulate ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_accumulate_kernel(const float *__restrict__ pts, const float *__restrict__ cols, const int64_t n,
+                       const float inv_vs, const HashTable T, const GridMeta G) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = pts[3 * i + 0], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    const int vx = voxel_coord(x, inv_vs), vy = voxel_coord(y, inv_vs), vz = voxel_coord(z, inv_vs);
+    const uint32_t slot = table_find(T, block_coord(vx), block_coord(vy), block_coord(vz));
+    if (slot == kEmpty) return;
+    const uint32_t idx = T.entries[slot].w;
+    if (idx >= G.capacity) return;
+    const int l = local_coord(vx) + (local_coord(vy) << 3) + (local_coord(vz) << 6);
+    uint32_t *blk = G.pool + static_cast<size_t>(idx) * kGridBlockWords;
+    float *fb = reinterpret_cast<float *>(blk);
+    atomicAdd(fb + 1 * kVox + l, x);
+    atomicAdd(fb + 2 * kVox + l, y);
+    atomicAdd(fb + 3 * kVox + l, z);
+    if (cols != nullptr) {
+        atomicAdd(fb + 4 * kVox + l, cols[3 * i + 0]);
+        atomicAdd(fb + 5 * kVox + l, cols[3 * i + 1]);
+        atomicAdd(fb + 6 * kVox + l, cols[3 * i + 2]);
+    }
+    atomicAdd(reinterpret_cast<int *>(blk) + l, 1);
+}
+
+// ---- get_voxels: count -> scan -> emit -------------------------------------------------------
+__global__ void __launch_bounds__(kVox)
+grid_count_kernel(const GridMeta G, const int min_count, uint32_t *__restrict__ sums) {
+    __shared__ uint32_t s_warp[16];
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    const int c = reinterpret_cast<const int *>(G.pool + static_cast<size_t>(b) * kGridBlockWords)[t];
+    uint32_t x = __reduce_add_sync(0xffffffffu, (c >= min_count) ? 1u : 0u);
+    if ((t & 31) == 0) s_warp[t >> 5] = x;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t s = 0;
+        for (int k = 0; k < 16; ++k) s += s_warp[k];
+        sums[b] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kVox)
+grid_emit_kernel(const GridMeta G, const int min_count, const uint32_t *__restrict__ offs,
+                 float *__restrict__ out_pts, float *__restrict__ out_cols) {
+    __shared__ uint32_t s_warp[16];
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    const uint32_t *blk = G.pool + static_cast<size_t>(b) * kGridBlockWords;
+    const float *fb = reinterpret_cast<const float *>(blk);
+    const int c = reinterpret_cast<const int *>(blk)[t];
+    const bool keep = c >= min_count;
+    const uint32_t pos = offs[b] + block_excl_scan_512(keep ? 1u : 0u, s_warp);
+    if (!keep) return;
+    const float fc = static_cast<float>(c);  // voxel_data.h:64-67,104-107: sum / (T)count
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        out_pts[3 * static_cast<size_t>(pos) + k] = __fdiv_rn(fb[(1 + k) * kVox + t], fc);
+        out_cols[3 * static_cast<size_t>(pos) + k] = __fdiv_rn(fb[(4 + k) * kVox + t], fc);
+    }
+}
+
+__global__ void __launch_bounds__(kVox)
+grid_remove_low_count_kernel(const GridMeta G, const int min_count) {
+    uint32_t *blk = G.pool + static_cast<size_t>(blockIdx.x) * kGridBlockWords;
+    const int t = threadIdx.x;
+    if (reinterpret_cast<const int *>(blk)[t] < min_count) {  // voxel_block_grid.hpp:641-643 -> reset()
+#pragma unroll
+        for (int k = 0; k < kGridPlanes; ++k) blk[k * kVox + t] = 0u;
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------
+cudaError_t launch_grid_integrate(const float *pts, const float *cols, int64_t n, float inv_vs,
+                                  const HashTable &table, const GridMeta &meta, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    grid_insert_kernel<<<grid, 256, 0, stream>>>(pts, n, inv_vs, table, meta);
+    grid_accumulate_kernel<<<grid, 256, 0, stream>>>(pts, cols, n, inv_vs, table, meta);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_count(const GridMeta &meta, uint32_t n_blocks, int min_count, uint32_t *sums,
+                              uint32_t *offs, uint32_t *total, cudaStream_t stream) {
+    if (n_blocks == 0) return cudaMemsetAsync(total, 0, sizeof(uint32_t), stream);
+    grid_count_kernel<<<n_blocks, kVox, 0, stream>>>(meta, min_count, sums);
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(sums, offs, total, n_blocks);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_emit(const GridMeta &meta, uint32_t n_blocks, int min_count,
+                             const uint32_t *offs, float *out_pts, float *out_cols,
+                             cudaStream_t stream) {
+    if (n_blocks == 0) return cudaSuccess;
+    grid_emit_kernel<<<n_blocks, kVox, 0, stream>>>(meta, min_count, offs, out_pts, out_cols);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_remove_low_count(const GridMeta &meta, uint32_t n_blocks, int min_count,
+                                         cudaStream_t stream) {
+    if (n_blocks == 0) return cudaSuccess;
+    grid_remove_low_count_kernel<<<n_blocks, kVox, 0, stream>>>(meta, min_count);
+    return cudaGetLastError();
+}
+
+}  // namespace b2v

@@ -1,0 +1,119 @@
+// b2v_internal.h — host-side state of a volume and the kernel launchers (one .cu per kernel family).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+
+#include "b2v_device.cuh"
+
+namespace b2v {
+
+// Per-frame constants, passed to the kernels by value (kernel-parameter space, no copies).
+struct FrameParams {
+    // f64 back-projection of the allocation samples (Open3D CreatePointCloudFromFloatDepthImage)
+    double fx, fy, cx, cy;
+    double Rwc[9];   // rigid inverse of Tcw, row-major
+    double twc[3];
+    double tau_d;    // (double)sdf_trunc
+    // f32 projective update (Open3D UniformTSDFVolume::Integrate...)
+    float E[12];     // Tcw rows 0..2 as float32
+    float fxf, fyf, cxf, cyf;
+    float inv_fx, inv_fy;   // 1.0f / fx, 1.0f / fy
+    float cxh, cyh;         // cx + 0.5f, cy + 0.5f
+    float safe_w, safe_h;   // W - 0.0001f, H - 0.0001f
+    float vs, inv_vs, tau, inv_tau, depth_trunc;
+    int32_t H, W, stride;
+    uint32_t frame_id;
+    int32_t shard_rank, shard_count;
+};
+
+// Device-resident bookkeeping of one volume.
+struct PoolMeta {
+    float *pool;              // [capacity][5][512] float32 planes: tsdf, weight, r, g, b
+    int4 *block_keys;         // [capacity] key of pool block i (w unused)
+    uint32_t *counters;       // device counters, see Counter
+    uint32_t *active_slots;   // [kActiveRing][capacity] table slots touched by a frame
+    uint32_t capacity;
+};
+
+enum Counter : int {
+    kCtrPool = 0,        // number of allocated blocks (may exceed capacity on overflow)
+    kCtrError = 1,       // sticky error flag (1 = pool overflow, 2 = table full)
+    kCtrUpdatesLo = 2,   // 64-bit total of (block, frame) updates since reset (8-byte aligned)
+    kCtrUpdatesHi = 3,
+    kCtrActive0 = 4,     // kActiveRing per-frame counts of touched blocks
+    kCtrNew0 = 8,        // kActiveRing per-frame counts of newly allocated blocks
+    kNumCounters = 16
+};
+constexpr int kActiveRing = 4;
+
+void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], int H, int W,
+                       int stride, float vs, float tau, float depth_trunc, uint32_t frame_id,
+                       int shard_rank, int shard_count);
+
+// ---- kernels (b2v_tsdf.cu) ----
+// allocation + touched-set of one frame; zeroes the next frame's active counter
+cudaError_t launch_allocate(const FrameParams &p, const float *depth, const HashTable &table,
+                            const PoolMeta &meta, int ring, cudaStream_t stream);
+// projective TSDF + colour update of every block touched by the frame
+cudaError_t launch_integrate(const FrameParams &p, const float *depth, const uint8_t *color,
+                             const HashTable &table, const PoolMeta &meta, int ring, int grid_ctas,
+                             cudaStream_t stream);
+// hashes[i] = BlockKeyHash(block_keys[i])
+cudaError_t launch_block_hashes(const int4 *block_keys, uint64_t *hashes, uint32_t n,
+                                cudaStream_t stream);
+// keys of the slots in an active list
+cudaError_t launch_gather_active_keys(const HashTable &table, const uint32_t *active_slots,
+                                      uint32_t n, int4 *out, cudaStream_t stream);
+
+// find-or-create the blocks of `keys` (unique) and copy `vox` [n][5][512] into them
+cudaError_t launch_upload_blocks(const int4 *keys, const float *vox, uint32_t n, uint32_t *scratch_idx,
+                                 const HashTable &table, const PoolMeta &meta, cudaStream_t stream);
+
+// ---- mesh (b2v_mesh.cu) ----
+// Scratch and outputs of one extraction.  Per-voxel scratch is indexed [pool block][voxel].
+struct MeshBuffers {
+    uint32_t n_blocks;
+    int32_t *nbr;            // [n_blocks][8] pool index of the block at +(dx,dy,dz) (bit0=x), -1 if missing
+    uint8_t *cube;           // [n_blocks][512] marching-cubes case of the cube rooted here (0 = none)
+    uint32_t *edge_mask;     // [n_blocks][128] byte per voxel: bit a = a vertex lives on its +a edge
+    uint32_t *vert_base;     // [n_blocks][512] index of the voxel's first vertex
+    uint32_t *sums;          // [2][n_blocks] per-block vertex / triangle counts
+    uint32_t *offs;          // [2][n_blocks] exclusive scans of sums
+    uint32_t *totals;        // [2] total vertices, triangles
+    float *vertices;         // [nv][3]
+    float *colors;           // [nv][3] in [0,1]
+    int32_t *edge_ids;       // [nv][4] canonical weld key (voxel x,y,z, axis)
+    int32_t *triangles;      // [nt][3]
+};
+cudaError_t launch_mesh_neighbors(const HashTable &table, const PoolMeta &meta,
+                                  const MeshBuffers &mb, cudaStream_t stream);
+// marching-cubes case per voxel + vertex ownership masks (Open3D ExtractTriangleMesh semantics)
+cudaError_t launch_mesh_classify(const PoolMeta &meta, const MeshBuffers &mb, cudaStream_t stream);
+// zero-crossing masks of Open3D ExtractPointCloud (no cube validity requirement)
+cudaError_t launch_point_masks(const PoolMeta &meta, const MeshBuffers &mb, cudaStream_t stream);
+// per-block sums + exclusive scans -> offs, totals
+cudaError_t launch_mesh_scan(const MeshBuffers &mb, cudaStream_t stream);
+cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, float vs,
+                                 cudaStream_t stream);
+cudaError_t launch_mesh_triangles(const MeshBuffers &mb, cudaStream_t stream);
+
+// ---- point-average grid (b2v_grid.cu) ----
+struct GridMeta {
+    uint32_t *pool;        // [capacity][7][512] planes: count(int32), px, py, pz, cr, cg, cb (float32)
+    int4 *block_keys;      // [capacity]
+    uint32_t *counters;    // kCtrPool, kCtrError
+    uint32_t capacity;
+};
+cudaError_t launch_grid_integrate(const float *pts, const float *cols, int64_t n, float inv_vs,
+                                  const HashTable &table, const GridMeta &meta, cudaStream_t stream);
+cudaError_t launch_grid_count(const GridMeta &meta, uint32_t n_blocks, int min_count, uint32_t *sums,
+                              uint32_t *offs, uint32_t *total, cudaStream_t stream);
+cudaError_t launch_grid_emit(const GridMeta &meta, uint32_t n_blocks, int min_count,
+                             const uint32_t *offs, float *out_pts, float *out_cols,
+                             cudaStream_t stream);
+cudaError_t launch_grid_remove_low_count(const GridMeta &meta, uint32_t n_blocks, int min_count,
+                                         cudaStream_t stream);
+
+}  // namespace b2v

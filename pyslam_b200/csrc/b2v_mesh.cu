@@ -1,0 +1,308 @@
+// b2v_mesh.cu — per-block marching-cubes triangle emission (sm_100a).
+//
+// Replaces Open3D ScalableTSDFVolume::ExtractTriangleMesh / ExtractPointCloud, called from
+// pyslam/dense/volumetric_integrator_tsdf.py:239,246,260,267.  Semantics:
+//   - a cube is rooted at every voxel; its 8 corners may live in up to 7 neighbouring blocks;
+//     a cube with any zero-weight (or missing) corner is skipped; cases 0 / 255 emit nothing
+//   - a vertex lives on an edge identified by (lower-corner voxel, axis) and is shared by every
+//     cube around that edge (welding): position = voxel centre + |f0| vs / (|f0| + |f1|) along axis
+//   - triangles come from the classic 256-case table with winding (i, i+2, i+1)
+// Deterministic three-pass structure: classify -> exclusive scan -> emit.  Output order is
+// (pool block, voxel index, axis) for vertices and (pool block, voxel index, case order) for
+// triangles.
+#include "b2v_internal.h"
+#include "b2v_scan.cuh"
+#include "mc_tables.h"
+
+namespace b2v {
+
+__constant__ unsigned short c_edge_table[256];
+__constant__ signed char c_tri_table[256][16];
+__constant__ unsigned char c_num_tris[256];
+__constant__ signed char c_edge_shift[12][4];
+
+static cudaError_t upload_tables_once() {
+    static bool done = false;
+    static int done_device = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done && done_device == dev) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_edge_table, MC_EDGE_TABLE, sizeof(MC_EDGE_TABLE))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_tri_table, MC_TRI_TABLE, sizeof(MC_TRI_TABLE))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_num_tris, MC_NUM_TRIS, sizeof(MC_NUM_TRIS))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_edge_shift, MC_EDGE_SHIFT, sizeof(MC_EDGE_SHIFT))) != cudaSuccess) return e;
+    done = true;
+    done_device = dev;
+    return cudaSuccess;
+}
+
+// ---- pass 0: neighbour block indices --------------------------------------------------------
+
+__global__ void mesh_neighbors_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mb.n_blocks * 8u) return;
+    const uint32_t b = i >> 3, o = i & 7;
+    const int4 k = M.block_keys[b];
+    int32_t idx = static_cast<int32_t>(b);
+    if (o != 0) {
+        const uint32_t s = table_find(T, k.x + (o & 1), k.y + ((o >> 1) & 1), k.z + ((o >> 2) & 1));
+        idx = -1;
+        if (s != kEmpty) {
+            const uint32_t w = T.entries[s].w;
+            if (w < M.capacity) idx = static_cast<int32_t>(w);
+        }
+    }
+    mb.nbr[i] = idx;
+}
+
+// owner voxel of cube edge e rooted at local (lx,ly,lz): returns flat index into per-voxel arrays
+__device__ __forceinline__ bool edge_owner(const int *s_nbr, int lx, int ly, int lz, int e,
+                                           size_t *flat, int *axis) {
+    const int ox = lx + c_edge_shift[e][0], oy = ly + c_edge_shift[e][1], oz = lz + c_edge_shift[e][2];
+    *axis = c_edge_shift[e][3];
+    const int nb = (ox >> 3) | ((oy >> 3) << 1) | ((oz >> 3) << 2);
+    const int ob = s_nbr[nb];
+    if (ob < 0) return false;
+    *flat = static_cast<size_t>(ob) * kVox + ((ox & 7) + ((oy & 7) << 3) + ((oz & 7) << 6));
+    return true;
+}
+
+// ---- pass 1a: marching-cubes case + vertex ownership (mesh) ---------------------------------
+
+__global__ void __launch_bounds__(kVox)
+mesh_classify_kernel(const PoolMeta M, const MeshBuffers mb) {
+    __shared__ float s_f[729];
+    __shared__ float s_w[729];
+    __shared__ int s_nbr[8];
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
+    __syncthreads();
+    for (int i = t; i < 729; i += kVox) {
+        const int x = i % 9, y = (i / 9) % 9, z = i / 81;
+        const int pb = s_nbr[(x >> 3) | ((y >> 3) << 1) | ((z >> 3) << 2)];
+        float f = 0.0f, w = 0.0f;
+        if (pb >= 0) {
+            const float *blk = M.pool + static_cast<size_t>(pb) * kBlockFloats;
+            const int v = (x & 7) + ((y & 7) << 3) + ((z & 7) << 6);
+            f = blk[v];
+            w = blk[kVox + v];
+        }
+        s_f[i] = f;
+        s_w[i] = w;
+    }
+    __syncthreads();
+    const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
+    int cube = 0;
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        // corner offsets {000,100,110,010,001,101,111,011} (SURVEY.md A.4 `shift`)
+        const int sx = ((c + 1) >> 1) & 1, sy = (c >> 1) & 1, sz = c >> 2;
+        const int i = (lx + sx) + (ly + sy) * 9 + (lz + sz) * 81;
+        ok = ok && (s_w[i] != 0.0f);
+        if (s_f[i] < 0.0f) cube |= (1 << c);
+    }
+    if (!ok || cube == 255) cube = 0;
+    mb.cube[static_cast<size_t>(b) * kVox + t] = static_cast<uint8_t>(cube);
+    if (cube) {
+        const unsigned em = c_edge_table[cube];
+        for (int e = 0; e < 12; ++e) {
+            if (!((em >> e) & 1u)) continue;
+            size_t flat;
+            int axis;
+            if (edge_owner(s_nbr, lx, ly, lz, e, &flat, &axis))
+                atomicOr(mb.edge_mask + (flat >> 2), (1u << axis) << ((flat & 3) * 8));
+        }
+    }
+}
+
+// ---- pass 1b: zero-crossing masks (point cloud) ---------------------------------------------
+
+__global__ void __launch_bounds__(kVox)
+point_masks_kernel(const PoolMeta M, const MeshBuffers mb) {
+    __shared__ int s_nbr[8];
+    __shared__ uint8_t s_m[kVox];
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
+    __syncthreads();
+    const float *blk = M.pool + static_cast<size_t>(b) * kBlockFloats;
+    const float f0 = blk[t], w0 = blk[kVox + t];
+    const int l[3] = {t & 7, (t >> 3) & 7, t >> 6};
+    unsigned m = 0;
+    if (w0 != 0.0f && f0 < 0.98f && f0 >= -0.98f) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int q[3] = {l[0], l[1], l[2]};
+            q[a] += 1;
+            const int pb = s_nbr[(q[0] >> 3) | ((q[1] >> 3) << 1) | ((q[2] >> 3) << 2)];
+            if (pb < 0) continue;
+            const float *nb = M.pool + static_cast<size_t>(pb) * kBlockFloats;
+            const int v = (q[0] & 7) + ((q[1] & 7) << 3) + ((q[2] & 7) << 6);
+            const float f1 = nb[v], w1 = nb[kVox + v];
+            if (w1 != 0.0f && f1 < 0.98f && f1 >= -0.98f && f0 * f1 < 0.0f) m |= 1u << a;
+        }
+    }
+    s_m[t] = static_cast<uint8_t>(m);
+    mb.cube[static_cast<size_t>(b) * kVox + t] = 0;
+    __syncthreads();
+    if (t < kVox / 4)
+        mb.edge_mask[static_cast<size_t>(b) * (kVox / 4) + t] = reinterpret_cast<const uint32_t *>(s_m)[t];
+}
+
+// ---- pass 2: per-block sums and their exclusive scans ---------------------------------------
+
+__global__ void __launch_bounds__(128)
+mesh_block_sums_kernel(const MeshBuffers mb) {
+    __shared__ uint32_t s_v[4], s_t[4];
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    const uint32_t m4 = mb.edge_mask[static_cast<size_t>(b) * 128 + t];
+    const uint32_t c4 = reinterpret_cast<const uint32_t *>(mb.cube)[static_cast<size_t>(b) * 128 + t];
+    uint32_t nv = __popc(m4 & 0x07070707u);
+    uint32_t nt = c_num_tris[c4 & 0xFF] + c_num_tris[(c4 >> 8) & 0xFF] + c_num_tris[(c4 >> 16) & 0xFF] +
+                  c_num_tris[c4 >> 24];
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    nt = __reduce_add_sync(0xffffffffu, nt);
+    if ((t & 31) == 0) {
+        s_v[t >> 5] = nv;
+        s_t[t >> 5] = nt;
+    }
+    __syncthreads();
+    if (t == 0) {
+        mb.sums[b] = s_v[0] + s_v[1] + s_v[2] + s_v[3];
+        mb.sums[mb.n_blocks + b] = s_t[0] + s_t[1] + s_t[2] + s_t[3];
+    }
+}
+
+// ---- pass 3a: vertices -----------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kVox)
+mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const float vs) {
+    __shared__ uint32_t s_warp[16];
+    __shared__ int s_nbr[8];
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
+    const size_t flat = static_cast<size_t>(b) * kVox + t;
+    const unsigned m = (mb.edge_mask[flat >> 2] >> ((flat & 3) * 8)) & 7u;
+    const uint32_t base = mb.offs[b] + block_excl_scan_512(__popc(m), s_warp);
+    mb.vert_base[flat] = base;
+    if (m == 0) return;
+    const int4 key = M.block_keys[b];
+    const int l[3] = {t & 7, (t >> 3) & 7, t >> 6};
+    const int g[3] = {key.x * kB + l[0], key.y * kB + l[1], key.z * kB + l[2]};
+    const float *blk = M.pool + static_cast<size_t>(b) * kBlockFloats;
+    const float f0 = fabsf(blk[t]);
+    const float c0[3] = {blk[2 * kVox + t], blk[3 * kVox + t], blk[4 * kVox + t]};
+    const float ctr[3] = {__fmul_rn(__fadd_rn(static_cast<float>(g[0]), 0.5f), vs),
+                          __fmul_rn(__fadd_rn(static_cast<float>(g[1]), 0.5f), vs),
+                          __fmul_rn(__fadd_rn(static_cast<float>(g[2]), 0.5f), vs)};
+    uint32_t vid = base;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (!((m >> a) & 1u)) continue;
+        int q[3] = {l[0], l[1], l[2]};
+        q[a] += 1;
+        const int pb = s_nbr[(q[0] >> 3) | ((q[1] >> 3) << 1) | ((q[2] >> 3) << 2)];
+        const float *nb = M.pool + static_cast<size_t>(pb) * kBlockFloats;
+        const int v = (q[0] & 7) + ((q[1] & 7) << 3) + ((q[2] & 7) << 6);
+        const float f1 = fabsf(nb[v]);
+        const float fs = __fadd_rn(f0, f1);
+        float p[3] = {ctr[0], ctr[1], ctr[2]};
+        p[a] = __fadd_rn(p[a], __fdiv_rn(__fmul_rn(f0, vs), fs));
+        mb.vertices[3 * static_cast<size_t>(vid) + 0] = p[0];
+        mb.vertices[3 * static_cast<size_t>(vid) + 1] = p[1];
+        mb.vertices[3 * static_cast<size_t>(vid) + 2] = p[2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float c1 = nb[(2 + k) * kVox + v];
+            const float num = __fmaf_rn(f1, c0[k], __fmul_rn(f0, c1));
+            mb.colors[3 * static_cast<size_t>(vid) + k] = __fdiv_rn(__fdiv_rn(num, fs), 255.0f);
+        }
+        reinterpret_cast<int4 *>(mb.edge_ids)[vid] = make_int4(g[0], g[1], g[2], a);
+        ++vid;
+    }
+}
+
+// ---- pass 3b: triangles ----------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kVox)
+mesh_triangles_kernel(const MeshBuffers mb) {
+    __shared__ uint32_t s_warp[16];
+    __shared__ int s_nbr[8];
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
+    const int cube = mb.cube[static_cast<size_t>(b) * kVox + t];
+    const uint32_t nt = c_num_tris[cube];
+    const uint32_t tbase = mb.offs[mb.n_blocks + b] + block_excl_scan_512(nt, s_warp);
+    if (nt == 0) return;
+    const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
+    int vid[12];
+    const unsigned em = c_edge_table[cube];
+    for (int e = 0; e < 12; ++e) {
+        vid[e] = -1;
+        if (!((em >> e) & 1u)) continue;
+        size_t flat;
+        int axis;
+        if (!edge_owner(s_nbr, lx, ly, lz, e, &flat, &axis)) continue;
+        const unsigned m = (mb.edge_mask[flat >> 2] >> ((flat & 3) * 8)) & 7u;
+        vid[e] = static_cast<int>(mb.vert_base[flat] + __popc(m & ((1u << axis) - 1u)));
+    }
+    for (uint32_t k = 0; k < nt; ++k) {
+        int32_t *tri = mb.triangles + 3 * static_cast<size_t>(tbase + k);
+        tri[0] = vid[c_tri_table[cube][3 * k + 0]];
+        tri[1] = vid[c_tri_table[cube][3 * k + 2]];  // winding (i, i+2, i+1)
+        tri[2] = vid[c_tri_table[cube][3 * k + 1]];
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------
+
+cudaError_t launch_mesh_neighbors(const HashTable &table, const PoolMeta &meta,
+                                  const MeshBuffers &mb, cudaStream_t stream) {
+    cudaError_t e = upload_tables_once();
+    if (e != cudaSuccess || mb.n_blocks == 0) return e;
+    const uint32_t n = mb.n_blocks * 8u;
+    mesh_neighbors_kernel<<<(n + 255) / 256, 256, 0, stream>>>(table, meta, mb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mesh_classify(const PoolMeta &meta, const MeshBuffers &mb, cudaStream_t stream) {
+    if (mb.n_blocks == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(mb.edge_mask, 0, static_cast<size_t>(mb.n_blocks) * kVox, stream);
+    if (e != cudaSuccess) return e;
+    mesh_classify_kernel<<<mb.n_blocks, kVox, 0, stream>>>(meta, mb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_point_masks(const PoolMeta &meta, const MeshBuffers &mb, cudaStream_t stream) {
+    if (mb.n_blocks == 0) return cudaSuccess;
+    point_masks_kernel<<<mb.n_blocks, kVox, 0, stream>>>(meta, mb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mesh_scan(const MeshBuffers &mb, cudaStream_t stream) {
+    if (mb.n_blocks == 0) return cudaMemsetAsync(mb.totals, 0, 2 * sizeof(uint32_t), stream);
+    mesh_block_sums_kernel<<<mb.n_blocks, 128, 0, stream>>>(mb);
+    exclusive_scan_kernel<<<2, 1024, 0, stream>>>(mb.sums, mb.offs, mb.totals, mb.n_blocks);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, float vs,
+                                 cudaStream_t stream) {
+    if (mb.n_blocks == 0) return cudaSuccess;
+    mesh_vertices_kernel<<<mb.n_blocks, kVox, 0, stream>>>(meta, mb, vs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mesh_triangles(const MeshBuffers &mb, cudaStream_t stream) {
+    if (mb.n_blocks == 0) return cudaSuccess;
+    mesh_triangles_kernel<<<mb.n_blocks, kVox, 0, stream>>>(mb);
+    return cudaGetLastError();
+}
+
+}  // namespace b2v

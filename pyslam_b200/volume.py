@@ -1,0 +1,400 @@
+"""Host-side mirror of the reference's volume objects, over the C ABI (include/b2v.h).
+
+Two duck types are provided, the two `self.volume` shapes pySLAM's dense front-end drives
+(SURVEY.md §8b):
+
+* `B200TsdfVolume` — the north_star API `integrate(depth, color, K, pose)` / `extract_mesh()`
+  plus the Open3D-style methods the TSDF backend calls
+  (`pyslam/dense/volumetric_integrator_tsdf.py:156,223,239,246,260,267`):
+  `integrate(rgbd, intrinsic, extrinsic)`, `extract_triangle_mesh()`, `extract_point_cloud()`,
+  `reset()`.
+* `VoxelBlockGrid` — pySLAM's own `volumetric.VoxelBlockGrid` surface
+  (`cpp/volumetric/volumetric_grid_module.h:732-935`): `integrate(points, colors)`,
+  `get_voxels(min_count)`, `get_points()`, `get_colors()`, `clear()`, `reset()`, `size()`,
+  `empty()`, `num_blocks()`, `get_block_size()`, `get_total_voxel_count()`,
+  `remove_low_count_voxels(n)`.
+
+Everything numeric happens in the CUDA library; these classes only validate arguments (same
+error behaviour as the reference: `RuntimeError` on shape / dtype mismatches,
+`volumetric_grid_module.h:140-258`) and move pointers.  There is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import B2VConfig, BLOCK_SIZE, BLOCK_VOXELS, VOXEL_PLANES
+
+
+def _as_K4(K) -> np.ndarray:
+    """Accept (fx, fy, cx, cy), a 3x3 matrix, or an object with fx/fy/cx/cy (camera / o3d-like)."""
+    if hasattr(K, "fx") and hasattr(K, "cx"):
+        return np.array([K.fx, K.fy, K.cx, K.cy], dtype=np.float64)
+    if hasattr(K, "intrinsic_matrix"):
+        K = np.asarray(K.intrinsic_matrix)
+    K = np.asarray(K, dtype=np.float64)
+    if K.shape == (3, 3):
+        return np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], dtype=np.float64)
+    if K.size == 4:
+        return np.ascontiguousarray(K.reshape(4))
+    raise RuntimeError("K must be (fx, fy, cx, cy) or a 3x3 intrinsic matrix")
+
+
+def _is_torch_cuda(x) -> bool:
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+class TriangleMesh:
+    """Arrays shaped like `VolumetricIntegrationMesh` (volumetric_integrator_base.py:213-226)."""
+
+    def __init__(self, vertices, triangles, vertex_colors, edge_ids=None):
+        self.vertices = vertices                 # [V,3] float64
+        self.triangles = triangles               # [T,3] int32
+        self.vertex_colors = vertex_colors       # [V,3] float64 in [0,1]
+        self.vertex_normals = np.zeros((0, 3), dtype=np.float64)  # Open3D leaves them empty too
+        self.edge_ids = edge_ids                 # [V,4] int32 canonical weld key (parity hook)
+
+
+class PointCloud:
+    """Arrays shaped like `VolumetricIntegrationPointCloud` (volumetric_integrator_base.py:159-210)."""
+
+    def __init__(self, points, colors):
+        self.points = points
+        self.colors = colors
+
+
+class B200TsdfVolume:
+    """B200-native TSDF + colour volume on 8^3 voxel blocks in a GPU hash table.
+
+    Parameters mirror `o3d.pipelines.integration.ScalableTSDFVolume(voxel_length, sdf_trunc, ...)`
+    as constructed at volumetric_integrator_tsdf.py:104-108, plus the depth truncation the reference
+    applies while building the RGBD image (tsdf.py:215-221).
+    """
+
+    def __init__(self, voxel_length: float, sdf_trunc: float, depth_trunc: float = 4.0,
+                 capacity_blocks: int = 1 << 18, device: int = 0, depth_sampling_stride: int = 4,
+                 block_size: int = BLOCK_SIZE, shard_rank: int = 0, shard_count: int = 1):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self.voxel_length = float(voxel_length)
+        self.sdf_trunc = float(sdf_trunc)
+        self.depth_trunc = float(depth_trunc)
+        self.block_size = int(block_size)
+        self.capacity_blocks = int(capacity_blocks)
+        cfg = B2VConfig(voxel_length, block_size, sdf_trunc, depth_trunc, depth_sampling_stride,
+                        capacity_blocks, device, shard_rank, shard_count)
+        rc = self._L.b2v_create(C.byref(cfg), C.byref(self._h))
+        if rc != _lib.B2V_OK:
+            msg = self._L.b2v_last_error(self._h).decode() if self._h else "invalid configuration"
+            if self._h:
+                self._L.b2v_destroy(self._h)
+                self._h = C.c_void_p()
+            raise RuntimeError(f"b2v_create failed (status {rc}): {msg}")
+        self._keepalive = []  # host arrays of frames still in flight
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b2v_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != _lib.B2V_OK:
+            raise RuntimeError(f"{what} failed (status {rc}): {self._L.b2v_last_error(self._h).decode()}")
+
+    # ---- integrate ----
+    def integrate(self, depth, color=None, K=None, pose=None):
+        """north_star: `integrate(depth, color, K, pose)` with depth float32 [H,W] metres, colour
+        uint8 RGB [H,W,3], K = (fx,fy,cx,cy) | 3x3, pose = Tcw 4x4 float64.
+        Open3D style (tsdf.py:223): `integrate(rgbd, intrinsic, extrinsic)` where `rgbd` has
+        `.color` / `.depth`.  Inputs may be numpy arrays or CUDA torch tensors.  Asynchronous."""
+        if hasattr(depth, "depth") and hasattr(depth, "color"):
+            rgbd, K, pose = depth, color, K
+            depth, color = rgbd.depth, rgbd.color
+        if K is None or pose is None or color is None:
+            raise RuntimeError("integrate(depth, color, K, pose): missing argument")
+        K4 = _as_K4(K)
+        T = np.ascontiguousarray(np.asarray(pose, dtype=np.float64).reshape(4, 4)).reshape(16)
+        if _is_torch_cuda(depth):
+            if not _is_torch_cuda(color):
+                raise RuntimeError("depth and color must both be CUDA tensors or both host arrays")
+            if str(depth.dtype) != "torch.float32" or str(color.dtype) != "torch.uint8":
+                raise RuntimeError("depth must be float32 and color uint8")
+            if not depth.is_contiguous() or not color.is_contiguous():
+                raise RuntimeError("depth and color must be contiguous")
+            H, W = int(depth.shape[0]), int(depth.shape[1])
+            if depth.dim() != 2 or tuple(color.shape) != (H, W, 3):
+                raise RuntimeError("depth must be [H,W] and color [H,W,3]")
+            dp, cp = depth.data_ptr(), color.data_ptr()
+            self._keepalive.append((depth, color))
+        else:
+            d = np.asarray(depth)
+            c = np.asarray(color)
+            if d.ndim != 2:
+                raise RuntimeError("depth must have 2 dimensions [H,W]")
+            if c.ndim != 3 or c.shape[2] != 3 or c.shape[:2] != d.shape:
+                raise RuntimeError("color must be [H,W,3] with the depth image's size")
+            if c.dtype != np.uint8:
+                raise RuntimeError("color must be uint8 RGB")
+            d = np.ascontiguousarray(d, dtype=np.float32)  # reference: depth.astype(float32), base.py:1008-1017
+            c = np.ascontiguousarray(c)
+            H, W = d.shape
+            dp, cp = d.ctypes.data, c.ctypes.data
+            self._keepalive.append((d, c))
+        rc = self._L.b2v_integrate(self._h, dp, cp, H, W, K4.ctypes.data, T.ctypes.data, None)
+        self._check(rc, "b2v_integrate")
+        if len(self._keepalive) > 8:
+            # staging ring is 4 deep: anything older has been consumed by the copy engine
+            del self._keepalive[:-8]
+
+    def integrate_batch(self, depths, colors, K, poses):
+        """n frames back to back: depths [n,H,W] f32, colors [n,H,W,3] u8, poses [n,4,4] Tcw."""
+        K4 = _as_K4(K)
+        T = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 16))
+        n = T.shape[0]
+        if _is_torch_cuda(depths):
+            if not (depths.is_contiguous() and colors.is_contiguous()):
+                raise RuntimeError("depths and colors must be contiguous")
+            H, W = int(depths.shape[1]), int(depths.shape[2])
+            dp, cp = depths.data_ptr(), colors.data_ptr()
+            hold = (depths, colors)
+        else:
+            d = np.ascontiguousarray(depths, dtype=np.float32)
+            c = np.ascontiguousarray(colors, dtype=np.uint8)
+            if d.ndim != 3 or c.shape != d.shape + (3,) or d.shape[0] != n:
+                raise RuntimeError("depths must be [n,H,W], colors [n,H,W,3], poses [n,4,4]")
+            H, W = d.shape[1:]
+            dp, cp = d.ctypes.data, c.ctypes.data
+            hold = (d, c)
+        rc = self._L.b2v_integrate_batch(self._h, n, dp, cp, H, W, K4.ctypes.data, T.ctypes.data)
+        self._check(rc, "b2v_integrate_batch")
+        self._keepalive = [hold]
+
+    def synchronize(self):
+        self._check(self._L.b2v_synchronize(self._h), "b2v_synchronize")
+        self._keepalive.clear()
+
+    def reset(self):
+        """`self.volume.reset()` (tsdf.py:156; base.py:642)."""
+        self._check(self._L.b2v_reset(self._h), "b2v_reset")
+        self._keepalive.clear()
+
+    # ---- inspection ----
+    def num_blocks(self) -> int:
+        n = self._L.b2v_num_blocks(self._h)
+        if n < 0:
+            raise RuntimeError(self._L.b2v_last_error(self._h).decode())
+        return int(n)
+
+    def last_frame_stats(self):
+        t, n = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.b2v_last_frame_stats(self._h, C.byref(t), C.byref(n)), "b2v_last_frame_stats")
+        return int(t.value), int(n.value)
+
+    def counters(self):
+        """(total block updates, kernel launches) since create/reset."""
+        u, k = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.b2v_counters(self._h, C.byref(u), C.byref(k)), "b2v_counters")
+        return int(u.value), int(k.value)
+
+    def last_touched_keys(self) -> np.ndarray:
+        n = self._L.b2v_last_touched_keys(self._h, None, 0)
+        keys = np.zeros((max(int(n), 0), 3), np.int32)
+        if n > 0:
+            self._L.b2v_last_touched_keys(self._h, keys.ctypes.data, int(n))
+        return keys
+
+    def dump_blocks(self):
+        """Parity hook: keys int32 [nb,3], hashes uint64 [nb] (reference BlockKeyHash),
+        vox float32 [nb,5,512] planes (tsdf, weight, r, g, b)."""
+        nb = self.num_blocks()
+        keys = np.zeros((nb, 3), np.int32)
+        hashes = np.zeros(nb, np.uint64)
+        vox = np.zeros((nb, VOXEL_PLANES, BLOCK_VOXELS), np.float32)
+        n = self._L.b2v_dump_blocks(self._h, keys.ctypes.data, hashes.ctypes.data, vox.ctypes.data)
+        if n != nb:
+            raise RuntimeError(f"b2v_dump_blocks returned {n}, expected {nb}")
+        return dict(keys=keys, hashes=hashes, vox=vox)
+
+    def upload_blocks(self, keys, vox):
+        """Restore / seed blocks: keys int32 [n,3] (unique), vox float32 [n,5,512]."""
+        k = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        x = np.ascontiguousarray(vox, np.float32).reshape(k.shape[0], VOXEL_PLANES, BLOCK_VOXELS)
+        self._check(self._L.b2v_upload_blocks(self._h, k.shape[0], k.ctypes.data, x.ctypes.data),
+                    "b2v_upload_blocks")
+
+    # ---- outputs ----
+    def extract_mesh(self) -> TriangleMesh:
+        """north_star `extract_mesh()` == Open3D `extract_triangle_mesh()` (tsdf.py:239,260)."""
+        nv, nt = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.b2v_extract_mesh(self._h, C.byref(nv), C.byref(nt)), "b2v_extract_mesh")
+        V = np.zeros((nv.value, 3), np.float32)
+        Cc = np.zeros((nv.value, 3), np.float32)
+        E = np.zeros((nv.value, 4), np.int32)
+        T = np.zeros((nt.value, 3), np.int32)
+        self._check(self._L.b2v_copy_mesh(self._h, V.ctypes.data, Cc.ctypes.data, E.ctypes.data,
+                                          T.ctypes.data), "b2v_copy_mesh")
+        return TriangleMesh(V.astype(np.float64), T, Cc.astype(np.float64), E)
+
+    extract_triangle_mesh = extract_mesh
+
+    def extract_point_cloud(self) -> PointCloud:
+        n = C.c_int64(0)
+        self._check(self._L.b2v_extract_points(self._h, C.byref(n)), "b2v_extract_points")
+        P = np.zeros((n.value, 3), np.float32)
+        Cc = np.zeros((n.value, 3), np.float32)
+        self._check(self._L.b2v_copy_points(self._h, P.ctypes.data, Cc.ctypes.data), "b2v_copy_points")
+        return PointCloud(P.astype(np.float64), Cc.astype(np.float64))
+
+
+class VoxelGridData:
+    """`VoxelGridDataT` (cpp/volumetric/voxel_grid_data.h:36-50): points / colors SoA."""
+
+    def __init__(self, points, colors):
+        self.points = points
+        self.colors = colors
+        self.class_ids = None
+        self.object_ids = None
+        self.confidences = None
+
+
+class VoxelBlockGrid:
+    """GPU drop-in for pySLAM's `volumetric.VoxelBlockGrid(voxel_size, block_size=8)`."""
+
+    def __init__(self, voxel_size: float, block_size: int = 8, capacity_blocks: int = 1 << 17,
+                 device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self.voxel_size = float(voxel_size)
+        self._block_size = int(block_size)
+        rc = self._L.b2v_grid_create(voxel_size, block_size, capacity_blocks, device, C.byref(self._h))
+        if rc != _lib.B2V_OK:
+            msg = self._L.b2v_grid_last_error(self._h).decode() if self._h else "invalid configuration"
+            if self._h:
+                self._L.b2v_grid_destroy(self._h)
+                self._h = C.c_void_p()
+            raise RuntimeError(f"b2v_grid_create failed (status {rc}): {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b2v_grid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != _lib.B2V_OK:
+            raise RuntimeError(f"{what} failed (status {rc}): {self._L.b2v_grid_last_error(self._h).decode()}")
+
+    def integrate(self, points, colors=None, class_ids=None, instance_ids=None, depths=None):
+        """integrate(points [N,3] f32|f64, colors [N,3] u8|f32 | None)
+        (volumetric_grid_module.h:131-467).  float64 points are narrowed to float32 (the reference
+        front-end always passes float32, volumetric_integrator_voxel_grid.py:281); uint8 colours are
+        scaled by the float32 constant 1/255 exactly as voxel_data.h:82-85 does."""
+        if class_ids is not None or instance_ids is not None or depths is not None:
+            raise NotImplementedError("semantic integration is a SURVEY.md §8(f) 'next' row")
+        pts = np.asarray(points)
+        if pts.ndim != 2 or pts.shape[1] != 3:
+            raise RuntimeError("points must be a 2D array with shape (N, 3)")
+        if pts.dtype not in (np.float32, np.float64):
+            raise RuntimeError("points must be float32 or float64")
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        cp = None
+        cols = None
+        if colors is not None and np.asarray(colors).size > 0:
+            cols = np.asarray(colors)
+            if cols.ndim != 2 or cols.shape[1] != 3:
+                raise RuntimeError("colors must be a 2D array with shape (N, 3)")
+            if cols.shape[0] != pts.shape[0]:
+                raise RuntimeError("points and colors must have the same number of rows")
+            if cols.dtype == np.uint8:
+                cols = cols.astype(np.float32) * (np.float32(1.0) / np.float32(255.0))
+            elif cols.dtype not in (np.float32, np.float64):
+                raise RuntimeError("colors must be uint8 or float32")
+            cols = np.ascontiguousarray(cols, dtype=np.float32)
+            cp = cols.ctypes.data
+        self._check(self._L.b2v_grid_integrate(self._h, pts.ctypes.data, cp, pts.shape[0]),
+                    "b2v_grid_integrate")
+        self._check(self._L.b2v_grid_synchronize(self._h), "b2v_grid_synchronize")
+
+    def get_voxels(self, min_count: int = 1, min_confidence: float = 0.0) -> VoxelGridData:
+        """get_voxels(min_count, min_confidence): min_confidence is ignored for the non-semantic grid,
+        as in the reference (voxel_block_grid.hpp:750-752)."""
+        n = self._L.b2v_grid_get_voxels(self._h, int(min_count))
+        if n < 0:
+            raise RuntimeError(self._L.b2v_grid_last_error(self._h).decode())
+        P = np.zeros((n, 3), np.float32)
+        Cc = np.zeros((n, 3), np.float32)
+        self._check(self._L.b2v_grid_copy_voxels(self._h, P.ctypes.data, Cc.ctypes.data),
+                    "b2v_grid_copy_voxels")
+        return VoxelGridData(P, Cc)
+
+    def get_points(self):
+        return self.get_voxels(1).points
+
+    def get_colors(self):
+        return self.get_voxels(1).colors
+
+    def clear(self):
+        self._check(self._L.b2v_grid_clear(self._h), "b2v_grid_clear")
+
+    reset = clear
+
+    def num_blocks(self) -> int:
+        return int(self._L.b2v_grid_num_blocks(self._h))
+
+    def size(self) -> int:
+        return int(self._L.b2v_grid_size(self._h))
+
+    def get_total_voxel_count(self) -> int:
+        return self.size()
+
+    def empty(self) -> bool:
+        return self.num_blocks() == 0
+
+    def get_block_size(self) -> int:
+        return self._block_size
+
+    def remove_low_count_voxels(self, min_count: int):
+        self._check(self._L.b2v_grid_remove_low_count_voxels(self._h, int(min_count)),
+                    "b2v_grid_remove_low_count_voxels")
+
+    def remove_low_confidence_voxels(self, min_confidence: float):
+        # no-op for the non-semantic grid, as in the reference (voxel_block_grid.hpp:650-676)
+        return None
+
+    def dump_blocks(self):
+        nb = self.num_blocks()
+        keys = np.zeros((nb, 3), np.int32)
+        hashes = np.zeros(nb, np.uint64)
+        count = np.zeros((nb, BLOCK_VOXELS), np.int32)
+        pos = np.zeros((nb, BLOCK_VOXELS, 3), np.float32)
+        col = np.zeros((nb, BLOCK_VOXELS, 3), np.float32)
+        n = self._L.b2v_grid_dump_blocks(self._h, keys.ctypes.data, hashes.ctypes.data,
+                                         count.ctypes.data, pos.ctypes.data, col.ctypes.data)
+        if n != nb:
+            raise RuntimeError(f"b2v_grid_dump_blocks returned {n}, expected {nb}")
+        return dict(keys=keys, hashes=hashes, count=count, pos_sum=pos, col_sum=col)
+
+    # duck-type B surface that belongs to SURVEY.md §8(f) "next" rows
+    def carve(self, *a, **k):
+        raise NotImplementedError("carve is a SURVEY.md §8(f) 'next' row (rank 3)")
+
+    def get_voxels_in_bb(self, *a, **k):
+        raise NotImplementedError("bounding-box queries are a SURVEY.md §8(f) 'next' row (rank 3)")
+
+    def get_voxels_in_camera_frustrum(self, *a, **k):
+        raise NotImplementedError("frustum queries are a SURVEY.md §8(f) 'next' row (rank 3)")

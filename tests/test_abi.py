@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library loads and exports every symbol include/b2v.h declares (no compute calls
+without a GPU), and the product never routes through the oracle."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "b2v.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2v_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_header_symbols_all_exported():
+    from pyslam_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "libb2v.so was not built"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/b2v.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    assert L.b2v_version() >= 100
+
+
+def test_library_is_sm100a_and_uses_128bit_cas():
+    import shutil
+    import subprocess
+    from pyslam_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "allocate_kernel" in sass and "integrate_kernel" in sass
+    assert "ATOMG.E.CAS.128" in sass  # 16-byte hash-table entries are inserted with one 128-bit CAS
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the CPU oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "pyslam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src and "libref_grid" not in src, f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from pyslam_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "pyslam_b200", "does_not_exist.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()

@@ -1,0 +1,109 @@
+"""GPU: the point-average grid (duck type B) against the UNMODIFIED compiled reference
+`volumetric::VoxelBlockGrid` — via the committed golden vectors (tests/golden/refgrid_T0.npz,
+produced by oracle/_ref here) and, when oracle/_ref travelled to this box, live.
+
+Bars: block keys, BlockKeyHash, per-voxel counts BIT-EXACT; position / colour sums within
+rel 1e-5 * sqrt(count) (float atomics reorder the reference's input-order sums);
+voxels with count <= 2 are bit-exact (two-term float sums commute)."""
+
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from pyslam_b200 import VoxelBlockGrid
+from tests._util import GOLDEN, sort_dump
+
+pytestmark = pytest.mark.gpu
+
+
+def _sum_close(a, b, count):
+    tol = 1e-5 * np.sqrt(np.maximum(count, 1))[..., None] * np.maximum(np.abs(b), 1e-3)
+    return np.all(np.abs(a - b) <= tol)
+
+
+def _feed(grid, g):
+    start = 0
+    for n in g["frame_counts"]:
+        grid.integrate(g["points"][start:start + n], g["colors"][start:start + n])
+        start += int(n)
+
+
+def test_golden_reference_vectors():
+    g = np.load(os.path.join(GOLDEN, "refgrid_T0.npz"))
+    grid = VoxelBlockGrid(float(g["voxel_size"]), 8, capacity_blocks=4096)
+    _feed(grid, g)
+    d = sort_dump(grid.dump_blocks())
+    assert np.array_equal(d["keys"], g["keys"])
+    assert np.array_equal(d["hashes"], g["hashes"])
+    assert np.array_equal(d["count"], g["count"])
+    assert _sum_close(d["pos_sum"], g["pos_sum"], g["count"])
+    assert _sum_close(d["col_sum"], g["col_sum"], g["count"])
+    few = g["count"] <= 2
+    assert np.array_equal(d["pos_sum"][few], g["pos_sum"][few])
+    assert np.array_equal(d["col_sum"][few], g["col_sum"][few])
+    assert grid.num_blocks() == len(g["keys"])
+    assert grid.size() == int((g["count"] > 0).sum()) == grid.get_total_voxel_count()
+    assert grid.get_block_size() == 8 and not grid.empty()
+    # get_voxels(min_count=2): compare as a set keyed by position order
+    out = grid.get_voxels(min_count=2)
+    order = np.lexsort((out.points[:, 2], out.points[:, 1], out.points[:, 0]))
+    assert out.points.shape == g["voxels_min2_points"].shape
+    assert np.allclose(out.points[order], g["voxels_min2_points"], rtol=2e-5, atol=1e-6)
+    assert np.allclose(out.colors[order], g["voxels_min2_colors"], rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="compiled reference (oracle/_ref) not on this box")
+def test_live_against_compiled_reference_with_removal():
+    rng = np.random.default_rng(5)
+    vs = 0.015  # reference default voxel size (config_parameters.py:311)
+    ref = oracle.RefGrid(vs, 8)
+    grid = VoxelBlockGrid(vs, 8, capacity_blocks=1 << 14)
+    for _ in range(3):
+        n = 20000
+        # a noisy sphere shell crossing the origin so negative keys are exercised
+        dirs = rng.normal(size=(n, 3))
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        pts = (dirs * (0.6 + 0.004 * rng.normal(size=(n, 1))) + [0.1, -0.2, 0.05]).astype(np.float32)
+        cols = rng.random((n, 3)).astype(np.float32)
+        ref.integrate(pts, cols)
+        grid.integrate(pts, cols)
+    a, b = sort_dump(grid.dump_blocks()), sort_dump(ref.dump_blocks())
+    assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["hashes"], b["hashes"])
+    assert np.array_equal(a["count"], b["count"])
+    assert _sum_close(a["pos_sum"], b["pos_sum"], b["count"])
+    assert _sum_close(a["col_sum"], b["col_sum"], b["count"])
+    ref.remove_low_count_voxels(3)
+    grid.remove_low_count_voxels(3)
+    a, b = sort_dump(grid.dump_blocks()), sort_dump(ref.dump_blocks())
+    assert np.array_equal(a["count"], b["count"])
+    assert grid.size() == int((b["count"] > 0).sum())
+    rp, rc = ref.get_voxels(min_count=1)
+    out = grid.get_voxels(min_count=1)
+    assert len(out.points) == len(rp)
+    o1 = np.lexsort((out.points[:, 2], out.points[:, 1], out.points[:, 0]))
+    o2 = np.lexsort((rp[:, 2], rp[:, 1], rp[:, 0]))
+    assert np.allclose(out.points[o1], rp[o2], rtol=2e-5, atol=1e-6)
+
+
+def test_argument_checks_and_clear():
+    grid = VoxelBlockGrid(0.05, 8, capacity_blocks=256)
+    assert grid.empty() and grid.size() == 0
+    grid.integrate(np.zeros((0, 3), np.float32))                       # empty input is a no-op
+    with pytest.raises(RuntimeError):
+        grid.integrate(np.zeros((4, 2), np.float32))                   # shape[1] must be 3
+    with pytest.raises(RuntimeError):
+        grid.integrate(np.zeros((4, 3), np.float32), np.zeros((3, 3), np.float32))
+    with pytest.raises(RuntimeError):
+        grid.integrate(np.zeros((4, 3), np.int32))
+    pts = np.array([[0.01, 0.02, 0.03], [0.01, 0.02, 0.03], [-0.01, 0.5, 1.2]], np.float32)
+    grid.integrate(pts, np.array([[255, 0, 0], [255, 0, 0], [0, 255, 0]], np.uint8))
+    assert grid.num_blocks() == 2 and grid.size() == 2
+    out = grid.get_voxels(min_count=2)
+    assert len(out.points) == 1 and np.allclose(out.points[0], pts[0])
+    assert np.allclose(out.colors[0], [1.0, 0.0, 0.0], atol=1e-6)
+    grid.clear()
+    assert grid.empty() and grid.size() == 0 and len(grid.get_points()) == 0
+    with pytest.raises(RuntimeError):
+        VoxelBlockGrid(0.05, 4)

@@ -1,0 +1,286 @@
+"""GPU: parity of the CUDA TSDF path (through the C ABI) against the CPU oracle and the golden
+fixtures.  Bars: block keys, hashes, touched sets, weights, triangle topology and
+canonical edge ids are BIT-EXACT; tsdf / rgb / vertex values are bit-exact against the oracle
+(both sides execute the same IEEE operations), and within the stated float tolerances
+(tsdf 1e-5, rgb 0.5/255, vertices 1e-6 m) of the independent float64 formulas."""
+
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from pyslam_b200 import B200TsdfVolume
+from pyslam_b200 import synthetic as S
+from tests._util import GOLDEN, blocks_checksum, sort_dump, sorted_keys
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(cfg, capacity=1 << 15, stride=4):
+    vol = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=capacity,
+                         depth_sampling_stride=stride)
+    orc = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, stride=stride)
+    return vol, orc
+
+
+def _assert_same_volume(vol, orc):
+    a = sort_dump(vol.dump_blocks())
+    b = sort_dump(orc.dump_blocks())
+    assert np.array_equal(a["keys"], b["keys"])
+    assert np.array_equal(a["hashes"], b["hashes"])
+    assert np.array_equal(a["vox"][:, 1], b["vox"][:, 1])            # weights
+    assert np.array_equal(a["vox"], b["vox"])                        # tsdf, rgb: bit-exact
+    return a
+
+
+def test_golden_fixture_bit_exact():
+    g = np.load(os.path.join(GOLDEN, "tsdf_T0.npz"))
+    vol = B200TsdfVolume(float(g["voxel_size"]), float(g["sdf_trunc"]), float(g["depth_trunc"]),
+                         capacity_blocks=4096)
+    for i in range(int(g["n_frames"])):
+        vol.integrate(g["depth"][i], g["color"][i], g["K"], g["Tcw"][i])
+        assert np.array_equal(sorted_keys(vol.last_touched_keys()), g[f"touched_{i}"])
+        touched, _ = vol.last_frame_stats()
+        assert touched == len(g[f"touched_{i}"])
+    d = sort_dump(vol.dump_blocks())
+    assert np.array_equal(d["keys"], g["keys"])
+    assert np.array_equal(d["hashes"], g["hashes"])
+    assert np.array_equal(d["vox"], g["vox"])
+    m = vol.extract_mesh()
+    cm = oracle.canonical_mesh(m.vertices.astype(np.float32), m.vertex_colors.astype(np.float32),
+                               m.edge_ids, m.triangles)
+    assert np.array_equal(cm["edges"], g["mesh_edges"])
+    assert np.array_equal(cm["triangles"], g["mesh_triangles"])
+    assert np.array_equal(cm["vertices"], g["mesh_vertices"])
+    assert np.array_equal(cm["colors"], g["mesh_colors"])
+    assert m.vertex_normals.shape == (0, 3)
+
+
+@pytest.mark.parametrize("cfg_name,frames,stride", [
+    ("T0", list(range(6)), 4),
+    ("T0", [0, 3], 1),                 # stride-1 superset mode
+    ("C1", [0, 1, 2, 50], 4),          # config 1 shape: 320x240, 1 cm
+    ("C4", [0, 1], 4),                 # ScanNet shape, 4 mm
+])
+def test_integrate_matches_oracle(cfg_name, frames, stride):
+    cfg = S.CONFIGS[cfg_name]
+    vol, orc = _pair(cfg, capacity=1 << 16, stride=stride)
+    total_new = 0
+    for i in frames:
+        d, c, T = S.render_frame(cfg, i)
+        vol.integrate(d, c, cfg.K, T)
+        n = orc.integrate(d, c, cfg.K, T)
+        assert np.array_equal(sorted_keys(vol.last_touched_keys()), sorted_keys(orc.last_touched()))
+        touched, new = vol.last_frame_stats()
+        assert touched == n
+        total_new += new
+    assert total_new == orc.num_blocks() == vol.num_blocks()
+    _assert_same_volume(vol, orc)
+    updates, launches = vol.counters()
+    assert launches >= 2 * len(frames) and updates > 0
+
+
+def test_full_size_tum_frames_match_oracle_and_properties():
+    """BASELINE config 2 at full size (640x480, 5 mm): checksum-of-checksums vs the oracle plus
+    size-independent properties (integer weights, bounded tsdf / colour, unique keys)."""
+    cfg = S.CONFIGS["C2"]
+    vol, orc = _pair(cfg, capacity=1 << 16)
+    for i in (0, 1, 2):
+        d, c, T = S.render_frame(cfg, i)
+        vol.integrate(d, c, cfg.K, T)
+        orc.integrate(d, c, cfg.K, T)
+    a = _assert_same_volume(vol, orc)
+    assert np.array_equal(blocks_checksum(a), blocks_checksum(sort_dump(orc.dump_blocks())))
+    assert len(np.unique(a["keys"], axis=0)) == len(a["keys"])
+    w = a["vox"][:, 1]
+    assert np.array_equal(w, np.round(w)) and w.max() == 3.0
+    assert a["vox"][:, 0].min() >= -1.0 and a["vox"][:, 0].max() <= 1.0
+    assert a["vox"][:, 2:].min() >= 0.0 and a["vox"][:, 2:].max() <= 255.0
+    # reported hash is the reference's BlockKeyHash (sign-extending u64 arithmetic)
+    k = a["keys"].astype(np.int64).astype(np.uint64)
+    assert np.array_equal(a["hashes"], k[:, 0] ^ (k[:, 1] << np.uint64(1)) ^ (k[:, 2] << np.uint64(2)))
+
+
+def test_mesh_matches_oracle_and_float64_formula():
+    cfg = S.CONFIGS["C1"]
+    vol, orc = _pair(cfg, capacity=1 << 15)
+    for i in (0, 1, 2, 3):
+        d, c, T = S.render_frame(cfg, i)
+        vol.integrate(d, c, cfg.K, T)
+        orc.integrate(d, c, cfg.K, T)
+    m = vol.extract_mesh()
+    ref = orc.extract_mesh()
+    assert len(m.vertices) == len(ref["vertices"]) and len(m.triangles) == len(ref["triangles"]) > 1000
+    a = oracle.canonical_mesh(m.vertices.astype(np.float32), m.vertex_colors.astype(np.float32),
+                              m.edge_ids, m.triangles)
+    b = oracle.canonical_mesh(ref["vertices"], ref["colors"], ref["edges"], ref["triangles"])
+    assert np.array_equal(a["edges"], b["edges"])
+    assert np.array_equal(a["triangles"], b["triangles"])
+    assert np.array_equal(a["vertices"], b["vertices"])
+    assert np.array_equal(a["colors"], b["colors"])
+    b64 = oracle.canonical_mesh(ref["vertices64"], ref["colors"], ref["edges"], ref["triangles"])
+    assert np.max(np.abs(a["vertices"].astype(np.float64) - b64["vertices"])) < 1e-6  # metres
+    assert a["colors"].min() >= 0.0 and a["colors"].max() <= 1.0
+    # a second extraction of the same volume is identical (deterministic count -> scan -> emit)
+    m2 = vol.extract_mesh()
+    assert np.array_equal(m.triangles, m2.triangles) and np.array_equal(m.vertices, m2.vertices)
+
+
+def test_upload_dump_round_trip_and_sphere_mesh():
+    """dump -> reset -> upload -> dump is the identity; an analytic sphere meshes closed."""
+    vs, tau, r = 0.02, 0.08, 0.5
+    vol = B200TsdfVolume(vs, tau, 4.0, capacity_blocks=4096)
+    nb = int(np.ceil((r + 3 * tau) / (8 * vs)))
+    l = np.arange(512)
+    lx, ly, lz = l % 8, (l // 8) % 8, l // 64
+    keys, vox = [], []
+    for bx in range(-nb, nb):
+        for by in range(-nb, nb):
+            for bz in range(-nb, nb):
+                c = np.stack([(bx * 8 + lx + 0.5) * vs, (by * 8 + ly + 0.5) * vs, (bz * 8 + lz + 0.5) * vs], 1)
+                v = np.zeros((5, 512), np.float32)
+                v[0] = np.clip((np.linalg.norm(c, axis=1) - r) / tau, -1, 1)
+                v[1] = 1.0
+                v[2:] = np.array([[200.0], [100.0], [50.0]])
+                keys.append((bx, by, bz))
+                vox.append(v)
+    keys, vox = np.array(keys, np.int32), np.stack(vox)
+    vol.upload_blocks(keys, vox)
+    d = sort_dump(vol.dump_blocks())
+    order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
+    assert np.array_equal(d["keys"], keys[order]) and np.array_equal(d["vox"], vox[order])
+    m = vol.extract_mesh()
+    T = m.triangles
+    e = np.concatenate([T[:, [0, 1]], T[:, [1, 2]], T[:, [2, 0]]])
+    _, cnt = np.unique(np.sort(e, axis=1), axis=0, return_counts=True)
+    assert np.all(cnt == 2)
+    assert len(m.vertices) - len(cnt) + len(T) == 2
+    assert np.max(np.abs(np.linalg.norm(m.vertices, axis=1) - r)) < 0.2 * vs
+    # same mesh as the oracle on the same volume
+    orc = oracle.TsdfOracle(vs, tau, 4.0)
+    for k, v in zip(keys, vox):
+        orc.set_block(k, v)
+    ref = orc.extract_mesh()
+    a = oracle.canonical_mesh(m.vertices.astype(np.float32), m.vertex_colors.astype(np.float32),
+                              m.edge_ids, m.triangles)
+    b = oracle.canonical_mesh(ref["vertices"], ref["colors"], ref["edges"], ref["triangles"])
+    for name in ("edges", "triangles", "vertices", "colors"):
+        assert np.array_equal(a[name], b[name]), name
+
+
+def test_reset_empty_and_ragged_inputs():
+    cfg = S.CONFIGS["T0"]
+    vol, orc = _pair(cfg, capacity=2048)
+    assert vol.num_blocks() == 0
+    m = vol.extract_mesh()
+    assert m.vertices.shape == (0, 3) and m.triangles.shape == (0, 3)
+    d, c, T = S.render_frame(cfg, 0)
+    # all-invalid depth (zeros, negatives, NaN, beyond depth_trunc) touches nothing
+    bad = np.zeros_like(d)
+    bad[::2] = -1.0
+    bad[1::3] = np.nan
+    bad[5] = cfg.depth_trunc + 1.0
+    vol.integrate(bad, c, cfg.K, T)
+    assert vol.last_frame_stats() == (0, 0) and vol.num_blocks() == 0
+    # ragged size (not a multiple of the stride or of the allocation tile)
+    dr, cr = np.ascontiguousarray(d[:61, :83]), np.ascontiguousarray(c[:61, :83])
+    vol.integrate(dr, cr, cfg.K, T)
+    orc.integrate(dr, cr, cfg.K, T)
+    _assert_same_volume(vol, orc)
+    vol.reset()
+    assert vol.num_blocks() == 0
+    orc.reset()
+    vol.integrate(d, c, cfg.K, T)
+    orc.integrate(d, c, cfg.K, T)
+    _assert_same_volume(vol, orc)
+
+
+def test_error_behaviour():
+    cfg = S.CONFIGS["T0"]
+    d, c, T = S.render_frame(cfg, 0)
+    with pytest.raises(RuntimeError):
+        B200TsdfVolume(0.0, 0.04)                      # invalid voxel size
+    with pytest.raises(RuntimeError):
+        B200TsdfVolume(0.01, 0.04, block_size=16)      # only the reference default block size 8
+    vol = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=64)
+    with pytest.raises(RuntimeError):
+        vol.integrate(d, c[:, :, :2], cfg.K, T)        # colour must be [H,W,3]
+    with pytest.raises(RuntimeError):
+        vol.integrate(d, c.astype(np.float32), cfg.K, T)
+    with pytest.raises(RuntimeError):
+        vol.integrate(d[None], c, cfg.K, T)
+    # pool overflow is reported, not silently dropped
+    vol.integrate(d, c, cfg.K, T)
+    with pytest.raises(RuntimeError, match="capacity"):
+        vol.synchronize()
+
+
+def test_device_pointer_inputs_and_batch_equal_host_path():
+    import torch
+    cfg = S.CONFIGS["T0"]
+    frames = [S.render_frame(cfg, i) for i in range(4)]
+    host, _ = _pair(cfg)
+    dev, _ = _pair(cfg)
+    bat, _ = _pair(cfg)
+    for d, c, T in frames:
+        host.integrate(d, c, cfg.K, T)
+        dev.integrate(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), cfg.K, T)
+    torch.cuda.synchronize()
+    bat.integrate_batch(np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames]), cfg.K,
+                        np.stack([f[2] for f in frames]))
+    a, b, c_ = (sort_dump(v.dump_blocks()) for v in (host, dev, bat))
+    for name in ("keys", "hashes", "vox"):
+        assert np.array_equal(a[name], b[name]) and np.array_equal(a[name], c_[name])
+
+
+def test_sharded_volumes_partition_the_blocks():
+    """Hash-bucket sharding: shard r owns BlockKeyHash % n == r; the union of the
+    shards equals the unsharded volume bit for bit and no block is owned twice."""
+    cfg = S.CONFIGS["T0"]
+    frames = [S.render_frame(cfg, i) for i in range(3)]
+    full, _ = _pair(cfg)
+    n = 4
+    shards = [B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=4096,
+                             shard_rank=r, shard_count=n) for r in range(n)]
+    for d, c, T in frames:
+        full.integrate(d, c, cfg.K, T)
+        for s in shards:
+            s.integrate(d, c, cfg.K, T)
+    ref = sort_dump(full.dump_blocks())
+    parts = [s.dump_blocks() for s in shards]
+    for r, p in enumerate(parts):
+        assert np.all(p["hashes"] % np.uint64(n) == r)
+    merged = sort_dump({k: np.concatenate([p[k] for p in parts]) for k in ("keys", "hashes", "vox")})
+    for name in ("keys", "hashes", "vox"):
+        assert np.array_equal(merged[name], ref[name])
+
+
+def test_point_cloud_extraction_matches_definition():
+    cfg = S.CONFIGS["T0"]
+    vol, orc = _pair(cfg)
+    for i in range(3):
+        d, c, T = S.render_frame(cfg, i)
+        vol.integrate(d, c, cfg.K, T)
+    pc = vol.extract_point_cloud()
+    dump = vol.dump_blocks()
+    # count zero crossings on the host straight from the dump (A.4 ExtractPointCloud definition)
+    idx = {tuple(k): i for i, k in enumerate(dump["keys"])}
+    expect = 0
+    for bi, key in enumerate(dump["keys"]):
+        f = dump["vox"][bi, 0].reshape(8, 8, 8)   # [z, y, x]
+        w = dump["vox"][bi, 1].reshape(8, 8, 8)
+        for axis, dk in ((2, (1, 0, 0)), (1, (0, 1, 0)), (0, (0, 0, 1))):
+            nk = (key[0] + dk[0], key[1] + dk[1], key[2] + dk[2])
+            if nk in idx:
+                fn = dump["vox"][idx[nk], 0].reshape(8, 8, 8)
+                wn = dump["vox"][idx[nk], 1].reshape(8, 8, 8)
+            else:
+                fn, wn = np.zeros((8, 8, 8), np.float32), np.zeros((8, 8, 8), np.float32)
+            f1 = np.concatenate([np.take(f, range(1, 8), axis), np.take(fn, [0], axis)], axis)
+            w1 = np.concatenate([np.take(w, range(1, 8), axis), np.take(wn, [0], axis)], axis)
+            ok0 = (w != 0) & (f < 0.98) & (f >= -0.98)
+            ok1 = (w1 != 0) & (f1 < 0.98) & (f1 >= -0.98)
+            expect += int((ok0 & ok1 & (f * f1 < 0)).sum())
+    assert len(pc.points) == expect > 100
+    assert pc.colors.min() >= 0.0 and pc.colors.max() <= 1.0
