@@ -73,6 +73,10 @@ int64_t b2v_num_blocks(b2v_volume *v);                 /* synchronises */
 int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int64_t *new_blocks);
 /* total (block,frame) updates and kernel launches since create/reset: bench accounting */
 int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches);
+/* Per-kernel device timing (CUDA events on the launching stream around each launch), for the
+ * roofline figure: enable, run frames, then read the summed durations (synchronises, resets). */
+int b2v_profile_enable(b2v_volume *v, int32_t enable);
+int b2v_profile_read(b2v_volume *v, double *allocate_ms, double *integrate_ms, int64_t *frames);
 /* keys int32[nb*3], hashes uint64[nb] (= reference BlockKeyHash, cpp/volumetric/voxel_hashing.h:106-113),
  * voxels float32[nb*5*512] (planes tsdf, weight, r, g, b; voxel index lx + 8*ly + 64*lz,
  * cpp/volumetric/voxel_block.h:67-70).  HOST outputs, any may be NULL; returns nb or <0. */

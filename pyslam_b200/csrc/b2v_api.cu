@@ -102,6 +102,10 @@ struct b2v_volume {
     size_t mesh_v_cap = 0, mesh_t_cap = 0;
     int64_t last_nv = 0, last_nt = 0;
     uint32_t *h_totals = nullptr;
+    // optional per-kernel timing (b2v_profile_*)
+    bool prof_enabled = false;
+    std::vector<cudaEvent_t> prof_events;  // triples: before allocate, between, after integrate
+    size_t prof_used = 0;
 };
 
 #define B2V_CUDA(v, call)                                                                  \
@@ -205,6 +209,8 @@ extern "C" int b2v_destroy(b2v_volume *v) {
     cudaFree(v->mb.triangles);
     cudaFreeHost(v->h_counters);
     cudaFreeHost(v->h_totals);
+    for (cudaEvent_t e : v->prof_events)
+        if (e) cudaEventDestroy(e);
     if (v->compute) cudaStreamDestroy(v->compute);
     if (v->copy) cudaStreamDestroy(v->copy);
     delete v;
@@ -304,8 +310,21 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
     fill_frame_params(&P, K, Tcw, height, width, v->cfg.depth_stride, v->cfg.voxel_size, v->cfg.sdf_trunc,
                       v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank, v->cfg.shard_count);
     const int ring = static_cast<int>(v->frame_id % kActiveRing);
+    cudaEvent_t *pe = nullptr;
+    if (v->prof_enabled) {
+        if (v->prof_used + 3 > v->prof_events.size()) {
+            const size_t old = v->prof_events.size();
+            v->prof_events.resize(old + 3 * 256, nullptr);
+            for (size_t k = old; k < v->prof_events.size(); ++k) B2V_CUDA(v, cudaEventCreate(&v->prof_events[k]));
+        }
+        pe = &v->prof_events[v->prof_used];
+        v->prof_used += 3;
+        B2V_CUDA(v, cudaEventRecord(pe[0], cs));
+    }
     B2V_CUDA(v, launch_allocate(P, d_depth, v->table, v->meta, ring, cs));
+    if (pe) B2V_CUDA(v, cudaEventRecord(pe[1], cs));
     B2V_CUDA(v, launch_integrate(P, d_depth, d_color, v->table, v->meta, ring, v->grid_ctas, cs));
+    if (pe) B2V_CUDA(v, cudaEventRecord(pe[2], cs));
     if (staged) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], cs));
     v->launches += 2;
     v->frame_id += 1;
@@ -349,6 +368,31 @@ extern "C" int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int6
     if (touched_blocks) *touched_blocks = v->frame_id ? v->h_counters[kCtrActive0 + ring] : 0;
     if (new_blocks) *new_blocks = v->frame_id ? v->h_counters[kCtrNew0 + ring] : 0;
     return rc;
+}
+
+extern "C" int b2v_profile_enable(b2v_volume *v, int32_t enable) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    v->prof_enabled = enable != 0;
+    return B2V_OK;
+}
+
+extern "C" int b2v_profile_read(b2v_volume *v, double *allocate_ms, double *integrate_ms, int64_t *frames) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    B2V_CUDA(v, cudaSetDevice(v->cfg.device));
+    double a = 0.0, b = 0.0;
+    for (size_t k = 0; k + 2 < v->prof_used + 0 && k < v->prof_used; k += 3) {
+        B2V_CUDA(v, cudaEventSynchronize(v->prof_events[k + 2]));
+        float ms = 0.0f;
+        B2V_CUDA(v, cudaEventElapsedTime(&ms, v->prof_events[k], v->prof_events[k + 1]));
+        a += ms;
+        B2V_CUDA(v, cudaEventElapsedTime(&ms, v->prof_events[k + 1], v->prof_events[k + 2]));
+        b += ms;
+    }
+    if (allocate_ms) *allocate_ms = a;
+    if (integrate_ms) *integrate_ms = b;
+    if (frames) *frames = static_cast<int64_t>(v->prof_used / 3);
+    v->prof_used = 0;
+    return B2V_OK;
 }
 
 extern "C" int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches) {

@@ -112,11 +112,12 @@ class B200TsdfVolume:
             raise RuntimeError(f"{what} failed (status {rc}): {self._L.b2v_last_error(self._h).decode()}")
 
     # ---- integrate ----
-    def integrate(self, depth, color=None, K=None, pose=None):
+    def integrate(self, depth, color=None, K=None, pose=None, stream=None):
         """north_star: `integrate(depth, color, K, pose)` with depth float32 [H,W] metres, colour
         uint8 RGB [H,W,3], K = (fx,fy,cx,cy) | 3x3, pose = Tcw 4x4 float64.
         Open3D style (tsdf.py:223): `integrate(rgbd, intrinsic, extrinsic)` where `rgbd` has
-        `.color` / `.depth`.  Inputs may be numpy arrays or CUDA torch tensors.  Asynchronous."""
+        `.color` / `.depth`.  Inputs may be numpy arrays or CUDA torch tensors.  Asynchronous.
+        `stream`: optional cudaStream_t handle (int) to launch on; device inputs only."""
         if hasattr(depth, "depth") and hasattr(depth, "color"):
             rgbd, K, pose = depth, color, K
             depth, color = rgbd.depth, rgbd.color
@@ -150,7 +151,8 @@ class B200TsdfVolume:
             H, W = d.shape
             dp, cp = d.ctypes.data, c.ctypes.data
             self._keepalive.append((d, c))
-        rc = self._L.b2v_integrate(self._h, dp, cp, H, W, K4.ctypes.data, T.ctypes.data, None)
+        rc = self._L.b2v_integrate(self._h, dp, cp, H, W, K4.ctypes.data, T.ctypes.data,
+                                   C.c_void_p(stream) if stream else None)
         self._check(rc, "b2v_integrate")
         if len(self._keepalive) > 8:
             # staging ring is 4 deep: anything older has been consumed by the copy engine
@@ -205,6 +207,16 @@ class B200TsdfVolume:
         u, k = C.c_int64(0), C.c_int64(0)
         self._check(self._L.b2v_counters(self._h, C.byref(u), C.byref(k)), "b2v_counters")
         return int(u.value), int(k.value)
+
+    def profile_enable(self, enable: bool = True):
+        self._check(self._L.b2v_profile_enable(self._h, 1 if enable else 0), "b2v_profile_enable")
+
+    def profile_read(self):
+        """(allocate_ms, integrate_ms, frames) summed over the frames since the last read."""
+        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        self._check(self._L.b2v_profile_read(self._h, C.byref(a), C.byref(b), C.byref(n)),
+                    "b2v_profile_read")
+        return a.value, b.value, int(n.value)
 
     def last_touched_keys(self) -> np.ndarray:
         n = self._L.b2v_last_touched_keys(self._h, None, 0)

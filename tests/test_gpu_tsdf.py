@@ -121,7 +121,7 @@ def test_mesh_matches_oracle_and_float64_formula():
     assert np.array_equal(a["colors"], b["colors"])
     b64 = oracle.canonical_mesh(ref["vertices64"], ref["colors"], ref["edges"], ref["triangles"])
     assert np.max(np.abs(a["vertices"].astype(np.float64) - b64["vertices"])) < 1e-6  # metres
-    assert a["colors"].min() >= 0.0 and a["colors"].max() <= 1.0
+    assert a["colors"].min() >= 0.0 and a["colors"].max() <= 1.0 + 1e-6  # fp32 blend of 255/255
     # a second extraction of the same volume is identical (deterministic count -> scan -> emit)
     m2 = vol.extract_mesh()
     assert np.array_equal(m.triangles, m2.triangles) and np.array_equal(m.vertices, m2.vertices)
@@ -283,4 +283,4 @@ def test_point_cloud_extraction_matches_definition():
             ok1 = (w1 != 0) & (f1 < 0.98) & (f1 >= -0.98)
             expect += int((ok0 & ok1 & (f * f1 < 0)).sum())
     assert len(pc.points) == expect > 100
-    assert pc.colors.min() >= 0.0 and pc.colors.max() <= 1.0
+    assert pc.colors.min() >= 0.0 and pc.colors.max() <= 1.0 + 1e-6
