@@ -63,7 +63,8 @@ int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *color, int32
 /* n frames back to back (the rebuild(map) bulk path, base.py:1242-1318): depth [n*H*W],
  * color [n*H*W*3], Tcw [n*16]; same K for all. */
 int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float *depth, const uint8_t *color,
-                        int32_t height, int32_t width, const double K[4], const double *Tcw);
+                        int32_t height, int32_t width, const double K[4], const double *Tcw,
+                        void *stream);
 /* wait for all enqueued work; returns B2V_ERR_CAPACITY if a frame overflowed the pool */
 int b2v_synchronize(b2v_volume *v);
 

@@ -79,7 +79,7 @@ def load() -> C.CDLL:
     L.b2v_integrate.restype = C.c_int
     L.b2v_integrate.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     L.b2v_integrate_batch.restype = C.c_int
-    L.b2v_integrate_batch.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp]
+    L.b2v_integrate_batch.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp, vp]
     L.b2v_synchronize.restype = C.c_int
     L.b2v_synchronize.argtypes = [vp]
     L.b2v_num_blocks.restype = i64

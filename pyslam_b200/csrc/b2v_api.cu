@@ -333,7 +333,7 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
 
 extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float *depth,
                                    const uint8_t *color, int32_t height, int32_t width,
-                                   const double K[4], const double *Tcw) {
+                                   const double K[4], const double *Tcw, void *stream) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
     if (n_frames < 0 || (n_frames > 0 && (!depth || !color || !Tcw))) {
         v->err = "b2v_integrate_batch: bad arguments";
@@ -342,7 +342,7 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
     const size_t pixels = static_cast<size_t>(height) * width;
     for (int32_t f = 0; f < n_frames; ++f) {
         const int rc = b2v_integrate(v, depth + pixels * f, color + pixels * 3 * f, height, width, K,
-                                     Tcw + 16 * static_cast<size_t>(f), nullptr);
+                                     Tcw + 16 * static_cast<size_t>(f), stream);
         if (rc != B2V_OK) return rc;
     }
     return B2V_OK;

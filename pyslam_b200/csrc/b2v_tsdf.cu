@@ -31,18 +31,6 @@ __device__ __forceinline__ unsigned long long pack_key(int x, int y, int z) {
            (static_cast<unsigned long long>(z & 0x1FFFFF) << 42);
 }
 
-// true if this CTA sees the key for the first time
-__device__ __forceinline__ bool cta_set_insert(unsigned long long *set, unsigned long long pk) {
-    uint32_t h = mix32(static_cast<uint32_t>(pk) ^ static_cast<uint32_t>(pk >> 32)) & (kSetSize - 1);
-    for (int i = 0; i < 48; ++i) {
-        const unsigned long long old = atomicCAS(set + h, ~0ull, pk);
-        if (old == ~0ull) return true;
-        if (old == pk) return false;
-        h = (h + 1) & (kSetSize - 1);
-    }
-    return true;  // set saturated: skip de-duplication, the global table still de-duplicates
-}
-
 __device__ __forceinline__ void assign_block(const HashTable &T, const PoolMeta &M, uint32_t slot,
                                              uint32_t idx) {
     uint32_t *w = reinterpret_cast<uint32_t *>(T.entries + slot) + 3;
@@ -57,6 +45,51 @@ __device__ __forceinline__ void assign_block(const HashTable &T, const PoolMeta 
     }
 }
 
+// recover a coordinate from its 21-bit packed field, given any reference within 2^20 of it
+__device__ __forceinline__ int unpack_axis(unsigned long long pk, int shift, int ref) {
+    const int d = (static_cast<int>((pk >> shift) & 0x1FFFFF) - ref) & 0x1FFFFF;
+    return ref + ((d ^ 0x100000) - 0x100000);  // sign-extend 21 bits
+}
+
+// Global find-or-insert of one block key + first-touch detection for this frame.  New slots and
+// first-touched slots are queued in shared-memory lists (flushed with one atomic per CTA).
+__device__ __forceinline__ void touch_key(const FrameParams &P, const HashTable &T, const PoolMeta &M,
+                                          int ring, int kx, int ky, int kz, uint32_t *s_new,
+                                          uint32_t *s_n_new, uint32_t *s_act, uint32_t *s_n_act) {
+    if (P.shard_count > 1 &&
+        static_cast<int>(block_key_hash(kx, ky, kz) % static_cast<uint64_t>(P.shard_count)) != P.shard_rank)
+        return;
+    bool is_new;
+    const uint32_t slot = table_insert(T, kx, ky, kz, &is_new);
+    if (slot == kEmpty) {
+        atomicOr(M.counters + kCtrError, 2u);
+        return;
+    }
+    if (is_new) {
+        const uint32_t pos = atomicAdd(s_n_new, 1u);
+        if (pos < kListCap) {
+            s_new[pos] = slot;
+        } else {  // list overflow: assign directly
+            assign_block(T, M, slot, atomicAdd(M.counters + kCtrPool, 1u));
+            atomicAdd(M.counters + kCtrNew0 + ring, 1u);
+        }
+    }
+    if (atomicExch(T.stamp + slot, P.frame_id) != P.frame_id) {
+        const uint32_t pos = atomicAdd(s_n_act, 1u);
+        if (pos < kListCap) {
+            s_act[pos] = slot;
+        } else {
+            const uint32_t g = atomicAdd(M.counters + kCtrActive0 + ring, 1u);
+            if (g < M.capacity) M.active_slots[static_cast<size_t>(ring) * M.capacity + g] = slot;
+        }
+    }
+}
+
+// Phase A  every sampled pixel enumerates the blocks of its [p - tau, p + tau] box; duplicates die
+//          first inside the warp (__match_any_sync ballot), then inside the CTA (shared-memory set).
+// Phase B  the CTA's unique keys probe / insert into the global table one key per thread, all in
+//          flight at once (the probes are independent L2 round trips), and exchange the frame stamp.
+// Phase C  one atomic per CTA hands out contiguous pool indices and active-list positions.
 __global__ void __launch_bounds__(kAllocThreads)
 allocate_kernel(const FrameParams P, const float *__restrict__ depth, const HashTable T,
                 const PoolMeta M, const int ring) {
@@ -64,6 +97,7 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const Hash
     __shared__ uint32_t s_new[kListCap];
     __shared__ uint32_t s_act[kListCap];
     __shared__ uint32_t s_n_new, s_n_act, s_base_new, s_base_act;
+    __shared__ int s_ref[4];  // s_ref[3]: 0 = unset, 1 = set
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -71,6 +105,7 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const Hash
     if (tid == 0) {
         s_n_new = 0;
         s_n_act = 0;
+        s_ref[3] = 0;
         if (blockIdx.x == 0 && blockIdx.y == 0) {
             // the ring slot the NEXT frame will count into (its last user finished 3 frames ago)
             const int nxt = (ring + 1) % kActiveRing;
@@ -79,9 +114,6 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const Hash
         }
     }
     __syncthreads();
-
-    uint32_t *active_count = M.counters + kCtrActive0 + ring;
-    uint32_t *active_out = M.active_slots + static_cast<size_t>(ring) * M.capacity;
 
     // ---- this thread's depth sample and its block range [lo, lo + n) per axis ----
     const int j = (blockIdx.x * kAllocTile + (tid & (kAllocTile - 1))) * P.stride;
@@ -108,11 +140,15 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const Hash
             lo0 = lo[0], lo1 = lo[1], lo2 = lo[2];
             n1 = n[1], n2 = n[2];
             ncand = n[0] * n[1] * n[2];
+            if (atomicCAS(&s_ref[3], 0, 1) == 0) {  // one reference key per CTA for unpacking
+                s_ref[0] = lo0;
+                s_ref[1] = lo1;
+                s_ref[2] = lo2;
+            }
         }
     }
 
-    // ---- candidates, warp-synchronously: ballot/match removes intra-warp duplicates, the CTA
-    //      set removes intra-CTA duplicates, survivors probe the global table one key per lane ----
+    // ---- phase A: shared-memory only ----
     const int wmax = __reduce_max_sync(0xffffffffu, ncand);
     for (int c = 0; c < wmax; ++c) {
         const bool have = c < ncand;
@@ -121,58 +157,48 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const Hash
         if (have) {
             const int dz = c % n2;
             const int r = c / n2;
-            const int dy = r % n1;
-            const int dx = r / n1;
-            kx = lo0 + dx;
-            ky = lo1 + dy;
+            kx = lo0 + r / n1;
+            ky = lo1 + r % n1;
             kz = lo2 + dz;
             pk = pack_key(kx, ky, kz);
         }
         const unsigned grp = __match_any_sync(0xffffffffu, pk);
-        const bool leader = have && ((__ffs(grp) - 1) == lane);
-        if (!leader) continue;
-        if (!cta_set_insert(s_set, pk)) continue;
-        if (P.shard_count > 1 &&
-            static_cast<int>(block_key_hash(kx, ky, kz) % static_cast<uint64_t>(P.shard_count)) !=
-                P.shard_rank)
-            continue;
-        bool is_new;
-        const uint32_t slot = table_insert(T, kx, ky, kz, &is_new);
-        if (slot == kEmpty) {
-            atomicOr(M.counters + kCtrError, 2u);
-            continue;
-        }
-        if (is_new) {
-            const uint32_t pos = atomicAdd(&s_n_new, 1u);
-            if (pos < kListCap) {
-                s_new[pos] = slot;
-            } else {  // list overflow: assign directly
-                assign_block(T, M, slot, atomicAdd(M.counters + kCtrPool, 1u));
-                atomicAdd(M.counters + kCtrNew0 + ring, 1u);
+        if (have && ((__ffs(grp) - 1) == lane)) {
+            uint32_t h = mix32(static_cast<uint32_t>(pk) ^ static_cast<uint32_t>(pk >> 32)) & (kSetSize - 1);
+            bool placed = false;
+            for (int k = 0; k < 64 && !placed; ++k) {
+                const unsigned long long old = atomicCAS(s_set + h, ~0ull, pk);
+                placed = (old == ~0ull) || (old == pk);
+                h = (h + 1) & (kSetSize - 1);
             }
-        }
-        if (atomicExch(T.stamp + slot, P.frame_id) != P.frame_id) {
-            const uint32_t pos = atomicAdd(&s_n_act, 1u);
-            if (pos < kListCap) {
-                s_act[pos] = slot;
-            } else {
-                const uint32_t g = atomicAdd(active_count, 1u);
-                if (g < M.capacity) active_out[g] = slot;
-            }
+            // saturated set (> ~1.5k distinct blocks under one 64x64-pixel tile): go straight to
+            // the global table, which de-duplicates anyway
+            if (!placed) touch_key(P, T, M, ring, kx, ky, kz, s_new, &s_n_new, s_act, &s_n_act);
         }
     }
     __syncthreads();
 
-    // ---- one global atomic per CTA for each list; pool indices are handed out contiguously ----
+    // ---- phase B: every unique key of the CTA, one per thread, all probes in flight ----
+    const int rx = s_ref[0], ry = s_ref[1], rz = s_ref[2];
+    for (int q = tid; q < kSetSize; q += kAllocThreads) {
+        const unsigned long long pk = s_set[q];
+        if (pk == ~0ull) continue;
+        touch_key(P, T, M, ring, unpack_axis(pk, 0, rx), unpack_axis(pk, 21, ry), unpack_axis(pk, 42, rz),
+                  s_new, &s_n_new, s_act, &s_n_act);
+    }
+    __syncthreads();
+
+    // ---- phase C: one global atomic per CTA for each list; pool indices are contiguous ----
     const uint32_t n_new = min(s_n_new, static_cast<uint32_t>(kListCap));
     const uint32_t n_act = min(s_n_act, static_cast<uint32_t>(kListCap));
     if (tid == 0) {
         s_base_new = n_new ? atomicAdd(M.counters + kCtrPool, n_new) : 0u;
         if (n_new) atomicAdd(M.counters + kCtrNew0 + ring, n_new);
-        s_base_act = n_act ? atomicAdd(active_count, n_act) : 0u;
+        s_base_act = n_act ? atomicAdd(M.counters + kCtrActive0 + ring, n_act) : 0u;
     }
     __syncthreads();
     for (uint32_t k = tid; k < n_new; k += kAllocThreads) assign_block(T, M, s_new[k], s_base_new + k);
+    uint32_t *active_out = M.active_slots + static_cast<size_t>(ring) * M.capacity;
     for (uint32_t k = tid; k < n_act; k += kAllocThreads) {
         const uint32_t g = s_base_act + k;
         if (g < M.capacity) active_out[g] = s_act[k];

@@ -158,8 +158,9 @@ class B200TsdfVolume:
             # staging ring is 4 deep: anything older has been consumed by the copy engine
             del self._keepalive[:-8]
 
-    def integrate_batch(self, depths, colors, K, poses):
-        """n frames back to back: depths [n,H,W] f32, colors [n,H,W,3] u8, poses [n,4,4] Tcw."""
+    def integrate_batch(self, depths, colors, K, poses, stream=None):
+        """n frames back to back (the rebuild(map) bulk path, base.py:1242-1318): depths [n,H,W] f32,
+        colors [n,H,W,3] u8, poses [n,4,4] Tcw.  One C call enqueues every frame."""
         K4 = _as_K4(K)
         T = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 16))
         n = T.shape[0]
@@ -177,7 +178,8 @@ class B200TsdfVolume:
             H, W = d.shape[1:]
             dp, cp = d.ctypes.data, c.ctypes.data
             hold = (d, c)
-        rc = self._L.b2v_integrate_batch(self._h, n, dp, cp, H, W, K4.ctypes.data, T.ctypes.data)
+        rc = self._L.b2v_integrate_batch(self._h, n, dp, cp, H, W, K4.ctypes.data, T.ctypes.data,
+                                         C.c_void_p(stream) if stream else None)
         self._check(rc, "b2v_integrate_batch")
         self._keepalive = [hold]
 

@@ -1,0 +1,141 @@
+"""Host logic of the plugin adapter (CPU, with a fake volume) and the same flow on the GPU."""
+
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from pyslam_b200 import integrator as I
+from pyslam_b200 import plugin_api as P
+from pyslam_b200 import synthetic as S
+
+
+class _FakeVolume:
+    """Records calls; stands in for B200TsdfVolume so the queue / task logic runs on CPU."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+        self.calls = []
+        self.closed = False
+
+    def integrate(self, depth, color, K, pose):
+        assert depth.dtype == np.float32 and color.dtype == np.uint8
+        self.calls.append(("integrate", tuple(K), np.asarray(pose).copy(), color[0, 0].copy()))
+
+    def reset(self):
+        self.calls.append(("reset",))
+
+    def extract_triangle_mesh(self):
+        self.calls.append(("mesh",))
+        return SimpleNamespace(vertices=np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float64),
+                               triangles=np.array([[0, 1, 2]], np.int32),
+                               vertex_colors=np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float64),
+                               vertex_normals=np.zeros((0, 3)))
+
+    def extract_point_cloud(self):
+        self.calls.append(("points",))
+        return SimpleNamespace(points=np.zeros((2, 3)), colors=np.ones((2, 3)))
+
+    def close(self):
+        self.closed = True
+
+
+def _camera(cfg):
+    return SimpleNamespace(fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy, width=cfg.width,
+                           height=cfg.height, D=None)
+
+
+def test_adapter_task_flow_with_fake_volume(monkeypatch, tmp_path):
+    monkeypatch.setattr(I, "B200TsdfVolume", _FakeVolume)
+    Cls = P.standalone_integrator_class()
+    cfg = S.CONFIGS["T0"]
+    integ = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_TSDF",
+                kVolumetricIntegrationVoxelLength=0.02)
+    assert integ.volume.kw["voxel_length"] == 0.02 and integ.volume.kw["depth_trunc"] == 4.0
+    d, c, T = S.render_frame(cfg, 0)
+    bgr = np.ascontiguousarray(c[..., ::-1])
+    kd = P.VolumetricIntegrationKeyframeData(id=7, pose=T, img=bgr, depth=(d * 1000).astype(np.uint16))
+    integ.add_keyframe_data(kd)
+    integ.step()
+    name, K, pose, px = integ.volume.calls[0]
+    assert name == "integrate" and K == (cfg.fx, cfg.fy, cfg.cx, cfg.cy) and np.array_equal(pose, T)
+    assert np.array_equal(px, c[0, 0])  # BGR -> RGB before the volume sees it (base.py:1054)
+    out = integ.pop_output()             # first integrate always produces an output
+    assert out.id == 7 and out.mesh.triangles.shape == (1, 3) and out.point_cloud is None
+    # a second frame inside the output interval integrates but does not extract
+    integ.add_keyframe_data(kd)
+    integ.step()
+    assert integ.pop_output() is None and integ.volume.calls[-1][0] == "integrate"
+    # UPDATE_OUTPUT forces an extraction
+    integ.add_update_output_task()
+    integ.step()
+    assert integ.pop_output().task_type == P.VolumetricIntegrationTaskType.UPDATE_OUTPUT
+    # SAVE writes dense_map.ply and signals completion
+    integ.save(str(tmp_path))
+    integ.step()
+    assert integ.save_request_completed.value == 1
+    ply = open(os.path.join(tmp_path, "dense_map.ply"), "rb").read()
+    assert ply.startswith(b"ply\nformat binary_little_endian 1.0\nelement vertex 3\n")
+    assert b"element face 1\n" in ply and len(ply.split(b"end_header\n", 1)[1]) == 3 * 15 + 13
+    # RESET arrives on the management queue and is honoured before the next task
+    integ.reset()
+    integ.add_update_output_task()
+    integ.step()
+    assert ("reset",) in integ.volume.calls
+    # exceptions inside a task are logged and do not kill the loop (tsdf.py:303-307)
+    integ.add_keyframe_data(P.VolumetricIntegrationKeyframeData(id=9, pose=T, img=bgr[:3], depth=d))
+    monkeypatch.setattr(_FakeVolume, "integrate", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("x")))
+    integ.step()
+    assert integ.is_running.value == 1
+    integ.add_task(None)
+    integ.step()
+    assert integ.is_running.value == 0
+    integ.quit()
+    assert integ.volume.closed
+
+
+def test_outdoor_depth_trunc_and_point_cloud_mode(monkeypatch):
+    monkeypatch.setattr(I, "B200TsdfVolume", _FakeVolume)
+    Cls = P.standalone_integrator_class()
+    cfg = S.CONFIGS["T0"]
+    integ = Cls(_camera(cfg), P.DatasetEnvironmentType.OUTDOOR, None, "B200_TSDF",
+                kVolumetricIntegrationTsdfExtractMesh=False)
+    assert integ.volume.kw["depth_trunc"] == 10.0
+    integ.add_update_output_task()
+    integ.step()
+    out = integ.pop_output()
+    assert out.mesh is None and out.point_cloud.points.shape == (2, 3)
+
+
+@pytest.mark.gpu
+def test_adapter_end_to_end_on_gpu(tmp_path):
+    import oracle
+    Cls = P.standalone_integrator_class()
+    cfg = S.CONFIGS["T0"]
+    integ = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_TSDF",
+                kVolumetricIntegrationVoxelLength=cfg.voxel_size,
+                kVolumetricIntegrationTSdfTrunc=cfg.sdf_trunc,
+                kVolumetricIntegrationB200CapacityBlocks=4096)
+    orc = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, 4.0)
+    for i in range(3):
+        d, c, T = S.render_frame(cfg, i)
+        integ.add_keyframe_data(P.VolumetricIntegrationKeyframeData(
+            id=i, pose=T, img=np.ascontiguousarray(c[..., ::-1]), depth=d))
+        orc.integrate(d, c, cfg.K, T)
+    integ.run_pending()
+    integ.add_update_output_task()
+    integ.step()
+    out = None
+    while True:
+        o = integ.pop_output()
+        if o is None:
+            break
+        out = o
+    ref = orc.extract_mesh()
+    assert out.mesh.vertices.shape == ref["vertices"].shape
+    assert out.mesh.triangles.shape == ref["triangles"].shape
+    integ.save(str(tmp_path))
+    integ.step()
+    assert os.path.getsize(os.path.join(tmp_path, "dense_map.ply")) > 15 * len(ref["vertices"])
+    integ.quit()
