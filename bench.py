@@ -276,7 +276,11 @@ def run_gpu_arm(args, rank, world, local_rank):
     capacity = args.capacity
     vol = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=capacity,
                          device=local_rank, shard_rank=rank, shard_count=world)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the legacy default stream has handle 0, which the C ABI reads
+    # as "use the library's own stream" and which torch events would not observe
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     d_dev = torch.from_numpy(depth).cuda()
     c_dev = torch.from_numpy(color).cuda()
     # pinned host copies for the end-to-end path

@@ -23,7 +23,8 @@
  *   allocate  (A.2) every `stride`-th pixel with 0 < d < depth_trunc: back-project in f64,
  *             p_w = Twc * p_c (rigid inverse of Tcw), touch every block in the key range of
  *             [p_w - tau, p_w + tau]
- *   update    (A.3) voxel centre c = ((float)v + 0.5f) * vs;  p = E*c (E = Tcw as f32, fmaf chain);
+ *   update    (A.3) voxel centre c = ((float)v + 0.5f) * vs;  p = E*c with E = Tcw as f32:
+ *             A = fmaf(E1, c.y, fmaf(E2, c.z, E3)) per x-row, p = fmaf(E0, c.x, A);
  *             u_f = fmaf(p.x*fx, 1/p.z, cx+0.5f) (same for v_f); Open3D's 0.0001 image margin;
  *             sdf = (d - p.z) * lambda(u,v);  if sdf > -tau:  t = min(1, sdf/tau),
  *             r = 1/(w+1), tsdf = fmaf(tsdf,w,t)*r, rgb_k = fmaf(rgb_k,w,RGB_k)*r, w += 1
@@ -235,11 +236,15 @@ static int64_t integrate_block(float *vox, key3 key, int B, float vs, float tau,
         const float cz = ((float)(key.z * B + lz) + 0.5f) * vs;
         for (int ly = 0; ly < B; ++ly) {
             const float cy_ = ((float)(key.y * B + ly) + 0.5f) * vs;
+            /* row part of E*c, shared by the voxels of one x-row */
+            const float ax = fmaf(E[1], cy_, fmaf(E[2], cz, E[3]));
+            const float ay = fmaf(E[5], cy_, fmaf(E[6], cz, E[7]));
+            const float az = fmaf(E[9], cy_, fmaf(E[10], cz, E[11]));
             for (int lx = 0; lx < B; ++lx) {
                 const float cx_ = ((float)(key.x * B + lx) + 0.5f) * vs;
-                const float px = fmaf(E[2], cz, fmaf(E[1], cy_, fmaf(E[0], cx_, E[3])));
-                const float py = fmaf(E[6], cz, fmaf(E[5], cy_, fmaf(E[4], cx_, E[7])));
-                const float pz = fmaf(E[10], cz, fmaf(E[9], cy_, fmaf(E[8], cx_, E[11])));
+                const float px = fmaf(E[0], cx_, ax);
+                const float py = fmaf(E[4], cx_, ay);
+                const float pz = fmaf(E[8], cx_, az);
                 if (!(pz > 0.0f)) continue;
                 const float inv_z = 1.0f / pz;
                 const float u_f = fmaf(px * fx, inv_z, cxh);

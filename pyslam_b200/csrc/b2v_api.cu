@@ -87,6 +87,10 @@ struct b2v_volume {
     cudaStream_t compute = nullptr, copy = nullptr;
     float *d_depth[kStage] = {};
     uint8_t *d_color[kStage] = {};
+    float4 *d_texel[kStage] = {};   // packed {depth, lambda, rgbx} frames read by integrate_kernel
+    float *d_lambda = nullptr;      // lambda image of the cached intrinsics
+    double lam_K[4] = {0, 0, 0, 0};
+    int lam_H = 0, lam_W = 0;
     size_t stage_pixels = 0;
     cudaEvent_t ev_ready[kStage] = {}, ev_free[kStage] = {};
     HashTable table{};
@@ -174,7 +178,8 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     int rc = volume_clear_device(v);
     if (rc != B2V_OK) return rc;
     const int sms = b2v_device_sm_count(cfg->device);
-    v->grid_ctas = (sms > 0 ? sms : 148) * 16;  // persistent: 16 resident 128-thread CTAs per SM
+    // persistent grid: exactly one wave of resident CTAs
+    v->grid_ctas = (sms > 0 ? sms : 148) * integrate_max_resident_ctas_per_sm();
     B2V_CUDA(v, cudaStreamSynchronize(v->compute));
     return B2V_OK;
 }
@@ -187,9 +192,11 @@ extern "C" int b2v_destroy(b2v_volume *v) {
     for (int s = 0; s < kStage; ++s) {
         cudaFree(v->d_depth[s]);
         cudaFree(v->d_color[s]);
+        cudaFree(v->d_texel[s]);
         if (v->ev_ready[s]) cudaEventDestroy(v->ev_ready[s]);
         if (v->ev_free[s]) cudaEventDestroy(v->ev_free[s]);
     }
+    cudaFree(v->d_lambda);
     cudaFree(v->table.entries);
     cudaFree(v->table.stamp);
     cudaFree(v->meta.pool);
@@ -258,11 +265,18 @@ static int ensure_staging(b2v_volume *v, size_t pixels) {
     for (int s = 0; s < kStage; ++s) {
         cudaFree(v->d_depth[s]);
         cudaFree(v->d_color[s]);
+        cudaFree(v->d_texel[s]);
         v->d_depth[s] = nullptr;
         v->d_color[s] = nullptr;
+        v->d_texel[s] = nullptr;
         B2V_CUDA(v, cudaMalloc(&v->d_depth[s], pixels * sizeof(float)));
         B2V_CUDA(v, cudaMalloc(&v->d_color[s], pixels * 3));
+        B2V_CUDA(v, cudaMalloc(&v->d_texel[s], pixels * sizeof(float4)));
     }
+    cudaFree(v->d_lambda);
+    v->d_lambda = nullptr;
+    B2V_CUDA(v, cudaMalloc(&v->d_lambda, pixels * sizeof(float)));
+    v->lam_H = v->lam_W = 0;
     v->stage_pixels = pixels;
     return B2V_OK;
 }
@@ -290,9 +304,11 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
     const float *d_depth = depth;
     const uint8_t *d_color = color;
     const bool staged = !(dev_depth && dev_color);
-    if (staged) {
-        int rc = ensure_staging(v, pixels);
+    {
+        const int rc = ensure_staging(v, pixels);
         if (rc != B2V_OK) return rc;
+    }
+    if (staged) {
         B2V_CUDA(v, cudaStreamWaitEvent(v->copy, v->ev_free[s], 0));
         if (!dev_depth) {
             B2V_CUDA(v, cudaMemcpyAsync(v->d_depth[s], depth, pixels * sizeof(float),
@@ -310,6 +326,13 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
     fill_frame_params(&P, K, Tcw, height, width, v->cfg.depth_stride, v->cfg.voxel_size, v->cfg.sdf_trunc,
                       v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank, v->cfg.shard_count);
     const int ring = static_cast<int>(v->frame_id % kActiveRing);
+    if (v->lam_H != height || v->lam_W != width || std::memcmp(v->lam_K, K, sizeof(v->lam_K)) != 0) {
+        B2V_CUDA(v, launch_lambda(P, v->d_lambda, cs));
+        std::memcpy(v->lam_K, K, sizeof(v->lam_K));
+        v->lam_H = height;
+        v->lam_W = width;
+        v->launches += 1;
+    }
     cudaEvent_t *pe = nullptr;
     if (v->prof_enabled) {
         if (v->prof_used + 3 > v->prof_events.size()) {
@@ -321,9 +344,9 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
         v->prof_used += 3;
         B2V_CUDA(v, cudaEventRecord(pe[0], cs));
     }
-    B2V_CUDA(v, launch_allocate(P, d_depth, v->table, v->meta, ring, cs));
+    B2V_CUDA(v, launch_allocate(P, d_depth, d_color, v->d_lambda, v->d_texel[s], v->table, v->meta, ring, cs));
     if (pe) B2V_CUDA(v, cudaEventRecord(pe[1], cs));
-    B2V_CUDA(v, launch_integrate(P, d_depth, d_color, v->table, v->meta, ring, v->grid_ctas, cs));
+    B2V_CUDA(v, launch_integrate(P, v->d_texel[s], v->table, v->meta, ring, v->grid_ctas, cs));
     if (pe) B2V_CUDA(v, cudaEventRecord(pe[2], cs));
     if (staged) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], cs));
     v->launches += 2;

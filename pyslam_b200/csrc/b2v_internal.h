@@ -53,13 +53,17 @@ void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], 
                        int shard_rank, int shard_count);
 
 // ---- kernels (b2v_tsdf.cu) ----
-// allocation + touched-set of one frame; zeroes the next frame's active counter
-cudaError_t launch_allocate(const FrameParams &p, const float *depth, const HashTable &table,
+// lambda image (Open3D's depth-to-camera-distance multiplier) for the current intrinsics
+cudaError_t launch_lambda(const FrameParams &p, float *lam, cudaStream_t stream);
+// frame packing ({valid depth, lambda, rgbx} texels) + allocation + touched-set of one frame;
+// zeroes the next frame's ring counters
+cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint8_t *color,
+                            const float *lam, float4 *texels, const HashTable &table,
                             const PoolMeta &meta, int ring, cudaStream_t stream);
 // projective TSDF + colour update of every block touched by the frame
-cudaError_t launch_integrate(const FrameParams &p, const float *depth, const uint8_t *color,
-                             const HashTable &table, const PoolMeta &meta, int ring, int grid_ctas,
-                             cudaStream_t stream);
+cudaError_t launch_integrate(const FrameParams &p, const float4 *texels, const HashTable &table,
+                             const PoolMeta &meta, int ring, int grid_ctas, cudaStream_t stream);
+int integrate_max_resident_ctas_per_sm();
 // hashes[i] = BlockKeyHash(block_keys[i])
 cudaError_t launch_block_hashes(const int4 *block_keys, uint64_t *hashes, uint32_t n,
                                 cudaStream_t stream);

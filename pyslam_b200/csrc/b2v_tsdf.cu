@@ -19,10 +19,12 @@ namespace b2v {
 // allocation
 // ------------------------------------------------------------------------------------------------
 
-constexpr int kAllocTile = 16;      // 16 x 16 stride-samples per CTA
-constexpr int kAllocThreads = kAllocTile * kAllocTile;
-constexpr int kSetSize = 2048;      // CTA-local de-duplication set (power of two)
-constexpr int kListCap = 1024;      // CTA-local lists of fresh / first-touched slots
+constexpr int kAllocTile = 8;       // 8 x 8 depth samples per CTA ...
+constexpr int kAllocSub = 4;        // ... x 4 lanes per sample: a sample's (typically 27) candidate blocks
+                                    // are split over 4 lanes, so the serial chain per warp is 7 long
+constexpr int kAllocThreads = kAllocTile * kAllocTile * kAllocSub;
+constexpr int kSetSize = 512;       // CTA-local de-duplication set (power of two)
+constexpr int kListCap = 512;       // CTA-local lists of fresh / first-touched slots
 
 // 21 low bits per axis: injective inside one frame's frustum (checked on the host at create)
 __device__ __forceinline__ unsigned long long pack_key(int x, int y, int z) {
@@ -91,13 +93,14 @@ __device__ __forceinline__ void touch_key(const FrameParams &P, const HashTable 
 //          flight at once (the probes are independent L2 round trips), and exchange the frame stamp.
 // Phase C  one atomic per CTA hands out contiguous pool indices and active-list positions.
 __global__ void __launch_bounds__(kAllocThreads)
-allocate_kernel(const FrameParams P, const float *__restrict__ depth, const HashTable T,
+allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint8_t *__restrict__ rgb,
+                const float *__restrict__ lam, float4 *__restrict__ tex, const HashTable T,
                 const PoolMeta M, const int ring) {
     __shared__ unsigned long long s_set[kSetSize];
     __shared__ uint32_t s_new[kListCap];
     __shared__ uint32_t s_act[kListCap];
     __shared__ uint32_t s_n_new, s_n_act, s_base_new, s_base_act;
-    __shared__ int s_ref[4];  // s_ref[3]: 0 = unset, 1 = set
+    __shared__ int s_ref[4];  // reference key for unpacking; s_ref[3]: 0 = unset, 1 = set
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -115,9 +118,29 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const Hash
     }
     __syncthreads();
 
-    // ---- this thread's depth sample and its block range [lo, lo + n) per axis ----
-    const int j = (blockIdx.x * kAllocTile + (tid & (kAllocTile - 1))) * P.stride;
-    const int i = (blockIdx.y * kAllocTile + (tid / kAllocTile)) * P.stride;
+    // ---- pack this CTA's pixel tile into 16-byte texels {valid depth | 0, lambda, rgbx, 0}: the
+    //      integrate kernel then needs one gather per voxel instead of four ----
+    {
+        const int tile = kAllocTile * P.stride;  // pixels per tile side
+        const int x0 = blockIdx.x * tile, y0 = blockIdx.y * tile;
+        for (int q = tid; q < tile * tile; q += kAllocThreads) {
+            const int x = x0 + q % tile, y = y0 + q / tile;
+            if (x < P.W && y < P.H) {
+                const size_t p = static_cast<size_t>(y) * P.W + x;
+                const float d = __ldg(depth + p);
+                const uint8_t *c = rgb + 3 * p;
+                const uint32_t rgbx = static_cast<uint32_t>(__ldg(c)) | (static_cast<uint32_t>(__ldg(c + 1)) << 8) |
+                                      (static_cast<uint32_t>(__ldg(c + 2)) << 16);
+                tex[p] = make_float4((d > 0.0f && d < P.depth_trunc) ? d : 0.0f, __ldg(lam + p),
+                                     __uint_as_float(rgbx), 0.0f);
+            }
+        }
+    }
+
+    // ---- this thread's depth sample (4 consecutive lanes share one) and its block range ----
+    const int sample = tid / kAllocSub, sub = tid % kAllocSub;
+    const int j = (blockIdx.x * kAllocTile + (sample & (kAllocTile - 1))) * P.stride;
+    const int i = (blockIdx.y * kAllocTile + (sample / kAllocTile)) * P.stride;
     int lo0 = 0, lo1 = 0, lo2 = 0, n1 = 1, n2 = 1, ncand = 0;
     if (j < P.W && i < P.H) {
         const float d = __ldg(depth + static_cast<size_t>(i) * P.W + j);
@@ -148,17 +171,23 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const Hash
         }
     }
 
-    // ---- phase A: shared-memory only ----
+    // ---- phase A: shared-memory only; lane `sub` of a sample takes candidates sub, sub+4, ... ----
     const int wmax = __reduce_max_sync(0xffffffffu, ncand);
-    for (int c = 0; c < wmax; ++c) {
+    int dx = 0, dy = 0, dz = sub;  // candidate c = (dx * n1 + dy) * n2 + dz, advanced incrementally
+    for (int c = sub; c - sub < wmax; c += kAllocSub, dz += kAllocSub) {
         const bool have = c < ncand;
         int kx = 0, ky = 0, kz = 0;
         unsigned long long pk = (1ull << 63) | static_cast<unsigned long long>(lane);
         if (have) {
-            const int dz = c % n2;
-            const int r = c / n2;
-            kx = lo0 + r / n1;
-            ky = lo1 + r % n1;
+            while (dz >= n2) {
+                dz -= n2;
+                if (++dy >= n1) {
+                    dy = 0;
+                    ++dx;
+                }
+            }
+            kx = lo0 + dx;
+            ky = lo1 + dy;
             kz = lo2 + dz;
             pk = pack_key(kx, ky, kz);
         }
@@ -171,7 +200,7 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const Hash
                 placed = (old == ~0ull) || (old == pk);
                 h = (h + 1) & (kSetSize - 1);
             }
-            // saturated set (> ~1.5k distinct blocks under one 64x64-pixel tile): go straight to
+            // saturated set (> ~400 distinct blocks under one 32x32-pixel tile): go straight to
             // the global table, which de-duplicates anyway
             if (!placed) touch_key(P, T, M, ring, kx, ky, kz, s_new, &s_n_new, s_act, &s_n_act);
         }
@@ -205,12 +234,13 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const Hash
     }
 }
 
-cudaError_t launch_allocate(const FrameParams &p, const float *depth, const HashTable &table,
+cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint8_t *color,
+                            const float *lam, float4 *texels, const HashTable &table,
                             const PoolMeta &meta, int ring, cudaStream_t stream) {
     const int gw = (p.W + p.stride - 1) / p.stride;
     const int gh = (p.H + p.stride - 1) / p.stride;
     const dim3 grid((gw + kAllocTile - 1) / kAllocTile, (gh + kAllocTile - 1) / kAllocTile);
-    allocate_kernel<<<grid, kAllocThreads, 0, stream>>>(p, depth, table, meta, ring);
+    allocate_kernel<<<grid, kAllocThreads, 0, stream>>>(p, depth, color, lam, texels, table, meta, ring);
     return cudaGetLastError();
 }
 
@@ -220,15 +250,16 @@ cudaError_t launch_allocate(const FrameParams &p, const float *depth, const Hash
 //
 // One CTA iteration = one touched block: 128 threads x 4 consecutive-x voxels.  A warp reads /
 // writes 512 contiguous bytes per plane (LDG.128 / STG.128), so every block-pool transaction is a
-// full 128-byte line.  Threads whose four voxels all fail the projection / truncation gate touch
-// no pool memory at all.
+// full 128-byte line.  The five plane loads of a block are issued first; the projection of the four
+// voxels and their texel gathers (one 16-byte {depth, lambda, rgbx} texel per voxel, packed by
+// allocate_kernel and L2-resident) overlap that HBM latency; the next block's table entry is
+// prefetched one iteration ahead.  Planes are written back only by threads that updated a voxel.
 
 constexpr int kIntThreads = 128;
 
 __global__ void __launch_bounds__(kIntThreads, 8)
-integrate_kernel(const FrameParams P, const float *__restrict__ depth,
-                 const uint8_t *__restrict__ rgb, const HashTable T, const PoolMeta M,
-                 const int ring) {
+integrate_kernel(const FrameParams P, const float4 *__restrict__ tex, const HashTable T,
+                 const PoolMeta M, const int ring) {
     const uint32_t n = min(M.counters[kCtrActive0 + ring], M.capacity);
     const uint32_t *__restrict__ act = M.active_slots + static_cast<size_t>(ring) * M.capacity;
     const int t = threadIdx.x;
@@ -237,78 +268,109 @@ integrate_kernel(const FrameParams P, const float *__restrict__ depth,
         atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrUpdatesLo),
                   static_cast<unsigned long long>(n));
 
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        const uint32_t slot = act[i];
-        const uint4 e = T.entries[slot];
-        if (e.w >= M.capacity) continue;  // pool overflowed for this key
-        float *blk = M.pool + static_cast<size_t>(e.w) * kBlockFloats + t * 4;
+    uint32_t i = blockIdx.x;
+    uint4 e = make_uint4(0u, 0u, 0u, kNoBlock);
+    if (i < n) e = T.entries[act[i]];
+    while (i < n) {
+        const uint32_t i_next = i + gridDim.x;
+        uint4 e_next = e;
+        if (i_next < n) e_next = T.entries[act[i_next]];  // in flight during this iteration
 
-        const int vx0 = static_cast<int>(e.x) * kB + lx0;
-        const float cy = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.y) * kB + ly), 0.5f), P.vs);
-        const float cz = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.z) * kB + lz), 0.5f), P.vs);
-
-        float tv[4];
-        int pix[4];
-        unsigned upd = 0;
+        if (e.w < M.capacity) {  // (>= capacity: the pool overflowed for this key)
+            float *blk = M.pool + static_cast<size_t>(e.w) * kBlockFloats + t * 4;
+            float4 q[kPlanes];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float cx = __fmul_rn(__fadd_rn(static_cast<float>(vx0 + k), 0.5f), P.vs);
-            const float px = __fmaf_rn(P.E[2], cz, __fmaf_rn(P.E[1], cy, __fmaf_rn(P.E[0], cx, P.E[3])));
-            const float py = __fmaf_rn(P.E[6], cz, __fmaf_rn(P.E[5], cy, __fmaf_rn(P.E[4], cx, P.E[7])));
-            const float pz = __fmaf_rn(P.E[10], cz, __fmaf_rn(P.E[9], cy, __fmaf_rn(P.E[8], cx, P.E[11])));
-            tv[k] = 0.0f;
-            pix[k] = 0;
-            if (!(pz > 0.0f)) continue;
-            const float inv_z = __frcp_rn(pz);
-            const float u_f = __fmaf_rn(__fmul_rn(px, P.fxf), inv_z, P.cxh);
-            const float v_f = __fmaf_rn(__fmul_rn(py, P.fyf), inv_z, P.cyh);
-            if (!(u_f >= 0.0001f && u_f < P.safe_w && v_f >= 0.0001f && v_f < P.safe_h)) continue;
-            const int u = __float2int_rz(u_f), v = __float2int_rz(v_f);
-            const int p = v * P.W + u;
-            const float d = __ldg(depth + p);
-            if (!(d > 0.0f && d < P.depth_trunc)) continue;
-            const float xx = __fmul_rn(__fsub_rn(static_cast<float>(u), P.cxf), P.inv_fx);
-            const float yy = __fmul_rn(__fsub_rn(static_cast<float>(v), P.cyf), P.inv_fy);
-            const float lam = __fsqrt_rn(__fmaf_rn(xx, xx, __fmaf_rn(yy, yy, 1.0f)));
-            const float sdf = __fmul_rn(__fsub_rn(d, pz), lam);
-            if (sdf > -P.tau) {
-                tv[k] = fminf(1.0f, __fmul_rn(sdf, P.inv_tau));
-                pix[k] = p;
-                upd |= 1u << k;
+            for (int c = 0; c < kPlanes; ++c) q[c] = *reinterpret_cast<const float4 *>(blk + c * kVox);
+
+            const int vx0 = static_cast<int>(e.x) * kB + lx0;
+            const float cy = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.y) * kB + ly), 0.5f), P.vs);
+            const float cz = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.z) * kB + lz), 0.5f), P.vs);
+            // row part of E * c, shared by the voxels of one x-row (contract: fmaf(E0, cx, A))
+            const float ax = __fmaf_rn(P.E[1], cy, __fmaf_rn(P.E[2], cz, P.E[3]));
+            const float ay = __fmaf_rn(P.E[5], cy, __fmaf_rn(P.E[6], cz, P.E[7]));
+            const float az = __fmaf_rn(P.E[9], cy, __fmaf_rn(P.E[10], cz, P.E[11]));
+
+            float pzs[4];
+            int pix[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float cx = __fmul_rn(__fadd_rn(static_cast<float>(vx0 + k), 0.5f), P.vs);
+                const float px = __fmaf_rn(P.E[0], cx, ax);
+                const float py = __fmaf_rn(P.E[4], cx, ay);
+                const float pz = __fmaf_rn(P.E[8], cx, az);
+                pzs[k] = pz;
+                pix[k] = -1;
+                if (pz > 0.0f) {
+                    const float inv_z = __frcp_rn(pz);
+                    const float u_f = __fmaf_rn(__fmul_rn(px, P.fxf), inv_z, P.cxh);
+                    const float v_f = __fmaf_rn(__fmul_rn(py, P.fyf), inv_z, P.cyh);
+                    if (u_f >= 0.0001f && u_f < P.safe_w && v_f >= 0.0001f && v_f < P.safe_h)
+                        pix[k] = __float2int_rz(v_f) * P.W + __float2int_rz(u_f);
+                }
+            }
+            float4 tx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tx[k] = pix[k] >= 0 ? __ldg(tex + pix[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+            float *ts = reinterpret_cast<float *>(&q[0]);
+            float *w = reinterpret_cast<float *>(&q[1]);
+            float *cr = reinterpret_cast<float *>(&q[2]);
+            float *cg = reinterpret_cast<float *>(&q[3]);
+            float *cb = reinterpret_cast<float *>(&q[4]);
+            bool upd = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float d = tx[k].x;  // 0 where the pixel is invalid (allocate_kernel pre-validates)
+                const float sdf = __fmul_rn(__fsub_rn(d, pzs[k]), tx[k].y);
+                if (d > 0.0f && sdf > -P.tau) {
+                    const float tv = fminf(1.0f, __fmul_rn(sdf, P.inv_tau));
+                    const uint32_t rgbx = __float_as_uint(tx[k].z);
+                    const float w0 = w[k];
+                    const float wn = __fadd_rn(w0, 1.0f);
+                    const float r = __frcp_rn(wn);
+                    ts[k] = __fmul_rn(__fmaf_rn(ts[k], w0, tv), r);
+                    cr[k] = __fmul_rn(__fmaf_rn(cr[k], w0, static_cast<float>(rgbx & 0xFFu)), r);
+                    cg[k] = __fmul_rn(__fmaf_rn(cg[k], w0, static_cast<float>((rgbx >> 8) & 0xFFu)), r);
+                    cb[k] = __fmul_rn(__fmaf_rn(cb[k], w0, static_cast<float>((rgbx >> 16) & 0xFFu)), r);
+                    w[k] = wn;
+                    upd = true;
+                }
+            }
+            if (upd) {
+#pragma unroll
+                for (int c = 0; c < kPlanes; ++c) *reinterpret_cast<float4 *>(blk + c * kVox) = q[c];
             }
         }
-        if (upd == 0) continue;
-
-        float4 q[kPlanes];
-#pragma unroll
-        for (int c = 0; c < kPlanes; ++c) q[c] = *reinterpret_cast<const float4 *>(blk + c * kVox);
-        float *ts = reinterpret_cast<float *>(&q[0]);
-        float *w = reinterpret_cast<float *>(&q[1]);
-        float *cr = reinterpret_cast<float *>(&q[2]);
-        float *cg = reinterpret_cast<float *>(&q[3]);
-        float *cb = reinterpret_cast<float *>(&q[4]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!((upd >> k) & 1u)) continue;
-            const uint8_t *c = rgb + static_cast<size_t>(pix[k]) * 3;
-            const float w0 = w[k];
-            const float wn = __fadd_rn(w0, 1.0f);
-            const float r = __frcp_rn(wn);
-            ts[k] = __fmul_rn(__fmaf_rn(ts[k], w0, tv[k]), r);
-            cr[k] = __fmul_rn(__fmaf_rn(cr[k], w0, static_cast<float>(__ldg(c + 0))), r);
-            cg[k] = __fmul_rn(__fmaf_rn(cg[k], w0, static_cast<float>(__ldg(c + 1))), r);
-            cb[k] = __fmul_rn(__fmaf_rn(cb[k], w0, static_cast<float>(__ldg(c + 2))), r);
-            w[k] = wn;
-        }
-#pragma unroll
-        for (int c = 0; c < kPlanes; ++c) *reinterpret_cast<float4 *>(blk + c * kVox) = q[c];
+        e = e_next;
+        i = i_next;
     }
 }
 
-cudaError_t launch_integrate(const FrameParams &p, const float *depth, const uint8_t *color,
-                             const HashTable &table, const PoolMeta &meta, int ring, int grid_ctas,
-                             cudaStream_t stream) {
-    integrate_kernel<<<grid_ctas, kIntThreads, 0, stream>>>(p, depth, color, table, meta, ring);
+cudaError_t launch_integrate(const FrameParams &p, const float4 *texels, const HashTable &table,
+                             const PoolMeta &meta, int ring, int grid_ctas, cudaStream_t stream) {
+    integrate_kernel<<<grid_ctas, kIntThreads, 0, stream>>>(p, texels, table, meta, ring);
+    return cudaGetLastError();
+}
+
+int integrate_max_resident_ctas_per_sm() {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, integrate_kernel, kIntThreads, 0) != cudaSuccess)
+        return 8;
+    return n > 0 ? n : 1;
+}
+
+// lambda(u, v) = sqrt(((u - cx)/fx)^2 + ((v - cy)/fy)^2 + 1): Open3D's depth-to-camera-distance
+// multiplier image, recomputed only when the intrinsics or the image size change
+__global__ void lambda_kernel(const FrameParams P, float *__restrict__ lam) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= P.W) return;
+    const float xx = __fmul_rn(__fsub_rn(static_cast<float>(u), P.cxf), P.inv_fx);
+    const float yy = __fmul_rn(__fsub_rn(static_cast<float>(v), P.cyf), P.inv_fy);
+    lam[static_cast<size_t>(v) * P.W + u] = __fsqrt_rn(__fmaf_rn(xx, xx, __fmaf_rn(yy, yy, 1.0f)));
+}
+
+cudaError_t launch_lambda(const FrameParams &p, float *lam, cudaStream_t stream) {
+    lambda_kernel<<<dim3((p.W + 127) / 128, p.H), 128, 0, stream>>>(p, lam);
     return cudaGetLastError();
 }
 
