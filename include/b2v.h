@@ -74,6 +74,10 @@ int64_t b2v_num_blocks(b2v_volume *v);                 /* synchronises */
 int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int64_t *new_blocks);
 /* total (block,frame) updates and kernel launches since create/reset: bench accounting */
 int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches);
+/* Scheduling option: 1 (default) runs allocate(f+1) on its own stream concurrently with integrate(f)
+ * (it has no data dependency on it); 0 serialises both kernels on one stream (clean per-kernel timing).
+ * Results are bit-identical either way.  Synchronises. */
+int b2v_set_overlap(b2v_volume *v, int32_t enable);
 /* Per-kernel device timing (CUDA events on the launching stream around each launch), for the
  * roofline figure: enable, run frames, then read the summed durations (synchronises, resets). */
 int b2v_profile_enable(b2v_volume *v, int32_t enable);

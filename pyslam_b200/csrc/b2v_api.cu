@@ -8,6 +8,7 @@
 // frame f.  Nothing synchronises with the host until b2v_synchronize / an inspection call.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -84,7 +85,12 @@ bool is_device_pointer(const void *p) {
 
 struct b2v_volume {
     b2v_config cfg{};
-    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t compute = nullptr, copy = nullptr, alloc = nullptr;
+    cudaStream_t last_stream = nullptr;  // caller stream of the most recent frame (synchronised on reads)
+    bool overlap = true;                 // allocate(f+1) on its own stream, concurrent with integrate(f)
+    bool use_tma = true;                 // stage image tiles with TMA when the layout allows it
+    bool inputs_fenced = false;          // batch call: device inputs already ordered before the alloc stream
+    cudaEvent_t ev_in = nullptr, ev_alloc_done[kActiveRing] = {}, ev_int_done[kActiveRing] = {};
     float *d_depth[kStage] = {};
     uint8_t *d_color[kStage] = {};
     float4 *d_texel[kStage] = {};   // packed {depth, lambda, rgbx} frames read by integrate_kernel
@@ -108,7 +114,7 @@ struct b2v_volume {
     uint32_t *h_totals = nullptr;
     // optional per-kernel timing (b2v_profile_*)
     bool prof_enabled = false;
-    std::vector<cudaEvent_t> prof_events;  // triples: before allocate, between, after integrate
+    std::vector<cudaEvent_t> prof_events;  // quadruples: allocate begin/end, integrate begin/end
     size_t prof_used = 0;
 };
 
@@ -157,6 +163,14 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     B2V_CUDA(v, cudaSetDevice(cfg->device));
     B2V_CUDA(v, cudaStreamCreateWithFlags(&v->compute, cudaStreamNonBlocking));
     B2V_CUDA(v, cudaStreamCreateWithFlags(&v->copy, cudaStreamNonBlocking));
+    B2V_CUDA(v, cudaStreamCreateWithFlags(&v->alloc, cudaStreamNonBlocking));
+    B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_in, cudaEventDisableTiming));
+    for (int r = 0; r < kActiveRing; ++r) {
+        B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_alloc_done[r], cudaEventDisableTiming));
+        B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_int_done[r], cudaEventDisableTiming));
+    }
+    if (const char *e = std::getenv("B2V_OVERLAP")) v->overlap = std::atoi(e) != 0;
+    if (const char *e = std::getenv("B2V_TMA")) v->use_tma = std::atoi(e) != 0;
     for (int s = 0; s < kStage; ++s) {
         B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_ready[s], cudaEventDisableTiming));
         B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_free[s], cudaEventDisableTiming));
@@ -178,8 +192,13 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     int rc = volume_clear_device(v);
     if (rc != B2V_OK) return rc;
     const int sms = b2v_device_sm_count(cfg->device);
-    // persistent grid: exactly one wave of resident CTAs
-    v->grid_ctas = (sms > 0 ? sms : 148) * integrate_max_resident_ctas_per_sm();
+    // persistent grid: exactly one wave of resident CTAs (B2V_INT_CTAS_PER_SM overrides, for tuning)
+    int per_sm = integrate_max_resident_ctas_per_sm();
+    if (const char *e = std::getenv("B2V_INT_CTAS_PER_SM")) {
+        const int n = std::atoi(e);
+        if (n >= 1 && n <= 32) per_sm = n;
+    }
+    v->grid_ctas = (sms > 0 ? sms : 148) * per_sm;
     B2V_CUDA(v, cudaStreamSynchronize(v->compute));
     return B2V_OK;
 }
@@ -187,8 +206,12 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
 extern "C" int b2v_destroy(b2v_volume *v) {
     if (!v) return B2V_OK;
     cudaSetDevice(v->cfg.device);
-    if (v->compute) cudaStreamSynchronize(v->compute);
-    if (v->copy) cudaStreamSynchronize(v->copy);
+    cudaDeviceSynchronize();
+    if (v->ev_in) cudaEventDestroy(v->ev_in);
+    for (int r = 0; r < kActiveRing; ++r) {
+        if (v->ev_alloc_done[r]) cudaEventDestroy(v->ev_alloc_done[r]);
+        if (v->ev_int_done[r]) cudaEventDestroy(v->ev_int_done[r]);
+    }
     for (int s = 0; s < kStage; ++s) {
         cudaFree(v->d_depth[s]);
         cudaFree(v->d_color[s]);
@@ -220,6 +243,7 @@ extern "C" int b2v_destroy(b2v_volume *v) {
         if (e) cudaEventDestroy(e);
     if (v->compute) cudaStreamDestroy(v->compute);
     if (v->copy) cudaStreamDestroy(v->copy);
+    if (v->alloc) cudaStreamDestroy(v->alloc);
     delete v;
     return B2V_OK;
 }
@@ -227,6 +251,8 @@ extern "C" int b2v_destroy(b2v_volume *v) {
 static int read_counters(b2v_volume *v) {
     B2V_CUDA(v, cudaSetDevice(v->cfg.device));
     B2V_CUDA(v, cudaStreamSynchronize(v->copy));
+    B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
+    if (v->last_stream) B2V_CUDA(v, cudaStreamSynchronize(v->last_stream));
     B2V_CUDA(v, cudaMemcpyAsync(v->h_counters, v->meta.counters, kNumCounters * sizeof(uint32_t),
                                 cudaMemcpyDeviceToHost, v->compute));
     B2V_CUDA(v, cudaStreamSynchronize(v->compute));
@@ -262,6 +288,8 @@ static int ensure_staging(b2v_volume *v, size_t pixels) {
     if (pixels <= v->stage_pixels) return B2V_OK;
     B2V_CUDA(v, cudaStreamSynchronize(v->compute));
     B2V_CUDA(v, cudaStreamSynchronize(v->copy));
+    B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
+    if (v->last_stream) B2V_CUDA(v, cudaStreamSynchronize(v->last_stream));
     for (int s = 0; s < kStage; ++s) {
         cudaFree(v->d_depth[s]);
         cudaFree(v->d_color[s]);
@@ -300,7 +328,10 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
         return B2V_ERR_INVALID_ARGUMENT;
     }
     cudaStream_t cs = stream ? static_cast<cudaStream_t>(stream) : v->compute;
+    cudaStream_t as = v->overlap ? v->alloc : cs;  // stream of the allocate kernel
+    v->last_stream = stream ? cs : nullptr;
     const int s = static_cast<int>(v->frame_id % kStage);
+    const int ring = static_cast<int>(v->frame_id % kActiveRing);
     const float *d_depth = depth;
     const uint8_t *d_color = color;
     const bool staged = !(dev_depth && dev_color);
@@ -320,14 +351,25 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
             d_color = v->d_color[s];
         }
         B2V_CUDA(v, cudaEventRecord(v->ev_ready[s], v->copy));
-        B2V_CUDA(v, cudaStreamWaitEvent(cs, v->ev_ready[s], 0));
+        B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_ready[s], 0));
+    } else if (v->overlap && !v->inputs_fenced) {
+        // device inputs were produced by earlier work on the caller's stream (a batch call fences once:
+        // an event recorded now would also wait for the previous frame's integrate kernel)
+        B2V_CUDA(v, cudaEventRecord(v->ev_in, cs));
+        B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_in, 0));
+    }
+    if (v->overlap && v->frame_id >= 3) {
+        // allocate(f) recycles the ring slot / texel buffer last read by integrate(f - 3) .. (f - 4)
+        B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_int_done[(v->frame_id - 3) % kActiveRing], 0));
     }
     FrameParams P;
     fill_frame_params(&P, K, Tcw, height, width, v->cfg.depth_stride, v->cfg.voxel_size, v->cfg.sdf_trunc,
                       v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank, v->cfg.shard_count);
-    const int ring = static_cast<int>(v->frame_id % kActiveRing);
     if (v->lam_H != height || v->lam_W != width || std::memcmp(v->lam_K, K, sizeof(v->lam_K)) != 0) {
-        B2V_CUDA(v, launch_lambda(P, v->d_lambda, cs));
+        if (v->overlap) {  // the lambda image is read by allocate kernels that may still be in flight
+            B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
+        }
+        B2V_CUDA(v, launch_lambda(P, v->d_lambda, as));
         std::memcpy(v->lam_K, K, sizeof(v->lam_K));
         v->lam_H = height;
         v->lam_W = width;
@@ -335,20 +377,30 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
     }
     cudaEvent_t *pe = nullptr;
     if (v->prof_enabled) {
-        if (v->prof_used + 3 > v->prof_events.size()) {
+        if (v->prof_used + 4 > v->prof_events.size()) {
             const size_t old = v->prof_events.size();
-            v->prof_events.resize(old + 3 * 256, nullptr);
+            v->prof_events.resize(old + 4 * 256, nullptr);
             for (size_t k = old; k < v->prof_events.size(); ++k) B2V_CUDA(v, cudaEventCreate(&v->prof_events[k]));
         }
         pe = &v->prof_events[v->prof_used];
-        v->prof_used += 3;
-        B2V_CUDA(v, cudaEventRecord(pe[0], cs));
+        v->prof_used += 4;
+        B2V_CUDA(v, cudaEventRecord(pe[0], as));
     }
-    B2V_CUDA(v, launch_allocate(P, d_depth, d_color, v->d_lambda, v->d_texel[s], v->table, v->meta, ring, cs));
-    if (pe) B2V_CUDA(v, cudaEventRecord(pe[1], cs));
-    B2V_CUDA(v, launch_integrate(P, v->d_texel[s], v->table, v->meta, ring, v->grid_ctas, cs));
+    FrameMaps maps;
+    const bool tma = v->use_tma && tma_tiles_usable(width, v->cfg.depth_stride, d_depth, d_color, v->d_lambda) &&
+                     encode_frame_maps(&maps, d_depth, d_color, v->d_lambda, height, width, 32);
+    B2V_CUDA(v, launch_allocate(P, d_depth, d_color, v->d_lambda, v->d_texel[s], v->table, v->meta, ring,
+                                tma ? &maps : nullptr, as));
+    if (pe) B2V_CUDA(v, cudaEventRecord(pe[1], as));
+    if (staged) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], as));  // the raw frame is consumed by allocate only
+    if (v->overlap) {
+        B2V_CUDA(v, cudaEventRecord(v->ev_alloc_done[ring], as));
+        B2V_CUDA(v, cudaStreamWaitEvent(cs, v->ev_alloc_done[ring], 0));
+    }
     if (pe) B2V_CUDA(v, cudaEventRecord(pe[2], cs));
-    if (staged) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], cs));
+    B2V_CUDA(v, launch_integrate(P, v->d_texel[s], v->table, v->meta, ring, v->grid_ctas, cs));
+    if (pe) B2V_CUDA(v, cudaEventRecord(pe[3], cs));
+    if (v->overlap) B2V_CUDA(v, cudaEventRecord(v->ev_int_done[ring], cs));
     v->launches += 2;
     v->frame_id += 1;
     return B2V_OK;
@@ -363,12 +415,19 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         return B2V_ERR_INVALID_ARGUMENT;
     }
     const size_t pixels = static_cast<size_t>(height) * width;
-    for (int32_t f = 0; f < n_frames; ++f) {
-        const int rc = b2v_integrate(v, depth + pixels * f, color + pixels * 3 * f, height, width, K,
-                                     Tcw + 16 * static_cast<size_t>(f), stream);
-        if (rc != B2V_OK) return rc;
+    if (v->overlap && n_frames > 0 && is_device_pointer(depth) && is_device_pointer(color)) {
+        cudaStream_t cs = stream ? static_cast<cudaStream_t>(stream) : v->compute;
+        B2V_CUDA(v, cudaSetDevice(v->cfg.device));
+        B2V_CUDA(v, cudaEventRecord(v->ev_in, cs));
+        B2V_CUDA(v, cudaStreamWaitEvent(v->alloc, v->ev_in, 0));
+        v->inputs_fenced = true;
     }
-    return B2V_OK;
+    int rc = B2V_OK;
+    for (int32_t f = 0; f < n_frames && rc == B2V_OK; ++f)
+        rc = b2v_integrate(v, depth + pixels * f, color + pixels * 3 * f, height, width, K,
+                           Tcw + 16 * static_cast<size_t>(f), stream);
+    v->inputs_fenced = false;
+    return rc;
 }
 
 extern "C" int b2v_synchronize(b2v_volume *v) {
@@ -393,6 +452,14 @@ extern "C" int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int6
     return rc;
 }
 
+extern "C" int b2v_set_overlap(b2v_volume *v, int32_t enable) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    const int rc = read_counters(v);  // drains every stream first
+    if (rc == B2V_ERR_CUDA) return rc;
+    v->overlap = enable != 0;
+    return B2V_OK;
+}
+
 extern "C" int b2v_profile_enable(b2v_volume *v, int32_t enable) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
     v->prof_enabled = enable != 0;
@@ -403,17 +470,18 @@ extern "C" int b2v_profile_read(b2v_volume *v, double *allocate_ms, double *inte
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
     B2V_CUDA(v, cudaSetDevice(v->cfg.device));
     double a = 0.0, b = 0.0;
-    for (size_t k = 0; k + 2 < v->prof_used + 0 && k < v->prof_used; k += 3) {
-        B2V_CUDA(v, cudaEventSynchronize(v->prof_events[k + 2]));
+    for (size_t k = 0; k + 3 < v->prof_used; k += 4) {
+        B2V_CUDA(v, cudaEventSynchronize(v->prof_events[k + 1]));
+        B2V_CUDA(v, cudaEventSynchronize(v->prof_events[k + 3]));
         float ms = 0.0f;
         B2V_CUDA(v, cudaEventElapsedTime(&ms, v->prof_events[k], v->prof_events[k + 1]));
         a += ms;
-        B2V_CUDA(v, cudaEventElapsedTime(&ms, v->prof_events[k + 1], v->prof_events[k + 2]));
+        B2V_CUDA(v, cudaEventElapsedTime(&ms, v->prof_events[k + 2], v->prof_events[k + 3]));
         b += ms;
     }
     if (allocate_ms) *allocate_ms = a;
     if (integrate_ms) *integrate_ms = b;
-    if (frames) *frames = static_cast<int64_t>(v->prof_used / 3);
+    if (frames) *frames = static_cast<int64_t>(v->prof_used / 4);
     v->prof_used = 0;
     return B2V_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <string>
 
@@ -55,11 +56,23 @@ void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], 
 // ---- kernels (b2v_tsdf.cu) ----
 // lambda image (Open3D's depth-to-camera-distance multiplier) for the current intrinsics
 cudaError_t launch_lambda(const FrameParams &p, float *lam, cudaStream_t stream);
+// TMA descriptors of one frame's images (2-D tiled: depth f32, colour u8 x3 interleaved, lambda f32)
+struct FrameMaps {
+    alignas(64) CUtensorMap depth;
+    alignas(64) CUtensorMap color;
+    alignas(64) CUtensorMap lam;
+};
+// TMA tile staging needs 16-byte aligned bases and row pitches (W % 16 == 0) and the 32x32 tile
+bool tma_tiles_usable(int W, int stride, const void *depth, const void *color, const void *lam);
+// returns false if the driver entry point is unavailable or encoding fails
+bool encode_frame_maps(FrameMaps *maps, const float *depth, const uint8_t *color, const float *lam,
+                       int H, int W, int tile);
 // frame packing ({valid depth, lambda, rgbx} texels) + allocation + touched-set of one frame;
-// zeroes the next frame's ring counters
+// zeroes the next frame's ring counters.  maps != nullptr: the image tiles are staged into shared
+// memory with TMA (cp.async.bulk.tensor.2d); nullptr: plain loads.
 cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint8_t *color,
                             const float *lam, float4 *texels, const HashTable &table,
-                            const PoolMeta &meta, int ring, cudaStream_t stream);
+                            const PoolMeta &meta, int ring, const FrameMaps *maps, cudaStream_t stream);
 // projective TSDF + colour update of every block touched by the frame
 cudaError_t launch_integrate(const FrameParams &p, const float4 *texels, const HashTable &table,
                              const PoolMeta &meta, int ring, int grid_ctas, cudaStream_t stream);

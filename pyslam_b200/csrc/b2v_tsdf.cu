@@ -19,19 +19,13 @@ namespace b2v {
 // allocation
 // ------------------------------------------------------------------------------------------------
 
-constexpr int kAllocTile = 8;       // 8 x 8 depth samples per CTA ...
-constexpr int kAllocSub = 4;        // ... x 4 lanes per sample: a sample's (typically 27) candidate blocks
-                                    // are split over 4 lanes, so the serial chain per warp is 7 long
-constexpr int kAllocThreads = kAllocTile * kAllocTile * kAllocSub;
-constexpr int kSetSize = 512;       // CTA-local de-duplication set (power of two)
+constexpr int kAllocTile = 8;       // 8 x 8 depth samples per CTA (32 x 32 pixels at stride 4)
+constexpr int kAllocThreads = 256;
+constexpr int kBoxSet = 128;        // distinct [lo, lo + n) boxes under one tile (power of two)
+constexpr int kBoxList = 64;        // ... compacted
+constexpr int kKeySet = 1024;       // distinct block keys under one tile (power of two)
 constexpr int kListCap = 512;       // CTA-local lists of fresh / first-touched slots
-
-// 21 low bits per axis: injective inside one frame's frustum (checked on the host at create)
-__device__ __forceinline__ unsigned long long pack_key(int x, int y, int z) {
-    return static_cast<unsigned long long>(x & 0x1FFFFF) |
-           (static_cast<unsigned long long>(y & 0x1FFFFF) << 21) |
-           (static_cast<unsigned long long>(z & 0x1FFFFF) << 42);
-}
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 
 __device__ __forceinline__ void assign_block(const HashTable &T, const PoolMeta &M, uint32_t slot,
                                              uint32_t idx) {
@@ -45,12 +39,6 @@ __device__ __forceinline__ void assign_block(const HashTable &T, const PoolMeta 
         *w = kNoBlock;
         atomicOr(M.counters + kCtrError, 1u);
     }
-}
-
-// recover a coordinate from its 21-bit packed field, given any reference within 2^20 of it
-__device__ __forceinline__ int unpack_axis(unsigned long long pk, int shift, int ref) {
-    const int d = (static_cast<int>((pk >> shift) & 0x1FFFFF) - ref) & 0x1FFFFF;
-    return ref + ((d ^ 0x100000) - 0x100000);  // sign-extend 21 bits
 }
 
 // Global find-or-insert of one block key + first-touch detection for this frame.  New slots and
@@ -87,25 +75,86 @@ __device__ __forceinline__ void touch_key(const FrameParams &P, const HashTable 
     }
 }
 
-// Phase A  every sampled pixel enumerates the blocks of its [p - tau, p + tau] box; duplicates die
-//          first inside the warp (__match_any_sync ballot), then inside the CTA (shared-memory set).
-// Phase B  the CTA's unique keys probe / insert into the global table one key per thread, all in
-//          flight at once (the probes are independent L2 round trips), and exchange the frame stamp.
-// Phase C  one atomic per CTA hands out contiguous pool indices and active-list positions.
-__global__ void __launch_bounds__(kAllocThreads)
+// block key -> 30-bit code relative to the tile's reference key (10 bits per axis); kNoKey if the
+// key is further than 511 blocks from the reference on some axis (then it takes the direct path)
+__device__ __forceinline__ uint32_t rel_key(int kx, int ky, int kz, const int *ref) {
+    const uint32_t rx = static_cast<uint32_t>(kx - ref[0] + 512), ry = static_cast<uint32_t>(ky - ref[1] + 512),
+                   rz = static_cast<uint32_t>(kz - ref[2] + 512);
+    if ((rx | ry | rz) >= 1024u) return kNoKey;
+    return rx | (ry << 10) | (rz << 20);
+}
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ----
+constexpr int kTmaTile = 32;  // = kAllocTile * 4: the TMA path serves the default stride 4
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 2-D tiled TMA load: global (tensor map, {c0, c1}) -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1,
+                                            unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Per frame: pack the frame into texels, find the touched blocks, allocate the new ones.
+//   pack    every CTA packs its 32x32-pixel tile into 16-byte {valid depth | 0, lambda, rgbx} texels
+//   boxes   one thread per depth sample: back-project (float64), block range [lo, lo+n) of the
+//           [p - tau, p + tau] box; neighbouring samples share boxes, so the DISTINCT boxes of the
+//           tile (typically 10-20, each 27 blocks) are collected in a shared-memory set
+//   keys    the distinct boxes are expanded, one candidate block per thread, into a shared-memory set
+//           of distinct block keys (typically ~100 per tile)
+//   probe   every distinct key probes / inserts into the global table - one key per thread, all
+//           probes in flight - and exchanges the slot's frame stamp (first toucher queues the slot)
+//   flush   one atomic per CTA hands out contiguous pool indices and active-list positions
+template <bool kTma>
+__global__ void __launch_bounds__(kAllocThreads, 4)
 allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint8_t *__restrict__ rgb,
                 const float *__restrict__ lam, float4 *__restrict__ tex, const HashTable T,
-                const PoolMeta M, const int ring) {
-    __shared__ unsigned long long s_set[kSetSize];
+                const PoolMeta M, const int ring, const __grid_constant__ FrameMaps maps) {
+    // TMA staging buffers of the 32x32-pixel tile (kTma only): depth, lambda (f32) and colour (u8 x3)
+    __shared__ alignas(128) float s_td[kTmaTile * kTmaTile];
+    __shared__ alignas(128) float s_tl[kTmaTile * kTmaTile];
+    __shared__ alignas(128) uint8_t s_tc[kTmaTile * kTmaTile * 3];
+    __shared__ alignas(8) unsigned long long s_bar;
+    __shared__ unsigned long long s_boxset[kBoxSet];
+    __shared__ unsigned long long s_box[kBoxList];
+    __shared__ uint32_t s_keyset[kKeySet];
+    __shared__ uint32_t s_keys[kListCap];  // the distinct keys, compacted
     __shared__ uint32_t s_new[kListCap];
     __shared__ uint32_t s_act[kListCap];
-    __shared__ uint32_t s_n_new, s_n_act, s_base_new, s_base_act;
-    __shared__ int s_ref[4];  // reference key for unpacking; s_ref[3]: 0 = unset, 1 = set
+    __shared__ uint32_t s_n_box, s_n_keys, s_n_new, s_n_act, s_base_new, s_base_act;
+    __shared__ int s_ref[4];  // reference key of the tile; s_ref[3]: 0 = unset, 1 = set
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    for (int i = tid; i < kSetSize; i += kAllocThreads) s_set[i] = ~0ull;
+    for (int i = tid; i < kKeySet; i += kAllocThreads) s_keyset[i] = kNoKey;
+    if (tid < kBoxSet) s_boxset[tid] = ~0ull;
     if (tid == 0) {
+        s_n_box = 0;
+        s_n_keys = 0;
         s_n_new = 0;
         s_n_act = 0;
         s_ref[3] = 0;
@@ -116,115 +165,193 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint
             M.counters[kCtrNew0 + nxt] = 0;
         }
     }
-    __syncthreads();
 
-    // ---- pack this CTA's pixel tile into 16-byte texels {valid depth | 0, lambda, rgbx, 0}: the
-    //      integrate kernel then needs one gather per voxel instead of four ----
-    {
+    if constexpr (kTma) {
+        // one thread arms an mbarrier with the tile's byte count and issues three 2-D TMA tile loads;
+        // they land in shared memory while the CTA back-projects its depth samples
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(&s_bar, kTmaTile * kTmaTile * (4 + 4 + 3));
+            const int x0 = blockIdx.x * kTmaTile, y0 = blockIdx.y * kTmaTile;
+            tma_load_2d(s_td, &maps.depth, x0, y0, &s_bar);
+            tma_load_2d(s_tl, &maps.lam, x0, y0, &s_bar);
+            tma_load_2d(s_tc, &maps.color, 3 * x0, y0, &s_bar);
+        }
+    }
+
+    // ---- boxes: thread s < 64 owns depth sample s of the tile ----
+    int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+    bool have = false;
+    if (tid < kAllocTile * kAllocTile) {
+        const int j = (blockIdx.x * kAllocTile + (tid & (kAllocTile - 1))) * P.stride;
+        const int i = (blockIdx.y * kAllocTile + (tid / kAllocTile)) * P.stride;
+        if (j < P.W && i < P.H) {
+            const float d = __ldg(depth + static_cast<size_t>(i) * P.W + j);
+            if (d > 0.0f && d < P.depth_trunc) {
+                const double z = static_cast<double>(d);
+                const double x = __ddiv_rn(__dmul_rn(__dsub_rn(static_cast<double>(j), P.cx), z), P.fx);
+                const double y = __ddiv_rn(__dmul_rn(__dsub_rn(static_cast<double>(i), P.cy), z), P.fy);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double pw = __dadd_rn(
+                        __dadd_rn(__dadd_rn(__dmul_rn(P.Rwc[3 * a + 0], x), __dmul_rn(P.Rwc[3 * a + 1], y)),
+                                  __dmul_rn(P.Rwc[3 * a + 2], z)),
+                        P.twc[a]);
+                    const int vlo = voxel_coord(__double2float_rn(__dsub_rn(pw, P.tau_d)), P.inv_vs);
+                    const int vhi = voxel_coord(__double2float_rn(__dadd_rn(pw, P.tau_d)), P.inv_vs);
+                    lo[a] = block_coord(vlo);
+                    n[a] = block_coord(vhi) - lo[a] + 1;
+                }
+                have = true;
+            }
+        }
+    }
+    __syncthreads();  // sets initialised
+    if (have && atomicCAS(&s_ref[3], 0, 1) == 0) {
+        s_ref[0] = lo[0];
+        s_ref[1] = lo[1];
+        s_ref[2] = lo[2];
+    }
+
+    // ---- pack this CTA's pixel tile into texels (independent of the allocation work) ----
+    if constexpr (kTma) {
+        mbar_wait(&s_bar, 0);  // s_bar was initialised before the first __syncthreads above
+        const int x0 = blockIdx.x * kTmaTile, y0 = blockIdx.y * kTmaTile;
+#pragma unroll
+        for (int k = 0; k < kTmaTile * kTmaTile / kAllocThreads; ++k) {
+            const int q = k * kAllocThreads + tid;
+            const int x = x0 + (q & (kTmaTile - 1)), y = y0 + q / kTmaTile;
+            if (x < P.W && y < P.H) {
+                const float d = s_td[q];
+                const uint32_t rgbx = static_cast<uint32_t>(s_tc[3 * q]) | (static_cast<uint32_t>(s_tc[3 * q + 1]) << 8) |
+                                      (static_cast<uint32_t>(s_tc[3 * q + 2]) << 16);
+                tex[static_cast<size_t>(y) * P.W + x] =
+                    make_float4((d > 0.0f && d < P.depth_trunc) ? d : 0.0f, s_tl[q], __uint_as_float(rgbx), 0.0f);
+            }
+        }
+    } else {
         const int tile = kAllocTile * P.stride;  // pixels per tile side
         const int x0 = blockIdx.x * tile, y0 = blockIdx.y * tile;
-        for (int q = tid; q < tile * tile; q += kAllocThreads) {
-            const int x = x0 + q % tile, y = y0 + q / tile;
-            if (x < P.W && y < P.H) {
-                const size_t p = static_cast<size_t>(y) * P.W + x;
-                const float d = __ldg(depth + p);
-                const uint8_t *c = rgb + 3 * p;
-                const uint32_t rgbx = static_cast<uint32_t>(__ldg(c)) | (static_cast<uint32_t>(__ldg(c + 1)) << 8) |
-                                      (static_cast<uint32_t>(__ldg(c + 2)) << 16);
-                tex[p] = make_float4((d > 0.0f && d < P.depth_trunc) ? d : 0.0f, __ldg(lam + p),
-                                     __uint_as_float(rgbx), 0.0f);
-            }
-        }
-    }
-
-    // ---- this thread's depth sample (4 consecutive lanes share one) and its block range ----
-    const int sample = tid / kAllocSub, sub = tid % kAllocSub;
-    const int j = (blockIdx.x * kAllocTile + (sample & (kAllocTile - 1))) * P.stride;
-    const int i = (blockIdx.y * kAllocTile + (sample / kAllocTile)) * P.stride;
-    int lo0 = 0, lo1 = 0, lo2 = 0, n1 = 1, n2 = 1, ncand = 0;
-    if (j < P.W && i < P.H) {
-        const float d = __ldg(depth + static_cast<size_t>(i) * P.W + j);
-        if (d > 0.0f && d < P.depth_trunc) {
-            const double z = static_cast<double>(d);
-            const double x = __ddiv_rn(__dmul_rn(__dsub_rn(static_cast<double>(j), P.cx), z), P.fx);
-            const double y = __ddiv_rn(__dmul_rn(__dsub_rn(static_cast<double>(i), P.cy), z), P.fy);
-            int lo[3], n[3];
+        for (int q0 = 0; q0 < tile * tile; q0 += 4 * kAllocThreads) {
+            float dv[4], lv[4];
+            uint32_t cv[4];
+            size_t pv[4];
+            bool ok[4];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const double pw = __dadd_rn(
-                    __dadd_rn(__dadd_rn(__dmul_rn(P.Rwc[3 * a + 0], x), __dmul_rn(P.Rwc[3 * a + 1], y)),
-                              __dmul_rn(P.Rwc[3 * a + 2], z)),
-                    P.twc[a]);
-                const int vlo = voxel_coord(__double2float_rn(__dsub_rn(pw, P.tau_d)), P.inv_vs);
-                const int vhi = voxel_coord(__double2float_rn(__dadd_rn(pw, P.tau_d)), P.inv_vs);
-                lo[a] = block_coord(vlo);
-                n[a] = block_coord(vhi) - lo[a] + 1;
+            for (int k = 0; k < 4; ++k) {  // four independent pixels per thread: loads issued together
+                const int q = q0 + k * kAllocThreads + tid;
+                const int x = x0 + q % tile, y = y0 + q / tile;
+                ok[k] = q < tile * tile && x < P.W && y < P.H;
+                pv[k] = ok[k] ? static_cast<size_t>(y) * P.W + x : 0;
+                dv[k] = __ldg(depth + pv[k]);
+                lv[k] = __ldg(lam + pv[k]);
+                const uint8_t *c = rgb + 3 * pv[k];
+                cv[k] = static_cast<uint32_t>(__ldg(c)) | (static_cast<uint32_t>(__ldg(c + 1)) << 8) |
+                        (static_cast<uint32_t>(__ldg(c + 2)) << 16);
             }
-            lo0 = lo[0], lo1 = lo[1], lo2 = lo[2];
-            n1 = n[1], n2 = n[2];
-            ncand = n[0] * n[1] * n[2];
-            if (atomicCAS(&s_ref[3], 0, 1) == 0) {  // one reference key per CTA for unpacking
-                s_ref[0] = lo0;
-                s_ref[1] = lo1;
-                s_ref[2] = lo2;
-            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (ok[k])
+                    tex[pv[k]] = make_float4((dv[k] > 0.0f && dv[k] < P.depth_trunc) ? dv[k] : 0.0f, lv[k],
+                                             __uint_as_float(cv[k]), 0.0f);
         }
     }
+    __syncthreads();  // reference key visible
 
-    // ---- phase A: shared-memory only; lane `sub` of a sample takes candidates sub, sub+4, ... ----
-    const int wmax = __reduce_max_sync(0xffffffffu, ncand);
-    int dx = 0, dy = 0, dz = sub;  // candidate c = (dx * n1 + dy) * n2 + dz, advanced incrementally
-    for (int c = sub; c - sub < wmax; c += kAllocSub, dz += kAllocSub) {
-        const bool have = c < ncand;
-        int kx = 0, ky = 0, kz = 0;
-        unsigned long long pk = (1ull << 63) | static_cast<unsigned long long>(lane);
-        if (have) {
-            while (dz >= n2) {
-                dz -= n2;
-                if (++dy >= n1) {
-                    dy = 0;
-                    ++dx;
+    // ---- distinct boxes of the tile ----
+    if (have) {
+        const uint32_t r0 = static_cast<uint32_t>(lo[0] - s_ref[0] + 32768), r1 = static_cast<uint32_t>(lo[1] - s_ref[1] + 32768),
+                       r2 = static_cast<uint32_t>(lo[2] - s_ref[2] + 32768);
+        bool placed = false;
+        if ((r0 | r1 | r2) < 65536u && n[0] <= 15 && n[1] <= 15 && n[2] <= 15) {
+            const unsigned long long bk = static_cast<unsigned long long>(r0) | (static_cast<unsigned long long>(r1) << 16) |
+                                          (static_cast<unsigned long long>(r2) << 32) |
+                                          (static_cast<unsigned long long>(n[0] | (n[1] << 4) | (n[2] << 8)) << 48);
+            uint32_t h = mix32(static_cast<uint32_t>(bk) ^ static_cast<uint32_t>(bk >> 32)) & (kBoxSet - 1);
+            for (int k = 0; k < kBoxSet && !placed; ++k) {
+                const unsigned long long old = atomicCAS(s_boxset + h, ~0ull, bk);
+                if (old == ~0ull) {
+                    const uint32_t pos = atomicAdd(&s_n_box, 1u);
+                    if (pos < kBoxList) {
+                        s_box[pos] = bk;
+                        placed = true;
+                    } else {
+                        break;  // list full: handle this box directly below
+                    }
+                } else if (old == bk) {
+                    placed = true;
                 }
+                h = (h + 1) & (kBoxSet - 1);
             }
-            kx = lo0 + dx;
-            ky = lo1 + dy;
-            kz = lo2 + dz;
-            pk = pack_key(kx, ky, kz);
         }
-        const unsigned grp = __match_any_sync(0xffffffffu, pk);
-        if (have && ((__ffs(grp) - 1) == lane)) {
-            uint32_t h = mix32(static_cast<uint32_t>(pk) ^ static_cast<uint32_t>(pk >> 32)) & (kSetSize - 1);
-            bool placed = false;
-            for (int k = 0; k < 64 && !placed; ++k) {
-                const unsigned long long old = atomicCAS(s_set + h, ~0ull, pk);
-                placed = (old == ~0ull) || (old == pk);
-                h = (h + 1) & (kSetSize - 1);
-            }
-            // saturated set (> ~400 distinct blocks under one 32x32-pixel tile): go straight to
-            // the global table, which de-duplicates anyway
-            if (!placed) touch_key(P, T, M, ring, kx, ky, kz, s_new, &s_n_new, s_act, &s_n_act);
+        if (!placed) {  // far-away or over-sized box, or > 64 distinct boxes: straight to the table
+            for (int dx = 0; dx < n[0]; ++dx)
+                for (int dy = 0; dy < n[1]; ++dy)
+                    for (int dz = 0; dz < n[2]; ++dz)
+                        touch_key(P, T, M, ring, lo[0] + dx, lo[1] + dy, lo[2] + dz, s_new, &s_n_new, s_act, &s_n_act);
         }
     }
     __syncthreads();
 
-    // ---- phase B: every unique key of the CTA, one per thread, all probes in flight ----
-    const int rx = s_ref[0], ry = s_ref[1], rz = s_ref[2];
-    for (int q = tid; q < kSetSize; q += kAllocThreads) {
-        const unsigned long long pk = s_set[q];
-        if (pk == ~0ull) continue;
-        touch_key(P, T, M, ring, unpack_axis(pk, 0, rx), unpack_axis(pk, 21, ry), unpack_axis(pk, 42, rz),
-                  s_new, &s_n_new, s_act, &s_n_act);
+    // ---- distinct keys: expand every distinct box, one candidate block per thread ----
+    {
+        const uint32_t nbox = min(s_n_box, static_cast<uint32_t>(kBoxList));
+        for (uint32_t item = tid; item < nbox * 64u; item += kAllocThreads) {
+            const unsigned long long bk = s_box[item >> 6];
+            const uint32_t c = item & 63u;
+            const uint32_t n0 = static_cast<uint32_t>(bk >> 48) & 15u, n1 = static_cast<uint32_t>(bk >> 52) & 15u,
+                           n2 = static_cast<uint32_t>(bk >> 56) & 15u;
+            // boxes with more than 64 blocks loop over the remainder (c, c + 64, ...)
+            for (uint32_t cc = c; cc < n0 * n1 * n2; cc += 64u) {
+                const uint32_t dz = cc % n2, r = cc / n2, dy = r % n1, dx = r / n1;
+                const int kx = s_ref[0] + static_cast<int>(static_cast<uint32_t>(bk) & 0xFFFFu) - 32768 + static_cast<int>(dx);
+                const int ky = s_ref[1] + static_cast<int>(static_cast<uint32_t>(bk >> 16) & 0xFFFFu) - 32768 + static_cast<int>(dy);
+                const int kz = s_ref[2] + static_cast<int>(static_cast<uint32_t>(bk >> 32) & 0xFFFFu) - 32768 + static_cast<int>(dz);
+                const uint32_t rk = rel_key(kx, ky, kz, s_ref);
+                bool placed = false;
+                if (rk != kNoKey) {
+                    uint32_t h = mix32(rk) & (kKeySet - 1);
+                    for (int k = 0; k < 96 && !placed; ++k) {
+                        const uint32_t old = atomicCAS(s_keyset + h, kNoKey, rk);
+                        if (old == kNoKey) {  // first sighting in this tile: queue it for the probe phase
+                            const uint32_t pos = atomicAdd(&s_n_keys, 1u);
+                            if (pos < kListCap) {
+                                s_keys[pos] = rk;
+                                placed = true;
+                            } else {
+                                break;  // list full: probe it right away (below)
+                            }
+                        } else if (old == rk) {
+                            placed = true;
+                        }
+                        h = (h + 1) & (kKeySet - 1);
+                    }
+                }
+                if (!placed) touch_key(P, T, M, ring, kx, ky, kz, s_new, &s_n_new, s_act, &s_n_act);
+            }
+        }
     }
     __syncthreads();
 
-    // ---- phase C: one global atomic per CTA for each list; pool indices are contiguous ----
+    // ---- probe: every distinct key of the tile, one per thread, all probes in flight ----
+    {
+        const uint32_t nkeys = min(s_n_keys, static_cast<uint32_t>(kListCap));
+        for (uint32_t q = tid; q < nkeys; q += kAllocThreads) {
+            const uint32_t rk = s_keys[q];
+            touch_key(P, T, M, ring, s_ref[0] + static_cast<int>(rk & 1023u) - 512,
+                      s_ref[1] + static_cast<int>((rk >> 10) & 1023u) - 512,
+                      s_ref[2] + static_cast<int>((rk >> 20) & 1023u) - 512, s_new, &s_n_new, s_act, &s_n_act);
+        }
+    }
+    __syncthreads();
+
+    // ---- flush: one global atomic per list and CTA (three threads, three independent round trips) ----
     const uint32_t n_new = min(s_n_new, static_cast<uint32_t>(kListCap));
     const uint32_t n_act = min(s_n_act, static_cast<uint32_t>(kListCap));
-    if (tid == 0) {
-        s_base_new = n_new ? atomicAdd(M.counters + kCtrPool, n_new) : 0u;
-        if (n_new) atomicAdd(M.counters + kCtrNew0 + ring, n_new);
-        s_base_act = n_act ? atomicAdd(M.counters + kCtrActive0 + ring, n_act) : 0u;
-    }
+    if (tid == 0) s_base_new = n_new ? atomicAdd(M.counters + kCtrPool, n_new) : 0u;
+    if (tid == 32) s_base_act = n_act ? atomicAdd(M.counters + kCtrActive0 + ring, n_act) : 0u;
+    if (tid == 64 && n_new) atomicAdd(M.counters + kCtrNew0 + ring, n_new);
     __syncthreads();
     for (uint32_t k = tid; k < n_new; k += kAllocThreads) assign_block(T, M, s_new[k], s_base_new + k);
     uint32_t *active_out = M.active_slots + static_cast<size_t>(ring) * M.capacity;
@@ -236,12 +363,64 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint
 
 cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint8_t *color,
                             const float *lam, float4 *texels, const HashTable &table,
-                            const PoolMeta &meta, int ring, cudaStream_t stream) {
+                            const PoolMeta &meta, int ring, const FrameMaps *maps, cudaStream_t stream) {
     const int gw = (p.W + p.stride - 1) / p.stride;
     const int gh = (p.H + p.stride - 1) / p.stride;
     const dim3 grid((gw + kAllocTile - 1) / kAllocTile, (gh + kAllocTile - 1) / kAllocTile);
-    allocate_kernel<<<grid, kAllocThreads, 0, stream>>>(p, depth, color, lam, texels, table, meta, ring);
+    if (maps != nullptr && p.stride * kAllocTile == kTmaTile) {
+        allocate_kernel<true><<<grid, kAllocThreads, 0, stream>>>(p, depth, color, lam, texels, table, meta,
+                                                                 ring, *maps);
+    } else {
+        static const FrameMaps dummy{};
+        allocate_kernel<false><<<grid, kAllocThreads, 0, stream>>>(p, depth, color, lam, texels, table, meta,
+                                                                  ring, dummy);
+    }
     return cudaGetLastError();
+}
+
+bool tma_tiles_usable(int W, int stride, const void *depth, const void *color, const void *lam) {
+    auto aligned = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    return stride * kAllocTile == kTmaTile && (W % 16) == 0 && aligned(depth) && aligned(color) && aligned(lam);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &st) == cudaSuccess &&
+            st == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+static bool encode_2d(CUtensorMap *m, CUtensorMapDataType dt, const void *base, uint64_t w_elems,
+                      uint64_t h, uint64_t pitch_bytes, uint32_t box_w, uint32_t box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {w_elems, h};
+    const cuuint64_t strides[1] = {pitch_bytes};
+    const cuuint32_t box[2] = {box_w, box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool encode_frame_maps(FrameMaps *maps, const float *depth, const uint8_t *color, const float *lam,
+                       int H, int W, int tile) {
+    return encode_2d(&maps->depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, depth, W, H, static_cast<uint64_t>(W) * 4, tile, tile) &&
+           encode_2d(&maps->lam, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, lam, W, H, static_cast<uint64_t>(W) * 4, tile, tile) &&
+           encode_2d(&maps->color, CU_TENSOR_MAP_DATA_TYPE_UINT8, color, static_cast<uint64_t>(W) * 3, H,
+                     static_cast<uint64_t>(W) * 3, 3 * tile, tile);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -84,6 +84,8 @@ class B200TsdfVolume:
         self.depth_trunc = float(depth_trunc)
         self.block_size = int(block_size)
         self.capacity_blocks = int(capacity_blocks)
+        self.device = int(device)
+        self.shard_rank, self.shard_count = int(shard_rank), int(shard_count)
         cfg = B2VConfig(voxel_length, block_size, sdf_trunc, depth_trunc, depth_sampling_stride,
                         capacity_blocks, device, shard_rank, shard_count)
         rc = self._L.b2v_create(C.byref(cfg), C.byref(self._h))
@@ -209,6 +211,10 @@ class B200TsdfVolume:
         u, k = C.c_int64(0), C.c_int64(0)
         self._check(self._L.b2v_counters(self._h, C.byref(u), C.byref(k)), "b2v_counters")
         return int(u.value), int(k.value)
+
+    def set_overlap(self, enable: bool):
+        """Run allocate(f+1) concurrently with integrate(f) (default) or serialise them."""
+        self._check(self._L.b2v_set_overlap(self._h, 1 if enable else 0), "b2v_set_overlap")
 
     def profile_enable(self, enable: bool = True):
         self._check(self._L.b2v_profile_enable(self._h, 1 if enable else 0), "b2v_profile_enable")

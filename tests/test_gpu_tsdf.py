@@ -284,3 +284,23 @@ def test_point_cloud_extraction_matches_definition():
             expect += int((ok0 & ok1 & (f * f1 < 0)).sum())
     assert len(pc.points) == expect > 100
     assert pc.colors.min() >= 0.0 and pc.colors.max() <= 1.0 + 1e-6
+
+
+@pytest.mark.parametrize("env", [{"B2V_TMA": "0"}, {"B2V_OVERLAP": "1"}, {"B2V_OVERLAP": "1", "B2V_INT_CTAS_PER_SM": "6"}])
+def test_execution_variants_are_bit_identical(env, monkeypatch):
+    """TMA tile staging vs plain loads, and allocate/integrate stream overlap, change scheduling only:
+    the resulting volume must be bit-identical to the default path's (and hence to the oracle's)."""
+    cfg = S.CONFIGS["C1"]
+    frames = [S.render_frame(cfg, i) for i in (0, 1, 2, 3, 4, 5)]
+    base, orc = _pair(cfg)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    var, _ = _pair(cfg)
+    for d, c, T in frames:
+        base.integrate(d, c, cfg.K, T)
+        var.integrate(d, c, cfg.K, T)
+        orc.integrate(d, c, cfg.K, T)
+    a, b = sort_dump(base.dump_blocks()), sort_dump(var.dump_blocks())
+    for name in ("keys", "hashes", "vox"):
+        assert np.array_equal(a[name], b[name]), name
+    _assert_same_volume(var, orc)
