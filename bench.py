@@ -346,27 +346,35 @@ def run_gpu_arm(args, rank, world, local_rank):
     e2e_value = args.steps * F / float(t.item())
     clocks = sampler.stop()  # sampled across the timed regions (resident + end-to-end)
 
-    # ---- roofline: per-launch CUDA events around integrate_kernel over passes of the same work ----
-    def profile_pass(overlap):
+    # ---- roofline: CUDA events around every integrate launch over passes of the same work ----
+    def profile_pass(overlap, fusion):
         vol.set_overlap(overlap)
+        vol.set_fusion(fusion)
         vol.profile_enable(True)
         u0, _ = vol.counters()
+        b0 = vol.block_visits()
         for _ in range(min(args.steps, 3)):
             step_resident()
         torch.cuda.synchronize()
-        a_ms, i_ms, nprof_ = vol.profile_read()
+        a_ms, i_ms, nfr, nl = vol.profile_read()
         u1, _ = vol.counters()
+        b1 = vol.block_visits()
         vol.profile_enable(False)
-        upd = u1 - u0
-        bytes_ = 2 * VOXEL_RECORD_BYTES * 512 * upd + 7 * W * H * nprof_
-        return dict(alloc_ms=a_ms, integ_ms=i_ms, n=nprof_, updates=upd, bytes=bytes_,
-                    gbs=bytes_ / (i_ms * 1e-3) / 1e9 if i_ms > 0 else 0.0)
+        upd, vis = u1 - u0, b1 - b0
+        survey_bytes = 2 * VOXEL_RECORD_BYTES * 512 * upd + 7 * W * H * nfr       # SURVEY.md §8d formula
+        moved_bytes = 2 * VOXEL_RECORD_BYTES * 512 * vis + 16 * W * H * nfr        # blocks visited + texels
+        sec = i_ms * 1e-3
+        return dict(alloc_ms=a_ms, integ_ms=i_ms, frames=nfr, launches=nl, updates=upd, visits=vis,
+                    survey_bytes=survey_bytes, moved_bytes=moved_bytes,
+                    gbs=survey_bytes / sec / 1e9 if sec > 0 else 0.0,
+                    moved_gbs=moved_bytes / sec / 1e9 if sec > 0 else 0.0)
 
-    situ = profile_pass(True)    # as in the timed region: allocate(f+1) overlaps integrate(f)
-    iso = profile_pass(False)    # kernels serialised: integrate_kernel alone on the GPU
+    situ = profile_pass(True, True)      # the timed-region schedule: fused groups, allocate overlapped
+    iso = profile_pass(False, False)     # one frame per launch, kernels serialised: the HBM-bound kernel alone
     vol.set_overlap(True)
-    alloc_ms, integ_ms, nprof = iso["alloc_ms"], situ["integ_ms"], situ["n"]
-    block_updates, algo_bytes, achieved = situ["updates"], situ["bytes"], situ["gbs"]
+    vol.set_fusion(True)
+    alloc_ms, integ_ms, nprof = iso["alloc_ms"], situ["integ_ms"], situ["frames"]
+    block_updates, algo_bytes, achieved = situ["updates"], situ["survey_bytes"], situ["gbs"]
     peak, peak_src = 6650.0, "fallback"
     try:
         mp_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -404,6 +412,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                           "(sequential branch; a different voxel model: point averaging, not TSDF)"}
 
     per_frame_blocks = block_updates / max(nprof, 1)
+    fps_unfused = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -417,17 +426,26 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "d2h_bytes_per_step": 64, "timing": "wall clock around a full device sync",
                 "api": "B200TsdfVolume.integrate_batch(depths, colors, K, poses) -> b2v_integrate_batch (pinned host frames)"},
         "gpu_launches": int(launches1 - launches0),
-        "roofline": {"kernel": "integrate_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                     "traffic": traffic,
-                     "algorithmic_bytes_per_launch": algo_bytes / max(nprof, 1),
-                     "avg_launch_us": 1e3 * integ_ms / max(nprof, 1),
-                     "measured": "in situ: CUDA events around every integrate_kernel launch while "
-                                 "allocate_kernel of the next frame runs beside it (the timed-region schedule)",
-                     "isolated": {"achieved": iso["gbs"], "frac": iso["gbs"] / peak if peak else None,
-                                  "avg_launch_us": 1e3 * iso["integ_ms"] / max(iso["n"], 1),
-                                  "allocate_kernel_avg_us": 1e3 * iso["alloc_ms"] / max(iso["n"], 1),
-                                  "note": "kernels serialised on one stream (b2v_set_overlap 0)"}},
+        "roofline": {
+            "kernel": "integrate_group_kernel (up to 8 frames applied per block visit)", "bound": "hbm",
+            "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+            "frac": achieved / peak if peak else None, "traffic": traffic,
+            "algorithmic_bytes_per_launch": algo_bytes / max(situ["launches"], 1),
+            "frames_per_launch": situ["frames"] / max(situ["launches"], 1),
+            "avg_launch_us": 1e3 * integ_ms / max(situ["launches"], 1),
+            "note": "achieved uses the per-frame SURVEY.md 8d formula 2*S*512*A_f + 7*W*H summed over the "
+                    "frames of a launch; frac > 1 means the fused kernel moves fewer bytes than frame-by-frame "
+                    "integration must (a block is read/written once per group instead of once per frame)",
+            "bytes_moved_per_launch": situ["moved_bytes"] / max(situ["launches"], 1),
+            "bytes_moved_gbs": situ["moved_gbs"],
+            "block_visits_per_update": situ["visits"] / max(situ["updates"], 1),
+            "measured": "in situ: CUDA events around every launch in the timed-region schedule "
+                        "(allocate kernels of the next group run beside it)",
+            "per_frame_kernel": {
+                "kernel": "integrate_kernel (one frame per launch, b2v_set_fusion 0, b2v_set_overlap 0)",
+                "bound": "hbm", "achieved": iso["gbs"], "frac": iso["gbs"] / peak if peak else None,
+                "avg_launch_us": 1e3 * iso["integ_ms"] / max(iso["launches"], 1),
+                "allocate_kernel_avg_us": 1e3 * iso["alloc_ms"] / max(iso["frames"], 1)}},
         "clocks": clocks,
         "cpu_baseline": cpu,
         **extra,

@@ -61,7 +61,9 @@ const char *b2v_last_error(const b2v_volume *v);
 int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
                   int32_t width, const double K[4], const double Tcw[16], void *stream);
 /* n frames back to back (the rebuild(map) bulk path, base.py:1242-1318): depth [n*H*W],
- * color [n*H*W*3], Tcw [n*16]; same K for all. */
+ * color [n*H*W*3], Tcw [n*16]; same K for all.  By default groups of up to 8 frames are FUSED: a block
+ * is read once, updated by the frames of the group in frame order, and written once - bit-identical
+ * to frame-by-frame integration (b2v_set_fusion(v, 0) forces frame-by-frame). */
 int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float *depth, const uint8_t *color,
                         int32_t height, int32_t width, const double K[4], const double *Tcw,
                         void *stream);
@@ -72,16 +74,19 @@ int b2v_synchronize(b2v_volume *v);
 int64_t b2v_num_blocks(b2v_volume *v);                 /* synchronises */
 /* blocks touched / newly allocated by the most recent frame (synchronises) */
 int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int64_t *new_blocks);
-/* total (block,frame) updates and kernel launches since create/reset: bench accounting */
-int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches);
+/* bench accounting since create/reset: (block, frame) updates applied; kernel launches; block visits
+ * (a visit = one block read + written; equals the updates frame by frame, fewer in fused batches) */
+int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches, int64_t *block_visits);
 /* Scheduling option: 1 (default) runs allocate(f+1) on its own stream concurrently with integrate(f)
  * (it has no data dependency on it); 0 serialises both kernels on one stream (clean per-kernel timing).
  * Results are bit-identical either way.  Synchronises. */
 int b2v_set_overlap(b2v_volume *v, int32_t enable);
+int b2v_set_fusion(b2v_volume *v, int32_t enable);
 /* Per-kernel device timing (CUDA events on the launching stream around each launch), for the
  * roofline figure: enable, run frames, then read the summed durations (synchronises, resets). */
 int b2v_profile_enable(b2v_volume *v, int32_t enable);
-int b2v_profile_read(b2v_volume *v, double *allocate_ms, double *integrate_ms, int64_t *frames);
+int b2v_profile_read(b2v_volume *v, double *allocate_ms, double *integrate_ms, int64_t *frames,
+                     int64_t *integrate_launches);
 /* keys int32[nb*3], hashes uint64[nb] (= reference BlockKeyHash, cpp/volumetric/voxel_hashing.h:106-113),
  * voxels float32[nb*5*512] (planes tsdf, weight, r, g, b; voxel index lx + 8*ly + 64*lz,
  * cpp/volumetric/voxel_block.h:67-70).  HOST outputs, any may be NULL; returns nb or <0. */

@@ -6,12 +6,14 @@
 //                                              event free[s]
 // with a ring of kStage device staging slots, so the upload of frame f+1 overlaps the kernels of
 // frame f.  Nothing synchronises with the host until b2v_synchronize / an inspection call.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/b2v.h"
@@ -58,13 +60,17 @@ void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], 
     p->frame_id = frame_id;
     p->shard_rank = shard_rank;
     p->shard_count = shard_count;
+    p->group_bit = -1;
+    p->group_buf = 0;
 }
 
 }  // namespace b2v
 
 namespace {
 
-constexpr int kStage = 4;
+constexpr int kFrameStage = 4;                       // staging ring of the frame-by-frame path
+constexpr int kGroupStage = 2 * kMaxGroup;           // two group buffers x kMaxGroup frames
+constexpr int kStage = kGroupStage + kFrameStage;    // raw-frame staging slots (device copies of host frames)
 
 uint32_t next_pow2(uint64_t v) {
     uint64_t p = 1;
@@ -90,6 +96,17 @@ struct b2v_volume {
     bool overlap = true;                 // allocate(f+1) on its own stream, concurrent with integrate(f)
     bool use_tma = true;                 // stage image tiles with TMA when the layout allows it
     bool inputs_fenced = false;          // batch call: device inputs already ordered before the alloc stream
+    bool fuse = true;                    // b2v_integrate_batch fuses groups of up to kMaxGroup frames
+    float4 *d_gtex[2 * kMaxGroup] = {};  // texel images of the two group buffers
+    size_t gtex_pixels = 0;
+    uint32_t group_id = 0;
+    cudaEvent_t ev_galloc[2] = {}, ev_group_done[2] = {};
+    int last_group_buf = -1, last_group_count = 0;  // most recent frame came from a fused group
+    int64_t prof_frames = 0, prof_int_launches = 0;
+    // TMA descriptors are cached per image address (encoding costs ~1 us of host time each)
+    std::unordered_map<uintptr_t, FrameMaps> map_cache;
+    int map_H = 0, map_W = 0;
+    const float *map_lam = nullptr;
     cudaEvent_t ev_in = nullptr, ev_alloc_done[kActiveRing] = {}, ev_int_done[kActiveRing] = {};
     float *d_depth[kStage] = {};
     uint8_t *d_color[kStage] = {};
@@ -131,6 +148,7 @@ static int volume_clear_device(b2v_volume *v) {
     const size_t tcap = static_cast<size_t>(v->table.mask) + 1;
     B2V_CUDA(v, cudaMemsetAsync(v->table.entries, 0xFF, tcap * sizeof(uint4), v->compute));
     B2V_CUDA(v, cudaMemsetAsync(v->table.stamp, 0, tcap * sizeof(uint32_t), v->compute));
+    B2V_CUDA(v, cudaMemsetAsync(v->meta.group_mask, 0, tcap * 2 * sizeof(uint32_t), v->compute));
     B2V_CUDA(v, cudaMemsetAsync(v->meta.counters, 0, kNumCounters * sizeof(uint32_t), v->compute));
     return B2V_OK;
 }
@@ -171,6 +189,11 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     }
     if (const char *e = std::getenv("B2V_OVERLAP")) v->overlap = std::atoi(e) != 0;
     if (const char *e = std::getenv("B2V_TMA")) v->use_tma = std::atoi(e) != 0;
+    if (const char *e = std::getenv("B2V_FUSE")) v->fuse = std::atoi(e) != 0;
+    for (int b = 0; b < 2; ++b) {
+        B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_galloc[b], cudaEventDisableTiming));
+        B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_group_done[b], cudaEventDisableTiming));
+    }
     for (int s = 0; s < kStage; ++s) {
         B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_ready[s], cudaEventDisableTiming));
         B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_free[s], cudaEventDisableTiming));
@@ -185,6 +208,8 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     B2V_CUDA(v, cudaMalloc(&v->meta.block_keys, static_cast<size_t>(cap) * sizeof(int4)));
     B2V_CUDA(v, cudaMalloc(&v->meta.counters, kNumCounters * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMalloc(&v->meta.active_slots, static_cast<size_t>(cap) * kActiveRing * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMalloc(&v->meta.group_mask, static_cast<size_t>(tcap) * 2 * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMalloc(&v->meta.union_slots, static_cast<size_t>(cap) * 2 * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMallocHost(&v->h_counters, kNumCounters * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMallocHost(&v->h_totals, 2 * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMemsetAsync(v->meta.pool, 0, static_cast<size_t>(cap) * kBlockFloats * sizeof(float),
@@ -220,6 +245,13 @@ extern "C" int b2v_destroy(b2v_volume *v) {
         if (v->ev_free[s]) cudaEventDestroy(v->ev_free[s]);
     }
     cudaFree(v->d_lambda);
+    for (float4 *t : v->d_gtex) cudaFree(t);
+    for (int b = 0; b < 2; ++b) {
+        if (v->ev_galloc[b]) cudaEventDestroy(v->ev_galloc[b]);
+        if (v->ev_group_done[b]) cudaEventDestroy(v->ev_group_done[b]);
+    }
+    cudaFree(v->meta.group_mask);
+    cudaFree(v->meta.union_slots);
     cudaFree(v->table.entries);
     cudaFree(v->table.stamp);
     cudaFree(v->meta.pool);
@@ -279,6 +311,8 @@ extern "C" int b2v_reset(b2v_volume *v) {
     rc = volume_clear_device(v);
     if (rc != B2V_OK) return rc;
     v->frame_id = 0;
+    v->group_id = 0;
+    v->last_group_buf = -1;
     v->err.clear();
     B2V_CUDA(v, cudaStreamSynchronize(v->compute));
     return B2V_OK;
@@ -309,9 +343,45 @@ static int ensure_staging(b2v_volume *v, size_t pixels) {
     return B2V_OK;
 }
 
-extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
-                             int32_t width, const double K[4], const double Tcw[16], void *stream) {
-    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+// Group context of a fused batch: frame k of group buffer `buf` packs its texels into `tex` and only
+// allocates; the fused kernel is launched by the caller once per group.
+struct GroupCtx {
+    int bit = -1, buf = 0;
+    float4 *tex = nullptr;
+    IntFrame *out = nullptr;  // per-frame constants for the fused kernel
+    bool first = false, last = false;
+};
+
+static int grow_profile_events(b2v_volume *v, size_t need) {
+    if (v->prof_used + need > v->prof_events.size()) {
+        const size_t old = v->prof_events.size();
+        v->prof_events.resize(old + 4 * 256, nullptr);
+        for (size_t k = old; k < v->prof_events.size(); ++k) B2V_CUDA(v, cudaEventCreate(&v->prof_events[k]));
+    }
+    return B2V_OK;
+}
+
+// cached TMA descriptors of a frame (keyed by the depth image address; colour address is checked)
+static const FrameMaps *frame_maps(b2v_volume *v, const float *d_depth, const uint8_t *d_color, int H, int W) {
+    if (!v->use_tma || !tma_tiles_usable(W, v->cfg.depth_stride, d_depth, d_color, v->d_lambda)) return nullptr;
+    if (v->map_H != H || v->map_W != W || v->map_lam != v->d_lambda || v->map_cache.size() > 4096) {
+        v->map_cache.clear();
+        v->map_H = H;
+        v->map_W = W;
+        v->map_lam = v->d_lambda;
+    }
+    auto it = v->map_cache.find(reinterpret_cast<uintptr_t>(d_depth));
+    if (it != v->map_cache.end() && it->second.color_ptr == d_color) return &it->second;
+    FrameMaps m;
+    if (!encode_frame_maps(&m, d_depth, d_color, v->d_lambda, H, W, 32)) return nullptr;
+    m.color_ptr = d_color;
+    auto res = v->map_cache.insert_or_assign(reinterpret_cast<uintptr_t>(d_depth), m);
+    return &res.first->second;
+}
+
+static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
+                           int32_t width, const double K[4], const double Tcw[16], void *stream,
+                           const GroupCtx *g, int dev_hint = -1) {
     if (!depth || !color || !K || !Tcw || height <= 0 || width <= 0) {
         v->err = "b2v_integrate: null pointer or non-positive image size";
         return B2V_ERR_INVALID_ARGUMENT;
@@ -320,17 +390,24 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
         v->err = "b2v_integrate: focal lengths must be positive";
         return B2V_ERR_INVALID_ARGUMENT;
     }
-    B2V_CUDA(v, cudaSetDevice(v->cfg.device));
     const size_t pixels = static_cast<size_t>(height) * width;
-    const bool dev_depth = is_device_pointer(depth), dev_color = is_device_pointer(color);
+    bool dev_depth, dev_color;
+    if (dev_hint >= 0) {  // batch call: queried once for the whole batch
+        dev_depth = dev_color = dev_hint != 0;
+    } else {
+        B2V_CUDA(v, cudaSetDevice(v->cfg.device));
+        dev_depth = is_device_pointer(depth);
+        dev_color = is_device_pointer(color);
+    }
     if (stream != nullptr && !(dev_depth && dev_color)) {
         v->err = "b2v_integrate: a caller stream requires device image pointers";
         return B2V_ERR_INVALID_ARGUMENT;
     }
+    const bool grouped = g != nullptr;
     cudaStream_t cs = stream ? static_cast<cudaStream_t>(stream) : v->compute;
     cudaStream_t as = v->overlap ? v->alloc : cs;  // stream of the allocate kernel
     v->last_stream = stream ? cs : nullptr;
-    const int s = static_cast<int>(v->frame_id % kStage);
+    const int s = kGroupStage + static_cast<int>(v->frame_id % kFrameStage);
     const int ring = static_cast<int>(v->frame_id % kActiveRing);
     const float *d_depth = depth;
     const uint8_t *d_color = color;
@@ -358,13 +435,17 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
         B2V_CUDA(v, cudaEventRecord(v->ev_in, cs));
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_in, 0));
     }
-    if (v->overlap && v->frame_id >= 3) {
+    if (!grouped && v->overlap && v->frame_id >= 3) {
         // allocate(f) recycles the ring slot / texel buffer last read by integrate(f - 3) .. (f - 4)
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_int_done[(v->frame_id - 3) % kActiveRing], 0));
     }
     FrameParams P;
     fill_frame_params(&P, K, Tcw, height, width, v->cfg.depth_stride, v->cfg.voxel_size, v->cfg.sdf_trunc,
                       v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank, v->cfg.shard_count);
+    if (grouped) {
+        P.group_bit = g->bit;
+        P.group_buf = g->buf;
+    }
     if (v->lam_H != height || v->lam_W != width || std::memcmp(v->lam_K, K, sizeof(v->lam_K)) != 0) {
         if (v->overlap) {  // the lambda image is read by allocate kernels that may still be in flight
             B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
@@ -376,23 +457,38 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
         v->launches += 1;
     }
     cudaEvent_t *pe = nullptr;
-    if (v->prof_enabled) {
-        if (v->prof_used + 4 > v->prof_events.size()) {
-            const size_t old = v->prof_events.size();
-            v->prof_events.resize(old + 4 * 256, nullptr);
-            for (size_t k = old; k < v->prof_events.size(); ++k) B2V_CUDA(v, cudaEventCreate(&v->prof_events[k]));
-        }
+    if (v->prof_enabled && (!grouped || g->first)) {
+        const int rc = grow_profile_events(v, 4);
+        if (rc != B2V_OK) return rc;
         pe = &v->prof_events[v->prof_used];
-        v->prof_used += 4;
+        if (!grouped) v->prof_used += 4;  // a group's quadruple is completed by the fused launch
         B2V_CUDA(v, cudaEventRecord(pe[0], as));
     }
-    FrameMaps maps;
-    const bool tma = v->use_tma && tma_tiles_usable(width, v->cfg.depth_stride, d_depth, d_color, v->d_lambda) &&
-                     encode_frame_maps(&maps, d_depth, d_color, v->d_lambda, height, width, 32);
-    B2V_CUDA(v, launch_allocate(P, d_depth, d_color, v->d_lambda, v->d_texel[s], v->table, v->meta, ring,
-                                tma ? &maps : nullptr, as));
-    if (pe) B2V_CUDA(v, cudaEventRecord(pe[1], as));
+    float4 *tex = grouped ? g->tex : v->d_texel[s];
+    B2V_CUDA(v, launch_allocate(P, d_depth, d_color, v->d_lambda, tex, v->table, v->meta, ring,
+                                frame_maps(v, d_depth, d_color, height, width), as));
     if (staged) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], as));  // the raw frame is consumed by allocate only
+    v->launches += 1;
+    v->frame_id += 1;
+    if (v->prof_enabled) v->prof_frames += 1;
+    if (grouped) {
+        IntFrame &F = *g->out;
+        std::memcpy(F.E, P.E, sizeof(F.E));
+        F.fxf = P.fxf;
+        F.fyf = P.fyf;
+        F.cxh = P.cxh;
+        F.cyh = P.cyh;
+        F.safe_w = P.safe_w;
+        F.safe_h = P.safe_h;
+        F.tau = P.tau;
+        F.inv_tau = P.inv_tau;
+        F.tex = tex;
+        F.W = width;
+        F.pad = 0;
+        return B2V_OK;
+    }
+    v->last_group_buf = -1;
+    if (pe) B2V_CUDA(v, cudaEventRecord(pe[1], as));
     if (v->overlap) {
         B2V_CUDA(v, cudaEventRecord(v->ev_alloc_done[ring], as));
         B2V_CUDA(v, cudaStreamWaitEvent(cs, v->ev_alloc_done[ring], 0));
@@ -401,8 +497,26 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
     B2V_CUDA(v, launch_integrate(P, v->d_texel[s], v->table, v->meta, ring, v->grid_ctas, cs));
     if (pe) B2V_CUDA(v, cudaEventRecord(pe[3], cs));
     if (v->overlap) B2V_CUDA(v, cudaEventRecord(v->ev_int_done[ring], cs));
-    v->launches += 2;
-    v->frame_id += 1;
+    v->launches += 1;
+    if (v->prof_enabled) v->prof_int_launches += 1;
+    return B2V_OK;
+}
+
+extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
+                             int32_t width, const double K[4], const double Tcw[16], void *stream) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    return integrate_frame(v, depth, color, height, width, K, Tcw, stream, nullptr);
+}
+
+static int ensure_group_buffers(b2v_volume *v, size_t pixels) {
+    if (pixels <= v->gtex_pixels) return B2V_OK;
+    B2V_CUDA(v, cudaDeviceSynchronize());
+    for (float4 *&t : v->d_gtex) {
+        cudaFree(t);
+        t = nullptr;
+        B2V_CUDA(v, cudaMalloc(&t, pixels * sizeof(float4)));
+    }
+    v->gtex_pixels = pixels;
     return B2V_OK;
 }
 
@@ -410,24 +524,151 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
                                    const uint8_t *color, int32_t height, int32_t width,
                                    const double K[4], const double *Tcw, void *stream) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
-    if (n_frames < 0 || (n_frames > 0 && (!depth || !color || !Tcw))) {
+    if (n_frames < 0 || (n_frames > 0 && (!depth || !color || !Tcw || !K)) || height <= 0 || width <= 0) {
         v->err = "b2v_integrate_batch: bad arguments";
         return B2V_ERR_INVALID_ARGUMENT;
     }
+    if (n_frames == 0) return B2V_OK;
+    B2V_CUDA(v, cudaSetDevice(v->cfg.device));
     const size_t pixels = static_cast<size_t>(height) * width;
-    if (v->overlap && n_frames > 0 && is_device_pointer(depth) && is_device_pointer(color)) {
-        cudaStream_t cs = stream ? static_cast<cudaStream_t>(stream) : v->compute;
-        B2V_CUDA(v, cudaSetDevice(v->cfg.device));
+    const bool dd = is_device_pointer(depth), dc = is_device_pointer(color);
+    const int dev_hint = dd == dc ? (dd ? 1 : 0) : -1;
+    cudaStream_t cs = stream ? static_cast<cudaStream_t>(stream) : v->compute;
+    cudaStream_t as = v->overlap ? v->alloc : cs;
+    if (v->overlap) {
+        // one fence for the whole batch: everything enqueued on the caller's stream so far (the inputs'
+        // producers, earlier per-frame work) happens before the batch's allocate kernels
         B2V_CUDA(v, cudaEventRecord(v->ev_in, cs));
         B2V_CUDA(v, cudaStreamWaitEvent(v->alloc, v->ev_in, 0));
         v->inputs_fenced = true;
     }
     int rc = B2V_OK;
-    for (int32_t f = 0; f < n_frames && rc == B2V_OK; ++f)
-        rc = b2v_integrate(v, depth + pixels * f, color + pixels * 3 * f, height, width, K,
-                           Tcw + 16 * static_cast<size_t>(f), stream);
+    if (!v->fuse || n_frames < 2) {
+        for (int32_t f = 0; f < n_frames && rc == B2V_OK; ++f)
+            rc = integrate_frame(v, depth + pixels * f, color + pixels * 3 * f, height, width, K,
+                                 Tcw + 16 * static_cast<size_t>(f), stream, nullptr, dev_hint);
+        v->inputs_fenced = false;
+        return rc;
+    }
+    rc = ensure_group_buffers(v, pixels);
+    if (rc == B2V_OK) rc = ensure_staging(v, pixels);
+    if (rc != B2V_OK) {
+        v->inputs_fenced = false;
+        return rc;
+    }
+    if (!(K[0] > 0.0) || !(K[1] > 0.0)) {
+        v->err = "b2v_integrate_batch: focal lengths must be positive";
+        v->inputs_fenced = false;
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    if (stream != nullptr && dev_hint != 1) {
+        v->err = "b2v_integrate_batch: a caller stream requires device image pointers";
+        v->inputs_fenced = false;
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    v->last_stream = stream ? cs : nullptr;
+    const bool staged = dev_hint != 1;
+    for (int32_t g0 = 0; g0 < n_frames; g0 += kMaxGroup) {
+        const int count = std::min<int32_t>(kMaxGroup, n_frames - g0);
+        const int buf = static_cast<int>(v->group_id % 2);
+        // the group buffer (masks, union list, texel images) was last used by group id - 2
+        B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_group_done[buf], 0));
+        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + kCtrUnion0 + buf, 0, sizeof(uint32_t), as));
+        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + kCtrGroupNext0 + buf, 0, sizeof(uint32_t), as));
+        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + kCtrGroupNew0 + buf, 0, sizeof(uint32_t), as));
+        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + kCtrGroupTouched0 + buf * kMaxGroup, 0,
+                                    kMaxGroup * sizeof(uint32_t), as));
+        static thread_local GroupAllocArgs aargs;  // 5.5 KB: keep it off the stack
+        GroupArgs args;
+        std::memset(&args, 0, sizeof(args));
+        args.vs = v->cfg.voxel_size;
+        args.count = count;
+        aargs.count = count;
+        aargs.use_tma = 1;
+        if (staged)  // the raw staging slots of this buffer were consumed by the allocate launch of group id - 2
+            B2V_CUDA(v, cudaStreamWaitEvent(v->copy, v->ev_galloc[buf], 0));
+        for (int k = 0; k < count; ++k) {
+            const size_t f = static_cast<size_t>(g0 + k);
+            const float *d_depth = depth + pixels * f;
+            const uint8_t *d_color = color + pixels * 3 * f;
+            if (staged) {
+                const int s = buf * kMaxGroup + k;
+                B2V_CUDA(v, cudaMemcpyAsync(v->d_depth[s], d_depth, pixels * sizeof(float), cudaMemcpyHostToDevice, v->copy));
+                B2V_CUDA(v, cudaMemcpyAsync(v->d_color[s], d_color, pixels * 3, cudaMemcpyHostToDevice, v->copy));
+                d_depth = v->d_depth[s];
+                d_color = v->d_color[s];
+            }
+            FrameParams &P = aargs.P[k];
+            fill_frame_params(&P, K, Tcw + 16 * f, height, width, v->cfg.depth_stride, v->cfg.voxel_size,
+                              v->cfg.sdf_trunc, v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank,
+                              v->cfg.shard_count);
+            P.group_bit = k;
+            P.group_buf = buf;
+            if (k == 0 && (v->lam_H != height || v->lam_W != width || std::memcmp(v->lam_K, K, sizeof(v->lam_K)) != 0)) {
+                if (v->overlap) B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
+                B2V_CUDA(v, launch_lambda(P, v->d_lambda, as));
+                std::memcpy(v->lam_K, K, sizeof(v->lam_K));
+                v->lam_H = height;
+                v->lam_W = width;
+                v->launches += 1;
+            }
+            float4 *tex = v->d_gtex[buf * kMaxGroup + k];
+            aargs.depth[k] = d_depth;
+            aargs.color[k] = d_color;
+            aargs.tex[k] = tex;
+            const FrameMaps *fm = frame_maps(v, d_depth, d_color, height, width);
+            if (fm) aargs.maps[k] = *fm; else aargs.use_tma = 0;
+            IntFrame &F = args.f[k];
+            std::memcpy(F.E, P.E, sizeof(F.E));
+            F.fxf = P.fxf;
+            F.fyf = P.fyf;
+            F.cxh = P.cxh;
+            F.cyh = P.cyh;
+            F.safe_w = P.safe_w;
+            F.safe_h = P.safe_h;
+            F.tau = P.tau;
+            F.inv_tau = P.inv_tau;
+            F.tex = tex;
+            F.W = width;
+            v->frame_id += 1;
+        }
+        if (staged) {
+            B2V_CUDA(v, cudaEventRecord(v->ev_ready[buf], v->copy));  // all frames of the group uploaded
+            B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_ready[buf], 0));
+        }
+        cudaEvent_t *pe = nullptr;
+        if (v->prof_enabled) {
+            const int prc = grow_profile_events(v, 4);
+            if (prc != B2V_OK) return prc;
+            pe = &v->prof_events[v->prof_used];
+            v->prof_used += 4;
+            v->prof_frames += count;
+            v->prof_int_launches += 1;
+            B2V_CUDA(v, cudaEventRecord(pe[0], as));
+        }
+        B2V_CUDA(v, launch_allocate_group(aargs, v->d_lambda, v->table, v->meta, as));
+        if (pe) B2V_CUDA(v, cudaEventRecord(pe[1], as));
+        B2V_CUDA(v, cudaEventRecord(v->ev_galloc[buf], as));
+        if (v->overlap) B2V_CUDA(v, cudaStreamWaitEvent(cs, v->ev_galloc[buf], 0));
+        if (pe) B2V_CUDA(v, cudaEventRecord(pe[2], cs));
+        B2V_CUDA(v, launch_integrate_group(args, v->table, v->meta, buf, v->grid_ctas, cs));
+        if (pe) B2V_CUDA(v, cudaEventRecord(pe[3], cs));
+        B2V_CUDA(v, cudaEventRecord(v->ev_group_done[buf], cs));
+        v->launches += 3;
+        v->last_group_buf = buf;
+        v->last_group_count = count;
+        v->group_id += 1;
+    }
     v->inputs_fenced = false;
-    return rc;
+    return B2V_OK;
+}
+
+extern "C" int b2v_set_fusion(b2v_volume *v, int32_t enable) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    const int rc = read_counters(v);
+    if (rc == B2V_ERR_CUDA) return rc;
+    v->fuse = enable != 0;
+    return B2V_OK;
 }
 
 extern "C" int b2v_synchronize(b2v_volume *v) {
@@ -447,8 +688,22 @@ extern "C" int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int6
     const int rc = read_counters(v);
     if (rc == B2V_ERR_CUDA) return rc;
     const int ring = v->frame_id ? static_cast<int>((v->frame_id - 1) % kActiveRing) : 0;
-    if (touched_blocks) *touched_blocks = v->frame_id ? v->h_counters[kCtrActive0 + ring] : 0;
-    if (new_blocks) *new_blocks = v->frame_id ? v->h_counters[kCtrNew0 + ring] : 0;
+    if (touched_blocks) {
+        if (v->frame_id == 0)
+            *touched_blocks = 0;
+        else if (v->last_group_buf >= 0)
+            *touched_blocks = v->h_counters[kCtrGroupTouched0 + v->last_group_buf * kMaxGroup + v->last_group_count - 1];
+        else
+            *touched_blocks = v->h_counters[kCtrActive0 + ring];
+    }
+    if (new_blocks) {
+        if (v->frame_id == 0)
+            *new_blocks = 0;
+        else if (v->last_group_buf >= 0)  // after a fused batch: blocks allocated by the last group
+            *new_blocks = v->h_counters[kCtrGroupNew0 + v->last_group_buf];
+        else
+            *new_blocks = v->h_counters[kCtrNew0 + ring];
+    }
     return rc;
 }
 
@@ -463,13 +718,28 @@ extern "C" int b2v_set_overlap(b2v_volume *v, int32_t enable) {
 extern "C" int b2v_profile_enable(b2v_volume *v, int32_t enable) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
     v->prof_enabled = enable != 0;
+    v->prof_used = 0;
+    v->prof_frames = 0;
+    v->prof_int_launches = 0;
     return B2V_OK;
 }
 
-extern "C" int b2v_profile_read(b2v_volume *v, double *allocate_ms, double *integrate_ms, int64_t *frames) {
+extern "C" int b2v_profile_read(b2v_volume *v, double *allocate_ms, double *integrate_ms, int64_t *frames,
+                                int64_t *integrate_launches) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
     B2V_CUDA(v, cudaSetDevice(v->cfg.device));
     double a = 0.0, b = 0.0;
+    if (std::getenv("B2V_DEBUG_TIMELINE") && v->prof_used >= 4) {  // debug: event times relative to the first
+        for (size_t k = 0; k + 3 < v->prof_used && k < 4 * 12; k += 4) {
+            float t[4];
+            for (int j = 0; j < 4; ++j) {
+                cudaEventSynchronize(v->prof_events[k + j]);
+                cudaEventElapsedTime(&t[j], v->prof_events[0], v->prof_events[k + j]);
+            }
+            std::fprintf(stderr, "[b2v timeline] launch %zu: alloc %.1f..%.1f us  integrate %.1f..%.1f us\n", k / 4,
+                         1e3 * t[0], 1e3 * t[1], 1e3 * t[2], 1e3 * t[3]);
+        }
+    }
     for (size_t k = 0; k + 3 < v->prof_used; k += 4) {
         B2V_CUDA(v, cudaEventSynchronize(v->prof_events[k + 1]));
         B2V_CUDA(v, cudaEventSynchronize(v->prof_events[k + 3]));
@@ -481,12 +751,16 @@ extern "C" int b2v_profile_read(b2v_volume *v, double *allocate_ms, double *inte
     }
     if (allocate_ms) *allocate_ms = a;
     if (integrate_ms) *integrate_ms = b;
-    if (frames) *frames = static_cast<int64_t>(v->prof_used / 4);
+    if (frames) *frames = v->prof_frames;
+    if (integrate_launches) *integrate_launches = v->prof_int_launches;
     v->prof_used = 0;
+    v->prof_frames = 0;
+    v->prof_int_launches = 0;
     return B2V_OK;
 }
 
-extern "C" int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches) {
+extern "C" int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches,
+                            int64_t *block_visits) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
     const int rc = read_counters(v);
     if (rc == B2V_ERR_CUDA) return rc;
@@ -494,6 +768,9 @@ extern "C" int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kern
         *block_updates = static_cast<int64_t>(static_cast<uint64_t>(v->h_counters[kCtrUpdatesLo]) |
                                               (static_cast<uint64_t>(v->h_counters[kCtrUpdatesHi]) << 32));
     if (kernel_launches) *kernel_launches = v->launches;
+    if (block_visits)
+        *block_visits = static_cast<int64_t>(static_cast<uint64_t>(v->h_counters[kCtrVisitsLo]) |
+                                             (static_cast<uint64_t>(v->h_counters[kCtrVisitsHi]) << 32));
     return rc;
 }
 
@@ -569,7 +846,8 @@ extern "C" int64_t b2v_last_touched_keys(b2v_volume *v, int32_t *keys, int64_t m
     if (read_counters(v) == B2V_ERR_CUDA) return -1;
     if (v->frame_id == 0) return 0;
     const int ring = static_cast<int>((v->frame_id - 1) % kActiveRing);
-    uint32_t n = v->h_counters[kCtrActive0 + ring];
+    const bool grp = v->last_group_buf >= 0;  // after a fused batch: the last group's union of touched blocks
+    uint32_t n = grp ? v->h_counters[kCtrUnion0 + v->last_group_buf] : v->h_counters[kCtrActive0 + ring];
     if (n > v->meta.capacity) n = v->meta.capacity;
     if (!keys) return n;
     if (static_cast<int64_t>(n) > max_keys) n = static_cast<uint32_t>(max_keys);
@@ -577,8 +855,9 @@ extern "C" int64_t b2v_last_touched_keys(b2v_volume *v, int32_t *keys, int64_t m
     int4 *d_k = nullptr;
     if (cudaMalloc(&d_k, n * sizeof(int4)) != cudaSuccess) return -1;
     std::vector<int4> tmp(n);
-    cudaError_t e = launch_gather_active_keys(
-        v->table, v->meta.active_slots + static_cast<size_t>(ring) * v->meta.capacity, n, d_k, v->compute);
+    const uint32_t *list = grp ? v->meta.union_slots + static_cast<size_t>(v->last_group_buf) * v->meta.capacity
+                               : v->meta.active_slots + static_cast<size_t>(ring) * v->meta.capacity;
+    cudaError_t e = launch_gather_active_keys(v->table, list, n, d_k, v->compute);
     if (e == cudaSuccess) e = cudaStreamSynchronize(v->compute);
     if (e == cudaSuccess) e = cudaMemcpy(tmp.data(), d_k, n * sizeof(int4), cudaMemcpyDeviceToHost);
     cudaFree(d_k);

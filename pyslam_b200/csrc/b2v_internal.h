@@ -27,6 +27,24 @@ struct FrameParams {
     int32_t H, W, stride;
     uint32_t frame_id;
     int32_t shard_rank, shard_count;
+    // fused group mode (b2v_integrate_batch): this frame is bit `group_bit` of group buffer
+    // `group_buf`; -1 = per-frame mode (frame stamps + per-frame active lists)
+    int32_t group_bit, group_buf;
+};
+
+// Fused group integration: up to kMaxGroup consecutive frames are applied to a block while it is
+// resident in registers.  Per-frame constants of the projective update only.
+constexpr int kMaxGroup = 8;
+struct IntFrame {
+    float E[12];
+    float fxf, fyf, cxh, cyh, safe_w, safe_h, tau, inv_tau;
+    const float4 *tex;
+    int32_t W, pad;
+};
+struct GroupArgs {
+    IntFrame f[kMaxGroup];
+    float vs;
+    int32_t count;
 };
 
 // Device-resident bookkeeping of one volume.
@@ -35,17 +53,25 @@ struct PoolMeta {
     int4 *block_keys;         // [capacity] key of pool block i (w unused)
     uint32_t *counters;       // device counters, see Counter
     uint32_t *active_slots;   // [kActiveRing][capacity] table slots touched by a frame
+    uint32_t *group_mask;     // [2][table capacity] bit k: the slot is touched by frame k of the group
+    uint32_t *union_slots;    // [2][capacity] slots touched by any frame of the group
     uint32_t capacity;
 };
 
 enum Counter : int {
-    kCtrPool = 0,        // number of allocated blocks (may exceed capacity on overflow)
-    kCtrError = 1,       // sticky error flag (1 = pool overflow, 2 = table full)
-    kCtrUpdatesLo = 2,   // 64-bit total of (block, frame) updates since reset (8-byte aligned)
+    kCtrPool = 0,            // number of allocated blocks (may exceed capacity on overflow)
+    kCtrError = 1,           // sticky error flag (1 = pool overflow, 2 = table full)
+    kCtrUpdatesLo = 2,       // 64-bit total of (block, frame) updates since reset (8-byte aligned)
     kCtrUpdatesHi = 3,
-    kCtrActive0 = 4,     // kActiveRing per-frame counts of touched blocks
-    kCtrNew0 = 8,        // kActiveRing per-frame counts of newly allocated blocks
-    kNumCounters = 16
+    kCtrActive0 = 4,         // [kActiveRing] per-frame counts of touched blocks
+    kCtrNew0 = 8,            // [kActiveRing] per-frame counts of newly allocated blocks
+    kCtrUnion0 = 12,         // [2] group buffers: number of slots in the group's union list
+    kCtrVisitsLo = 14,       // 64-bit total of block visits (one block read + written) since reset
+    kCtrVisitsHi = 15,
+    kCtrGroupTouched0 = 16,  // [2][kMaxGroup] blocks touched by frame k of the group
+    kCtrGroupNext0 = 32,     // [2] work-stealing cursor of the fused kernel
+    kCtrGroupNew0 = 34,      // [2] blocks newly allocated by the group
+    kNumCounters = 40
 };
 constexpr int kActiveRing = 4;
 
@@ -61,6 +87,7 @@ struct FrameMaps {
     alignas(64) CUtensorMap depth;
     alignas(64) CUtensorMap color;
     alignas(64) CUtensorMap lam;
+    const void *color_ptr = nullptr;  // host-side cache validation only
 };
 // TMA tile staging needs 16-byte aligned bases and row pitches (W % 16 == 0) and the 32x32 tile
 bool tma_tiles_usable(int W, int stride, const void *depth, const void *color, const void *lam);
@@ -76,7 +103,21 @@ cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint
 // projective TSDF + colour update of every block touched by the frame
 cudaError_t launch_integrate(const FrameParams &p, const float4 *texels, const HashTable &table,
                              const PoolMeta &meta, int ring, int grid_ctas, cudaStream_t stream);
+// all frames of a group in ONE launch (blockIdx.z = frame): the per-frame latency chains overlap
+struct GroupAllocArgs {
+    FrameParams P[kMaxGroup];
+    const float *depth[kMaxGroup];
+    const uint8_t *color[kMaxGroup];
+    float4 *tex[kMaxGroup];
+    FrameMaps maps[kMaxGroup];
+    int32_t count, use_tma;
+};
+cudaError_t launch_allocate_group(const GroupAllocArgs &args, const float *lam, const HashTable &table,
+                                  const PoolMeta &meta, cudaStream_t stream);
 int integrate_max_resident_ctas_per_sm();
+// fused update of a group of frames (each block is read and written once per group)
+cudaError_t launch_integrate_group(const GroupArgs &args, const HashTable &table, const PoolMeta &meta,
+                                   int group_buf, int grid_ctas, cudaStream_t stream);
 // hashes[i] = BlockKeyHash(block_keys[i])
 cudaError_t launch_block_hashes(const int4 *block_keys, uint64_t *hashes, uint32_t n,
                                 cudaStream_t stream);

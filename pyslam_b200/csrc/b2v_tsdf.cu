@@ -61,13 +61,23 @@ __device__ __forceinline__ void touch_key(const FrameParams &P, const HashTable 
             s_new[pos] = slot;
         } else {  // list overflow: assign directly
             assign_block(T, M, slot, atomicAdd(M.counters + kCtrPool, 1u));
-            atomicAdd(M.counters + kCtrNew0 + ring, 1u);
+            atomicAdd(P.group_bit >= 0 ? M.counters + kCtrGroupNew0 + P.group_buf : M.counters + kCtrNew0 + ring, 1u);
         }
     }
-    if (atomicExch(T.stamp + slot, P.frame_id) != P.frame_id) {
+    bool first;
+    if (P.group_bit >= 0) {  // fused group mode: membership bit; the first frame to touch queues the slot
+        uint32_t *mask = M.group_mask + static_cast<size_t>(P.group_buf) * (static_cast<size_t>(T.mask) + 1);
+        first = atomicOr(mask + slot, 1u << P.group_bit) == 0u;
+    } else {
+        first = atomicExch(T.stamp + slot, P.frame_id) != P.frame_id;
+    }
+    if (first) {
         const uint32_t pos = atomicAdd(s_n_act, 1u);
         if (pos < kListCap) {
             s_act[pos] = slot;
+        } else if (P.group_bit >= 0) {
+            const uint32_t g = atomicAdd(M.counters + kCtrUnion0 + P.group_buf, 1u);
+            if (g < M.capacity) M.union_slots[static_cast<size_t>(P.group_buf) * M.capacity + g] = slot;
         } else {
             const uint32_t g = atomicAdd(M.counters + kCtrActive0 + ring, 1u);
             if (g < M.capacity) M.active_slots[static_cast<size_t>(ring) * M.capacity + g] = slot;
@@ -131,10 +141,10 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 //           probes in flight - and exchanges the slot's frame stamp (first toucher queues the slot)
 //   flush   one atomic per CTA hands out contiguous pool indices and active-list positions
 template <bool kTma>
-__global__ void __launch_bounds__(kAllocThreads, 4)
-allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint8_t *__restrict__ rgb,
-                const float *__restrict__ lam, float4 *__restrict__ tex, const HashTable T,
-                const PoolMeta M, const int ring, const __grid_constant__ FrameMaps maps) {
+__device__ __forceinline__ void allocate_body(const FrameParams &P, const float *__restrict__ depth,
+                                              const uint8_t *__restrict__ rgb, const float *__restrict__ lam,
+                                              float4 *__restrict__ tex, const HashTable &T, const PoolMeta &M,
+                                              const int ring, const FrameMaps &maps) {
     // TMA staging buffers of the 32x32-pixel tile (kTma only): depth, lambda (f32) and colour (u8 x3)
     __shared__ alignas(128) float s_td[kTmaTile * kTmaTile];
     __shared__ alignas(128) float s_tl[kTmaTile * kTmaTile];
@@ -158,7 +168,7 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint
         s_n_new = 0;
         s_n_act = 0;
         s_ref[3] = 0;
-        if (blockIdx.x == 0 && blockIdx.y == 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && P.group_bit < 0) {
             // the ring slot the NEXT frame will count into (its last user finished 3 frames ago)
             const int nxt = (ring + 1) % kActiveRing;
             M.counters[kCtrActive0 + nxt] = 0;
@@ -350,15 +360,48 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint
     const uint32_t n_new = min(s_n_new, static_cast<uint32_t>(kListCap));
     const uint32_t n_act = min(s_n_act, static_cast<uint32_t>(kListCap));
     if (tid == 0) s_base_new = n_new ? atomicAdd(M.counters + kCtrPool, n_new) : 0u;
-    if (tid == 32) s_base_act = n_act ? atomicAdd(M.counters + kCtrActive0 + ring, n_act) : 0u;
-    if (tid == 64 && n_new) atomicAdd(M.counters + kCtrNew0 + ring, n_new);
+    uint32_t *list_count = P.group_bit >= 0 ? M.counters + kCtrUnion0 + P.group_buf : M.counters + kCtrActive0 + ring;
+    if (tid == 32) s_base_act = n_act ? atomicAdd(list_count, n_act) : 0u;
+    if (tid == 64 && n_new)
+        atomicAdd(P.group_bit >= 0 ? M.counters + kCtrGroupNew0 + P.group_buf : M.counters + kCtrNew0 + ring, n_new);
     __syncthreads();
     for (uint32_t k = tid; k < n_new; k += kAllocThreads) assign_block(T, M, s_new[k], s_base_new + k);
-    uint32_t *active_out = M.active_slots + static_cast<size_t>(ring) * M.capacity;
+    uint32_t *active_out = P.group_bit >= 0 ? M.union_slots + static_cast<size_t>(P.group_buf) * M.capacity
+                                            : M.active_slots + static_cast<size_t>(ring) * M.capacity;
     for (uint32_t k = tid; k < n_act; k += kAllocThreads) {
         const uint32_t g = s_base_act + k;
         if (g < M.capacity) active_out[g] = s_act[k];
     }
+}
+
+template <bool kTma>
+__global__ void __launch_bounds__(kAllocThreads, 4)
+allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint8_t *__restrict__ rgb,
+                const float *__restrict__ lam, float4 *__restrict__ tex, const HashTable T,
+                const PoolMeta M, const int ring, const __grid_constant__ FrameMaps maps) {
+    allocate_body<kTma>(P, depth, rgb, lam, tex, T, M, ring, maps);
+}
+
+// blockIdx.z = frame of the group: one launch allocates for up to kMaxGroup frames
+template <bool kTma>
+__global__ void __launch_bounds__(kAllocThreads, 4)
+allocate_group_kernel(const __grid_constant__ GroupAllocArgs A, const float *__restrict__ lam,
+                      const HashTable T, const PoolMeta M) {
+    const int k = blockIdx.z;
+    allocate_body<kTma>(A.P[k], A.depth[k], A.color[k], lam, A.tex[k], T, M, 0, A.maps[k]);
+}
+
+cudaError_t launch_allocate_group(const GroupAllocArgs &args, const float *lam, const HashTable &table,
+                                  const PoolMeta &meta, cudaStream_t stream) {
+    const FrameParams &p = args.P[0];
+    const int gw = (p.W + p.stride - 1) / p.stride;
+    const int gh = (p.H + p.stride - 1) / p.stride;
+    const dim3 grid((gw + kAllocTile - 1) / kAllocTile, (gh + kAllocTile - 1) / kAllocTile, args.count);
+    if (args.use_tma && p.stride * kAllocTile == kTmaTile)
+        allocate_group_kernel<true><<<grid, kAllocThreads, 0, stream>>>(args, lam, table, meta);
+    else
+        allocate_group_kernel<false><<<grid, kAllocThreads, 0, stream>>>(args, lam, table, meta);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint8_t *color,
@@ -443,9 +486,12 @@ integrate_kernel(const FrameParams P, const float4 *__restrict__ tex, const Hash
     const uint32_t *__restrict__ act = M.active_slots + static_cast<size_t>(ring) * M.capacity;
     const int t = threadIdx.x;
     const int lx0 = (t & 1) * 4, ly = (t >> 1) & 7, lz = t >> 4;
-    if (blockIdx.x == 0 && t == 0)
+    if (blockIdx.x == 0 && t == 0) {
         atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrUpdatesLo),
                   static_cast<unsigned long long>(n));
+        atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrVisitsLo),
+                  static_cast<unsigned long long>(n));
+    }
 
     uint32_t i = blockIdx.x;
     uint4 e = make_uint4(0u, 0u, 0u, kNoBlock);
@@ -528,6 +574,158 @@ integrate_kernel(const FrameParams P, const float4 *__restrict__ tex, const Hash
 cudaError_t launch_integrate(const FrameParams &p, const float4 *texels, const HashTable &table,
                              const PoolMeta &meta, int ring, int grid_ctas, cudaStream_t stream) {
     integrate_kernel<<<grid_ctas, kIntThreads, 0, stream>>>(p, texels, table, meta, ring);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused group update: a block is loaded once, the frames of the group that touch it are applied in
+// frame order while it sits in registers, and it is stored once.  Per voxel the arithmetic is the
+// same sequence as frame-by-frame integration, so results are bit-identical; HBM traffic per frame
+// drops by the group's overlap factor (consecutive keyframes see mostly the same blocks).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIntThreads, 8)
+integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, const PoolMeta M,
+                       const int gbuf) {
+    __shared__ IntFrame s_f[kMaxGroup];   // per-frame constants (dynamic indexing by frame bit)
+    __shared__ float s_rcp[256];          // correctly rounded 1/n for the small integer weights
+    __shared__ uint32_t s_next;           // work-stealing: next list position of this CTA
+    const uint32_t n = min(M.counters[kCtrUnion0 + gbuf], M.capacity);
+    const uint32_t *__restrict__ list = M.union_slots + static_cast<size_t>(gbuf) * M.capacity;
+    const uint32_t *__restrict__ mask = M.group_mask + static_cast<size_t>(gbuf) * (static_cast<size_t>(T.mask) + 1);
+    uint32_t *cursor = M.counters + kCtrGroupNext0 + gbuf;
+    const int t = threadIdx.x;
+    const int lx0 = (t & 1) * 4, ly = (t >> 1) & 7, lz = t >> 4;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.f);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_f);
+        for (int k = t; k < static_cast<int>(sizeof(IntFrame) * kMaxGroup / 4); k += kIntThreads) dst[k] = src[k];
+        s_rcp[t] = __frcp_rn(static_cast<float>(t));
+        s_rcp[t + 128] = __frcp_rn(static_cast<float>(t + 128));
+    }
+    if (blockIdx.x == 0 && t == 0)
+        atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrVisitsLo),
+                  static_cast<unsigned long long>(n));
+    uint32_t my_cnt = 0;  // thread k < 8: blocks touched by frame k, seen by this CTA
+
+    // dynamic work distribution: blocks cost 1..8 frame updates, static striding leaves a long tail
+    uint32_t i = blockIdx.x;  // first item is static; later ones come from the shared cursor
+    uint4 e = make_uint4(0u, 0u, 0u, kNoBlock);
+    uint32_t m = 0;
+    if (i < n) {
+        const uint32_t slot = list[i];
+        e = T.entries[slot];
+        m = mask[slot];
+    }
+    __syncthreads();
+    while (i < n) {
+        if (t == 0) s_next = atomicAdd(cursor, 1u) + gridDim.x;
+        __syncthreads();
+        const uint32_t i_next = s_next;
+        uint4 e_next = e;
+        uint32_t m_next = 0;
+        if (i_next < n) {  // in flight during this iteration
+            const uint32_t slot = list[i_next];
+            e_next = T.entries[slot];
+            m_next = mask[slot];
+        }
+        if (t < kMaxGroup) my_cnt += (m >> t) & 1u;
+
+        if (e.w < M.capacity) {
+            float *blk = M.pool + static_cast<size_t>(e.w) * kBlockFloats + t * 4;
+            float4 q[kPlanes];
+#pragma unroll
+            for (int c = 0; c < kPlanes; ++c) q[c] = *reinterpret_cast<const float4 *>(blk + c * kVox);
+            float *ts = reinterpret_cast<float *>(&q[0]);
+            float *w = reinterpret_cast<float *>(&q[1]);
+            float *cr = reinterpret_cast<float *>(&q[2]);
+            float *cg = reinterpret_cast<float *>(&q[3]);
+            float *cb = reinterpret_cast<float *>(&q[4]);
+
+            // voxel centres are frame independent
+            const int vx0 = static_cast<int>(e.x) * kB + lx0;
+            float cx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cx[k] = __fmul_rn(__fadd_rn(static_cast<float>(vx0 + k), 0.5f), A.vs);
+            const float cy = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.y) * kB + ly), 0.5f), A.vs);
+            const float cz = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.z) * kB + lz), 0.5f), A.vs);
+
+            bool upd = false;
+            for (uint32_t mm = m; mm; mm &= mm - 1) {  // ascending bits = frame order
+                const IntFrame &F = s_f[__ffs(mm) - 1];
+                const float ax = __fmaf_rn(F.E[1], cy, __fmaf_rn(F.E[2], cz, F.E[3]));
+                const float ay = __fmaf_rn(F.E[5], cy, __fmaf_rn(F.E[6], cz, F.E[7]));
+                const float az = __fmaf_rn(F.E[9], cy, __fmaf_rn(F.E[10], cz, F.E[11]));
+                float pzs[4];
+                int pix[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float px = __fmaf_rn(F.E[0], cx[k], ax);
+                    const float py = __fmaf_rn(F.E[4], cx[k], ay);
+                    const float pz = __fmaf_rn(F.E[8], cx[k], az);
+                    pzs[k] = pz;
+                    pix[k] = -1;
+                    if (pz > 0.0f) {
+                        const float inv_z = __frcp_rn(pz);
+                        const float u_f = __fmaf_rn(__fmul_rn(px, F.fxf), inv_z, F.cxh);
+                        const float v_f = __fmaf_rn(__fmul_rn(py, F.fyf), inv_z, F.cyh);
+                        if (u_f >= 0.0001f && u_f < F.safe_w && v_f >= 0.0001f && v_f < F.safe_h)
+                            pix[k] = __float2int_rz(v_f) * F.W + __float2int_rz(u_f);
+                    }
+                }
+                float4 tx[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tx[k] = pix[k] >= 0 ? __ldg(F.tex + pix[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float d = tx[k].x;
+                    const float sdf = __fmul_rn(__fsub_rn(d, pzs[k]), tx[k].y);
+                    if (d > 0.0f && sdf > -F.tau) {
+                        const float tv = fminf(1.0f, __fmul_rn(sdf, F.inv_tau));
+                        const uint32_t rgbx = __float_as_uint(tx[k].z);
+                        const float w0 = w[k];
+                        const float wn = __fadd_rn(w0, 1.0f);
+                        // 1/wn: weights are small integers, so the correctly rounded reciprocal comes
+                        // from a table (same value __frcp_rn would give); large weights take the slow path
+                        const float r = wn < 256.0f ? s_rcp[__float2int_rz(wn)] : __frcp_rn(wn);
+                        ts[k] = __fmul_rn(__fmaf_rn(ts[k], w0, tv), r);
+                        cr[k] = __fmul_rn(__fmaf_rn(cr[k], w0, static_cast<float>(rgbx & 0xFFu)), r);
+                        cg[k] = __fmul_rn(__fmaf_rn(cg[k], w0, static_cast<float>((rgbx >> 8) & 0xFFu)), r);
+                        cb[k] = __fmul_rn(__fmaf_rn(cb[k], w0, static_cast<float>((rgbx >> 16) & 0xFFu)), r);
+                        w[k] = wn;
+                        upd = true;
+                    }
+                }
+            }
+            if (upd) {
+#pragma unroll
+                for (int c = 0; c < kPlanes; ++c) *reinterpret_cast<float4 *>(blk + c * kVox) = q[c];
+            }
+        }
+        e = e_next;
+        m = m_next;
+        i = i_next;
+        __syncthreads();  // s_next is rewritten at the top of the next iteration
+    }
+    if (t < kMaxGroup && my_cnt) {
+        atomicAdd(M.counters + kCtrGroupTouched0 + gbuf * kMaxGroup + t, my_cnt);
+        atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrUpdatesLo),
+                  static_cast<unsigned long long>(my_cnt));
+    }
+}
+
+// clears the membership masks of a finished group (its buffer is reused two groups later)
+__global__ void group_clear_kernel(const HashTable T, const PoolMeta M, const int gbuf) {
+    const uint32_t n = min(M.counters[kCtrUnion0 + gbuf], M.capacity);
+    uint32_t *mask = M.group_mask + static_cast<size_t>(gbuf) * (static_cast<size_t>(T.mask) + 1);
+    const uint32_t *list = M.union_slots + static_cast<size_t>(gbuf) * M.capacity;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mask[list[i]] = 0u;
+}
+
+cudaError_t launch_integrate_group(const GroupArgs &args, const HashTable &table, const PoolMeta &meta,
+                                   int group_buf, int grid_ctas, cudaStream_t stream) {
+    integrate_group_kernel<<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
+    group_clear_kernel<<<148, 256, 0, stream>>>(table, meta, group_buf);
     return cudaGetLastError();
 }
 

@@ -207,10 +207,20 @@ class B200TsdfVolume:
         return int(t.value), int(n.value)
 
     def counters(self):
-        """(total block updates, kernel launches) since create/reset."""
-        u, k = C.c_int64(0), C.c_int64(0)
-        self._check(self._L.b2v_counters(self._h, C.byref(u), C.byref(k)), "b2v_counters")
+        """(total (block, frame) updates, kernel launches) since create/reset."""
+        u, k, b = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self._L.b2v_counters(self._h, C.byref(u), C.byref(k), C.byref(b)), "b2v_counters")
         return int(u.value), int(k.value)
+
+    def block_visits(self) -> int:
+        """Blocks read + written since create/reset (== updates frame by frame; fewer when fused)."""
+        u, k, b = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self._L.b2v_counters(self._h, C.byref(u), C.byref(k), C.byref(b)), "b2v_counters")
+        return int(b.value)
+
+    def set_fusion(self, enable: bool):
+        """integrate_batch: fuse groups of up to 8 frames per block visit (default) or go frame by frame."""
+        self._check(self._L.b2v_set_fusion(self._h, 1 if enable else 0), "b2v_set_fusion")
 
     def set_overlap(self, enable: bool):
         """Run allocate(f+1) concurrently with integrate(f) (default) or serialise them."""
@@ -220,11 +230,11 @@ class B200TsdfVolume:
         self._check(self._L.b2v_profile_enable(self._h, 1 if enable else 0), "b2v_profile_enable")
 
     def profile_read(self):
-        """(allocate_ms, integrate_ms, frames) summed over the frames since the last read."""
-        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
-        self._check(self._L.b2v_profile_read(self._h, C.byref(a), C.byref(b), C.byref(n)),
+        """(allocate_ms, integrate_ms, frames, integrate launches) summed since the last read."""
+        a, b, n, l = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
+        self._check(self._L.b2v_profile_read(self._h, C.byref(a), C.byref(b), C.byref(n), C.byref(l)),
                     "b2v_profile_read")
-        return a.value, b.value, int(n.value)
+        return a.value, b.value, int(n.value), int(l.value)
 
     def last_touched_keys(self) -> np.ndarray:
         n = self._L.b2v_last_touched_keys(self._h, None, 0)

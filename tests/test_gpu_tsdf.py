@@ -304,3 +304,36 @@ def test_execution_variants_are_bit_identical(env, monkeypatch):
     for name in ("keys", "hashes", "vox"):
         assert np.array_equal(a[name], b[name]), name
     _assert_same_volume(var, orc)
+
+
+def test_fused_batch_equals_frame_by_frame_and_oracle():
+    """integrate_batch fuses groups of 8 frames per block visit; 19 frames = 8 + 8 + 3 exercises full and
+    partial groups and the double-buffered group state.  Bit-identical to frame-by-frame and the oracle."""
+    cfg = S.CONFIGS["C1"]
+    n = 19
+    frames = [S.render_frame(cfg, i) for i in range(n)]
+    D, Cc, T = (np.stack([f[k] for f in frames]) for k in range(3))
+    fused, orc = _pair(cfg, capacity=1 << 16)
+    plain, _ = _pair(cfg, capacity=1 << 16)
+    plain.set_fusion(False)
+    fused.integrate_batch(D, Cc, cfg.K, T)
+    plain.integrate_batch(D, Cc, cfg.K, T)
+    for d, c, t in frames:
+        orc.integrate(d, c, cfg.K, t)
+    a, b = sort_dump(fused.dump_blocks()), sort_dump(plain.dump_blocks())
+    for name in ("keys", "hashes", "vox"):
+        assert np.array_equal(a[name], b[name]), name
+    _assert_same_volume(fused, orc)
+    upd_f, _ = fused.counters()
+    upd_p, _ = plain.counters()
+    assert upd_f == upd_p                               # every (block, frame) update is still applied
+    assert fused.block_visits() < 0.5 * plain.block_visits() == 0.5 * upd_p   # ... with far fewer block visits
+    touched, _ = fused.last_frame_stats()
+    assert touched == len(orc.last_touched())
+    # a second batch into the same volume, then single frames again (mode switches share the table)
+    fused.integrate_batch(D[:5], Cc[:5], cfg.K, T[:5])
+    fused.integrate(frames[5][0], frames[5][1], cfg.K, frames[5][2])
+    for d, c, t in frames[:6]:
+        orc.integrate(d, c, cfg.K, t)
+    _assert_same_volume(fused, orc)
+    assert np.array_equal(sorted_keys(fused.last_touched_keys()), sorted_keys(orc.last_touched()))
