@@ -343,15 +343,6 @@ static int ensure_staging(b2v_volume *v, size_t pixels) {
     return B2V_OK;
 }
 
-// Group context of a fused batch: frame k of group buffer `buf` packs its texels into `tex` and only
-// allocates; the fused kernel is launched by the caller once per group.
-struct GroupCtx {
-    int bit = -1, buf = 0;
-    float4 *tex = nullptr;
-    IntFrame *out = nullptr;  // per-frame constants for the fused kernel
-    bool first = false, last = false;
-};
-
 static int grow_profile_events(b2v_volume *v, size_t need) {
     if (v->prof_used + need > v->prof_events.size()) {
         const size_t old = v->prof_events.size();
@@ -381,7 +372,7 @@ static const FrameMaps *frame_maps(b2v_volume *v, const float *d_depth, const ui
 
 static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
                            int32_t width, const double K[4], const double Tcw[16], void *stream,
-                           const GroupCtx *g, int dev_hint = -1) {
+                           int dev_hint = -1) {
     if (!depth || !color || !K || !Tcw || height <= 0 || width <= 0) {
         v->err = "b2v_integrate: null pointer or non-positive image size";
         return B2V_ERR_INVALID_ARGUMENT;
@@ -403,7 +394,6 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
         v->err = "b2v_integrate: a caller stream requires device image pointers";
         return B2V_ERR_INVALID_ARGUMENT;
     }
-    const bool grouped = g != nullptr;
     cudaStream_t cs = stream ? static_cast<cudaStream_t>(stream) : v->compute;
     cudaStream_t as = v->overlap ? v->alloc : cs;  // stream of the allocate kernel
     v->last_stream = stream ? cs : nullptr;
@@ -435,17 +425,13 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
         B2V_CUDA(v, cudaEventRecord(v->ev_in, cs));
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_in, 0));
     }
-    if (!grouped && v->overlap && v->frame_id >= 3) {
+    if (v->overlap && v->frame_id >= 3) {
         // allocate(f) recycles the ring slot / texel buffer last read by integrate(f - 3) .. (f - 4)
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_int_done[(v->frame_id - 3) % kActiveRing], 0));
     }
     FrameParams P;
     fill_frame_params(&P, K, Tcw, height, width, v->cfg.depth_stride, v->cfg.voxel_size, v->cfg.sdf_trunc,
                       v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank, v->cfg.shard_count);
-    if (grouped) {
-        P.group_bit = g->bit;
-        P.group_buf = g->buf;
-    }
     if (v->lam_H != height || v->lam_W != width || std::memcmp(v->lam_K, K, sizeof(v->lam_K)) != 0) {
         if (v->overlap) {  // the lambda image is read by allocate kernels that may still be in flight
             B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
@@ -457,36 +443,20 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
         v->launches += 1;
     }
     cudaEvent_t *pe = nullptr;
-    if (v->prof_enabled && (!grouped || g->first)) {
+    if (v->prof_enabled) {
         const int rc = grow_profile_events(v, 4);
         if (rc != B2V_OK) return rc;
         pe = &v->prof_events[v->prof_used];
-        if (!grouped) v->prof_used += 4;  // a group's quadruple is completed by the fused launch
+        v->prof_used += 4;
         B2V_CUDA(v, cudaEventRecord(pe[0], as));
     }
-    float4 *tex = grouped ? g->tex : v->d_texel[s];
+    float4 *tex = v->d_texel[s];
     B2V_CUDA(v, launch_allocate(P, d_depth, d_color, v->d_lambda, tex, v->table, v->meta, ring,
                                 frame_maps(v, d_depth, d_color, height, width), as));
     if (staged) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], as));  // the raw frame is consumed by allocate only
     v->launches += 1;
     v->frame_id += 1;
     if (v->prof_enabled) v->prof_frames += 1;
-    if (grouped) {
-        IntFrame &F = *g->out;
-        std::memcpy(F.E, P.E, sizeof(F.E));
-        F.fxf = P.fxf;
-        F.fyf = P.fyf;
-        F.cxh = P.cxh;
-        F.cyh = P.cyh;
-        F.safe_w = P.safe_w;
-        F.safe_h = P.safe_h;
-        F.tau = P.tau;
-        F.inv_tau = P.inv_tau;
-        F.tex = tex;
-        F.W = width;
-        F.pad = 0;
-        return B2V_OK;
-    }
     v->last_group_buf = -1;
     if (pe) B2V_CUDA(v, cudaEventRecord(pe[1], as));
     if (v->overlap) {
@@ -505,7 +475,7 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
 extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
                              int32_t width, const double K[4], const double Tcw[16], void *stream) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
-    return integrate_frame(v, depth, color, height, width, K, Tcw, stream, nullptr);
+    return integrate_frame(v, depth, color, height, width, K, Tcw, stream);
 }
 
 static int ensure_group_buffers(b2v_volume *v, size_t pixels) {
@@ -546,7 +516,7 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
     if (!v->fuse || n_frames < 2) {
         for (int32_t f = 0; f < n_frames && rc == B2V_OK; ++f)
             rc = integrate_frame(v, depth + pixels * f, color + pixels * 3 * f, height, width, K,
-                                 Tcw + 16 * static_cast<size_t>(f), stream, nullptr, dev_hint);
+                                 Tcw + 16 * static_cast<size_t>(f), stream, dev_hint);
         v->inputs_fenced = false;
         return rc;
     }
