@@ -128,6 +128,18 @@ int64_t b2v_grid_get_voxels(b2v_grid *g, int32_t min_count);
 int b2v_grid_copy_voxels(b2v_grid *g, float *points, float *colors);
 /* remove_low_count_voxels(min_count) (voxel_block_grid.hpp:625-647) */
 int b2v_grid_remove_low_count_voxels(b2v_grid *g, int32_t min_count);
+/* carve(camera_frustrum, depth_image, depth_threshold) (voxel_block_grid.hpp:616-622;
+ * voxel_grid_carving.h:47-80; CameraFrustrum: camera_frustrum.h:36-48): K = {fx,fy,cx,cy} float32,
+ * Tcw float64[16] row-major, depth float32 [height*width] (host or device). */
+int b2v_grid_carve(b2v_grid *g, const float K[4], int32_t width, int32_t height, const double Tcw[16],
+                   float depth_max, float depth_min, const float *depth, float depth_threshold);
+/* get_voxels_in_camera_frustrum(frustum, min_count) (voxel_block_grid.hpp:1019-1195) and
+ * get_voxels_in_bb(bbox, min_count) (voxel_block_grid.hpp:822-1016), bbox = {min xyz, max xyz} float64.
+ * Return n; fetch with b2v_grid_copy_voxels. */
+int64_t b2v_grid_get_voxels_in_frustum(b2v_grid *g, const float K[4], int32_t width, int32_t height,
+                                       const double Tcw[16], float depth_max, float depth_min,
+                                       int32_t min_count);
+int64_t b2v_grid_get_voxels_in_bb(b2v_grid *g, const double bbox[6], int32_t min_count);
 /* parity hook: keys int32[nb*3], hashes u64[nb], count int32[nb*512], pos_sum f32[nb*512*3],
  * col_sum f32[nb*512*3]  (same layout as the reference's VoxelData, voxel_data.h:118-133) */
 int64_t b2v_grid_dump_blocks(b2v_grid *g, int32_t *keys, uint64_t *hashes, int32_t *count,

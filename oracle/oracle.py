@@ -93,6 +93,12 @@ def _ref():
         L.refgrid_remove_low_count_voxels.argtypes = [C.c_void_p, C.c_int]
         L.refgrid_carve.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                     C.c_int, _f64p, C.c_float, C.c_float, _f32p, C.c_float]
+        L.refgrid_get_voxels_in_frustum.restype = C.c_int64
+        L.refgrid_get_voxels_in_frustum.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                                    C.c_int, C.c_int, _f64p, C.c_float, C.c_float, C.c_int,
+                                                    C.c_void_p, C.c_void_p]
+        L.refgrid_get_voxels_in_bb.restype = C.c_int64
+        L.refgrid_get_voxels_in_bb.argtypes = [C.c_void_p, _f64p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_voxel_key_inv.argtypes = [C.c_float] * 4 + [_i32p]
         L.ref_floor_div.restype = C.c_int64
         L.ref_floor_div.argtypes = [C.c_int64, C.c_int64]
@@ -184,6 +190,23 @@ class RefGrid:
 
     def remove_low_count_voxels(self, min_count):
         self._L.refgrid_remove_low_count_voxels(self._h, int(min_count))
+
+    def get_voxels_in_frustum(self, K, width, height, Tcw, min_count=1, depth_max=10.0, depth_min=1e-2):
+        T = np.ascontiguousarray(Tcw, np.float64).reshape(16)
+        a = (self._h, K[0], K[1], K[2], K[3], int(width), int(height), T, depth_max, depth_min, int(min_count))
+        n = self._L.refgrid_get_voxels_in_frustum(*a, None, None)
+        pts, cols = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        if n:
+            self._L.refgrid_get_voxels_in_frustum(*a, pts.ctypes.data, cols.ctypes.data)
+        return pts, cols
+
+    def get_voxels_in_bb(self, bbox, min_count=1):
+        bb = np.ascontiguousarray(bbox, np.float64).reshape(6)
+        n = self._L.refgrid_get_voxels_in_bb(self._h, bb, int(min_count), None, None)
+        pts, cols = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        if n:
+            self._L.refgrid_get_voxels_in_bb(self._h, bb, int(min_count), pts.ctypes.data, cols.ctypes.data)
+        return pts, cols
 
     def carve(self, K, width, height, Tcw, depth, depth_threshold=1e-2, depth_max=10.0,
               depth_min=1e-2):

@@ -34,6 +34,21 @@ class DumpableGrid : public VoxelBlockGrid {
 
 } // namespace
 
+static volumetric::CameraFrustrum make_frustum(float fx, float fy, float cx, float cy, int width, int height,
+                                               const double *Tcw, float depth_max, float depth_min) {
+    Eigen::Matrix4d T;
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) T(r, c) = Tcw[4 * r + c];
+    return volumetric::CameraFrustrum(fx, fy, cx, cy, width, height, T, depth_max, depth_min);
+}
+
+template <typename Data> static int64_t copy_out(const Data &out, float *points, float *colors) {
+    const int64_t n = static_cast<int64_t>(out.points.size());
+    if (points) std::memcpy(points, out.points.data(), sizeof(float) * 3 * n);
+    if (colors) std::memcpy(colors, out.colors.data(), sizeof(float) * 3 * n);
+    return n;
+}
+
 extern "C" {
 
 void *refgrid_create(float voxel_size, int block_size) {
@@ -133,6 +148,22 @@ void refgrid_carve(void *h, float fx, float fy, float cx, float cy, int width, i
     volumetric::CameraFrustrum frustum(fx, fy, cx, cy, width, height, T, depth_max, depth_min);
     cv::Mat img(height, width, CV_32FC1, const_cast<float *>(depth));
     g->carve(frustum, img, depth_threshold);
+}
+
+// reference: VoxelBlockGridT::get_voxels_in_camera_frustrum (voxel_block_grid.hpp:1019-1195); two-call pattern
+int64_t refgrid_get_voxels_in_frustum(void *h, float fx, float fy, float cx, float cy, int width, int height,
+                                      const double *Tcw, float depth_max, float depth_min, int min_count,
+                                      float *points, float *colors) {
+    auto *g = static_cast<DumpableGrid *>(h);
+    const auto fr = make_frustum(fx, fy, cx, cy, width, height, Tcw, depth_max, depth_min);
+    return copy_out(g->get_voxels_in_camera_frustrum(fr, min_count, 0.0f), points, colors);
+}
+
+// reference: VoxelBlockGridT::get_voxels_in_bb (voxel_block_grid.hpp:822-1016); bbox = min xyz, max xyz
+int64_t refgrid_get_voxels_in_bb(void *h, const double *bb, int min_count, float *points, float *colors) {
+    auto *g = static_cast<DumpableGrid *>(h);
+    const volumetric::BoundingBox3D box(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5]);
+    return copy_out(g->get_voxels_in_bb(box, min_count, 0.0f), points, colors);
 }
 
 // ---- leaf helpers straight from voxel_hashing.h, for known-answer tests ----

@@ -5,6 +5,8 @@ update, per-block marching cubes, and the point-average compat grid).  `csrc/` h
 CUDA kernels and the C ABI (include/b2v.h); the Python modules mirror the reference's interface.
 """
 
-from .volume import B200TsdfVolume, PointCloud, TriangleMesh, VoxelBlockGrid, VoxelGridData
+from .volume import (B200TsdfVolume, BoundingBox3D, CameraFrustrum, PointCloud, TriangleMesh,
+                     VoxelBlockGrid, VoxelGridData)
 
-__all__ = ["B200TsdfVolume", "PointCloud", "TriangleMesh", "VoxelBlockGrid", "VoxelGridData"]
+__all__ = ["B200TsdfVolume", "BoundingBox3D", "CameraFrustrum", "PointCloud", "TriangleMesh",
+           "VoxelBlockGrid", "VoxelGridData"]

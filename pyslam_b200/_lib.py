@@ -30,7 +30,8 @@ EXPORTED_SYMBOLS = [
     "b2v_extract_points", "b2v_copy_points", "b2v_grid_create", "b2v_grid_destroy", "b2v_grid_clear",
     "b2v_grid_last_error", "b2v_grid_integrate", "b2v_grid_synchronize", "b2v_grid_num_blocks",
     "b2v_grid_size", "b2v_grid_get_voxels", "b2v_grid_copy_voxels",
-    "b2v_grid_remove_low_count_voxels", "b2v_grid_dump_blocks", "b2v_version", "b2v_device_sm_count",
+    "b2v_grid_remove_low_count_voxels", "b2v_grid_dump_blocks", "b2v_grid_carve",
+    "b2v_grid_get_voxels_in_frustum", "b2v_grid_get_voxels_in_bb", "b2v_version", "b2v_device_sm_count",
 ]
 
 
@@ -133,6 +134,12 @@ def load() -> C.CDLL:
     L.b2v_grid_copy_voxels.argtypes = [vp, vp, vp]
     L.b2v_grid_remove_low_count_voxels.restype = C.c_int
     L.b2v_grid_remove_low_count_voxels.argtypes = [vp, i32]
+    L.b2v_grid_carve.restype = C.c_int
+    L.b2v_grid_carve.argtypes = [vp, vp, i32, i32, vp, C.c_float, C.c_float, vp, C.c_float]
+    L.b2v_grid_get_voxels_in_frustum.restype = i64
+    L.b2v_grid_get_voxels_in_frustum.argtypes = [vp, vp, i32, i32, vp, C.c_float, C.c_float, i32]
+    L.b2v_grid_get_voxels_in_bb.restype = i64
+    L.b2v_grid_get_voxels_in_bb.argtypes = [vp, vp, i32]
     L.b2v_grid_dump_blocks.restype = i64
     L.b2v_grid_dump_blocks.argtypes = [vp, vp, vp, vp, vp, vp]
     _lib = L

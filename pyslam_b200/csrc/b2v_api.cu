@@ -1144,6 +1144,132 @@ extern "C" int b2v_grid_remove_low_count_voxels(b2v_grid *g, int32_t min_count) 
     return B2V_OK;
 }
 
+// frustum -> GridQuery: AABB of the 8 frustum corners (camera_frustrum.cpp:209-260) -> voxel key bounds in
+// double (voxel_block_grid.hpp:1340-1345: get_voxel_key_inv<double,double> with the float inv_voxel_size)
+static void fill_key_bounds(GridQuery *q, float inv_vs) {
+    for (int a = 0; a < 3; ++a) {
+        q->min_key[a] = static_cast<int32_t>(std::floor(q->bb[a] * static_cast<double>(inv_vs)));
+        q->max_key[a] = static_cast<int32_t>(std::floor(q->bb[3 + a] * static_cast<double>(inv_vs)));
+    }
+}
+
+static void fill_frustum_query(GridQuery *q, const float K[4], int W, int H, const double Tcw[16],
+                               float depth_max, float depth_min, int min_count, float inv_vs) {
+    std::memset(q, 0, sizeof(*q));
+    q->mode = 1;
+    q->min_count = min_count;
+    q->fx = K[0];
+    q->fy = K[1];
+    q->cx = K[2];
+    q->cy = K[3];
+    q->depth_min = depth_min;
+    q->depth_max = depth_max;
+    q->W = W;
+    q->H = H;
+    double Rwc[9], twc[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            q->R[3 * i + j] = Tcw[4 * i + j];
+            Rwc[3 * i + j] = Tcw[4 * j + i];
+        }
+        q->t[i] = Tcw[4 * i + 3];
+    }
+    for (int i = 0; i < 3; ++i) twc[i] = -(Rwc[3 * i] * q->t[0] + Rwc[3 * i + 1] * q->t[1] + Rwc[3 * i + 2] * q->t[2]);
+    for (int a = 0; a < 3; ++a) {
+        q->bb[a] = 1e300;
+        q->bb[3 + a] = -1e300;
+    }
+    const double us[4] = {0.0, static_cast<double>(W), static_cast<double>(W), 0.0};
+    const double vs[4] = {0.0, 0.0, static_cast<double>(H), static_cast<double>(H)};
+    for (int c = 0; c < 4; ++c) {
+        const double xn = (us[c] - static_cast<double>(q->cx)) / static_cast<double>(q->fx);
+        const double yn = (vs[c] - static_cast<double>(q->cy)) / static_cast<double>(q->fy);
+        for (int far = 0; far < 2; ++far) {
+            const double d = far ? static_cast<double>(depth_max) : static_cast<double>(depth_min);
+            const double pc[3] = {xn * d, yn * d, d};
+            for (int a = 0; a < 3; ++a) {
+                const double w = Rwc[3 * a] * pc[0] + Rwc[3 * a + 1] * pc[1] + Rwc[3 * a + 2] * pc[2] + twc[a];
+                q->bb[a] = std::min(q->bb[a], w);
+                q->bb[3 + a] = std::max(q->bb[3 + a], w);
+            }
+        }
+    }
+    fill_key_bounds(q, inv_vs);
+}
+
+static int64_t grid_run_query(b2v_grid *g, const GridQuery &q) {
+    if (grid_read_counters(g) == B2V_ERR_CUDA) return -1;
+    const uint32_t nb = grid_block_count(g);
+    if (grid_ensure_scan(g, nb) != B2V_OK) return -1;
+    if (launch_grid_query_count(g->meta, nb, q, g->d_sums, g->d_offs, g->d_total, g->stream) != cudaSuccess) return -1;
+    uint32_t total = 0;
+    if (cudaMemcpyAsync(&total, g->d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(g->stream) != cudaSuccess) return -1;
+    if (static_cast<size_t>(total) > g->out_cap) {
+        if (regrow(&g->d_out_pts, static_cast<size_t>(total) * 3) != cudaSuccess) return -1;
+        if (regrow(&g->d_out_cols, static_cast<size_t>(total) * 3) != cudaSuccess) return -1;
+        g->out_cap = total;
+    }
+    if (launch_grid_query_emit(g->meta, nb, q, g->d_offs, g->d_out_pts, g->d_out_cols, g->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(g->stream) != cudaSuccess) return -1;
+    g->last_n = total;
+    return total;
+}
+
+extern "C" int64_t b2v_grid_get_voxels_in_frustum(b2v_grid *g, const float K[4], int32_t width, int32_t height,
+                                                  const double Tcw[16], float depth_max, float depth_min,
+                                                  int32_t min_count) {
+    if (!g || !K || !Tcw || width <= 0 || height <= 0) return -1;
+    GridQuery q;
+    fill_frustum_query(&q, K, width, height, Tcw, depth_max, depth_min, min_count, g->inv_voxel_size);
+    return grid_run_query(g, q);
+}
+
+extern "C" int64_t b2v_grid_get_voxels_in_bb(b2v_grid *g, const double bbox[6], int32_t min_count) {
+    if (!g || !bbox) return -1;
+    GridQuery q;
+    std::memset(&q, 0, sizeof(q));
+    q.mode = 0;
+    q.min_count = min_count;
+    for (int a = 0; a < 6; ++a) q.bb[a] = bbox[a];
+    fill_key_bounds(&q, g->inv_voxel_size);
+    return grid_run_query(g, q);
+}
+
+extern "C" int b2v_grid_carve(b2v_grid *g, const float K[4], int32_t width, int32_t height, const double Tcw[16],
+                              float depth_max, float depth_min, const float *depth, float depth_threshold) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    if (!K || !Tcw || !depth || width <= 0 || height <= 0) {
+        g->err = "b2v_grid_carve: bad arguments";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    const int rc = grid_read_counters(g);
+    if (rc == B2V_ERR_CUDA) return rc;
+    const size_t pixels = static_cast<size_t>(width) * height;
+    const float *d_depth = depth;
+    float *tmp = nullptr;
+    if (!is_device_pointer(depth)) {
+        B2V_CUDA(g, cudaMalloc(&tmp, pixels * sizeof(float)));
+        cudaError_t e = cudaMemcpyAsync(tmp, depth, pixels * sizeof(float), cudaMemcpyHostToDevice, g->stream);
+        if (e != cudaSuccess) {
+            cudaFree(tmp);
+            g->err = cudaGetErrorString(e);
+            return B2V_ERR_CUDA;
+        }
+        d_depth = tmp;
+    }
+    GridQuery q;
+    fill_frustum_query(&q, K, width, height, Tcw, depth_max, depth_min, 1, g->inv_voxel_size);
+    cudaError_t e = launch_grid_carve(g->meta, grid_block_count(g), q, d_depth, depth_threshold, g->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) {
+        g->err = cudaGetErrorString(e);
+        return B2V_ERR_CUDA;
+    }
+    return B2V_OK;
+}
+
 extern "C" int64_t b2v_grid_dump_blocks(b2v_grid *g, int32_t *keys, uint64_t *hashes, int32_t *count,
                                         float *pos_sum, float *col_sum) {
     if (!g) return -1;

@@ -131,6 +131,144 @@ grid_remove_low_count_kernel(const GridMeta G, const int min_count) {
     }
 }
 
+// ---- spatial queries and carving ---------------------------------------------------------------
+struct ImagePoint {
+    float u, v, depth;
+};
+
+// CameraFrustrum::contains (camera_frustrum.cpp:174-196): world point -> (inside?, pixel, depth)
+__device__ __forceinline__ bool frustum_contains(const GridQuery &Q, const float p[3], ImagePoint *ip) {
+    const double x = p[0], y = p[1], z = p[2];
+    double pc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        pc[a] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(Q.R[3 * a], x), __dmul_rn(Q.R[3 * a + 1], y)),
+                                    __dmul_rn(Q.R[3 * a + 2], z)),
+                          Q.t[a]);
+    const float depth = static_cast<float>(pc[2]);
+    if (!(depth >= Q.depth_min && depth <= Q.depth_max)) return false;
+    const float u = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(Q.fx), __ddiv_rn(pc[0], pc[2])),
+                                                 static_cast<double>(Q.cx)));
+    const float v = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(Q.fy), __ddiv_rn(pc[1], pc[2])),
+                                                 static_cast<double>(Q.cy)));
+    ip->u = u;
+    ip->v = v;
+    ip->depth = depth;
+    return u >= 0.0f && u < static_cast<float>(Q.W) && v >= 0.0f && v < static_cast<float>(Q.H);
+}
+
+// the reference's per-voxel filter chain; returns true and the mean position if the voxel qualifies
+__device__ __forceinline__ bool query_voxel(const GridQuery &Q, const uint32_t *blk, const int4 key, int t,
+                                            float pos[3], ImagePoint *ip) {
+    const int c = reinterpret_cast<const int *>(blk)[t];
+    if (c < Q.min_count) return false;
+    const int vk[3] = {key.x * kB + (t & 7), key.y * kB + ((t >> 3) & 7), key.z * kB + (t >> 6)};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (vk[a] < Q.min_key[a] || vk[a] > Q.max_key[a]) return false;
+    const float *fb = reinterpret_cast<const float *>(blk);
+    const float fc = static_cast<float>(c);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) pos[a] = __fdiv_rn(fb[(1 + a) * kVox + t], fc);  // voxel_data.h:58-69
+    if (Q.mode == 0) {
+        const double x = pos[0], y = pos[1], z = pos[2];  // BoundingBox3D::contains (bounding_boxes_3d.cpp:207-210)
+        return x >= Q.bb[0] && x <= Q.bb[3] && y >= Q.bb[1] && y <= Q.bb[4] && z >= Q.bb[2] && z <= Q.bb[5];
+    }
+    return frustum_contains(Q, pos, ip);
+}
+
+__device__ __forceinline__ bool block_in_range(const GridQuery &Q, const int4 key) {
+    const int k[3] = {key.x, key.y, key.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (k[a] < block_coord(Q.min_key[a]) || k[a] > block_coord(Q.max_key[a])) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(kVox)
+grid_query_count_kernel(const GridMeta G, const GridQuery Q, uint32_t *__restrict__ sums) {
+    __shared__ uint32_t s_warp[16];
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    const int4 key = G.block_keys[b];
+    float pos[3];
+    ImagePoint ip;
+    const bool keep = block_in_range(Q, key) &&
+                      query_voxel(Q, G.pool + static_cast<size_t>(b) * kGridBlockWords, key, t, pos, &ip);
+    const uint32_t x = __reduce_add_sync(0xffffffffu, keep ? 1u : 0u);
+    if ((t & 31) == 0) s_warp[t >> 5] = x;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t s = 0;
+        for (int k = 0; k < 16; ++k) s += s_warp[k];
+        sums[b] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kVox)
+grid_query_emit_kernel(const GridMeta G, const GridQuery Q, const uint32_t *__restrict__ offs,
+                       float *__restrict__ out_pts, float *__restrict__ out_cols) {
+    __shared__ uint32_t s_warp[16];
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    const int4 key = G.block_keys[b];
+    const uint32_t *blk = G.pool + static_cast<size_t>(b) * kGridBlockWords;
+    float pos[3];
+    ImagePoint ip;
+    const bool keep = block_in_range(Q, key) && query_voxel(Q, blk, key, t, pos, &ip);
+    const uint32_t o = offs[b] + block_excl_scan_512(keep ? 1u : 0u, s_warp);
+    if (!keep) return;
+    const float *fb = reinterpret_cast<const float *>(blk);
+    const float fc = static_cast<float>(reinterpret_cast<const int *>(blk)[t]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        out_pts[3 * static_cast<size_t>(o) + k] = pos[k];
+        out_cols[3 * static_cast<size_t>(o) + k] = __fdiv_rn(fb[(4 + k) * kVox + t], fc);
+    }
+}
+
+// carve (voxel_grid_carving.h:47-80): reset voxels that lie in front of the observed depth by more
+// than the threshold.  The depth image is indexed with TRUNCATED pixel coordinates, like at<float>(v, u).
+__global__ void __launch_bounds__(kVox)
+grid_carve_kernel(const GridMeta G, const GridQuery Q, const float *__restrict__ depth, const float thr) {
+    const uint32_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    const int4 key = G.block_keys[b];
+    if (!block_in_range(Q, key)) return;
+    uint32_t *blk = G.pool + static_cast<size_t>(b) * kGridBlockWords;
+    float pos[3];
+    ImagePoint ip;
+    if (!query_voxel(Q, blk, key, t, pos, &ip)) return;
+    const float image_depth = depth[static_cast<size_t>(static_cast<int>(ip.v)) * Q.W + static_cast<int>(ip.u)];
+    if (image_depth <= 0.0f || !isfinite(image_depth)) return;
+    if (ip.depth < image_depth - thr) {
+#pragma unroll
+        for (int k = 0; k < kGridPlanes; ++k) blk[k * kVox + t] = 0u;
+    }
+}
+
+cudaError_t launch_grid_query_count(const GridMeta &meta, uint32_t n_blocks, const GridQuery &q,
+                                    uint32_t *sums, uint32_t *offs, uint32_t *total, cudaStream_t stream) {
+    if (n_blocks == 0) return cudaMemsetAsync(total, 0, sizeof(uint32_t), stream);
+    grid_query_count_kernel<<<n_blocks, kVox, 0, stream>>>(meta, q, sums);
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(sums, offs, total, n_blocks);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_query_emit(const GridMeta &meta, uint32_t n_blocks, const GridQuery &q,
+                                   const uint32_t *offs, float *out_pts, float *out_cols, cudaStream_t stream) {
+    if (n_blocks == 0) return cudaSuccess;
+    grid_query_emit_kernel<<<n_blocks, kVox, 0, stream>>>(meta, q, offs, out_pts, out_cols);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_carve(const GridMeta &meta, uint32_t n_blocks, const GridQuery &q, const float *depth,
+                              float depth_threshold, cudaStream_t stream) {
+    if (n_blocks == 0) return cudaSuccess;
+    grid_carve_kernel<<<n_blocks, kVox, 0, stream>>>(meta, q, depth, depth_threshold);
+    return cudaGetLastError();
+}
+
 // ---- launchers -------------------------------------------------------------------------------
 cudaError_t launch_grid_integrate(const float *pts, const float *cols, int64_t n, float inv_vs,
                                   const HashTable &table, const GridMeta &meta, cudaStream_t stream) {

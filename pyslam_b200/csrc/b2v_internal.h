@@ -174,4 +174,23 @@ cudaError_t launch_grid_emit(const GridMeta &meta, uint32_t n_blocks, int min_co
 cudaError_t launch_grid_remove_low_count(const GridMeta &meta, uint32_t n_blocks, int min_count,
                                          cudaStream_t stream);
 
+// Spatial queries / carving over the existing blocks (voxel_block_grid.hpp:822-1195, 1334-1540;
+// voxel_grid_carving.h:47-80; camera_frustrum.cpp:174-196).  mode 0: axis-aligned box, mode 1: camera
+// frustum.  A voxel qualifies if count >= min_count, its key lies in [min_key, max_key] and its mean
+// position passes the fine test (double arithmetic like the reference).
+struct GridQuery {
+    int32_t mode, min_count;
+    int32_t min_key[3], max_key[3];
+    double bb[6];                 // min xyz, max xyz
+    double R[9], t[3];            // world -> camera
+    float fx, fy, cx, cy, depth_min, depth_max;
+    int32_t W, H;
+};
+cudaError_t launch_grid_query_count(const GridMeta &meta, uint32_t n_blocks, const GridQuery &q,
+                                    uint32_t *sums, uint32_t *offs, uint32_t *total, cudaStream_t stream);
+cudaError_t launch_grid_query_emit(const GridMeta &meta, uint32_t n_blocks, const GridQuery &q,
+                                   const uint32_t *offs, float *out_pts, float *out_cols, cudaStream_t stream);
+cudaError_t launch_grid_carve(const GridMeta &meta, uint32_t n_blocks, const GridQuery &q, const float *depth,
+                              float depth_threshold, cudaStream_t stream);
+
 }  // namespace b2v

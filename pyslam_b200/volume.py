@@ -286,6 +286,39 @@ class B200TsdfVolume:
         return PointCloud(P.astype(np.float64), Cc.astype(np.float64))
 
 
+class CameraFrustrum:
+    """Mirror of `volumetric.CameraFrustrum(fx, fy, cx, cy, width, height, T_cw, depth_max, depth_min)`
+    (cpp/volumetric/camera_frustrum.h:36-48): the arguments of carve / frustum queries."""
+
+    def __init__(self, fx, fy, cx, cy, width, height, T_cw=None, depth_max=10.0, depth_min=1e-2):
+        self.fx, self.fy, self.cx, self.cy = float(fx), float(fy), float(cx), float(cy)
+        self.width, self.height = int(width), int(height)
+        self.depth_max, self.depth_min = float(depth_max), float(depth_min)
+        self.T_cw = np.eye(4) if T_cw is None else np.asarray(T_cw, np.float64).reshape(4, 4)
+
+    def set_T_cw(self, T_cw):
+        self.T_cw = np.asarray(T_cw, np.float64).reshape(4, 4)
+
+    def get_width(self):
+        return self.width
+
+    def get_height(self):
+        return self.height
+
+    def _args(self):
+        K = np.array([self.fx, self.fy, self.cx, self.cy], np.float32)
+        T = np.ascontiguousarray(self.T_cw, np.float64).reshape(16)
+        return K, T
+
+
+class BoundingBox3D:
+    """Mirror of `volumetric.BoundingBox3D(min_x, min_y, min_z, max_x, max_y, max_z)`
+    (cpp/volumetric/bounding_boxes_3d.h:40-80)."""
+
+    def __init__(self, min_x, min_y, min_z, max_x, max_y, max_z):
+        self.bounds = np.array([min_x, min_y, min_z, max_x, max_y, max_z], np.float64)
+
+
 class VoxelGridData:
     """`VoxelGridDataT` (cpp/volumetric/voxel_grid_data.h:36-50): points / colors SoA."""
 
@@ -419,12 +452,35 @@ class VoxelBlockGrid:
             raise RuntimeError(f"b2v_grid_dump_blocks returned {n}, expected {nb}")
         return dict(keys=keys, hashes=hashes, count=count, pos_sum=pos, col_sum=col)
 
-    # duck-type B surface that belongs to SURVEY.md §8(f) "next" rows
-    def carve(self, *a, **k):
-        raise NotImplementedError("carve is a SURVEY.md §8(f) 'next' row (rank 3)")
+    # ---- spatial queries and carving ----
+    def _collect(self, n):
+        if n < 0:
+            raise RuntimeError(self._L.b2v_grid_last_error(self._h).decode())
+        P = np.zeros((n, 3), np.float32)
+        Cc = np.zeros((n, 3), np.float32)
+        self._check(self._L.b2v_grid_copy_voxels(self._h, P.ctypes.data, Cc.ctypes.data), "b2v_grid_copy_voxels")
+        return VoxelGridData(P, Cc)
 
-    def get_voxels_in_bb(self, *a, **k):
-        raise NotImplementedError("bounding-box queries are a SURVEY.md §8(f) 'next' row (rank 3)")
+    def carve(self, camera_frustrum, depth_image, depth_threshold: float = 1e-2):
+        """carve(camera_frustrum, depth_image, depth_threshold) (voxel_block_grid.hpp:616-622): reset voxels
+        in the frustum that lie in front of the observed depth by more than the threshold.  Like the
+        reference (voxel_grid_carving.h:51-58) an empty or wrongly sized image is a soft failure."""
+        d = np.asarray(depth_image)
+        if d.size == 0 or d.shape != (camera_frustrum.height, camera_frustrum.width):
+            print("volumetric::carve: depth image is empty or has the wrong size")
+            return
+        d = np.ascontiguousarray(d, dtype=np.float32)
+        K, T = camera_frustrum._args()
+        self._check(self._L.b2v_grid_carve(self._h, K.ctypes.data, camera_frustrum.width, camera_frustrum.height,
+                                           T.ctypes.data, camera_frustrum.depth_max, camera_frustrum.depth_min,
+                                           d.ctypes.data, float(depth_threshold)), "b2v_grid_carve")
 
-    def get_voxels_in_camera_frustrum(self, *a, **k):
-        raise NotImplementedError("frustum queries are a SURVEY.md §8(f) 'next' row (rank 3)")
+    def get_voxels_in_camera_frustrum(self, camera_frustrum, min_count: int = 1, min_confidence: float = 0.0):
+        K, T = camera_frustrum._args()
+        return self._collect(self._L.b2v_grid_get_voxels_in_frustum(
+            self._h, K.ctypes.data, camera_frustrum.width, camera_frustrum.height, T.ctypes.data,
+            camera_frustrum.depth_max, camera_frustrum.depth_min, int(min_count)))
+
+    def get_voxels_in_bb(self, bbox, min_count: int = 1, min_confidence: float = 0.0):
+        bb = np.ascontiguousarray(getattr(bbox, "bounds", bbox), np.float64).reshape(6)
+        return self._collect(self._L.b2v_grid_get_voxels_in_bb(self._h, bb.ctypes.data, int(min_count)))

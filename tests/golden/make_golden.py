@@ -75,6 +75,21 @@ def main():
         pts_all.append(p)
         col_all.append(col)
         counts.append(len(p))
+    # spatial queries + carving with the 4th frame's camera
+    d3, _, T3 = frames[3]
+    Kf = np.array(cfg.K, np.float32)
+    fp, fc = g.get_voxels_in_frustum(Kf, cfg.width, cfg.height, T3, min_count=1, depth_max=3.0, depth_min=0.05)
+    allp = np.concatenate(pts_all)
+    bbox = np.concatenate([np.quantile(allp, 0.2, axis=0), np.quantile(allp, 0.75, axis=0)])
+    bp, bc = g.get_voxels_in_bb(bbox, min_count=1)
+    g2 = oracle.RefGrid(cfg.voxel_size, 8)
+    for p_, c_ in zip(pts_all, col_all):
+        g2.integrate(p_, c_)
+    # carve against a depth image in which the scene has receded by 0.3 m (valid pixels only): every
+    # stored voxel seen by this camera now floats in front of the observed surface
+    d3 = np.where(d3 > 0, d3 + np.float32(0.3), d3).astype(np.float32)
+    g2.carve(Kf, cfg.width, cfg.height, T3, d3, depth_threshold=0.05, depth_max=3.0, depth_min=0.05)
+    carved = sort_dump(g2.dump_blocks())
     rd = sort_dump(g.dump_blocks())
     vp, vc = g.get_voxels(min_count=2)
     order = np.lexsort((vp[:, 2], vp[:, 1], vp[:, 0]))
@@ -82,7 +97,13 @@ def main():
                         points=np.concatenate(pts_all), colors=np.concatenate(col_all),
                         frame_counts=np.array(counts), keys=rd["keys"], hashes=rd["hashes"],
                         count=rd["count"], pos_sum=rd["pos_sum"], col_sum=rd["col_sum"],
-                        voxels_min2_points=vp[order], voxels_min2_colors=vc[order])
+                        voxels_min2_points=vp[order], voxels_min2_colors=vc[order],
+                        query_K=Kf, query_Tcw=T3, query_depth=d3, query_bbox=bbox,
+                        frustum_points=fp[np.lexsort((fp[:, 2], fp[:, 1], fp[:, 0]))],
+                        bbox_points=bp[np.lexsort((bp[:, 2], bp[:, 1], bp[:, 0]))],
+                        carved_count=carved["count"])
+    print("queries:", len(fp), "in frustum,", len(bp), "in bbox,",
+          int((rd["count"] > 0).sum() - (carved["count"] > 0).sum()), "voxels carved")
     print("refgrid_T0:", len(rd["keys"]), "blocks,", int((rd["count"] > 0).sum()), "voxels,",
           len(vp), "voxels with count >= 2")
 

@@ -107,3 +107,39 @@ def test_argument_checks_and_clear():
     assert grid.empty() and grid.size() == 0 and len(grid.get_points()) == 0
     with pytest.raises(RuntimeError):
         VoxelBlockGrid(0.05, 4)
+
+
+def _sorted_pts(p):
+    return p[np.lexsort((p[:, 2], p[:, 1], p[:, 0]))]
+
+
+def test_spatial_queries_and_carve_match_reference_golden():
+    """get_voxels_in_camera_frustrum / get_voxels_in_bb / carve against the UNMODIFIED reference's
+    outputs (tests/golden/refgrid_T0.npz).  The selected SETS must match (a voxel whose projection
+    lands within float rounding of a bound may flip: at most 0.2 % of the voxels), positions to 2e-5."""
+    from pyslam_b200 import BoundingBox3D, CameraFrustrum
+    g = np.load(os.path.join(GOLDEN, "refgrid_T0.npz"))
+    grid = VoxelBlockGrid(float(g["voxel_size"]), 8, capacity_blocks=4096)
+    _feed(grid, g)
+    K = g["query_K"]
+    H, W = g["query_depth"].shape
+    fr = CameraFrustrum(K[0], K[1], K[2], K[3], W, H, g["query_Tcw"], depth_max=3.0, depth_min=0.05)
+    out = grid.get_voxels_in_camera_frustrum(fr, min_count=1)
+    ref = g["frustum_points"]
+    assert abs(len(out.points) - len(ref)) <= max(2, 0.002 * len(ref)) and len(ref) > 1000
+    if len(out.points) == len(ref):
+        assert np.allclose(_sorted_pts(out.points), ref, rtol=2e-5, atol=1e-6)
+    bb = grid.get_voxels_in_bb(BoundingBox3D(*g["query_bbox"]), min_count=1)
+    refb = g["bbox_points"]
+    assert abs(len(bb.points) - len(refb)) <= max(2, 0.002 * len(refb)) and len(refb) > 100
+    if len(bb.points) == len(refb):
+        assert np.allclose(_sorted_pts(bb.points), refb, rtol=2e-5, atol=1e-6)
+    grid.carve(fr, g["query_depth"], depth_threshold=0.05)
+    d = sort_dump(grid.dump_blocks())
+    ref_c = g["carved_count"]
+    assert (g["count"] > 0).sum() - (ref_c > 0).sum() > 100          # the carve removed something
+    mism = int(((d["count"] > 0) != (ref_c > 0)).sum())
+    assert mism <= max(2, 0.002 * int((ref_c > 0).sum())), mism
+    # a wrongly sized depth image is a soft failure (voxel_grid_carving.h:51-58): nothing changes
+    grid.carve(fr, g["query_depth"][:10], depth_threshold=0.05)
+    assert np.array_equal(sort_dump(grid.dump_blocks())["count"], d["count"])
