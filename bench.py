@@ -384,7 +384,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "latest.json")))
-        traffic = prof.get("integrate_kernel", {}).get("dram_bytes_per_launch")
+        traffic = prof.get("integrate_group_kernel", {}).get("dram_bytes_per_launch")
     except Exception:
         pass
 
