@@ -120,6 +120,14 @@ const char *b2v_grid_last_error(const b2v_grid *g);
 /* integrate(points f32[n*3], colors f32[n*3] | NULL)  (volumetric_grid_module.h:131-467 ->
  * voxel_block_grid.hpp:115-136) */
 int b2v_grid_integrate(b2v_grid *g, const float *points, const float *colors, int64_t n_points);
+/* Fused front-end of VolumetricIntegratorVoxelGrid: depth2pointcloud (pyslam/utilities/depth.py:45-85) +
+ * world transform + integrate (pyslam/dense/volumetric_integrator_voxel_grid.py:247-300) in one call, no
+ * point cloud materialised.  depth float32 [H*W], color uint8 RGB [H*W*3] (host or device), K = {fx,fy,cx,cy}
+ * float64, Twc float64[16] row-major camera->world (the reference's inv_T(pose)), valid pixels are
+ * min_depth < d < max_depth.  Same keys / counts as integrating the front-end's float32 points. */
+int b2v_grid_integrate_rgbd(b2v_grid *g, const float *depth, const uint8_t *color, int32_t height,
+                            int32_t width, const double K[4], const double Twc[16], float max_depth,
+                            float min_depth);
 int b2v_grid_synchronize(b2v_grid *g);
 int64_t b2v_grid_num_blocks(b2v_grid *g);              /* num_blocks() */
 int64_t b2v_grid_size(b2v_grid *g);                    /* size(): voxels with count > 0 */

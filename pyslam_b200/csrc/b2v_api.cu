@@ -237,9 +237,9 @@ extern "C" int b2v_destroy(b2v_volume *v) {
         if (v->ev_alloc_done[r]) cudaEventDestroy(v->ev_alloc_done[r]);
         if (v->ev_int_done[r]) cudaEventDestroy(v->ev_int_done[r]);
     }
+    cudaFree(v->d_depth[0]);  // slots 1.. point into the same two allocations
+    cudaFree(v->d_color[0]);
     for (int s = 0; s < kStage; ++s) {
-        cudaFree(v->d_depth[s]);
-        cudaFree(v->d_color[s]);
         cudaFree(v->d_texel[s]);
         if (v->ev_ready[s]) cudaEventDestroy(v->ev_ready[s]);
         if (v->ev_free[s]) cudaEventDestroy(v->ev_free[s]);
@@ -324,15 +324,25 @@ static int ensure_staging(b2v_volume *v, size_t pixels) {
     B2V_CUDA(v, cudaStreamSynchronize(v->copy));
     B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
     if (v->last_stream) B2V_CUDA(v, cudaStreamSynchronize(v->last_stream));
+    // raw staging slots are carved out of two contiguous allocations, so the frames of a group (which
+    // are contiguous in the caller's arrays) upload with ONE copy per image type
+    cudaFree(v->d_depth[0]);
+    cudaFree(v->d_color[0]);
     for (int s = 0; s < kStage; ++s) {
-        cudaFree(v->d_depth[s]);
-        cudaFree(v->d_color[s]);
         cudaFree(v->d_texel[s]);
         v->d_depth[s] = nullptr;
         v->d_color[s] = nullptr;
         v->d_texel[s] = nullptr;
-        B2V_CUDA(v, cudaMalloc(&v->d_depth[s], pixels * sizeof(float)));
-        B2V_CUDA(v, cudaMalloc(&v->d_color[s], pixels * 3));
+    }
+    float *dbase = nullptr;
+    uint8_t *cbase = nullptr;
+    B2V_CUDA(v, cudaMalloc(&dbase, pixels * sizeof(float) * kStage));
+    v->d_depth[0] = dbase;
+    B2V_CUDA(v, cudaMalloc(&cbase, pixels * 3 * kStage));
+    v->d_color[0] = cbase;
+    for (int s = 0; s < kStage; ++s) {
+        v->d_depth[s] = dbase + pixels * s;
+        v->d_color[s] = cbase + pixels * 3 * s;
         B2V_CUDA(v, cudaMalloc(&v->d_texel[s], pixels * sizeof(float4)));
     }
     cudaFree(v->d_lambda);
@@ -555,16 +565,22 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         args.count = count;
         aargs.count = count;
         aargs.use_tma = 1;
-        if (staged)  // the raw staging slots of this buffer were consumed by the allocate launch of group id - 2
+        if (staged) {
+            // the raw staging slots of this buffer were consumed by the allocate launch of group id - 2;
+            // the group's frames are contiguous on both sides: one H2D copy per image type
             B2V_CUDA(v, cudaStreamWaitEvent(v->copy, v->ev_galloc[buf], 0));
+            const int s0 = buf * kMaxGroup;
+            B2V_CUDA(v, cudaMemcpyAsync(v->d_depth[s0], depth + pixels * g0, pixels * sizeof(float) * count,
+                                        cudaMemcpyHostToDevice, v->copy));
+            B2V_CUDA(v, cudaMemcpyAsync(v->d_color[s0], color + pixels * 3 * g0, pixels * 3 * count,
+                                        cudaMemcpyHostToDevice, v->copy));
+        }
         for (int k = 0; k < count; ++k) {
             const size_t f = static_cast<size_t>(g0 + k);
             const float *d_depth = depth + pixels * f;
             const uint8_t *d_color = color + pixels * 3 * f;
             if (staged) {
                 const int s = buf * kMaxGroup + k;
-                B2V_CUDA(v, cudaMemcpyAsync(v->d_depth[s], d_depth, pixels * sizeof(float), cudaMemcpyHostToDevice, v->copy));
-                B2V_CUDA(v, cudaMemcpyAsync(v->d_color[s], d_color, pixels * 3, cudaMemcpyHostToDevice, v->copy));
                 d_depth = v->d_depth[s];
                 d_color = v->d_color[s];
             }
@@ -1070,6 +1086,57 @@ extern "C" int b2v_grid_integrate(b2v_grid *g, const float *points, const float 
         }
     }
     B2V_CUDA(g, launch_grid_integrate(d_p, d_c, n_points, g->inv_voxel_size, g->table, g->meta, g->stream));
+    return B2V_OK;
+}
+
+extern "C" int b2v_grid_integrate_rgbd(b2v_grid *g, const float *depth, const uint8_t *color, int32_t height,
+                                       int32_t width, const double K[4], const double Twc[16], float max_depth,
+                                       float min_depth) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    if (!depth || !color || !K || !Twc || height <= 0 || width <= 0) {
+        g->err = "b2v_grid_integrate_rgbd: bad arguments";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    B2V_CUDA(g, cudaSetDevice(g->device));
+    const size_t pixels = static_cast<size_t>(height) * width;
+    const float *d_depth = depth;
+    const uint8_t *d_color = color;
+    float *tmp_d = nullptr;
+    uint8_t *tmp_c = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!is_device_pointer(depth)) {
+        e = cudaMalloc(&tmp_d, pixels * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tmp_d, depth, pixels * sizeof(float), cudaMemcpyHostToDevice, g->stream);
+        d_depth = tmp_d;
+    }
+    if (e == cudaSuccess && !is_device_pointer(color)) {
+        e = cudaMalloc(&tmp_c, pixels * 3);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tmp_c, color, pixels * 3, cudaMemcpyHostToDevice, g->stream);
+        d_color = tmp_c;
+    }
+    if (e == cudaSuccess) {
+        RgbdParams P;
+        P.fx_inv = 1.0 / K[0];
+        P.fy_inv = 1.0 / K[1];
+        P.cx = K[2];
+        P.cy = K[3];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) P.R[3 * i + j] = Twc[4 * i + j];
+            P.t[i] = Twc[4 * i + 3];
+        }
+        P.min_depth = min_depth;
+        P.max_depth = max_depth;
+        P.H = height;
+        P.W = width;
+        e = launch_grid_integrate_rgbd(P, d_depth, d_color, g->inv_voxel_size, g->table, g->meta, g->stream);
+    }
+    if (e == cudaSuccess && (tmp_d || tmp_c)) e = cudaStreamSynchronize(g->stream);
+    cudaFree(tmp_d);
+    cudaFree(tmp_c);
+    if (e != cudaSuccess) {
+        g->err = std::string("b2v_grid_integrate_rgbd: ") + cudaGetErrorString(e);
+        return B2V_ERR_CUDA;
+    }
     return B2V_OK;
 }
 

@@ -84,6 +84,100 @@ grid_accumulate_kernel(const float *__restrict__ pts, const float *__restrict__ 
     atomicAdd(reinterpret_cast<int *>(blk) + l, 1);
 }
 
+// ---- fused RGBD front-end: back-project + insert / accumulate ---------------------------------
+__device__ __forceinline__ bool rgbd_point(const RgbdParams &P, const float *__restrict__ depth, int64_t i,
+                                           float pt[3]) {
+    const float d = depth[i];
+    if (!(d > P.min_depth && d < P.max_depth)) return false;  // depth.py:62
+    const int row = static_cast<int>(i / P.W), col = static_cast<int>(i % P.W);
+    const double z = static_cast<double>(d);
+    const double x = __dmul_rn(__dmul_rn(__dsub_rn(static_cast<double>(col), P.cx), z), P.fx_inv);  // depth.py:72
+    const double y = __dmul_rn(__dmul_rn(__dsub_rn(static_cast<double>(row), P.cy), z), P.fy_inv);  // depth.py:73
+#pragma unroll
+    for (int a = 0; a < 3; ++a)  // voxel_grid.py:262-265, then ascontiguousarray(float32) :281
+        pt[a] = __double2float_rn(__dadd_rn(
+            __dadd_rn(__dadd_rn(__dmul_rn(x, P.R[3 * a]), __dmul_rn(y, P.R[3 * a + 1])), __dmul_rn(z, P.R[3 * a + 2])),
+            P.t[a]));
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+grid_rgbd_insert_kernel(const RgbdParams P, const float *__restrict__ depth, const float inv_vs,
+                        const HashTable T, const GridMeta G) {
+    const int64_t n = static_cast<int64_t>(P.H) * P.W;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    float pt[3];
+    const bool have = i < n && rgbd_point(P, depth, i, pt);
+    int bx = 0, by = 0, bz = 0;
+    if (have) {
+        bx = block_coord(voxel_coord(pt[0], inv_vs));
+        by = block_coord(voxel_coord(pt[1], inv_vs));
+        bz = block_coord(voxel_coord(pt[2], inv_vs));
+    }
+    const unsigned long long pk = have ? (static_cast<unsigned long long>(slot_hash(bx, by, bz)) << 32 |
+                                          static_cast<uint32_t>(bx * 73856093 ^ by * 19349663 ^ bz * 83492791))
+                                       : ((1ull << 63) | static_cast<unsigned long long>(lane) << 40 | 0xFFFFFFull);
+    const unsigned grp = __match_any_sync(0xffffffffu, pk);
+    const int leader = __ffs(grp) - 1;
+    const int lbx = __shfl_sync(0xffffffffu, bx, leader), lby = __shfl_sync(0xffffffffu, by, leader),
+              lbz = __shfl_sync(0xffffffffu, bz, leader);
+    if (!have) return;
+    if (leader != lane && lbx == bx && lby == by && lbz == bz) return;
+    bool is_new;
+    const uint32_t slot = table_insert(T, bx, by, bz, &is_new);
+    if (slot == kEmpty) {
+        atomicOr(G.counters + kCtrError, 2u);
+        return;
+    }
+    if (is_new) {
+        const uint32_t idx = atomicAdd(G.counters + kCtrPool, 1u);
+        uint32_t *w = reinterpret_cast<uint32_t *>(T.entries + slot) + 3;
+        if (idx < G.capacity) {
+            G.block_keys[idx] = make_int4(bx, by, bz, 0);
+            *w = idx;
+        } else {
+            *w = kNoBlock;
+            atomicOr(G.counters + kCtrError, 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+grid_rgbd_accumulate_kernel(const RgbdParams P, const float *__restrict__ depth, const uint8_t *__restrict__ rgb,
+                            const float inv_vs, const HashTable T, const GridMeta G) {
+    const int64_t n = static_cast<int64_t>(P.H) * P.W;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    float pt[3];
+    if (i >= n || !rgbd_point(P, depth, i, pt)) return;
+    const int vx = voxel_coord(pt[0], inv_vs), vy = voxel_coord(pt[1], inv_vs), vz = voxel_coord(pt[2], inv_vs);
+    const uint32_t slot = table_find(T, block_coord(vx), block_coord(vy), block_coord(vz));
+    if (slot == kEmpty) return;
+    const uint32_t idx = T.entries[slot].w;
+    if (idx >= G.capacity) return;
+    const int l = local_coord(vx) + (local_coord(vy) << 3) + (local_coord(vz) << 6);
+    uint32_t *blk = G.pool + static_cast<size_t>(idx) * kGridBlockWords;
+    float *fb = reinterpret_cast<float *>(blk);
+    atomicAdd(fb + 1 * kVox + l, pt[0]);
+    atomicAdd(fb + 2 * kVox + l, pt[1]);
+    atomicAdd(fb + 3 * kVox + l, pt[2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)  // image[valid] / 255.0 in float64, then float32 (depth.py:76, voxel_grid.py:271-273)
+        atomicAdd(fb + (4 + c) * kVox + l, __double2float_rn(__ddiv_rn(static_cast<double>(rgb[3 * i + c]), 255.0)));
+    atomicAdd(reinterpret_cast<int *>(blk) + l, 1);
+}
+
+cudaError_t launch_grid_integrate_rgbd(const RgbdParams &p, const float *depth, const uint8_t *rgb,
+                                       float inv_vs, const HashTable &table, const GridMeta &meta,
+                                       cudaStream_t stream) {
+    const int64_t n = static_cast<int64_t>(p.H) * p.W;
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    grid_rgbd_insert_kernel<<<grid, 256, 0, stream>>>(p, depth, inv_vs, table, meta);
+    grid_rgbd_accumulate_kernel<<<grid, 256, 0, stream>>>(p, depth, rgb, inv_vs, table, meta);
+    return cudaGetLastError();
+}
+
 // ---- get_voxels: count -> scan -> emit -------------------------------------------------------
 __global__ void __launch_bounds__(kVox)
 grid_count_kernel(const GridMeta G, const int min_count, uint32_t *__restrict__ sums) {

@@ -174,6 +174,19 @@ cudaError_t launch_grid_emit(const GridMeta &meta, uint32_t n_blocks, int min_co
 cudaError_t launch_grid_remove_low_count(const GridMeta &meta, uint32_t n_blocks, int min_count,
                                          cudaStream_t stream);
 
+// Fused front-end of the point-average path: depth2pointcloud (pyslam/utilities/depth.py:45-85) + world
+// transform (pyslam/dense/volumetric_integrator_voxel_grid.py:262-281) + integrate, without materialising
+// the point cloud.  float64 arithmetic in the reference's operation order, then float32 like the front-end.
+struct RgbdParams {
+    double fx_inv, fy_inv, cx, cy;   // 1.0 / fx, 1.0 / fy (depth.py:67-68)
+    double R[9], t[3];               // Twc (camera -> world)
+    float min_depth, max_depth;
+    int32_t H, W;
+};
+cudaError_t launch_grid_integrate_rgbd(const RgbdParams &p, const float *depth, const uint8_t *rgb,
+                                       float inv_vs, const HashTable &table, const GridMeta &meta,
+                                       cudaStream_t stream);
+
 // Spatial queries / carving over the existing blocks (voxel_block_grid.hpp:822-1195, 1334-1540;
 // voxel_grid_carving.h:47-80; camera_frustrum.cpp:174-196).  mode 0: axis-aligned box, mode 1: camera
 // frustum.  A voxel qualifies if count >= min_count, its key lies in [min_key, max_key] and its mean

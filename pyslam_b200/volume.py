@@ -393,6 +393,23 @@ class VoxelBlockGrid:
                     "b2v_grid_integrate")
         self._check(self._L.b2v_grid_synchronize(self._h), "b2v_grid_synchronize")
 
+    def integrate_rgbd(self, depth, color, K, Twc, max_depth=np.inf, min_depth=0.0):
+        """Fused front-end of `VolumetricIntegratorVoxelGrid.volume_integration`
+        (volumetric_integrator_voxel_grid.py:247-300): `depth2pointcloud(depth, color, fx, fy, cx, cy,
+        max_depth)` + `Twc` transform + `integrate(points, colors)` in one GPU call.  depth float32 [H,W]
+        metres, color uint8 RGB [H,W,3], Twc = inv_T(pose) 4x4 float64."""
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        c = np.ascontiguousarray(color)
+        if d.ndim != 2 or c.shape != d.shape + (3,) or c.dtype != np.uint8:
+            raise RuntimeError("depth must be float32 [H,W] and color uint8 [H,W,3]")
+        K4 = _as_K4(K)
+        T = np.ascontiguousarray(np.asarray(Twc, np.float64).reshape(4, 4)).reshape(16)
+        mx = float(np.finfo(np.float32).max) if not np.isfinite(max_depth) else float(max_depth)
+        self._check(self._L.b2v_grid_integrate_rgbd(self._h, d.ctypes.data, c.ctypes.data, d.shape[0], d.shape[1],
+                                                    K4.ctypes.data, T.ctypes.data, mx, float(min_depth)),
+                    "b2v_grid_integrate_rgbd")
+        self._check(self._L.b2v_grid_synchronize(self._h), "b2v_grid_synchronize")
+
     def get_voxels(self, min_count: int = 1, min_confidence: float = 0.0) -> VoxelGridData:
         """get_voxels(min_count, min_confidence): min_confidence is ignored for the non-semantic grid,
         as in the reference (voxel_block_grid.hpp:750-752)."""

@@ -143,3 +143,24 @@ def test_spatial_queries_and_carve_match_reference_golden():
     # a wrongly sized depth image is a soft failure (voxel_grid_carving.h:51-58): nothing changes
     grid.carve(fr, g["query_depth"][:10], depth_threshold=0.05)
     assert np.array_equal(sort_dump(grid.dump_blocks())["count"], d["count"])
+
+
+def test_fused_rgbd_front_end_equals_reference_pipeline():
+    """integrate_rgbd(depth, color, K, Twc) == the reference front-end (depth2pointcloud + Twc transform
+    in float64 -> float32) followed by the reference grid: keys / hashes / counts bit-exact vs the golden
+    dump of the compiled reference, sums within the atomic-order tolerance."""
+    from pyslam_b200 import synthetic as S
+    g = np.load(os.path.join(GOLDEN, "refgrid_T0.npz"))
+    t = np.load(os.path.join(GOLDEN, "tsdf_T0.npz"))
+    grid = VoxelBlockGrid(float(g["voxel_size"]), 8, capacity_blocks=4096)
+    for i in range(len(g["frame_counts"])):
+        grid.integrate_rgbd(t["depth"][i], t["color"][i], t["K"], S.inv_T(t["Tcw"][i]),
+                            max_depth=float(t["depth_trunc"]))
+    d = sort_dump(grid.dump_blocks())
+    assert np.array_equal(d["keys"], g["keys"]) and np.array_equal(d["hashes"], g["hashes"])
+    assert np.array_equal(d["count"], g["count"])
+    assert _sum_close(d["pos_sum"], g["pos_sum"], g["count"])
+    assert _sum_close(d["col_sum"], g["col_sum"], g["count"])
+    one = g["count"] == 1
+    assert np.array_equal(d["pos_sum"][one], g["pos_sum"][one])   # single-sample voxels: the point itself
+    assert np.array_equal(d["col_sum"][one], g["col_sum"][one])
