@@ -389,6 +389,21 @@ def run_gpu_arm(args, rank, world, local_rank):
     except Exception:
         pass
 
+    # ---- mesh extraction, reported separately: marching cubes over the whole map ----
+    mesh_info = None
+    if world == 1:
+        import ctypes as C
+        nv_, nt_ = C.c_int64(0), C.c_int64(0)
+        vol.synchronize()
+        vol._L.b2v_extract_mesh(vol._h, C.byref(nv_), C.byref(nt_))   # warm-up (allocates scratch)
+        t0 = time.perf_counter()
+        vol._L.b2v_extract_mesh(vol._h, C.byref(nv_), C.byref(nt_))   # kernels + size read-back, no bulk copy
+        mesh_ms = 1e3 * (time.perf_counter() - t0)
+        mesh_info = {"ms_per_extract": mesh_ms, "vertices": int(nv_.value), "triangles": int(nt_.value),
+                     "blocks": int(nb), "triangles_per_s": nt_.value / (mesh_ms * 1e-3),
+                     "note": "b2v_extract_mesh on the populated map: neighbours, classify, scan, vertices, "
+                             "triangles kernels + a 8-byte size read-back; arrays stay on the device"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -448,6 +463,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "avg_launch_us": 1e3 * iso["integ_ms"] / max(iso["launches"], 1),
                 "allocate_kernel_avg_us": 1e3 * iso["alloc_ms"] / max(iso["frames"], 1)}},
         "clocks": clocks,
+        "mesh": mesh_info,
         "cpu_baseline": cpu,
         **extra,
     }

@@ -11,8 +11,6 @@
 // Arithmetic contract: DESIGN.md §"Arithmetic contract".  Every floating-point operation that
 // decides a key, a pixel or a stored value is written with an explicit-rounding intrinsic so the
 // compiler can neither contract nor reorder it; the CPU oracle performs the same IEEE operations.
-#include <cstdlib>
-
 #include "b2v_internal.h"
 
 namespace b2v {
@@ -309,17 +307,21 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
     // ---- distinct keys: expand every distinct box, one candidate block per thread ----
     {
         const uint32_t nbox = min(s_n_box, static_cast<uint32_t>(kBoxList));
-        for (uint32_t item = tid; item < nbox * 64u; item += kAllocThreads) {
-            const unsigned long long bk = s_box[item >> 6];
-            const uint32_t c = item & 63u;
+        for (uint32_t item = tid; item < nbox * 32u; item += kAllocThreads) {  // 32 lanes per box (27 typical)
+            const unsigned long long bk = s_box[item >> 5];
+            const uint32_t c = item & 31u;
             const uint32_t n0 = static_cast<uint32_t>(bk >> 48) & 15u, n1 = static_cast<uint32_t>(bk >> 52) & 15u,
                            n2 = static_cast<uint32_t>(bk >> 56) & 15u;
-            // boxes with more than 64 blocks loop over the remainder (c, c + 64, ...)
-            for (uint32_t cc = c; cc < n0 * n1 * n2; cc += 64u) {
+            // boxes with more than 32 blocks loop over the remainder (c, c + 32, ...)
+            for (uint32_t cc = c; cc < n0 * n1 * n2; cc += 32u) {
                 const uint32_t dz = cc % n2, r = cc / n2, dy = r % n1, dx = r / n1;
                 const int kx = s_ref[0] + static_cast<int>(static_cast<uint32_t>(bk) & 0xFFFFu) - 32768 + static_cast<int>(dx);
                 const int ky = s_ref[1] + static_cast<int>(static_cast<uint32_t>(bk >> 16) & 0xFFFFu) - 32768 + static_cast<int>(dy);
                 const int kz = s_ref[2] + static_cast<int>(static_cast<uint32_t>(bk >> 32) & 0xFFFFu) - 32768 + static_cast<int>(dz);
+                // sharded volumes: keys of other ranks are dropped before they cost a set insert or a probe
+                if (P.shard_count > 1 &&
+                    static_cast<int>(block_key_hash(kx, ky, kz) % static_cast<uint64_t>(P.shard_count)) != P.shard_rank)
+                    continue;
                 const uint32_t rk = rel_key(kx, ky, kz, s_ref);
                 bool placed = false;
                 if (rk != kNoKey) {
@@ -716,148 +718,6 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
     }
 }
 
-__global__ void __launch_bounds__(kIntThreads, 6)
-integrate_group_pipe_kernel(const __grid_constant__ GroupArgs A, const HashTable T, const PoolMeta M,
-                       const int gbuf) {
-    __shared__ IntFrame s_f[kMaxGroup];   // per-frame constants (dynamic indexing by frame bit)
-    __shared__ float s_rcp[256];          // correctly rounded 1/n for the small integer weights
-    __shared__ uint32_t s_next;           // work-stealing: next list position of this CTA
-    const uint32_t n = min(M.counters[kCtrUnion0 + gbuf], M.capacity);
-    const uint32_t *__restrict__ list = M.union_slots + static_cast<size_t>(gbuf) * M.capacity;
-    const uint32_t *__restrict__ mask = M.group_mask + static_cast<size_t>(gbuf) * (static_cast<size_t>(T.mask) + 1);
-    uint32_t *cursor = M.counters + kCtrGroupNext0 + gbuf;
-    const int t = threadIdx.x;
-    const int lx0 = (t & 1) * 4, ly = (t >> 1) & 7, lz = t >> 4;
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.f);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(s_f);
-        for (int k = t; k < static_cast<int>(sizeof(IntFrame) * kMaxGroup / 4); k += kIntThreads) dst[k] = src[k];
-        s_rcp[t] = __frcp_rn(static_cast<float>(t));
-        s_rcp[t + 128] = __frcp_rn(static_cast<float>(t + 128));
-    }
-    if (blockIdx.x == 0 && t == 0)
-        atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrVisitsLo),
-                  static_cast<unsigned long long>(n));
-    uint32_t my_cnt = 0;  // thread k < 8: blocks touched by frame k, seen by this CTA
-
-    // dynamic work distribution: blocks cost 1..8 frame updates, static striding leaves a long tail
-    uint32_t i = blockIdx.x;  // first item is static; later ones come from the shared cursor
-    uint4 e = make_uint4(0u, 0u, 0u, kNoBlock);
-    uint32_t m = 0;
-    if (i < n) {
-        const uint32_t slot = list[i];
-        e = T.entries[slot];
-        m = mask[slot];
-    }
-    __syncthreads();
-    while (i < n) {
-        if (t == 0) s_next = atomicAdd(cursor, 1u) + gridDim.x;
-        __syncthreads();
-        const uint32_t i_next = s_next;
-        uint4 e_next = e;
-        uint32_t m_next = 0;
-        if (i_next < n) {  // in flight during this iteration
-            const uint32_t slot = list[i_next];
-            e_next = T.entries[slot];
-            m_next = mask[slot];
-        }
-        if (t < kMaxGroup) my_cnt += (m >> t) & 1u;
-
-        if (e.w < M.capacity) {
-            float *blk = M.pool + static_cast<size_t>(e.w) * kBlockFloats + t * 4;
-            float4 q[kPlanes];
-#pragma unroll
-            for (int c = 0; c < kPlanes; ++c) q[c] = *reinterpret_cast<const float4 *>(blk + c * kVox);
-            float *ts = reinterpret_cast<float *>(&q[0]);
-            float *w = reinterpret_cast<float *>(&q[1]);
-            float *cr = reinterpret_cast<float *>(&q[2]);
-            float *cg = reinterpret_cast<float *>(&q[3]);
-            float *cb = reinterpret_cast<float *>(&q[4]);
-
-            // voxel centres are frame independent
-            const int vx0 = static_cast<int>(e.x) * kB + lx0;
-            float cx[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cx[k] = __fmul_rn(__fadd_rn(static_cast<float>(vx0 + k), 0.5f), A.vs);
-            const float cy = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.y) * kB + ly), 0.5f), A.vs);
-            const float cz = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.z) * kB + lz), 0.5f), A.vs);
-
-            bool upd = false;
-            // software pipeline over the frames of the group: the texel gathers of frame j+1 are issued
-            // before the updates of frame j are applied, so their L2 latency overlaps arithmetic
-            float pz0[4];
-            float4 tx0[4];
-            uint32_t mm = m;
-            auto project = [&](const IntFrame &F, float *pzs, float4 *tx) {
-                const float ax = __fmaf_rn(F.E[1], cy, __fmaf_rn(F.E[2], cz, F.E[3]));
-                const float ay = __fmaf_rn(F.E[5], cy, __fmaf_rn(F.E[6], cz, F.E[7]));
-                const float az = __fmaf_rn(F.E[9], cy, __fmaf_rn(F.E[10], cz, F.E[11]));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float px = __fmaf_rn(F.E[0], cx[k], ax);
-                    const float py = __fmaf_rn(F.E[4], cx[k], ay);
-                    const float pz = __fmaf_rn(F.E[8], cx[k], az);
-                    pzs[k] = pz;
-                    int pix = -1;
-                    if (pz > 0.0f) {
-                        const float inv_z = __frcp_rn(pz);
-                        const float u_f = __fmaf_rn(__fmul_rn(px, F.fxf), inv_z, F.cxh);
-                        const float v_f = __fmaf_rn(__fmul_rn(py, F.fyf), inv_z, F.cyh);
-                        if (u_f >= 0.0001f && u_f < F.safe_w && v_f >= 0.0001f && v_f < F.safe_h)
-                            pix = __float2int_rz(v_f) * F.W + __float2int_rz(u_f);
-                    }
-                    tx[k] = pix >= 0 ? __ldg(F.tex + pix) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            if (mm) project(s_f[__ffs(mm) - 1], pz0, tx0);
-            while (mm) {
-                const IntFrame &F = s_f[__ffs(mm) - 1];
-                const uint32_t mm_next = mm & (mm - 1);
-                float pz1[4];
-                float4 tx1[4];
-                if (mm_next) project(s_f[__ffs(mm_next) - 1], pz1, tx1);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float d = tx0[k].x;
-                    const float sdf = __fmul_rn(__fsub_rn(d, pz0[k]), tx0[k].y);
-                    if (d > 0.0f && sdf > -F.tau) {
-                        const float tv = fminf(1.0f, __fmul_rn(sdf, F.inv_tau));
-                        const uint32_t rgbx = __float_as_uint(tx0[k].z);
-                        const float w0 = w[k];
-                        const float wn = __fadd_rn(w0, 1.0f);
-                        const float r = wn < 256.0f ? s_rcp[__float2int_rz(wn)] : __frcp_rn(wn);
-                        ts[k] = __fmul_rn(__fmaf_rn(ts[k], w0, tv), r);
-                        cr[k] = __fmul_rn(__fmaf_rn(cr[k], w0, static_cast<float>(rgbx & 0xFFu)), r);
-                        cg[k] = __fmul_rn(__fmaf_rn(cg[k], w0, static_cast<float>((rgbx >> 8) & 0xFFu)), r);
-                        cb[k] = __fmul_rn(__fmaf_rn(cb[k], w0, static_cast<float>((rgbx >> 16) & 0xFFu)), r);
-                        w[k] = wn;
-                        upd = true;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    pz0[k] = pz1[k];
-                    tx0[k] = tx1[k];
-                }
-                mm = mm_next;
-            }
-            if (upd) {
-#pragma unroll
-                for (int c = 0; c < kPlanes; ++c) *reinterpret_cast<float4 *>(blk + c * kVox) = q[c];
-            }
-        }
-        e = e_next;
-        m = m_next;
-        i = i_next;
-        __syncthreads();  // s_next is rewritten at the top of the next iteration
-    }
-    if (t < kMaxGroup && my_cnt) {
-        atomicAdd(M.counters + kCtrGroupTouched0 + gbuf * kMaxGroup + t, my_cnt);
-        atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrUpdatesLo),
-                  static_cast<unsigned long long>(my_cnt));
-    }
-}
-
 // clears the membership masks of a finished group (its buffer is reused two groups later)
 __global__ void group_clear_kernel(const HashTable T, const PoolMeta M, const int gbuf) {
     const uint32_t n = min(M.counters[kCtrUnion0 + gbuf], M.capacity);
@@ -868,14 +728,7 @@ __global__ void group_clear_kernel(const HashTable T, const PoolMeta M, const in
 
 cudaError_t launch_integrate_group(const GroupArgs &args, const HashTable &table, const PoolMeta &meta,
                                    int group_buf, int grid_ctas, cudaStream_t stream) {
-    static const int pipe = [] {
-        const char *e = std::getenv("B2V_GROUP_PIPE");
-        return e ? std::atoi(e) : 0;
-    }();
-    if (pipe)
-        integrate_group_pipe_kernel<<<grid_ctas * 6 / 8, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
-    else
-        integrate_group_kernel<<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
+    integrate_group_kernel<<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
     group_clear_kernel<<<148, 256, 0, stream>>>(table, meta, group_buf);
     return cudaGetLastError();
 }

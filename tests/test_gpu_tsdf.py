@@ -62,6 +62,8 @@ def test_golden_fixture_bit_exact():
     ("T0", [0, 3], 1),                 # stride-1 superset mode
     ("C1", [0, 1, 2, 50], 4),          # config 1 shape: 320x240, 1 cm
     ("C4", [0, 1], 4),                 # ScanNet shape, 4 mm
+    ("C3", [0], 4),                    # Replica shape 1200x680, 5 mm
+    ("C5", [0, 40], 4),                # KITTI shape 1241x376 (W % 16 != 0: plain-load path), 10 cm, tau 0.4
 ])
 def test_integrate_matches_oracle(cfg_name, frames, stride):
     cfg = S.CONFIGS[cfg_name]
