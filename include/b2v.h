@@ -127,7 +127,13 @@ int b2v_grid_integrate(b2v_grid *g, const float *points, const float *colors, in
  * min_depth < d < max_depth.  Same keys / counts as integrating the front-end's float32 points. */
 int b2v_grid_integrate_rgbd(b2v_grid *g, const float *depth, const uint8_t *color, int32_t height,
                             int32_t width, const double K[4], const double Twc[16], float max_depth,
-                            float min_depth);
+                            float min_depth, int32_t filter_shadow_points);
+/* filter_shadow_points(depth, delta_depth=None, delta_x, delta_y, fill_value) (pyslam/utilities/depth.py:103-146)
+ * on the GPU: exact global median (radix select) of the positive depth differences, threshold
+ * 3 * 1.4826 * median, pixels on either side of a larger jump are set to fill_value.
+ * depth / out: float32 [height*width], host or device (out may alias depth only on the host). */
+int b2v_filter_shadow_points(const float *depth, int32_t height, int32_t width, int32_t delta_x,
+                             int32_t delta_y, float fill_value, float *out, int32_t device);
 int b2v_grid_synchronize(b2v_grid *g);
 int64_t b2v_grid_num_blocks(b2v_grid *g);              /* num_blocks() */
 int64_t b2v_grid_size(b2v_grid *g);                    /* size(): voxels with count > 0 */

@@ -6,7 +6,7 @@ CUDA kernels and the C ABI (include/b2v.h); the Python modules mirror the refere
 """
 
 from .volume import (B200TsdfVolume, BoundingBox3D, CameraFrustrum, PointCloud, TriangleMesh,
-                     VoxelBlockGrid, VoxelGridData)
+                     VoxelBlockGrid, VoxelGridData, filter_shadow_points)
 
 __all__ = ["B200TsdfVolume", "BoundingBox3D", "CameraFrustrum", "PointCloud", "TriangleMesh",
-           "VoxelBlockGrid", "VoxelGridData"]
+           "VoxelBlockGrid", "VoxelGridData", "filter_shadow_points"]

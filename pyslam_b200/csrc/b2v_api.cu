@@ -1089,9 +1089,36 @@ extern "C" int b2v_grid_integrate(b2v_grid *g, const float *points, const float 
     return B2V_OK;
 }
 
+extern "C" int b2v_filter_shadow_points(const float *depth, int32_t height, int32_t width, int32_t delta_x,
+                                        int32_t delta_y, float fill_value, float *out, int32_t device) {
+    if (!depth || !out || height <= 0 || width <= 0 || delta_x < 0 || delta_y < 0 || delta_x >= width ||
+        delta_y >= height)
+        return B2V_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) return B2V_ERR_CUDA;
+    const size_t pixels = static_cast<size_t>(height) * width;
+    const bool din = is_device_pointer(depth), dout = is_device_pointer(out);
+    float *d_in = nullptr, *d_out = nullptr;
+    void *scratch = nullptr;
+    cudaError_t e = cudaMalloc(&scratch, kShadowScratchBytes);
+    if (e == cudaSuccess && !din) {
+        e = cudaMalloc(&d_in, pixels * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(d_in, depth, pixels * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && !dout) e = cudaMalloc(&d_out, pixels * sizeof(float));
+    if (e == cudaSuccess)
+        e = launch_filter_shadow_points(din ? depth : d_in, height, width, delta_x, delta_y, fill_value,
+                                        dout ? out : d_out, scratch, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && !dout) e = cudaMemcpy(out, d_out, pixels * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(scratch);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return e == cudaSuccess ? B2V_OK : B2V_ERR_CUDA;
+}
+
 extern "C" int b2v_grid_integrate_rgbd(b2v_grid *g, const float *depth, const uint8_t *color, int32_t height,
                                        int32_t width, const double K[4], const double Twc[16], float max_depth,
-                                       float min_depth) {
+                                       float min_depth, int32_t filter_shadow_points) {
     if (!g) return B2V_ERR_INVALID_ARGUMENT;
     if (!depth || !color || !K || !Twc || height <= 0 || width <= 0) {
         g->err = "b2v_grid_integrate_rgbd: bad arguments";
@@ -1114,6 +1141,15 @@ extern "C" int b2v_grid_integrate_rgbd(b2v_grid *g, const float *depth, const ui
         if (e == cudaSuccess) e = cudaMemcpyAsync(tmp_c, color, pixels * 3, cudaMemcpyHostToDevice, g->stream);
         d_color = tmp_c;
     }
+    float *filtered = nullptr;
+    void *scratch = nullptr;
+    if (e == cudaSuccess && filter_shadow_points) {  // voxel_grid.py:238-245: depth2pointcloud sees the filtered depth
+        e = cudaMalloc(&filtered, pixels * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&scratch, kShadowScratchBytes);
+        if (e == cudaSuccess && (height <= 2 || width <= 2)) e = cudaErrorInvalidValue;
+        if (e == cudaSuccess) e = launch_filter_shadow_points(d_depth, height, width, 2, 2, -1.0f, filtered, scratch, g->stream);
+        d_depth = filtered;
+    }
     if (e == cudaSuccess) {
         RgbdParams P;
         P.fx_inv = 1.0 / K[0];
@@ -1130,9 +1166,11 @@ extern "C" int b2v_grid_integrate_rgbd(b2v_grid *g, const float *depth, const ui
         P.W = width;
         e = launch_grid_integrate_rgbd(P, d_depth, d_color, g->inv_voxel_size, g->table, g->meta, g->stream);
     }
-    if (e == cudaSuccess && (tmp_d || tmp_c)) e = cudaStreamSynchronize(g->stream);
+    if (e == cudaSuccess && (tmp_d || tmp_c || filtered)) e = cudaStreamSynchronize(g->stream);
     cudaFree(tmp_d);
     cudaFree(tmp_c);
+    cudaFree(filtered);
+    cudaFree(scratch);
     if (e != cudaSuccess) {
         g->err = std::string("b2v_grid_integrate_rgbd: ") + cudaGetErrorString(e);
         return B2V_ERR_CUDA;

@@ -187,6 +187,11 @@ cudaError_t launch_grid_integrate_rgbd(const RgbdParams &p, const float *depth, 
                                        float inv_vs, const HashTable &table, const GridMeta &meta,
                                        cudaStream_t stream);
 
+// filter_shadow_points (pyslam/utilities/depth.py:103-146) on the device; scratch: 64 + 16384 bytes
+constexpr size_t kShadowScratchBytes = 64 + 4096 * sizeof(uint32_t);
+cudaError_t launch_filter_shadow_points(const float *depth, int H, int W, int dx, int dy, float fill, float *out,
+                                        void *scratch, cudaStream_t stream);
+
 // Spatial queries / carving over the existing blocks (voxel_block_grid.hpp:822-1195, 1334-1540;
 // voxel_grid_carving.h:47-80; camera_frustrum.cpp:174-196).  mode 0: axis-aligned box, mode 1: camera
 // frustum.  A voxel qualifies if count >= min_count, its key lies in [min_key, max_key] and its mean

@@ -1,0 +1,147 @@
+// b2v_prep.cu — per-frame depth preparation on the GPU ("next" row f#1).
+//
+// filter_shadow_points (pyslam/utilities/depth.py:103-146): remove the ghost points on depth
+// discontinuities.  delta_y = |d[r+2,c] - d[r,c]|, delta_x = |d[r,c+2] - d[r,c]|; the threshold is
+// 3 * 1.4826 * median(all positive deltas) (float32 arithmetic, like numpy on float32 input); a pixel is
+// set to fill_value if any delta it takes part in exceeds the threshold.
+//
+// The global median is an exact order statistic: a 3-pass radix select over the float bit patterns
+// (positive floats order like their bits), entirely on the device.  For an even count numpy averages the
+// two middle elements in float32; both ranks are selected in the same passes.
+#include "b2v_internal.h"
+
+namespace b2v {
+
+struct SelectState {
+    uint32_t prefix[2];  // bits fixed so far, for rank 0 (lower middle) and rank 1 (upper middle)
+    uint32_t rank[2];    // residual rank inside the prefix bucket
+    uint32_t total;      // number of positive deltas
+    float threshold;     // 3 * 1.4826 * median
+};
+
+__device__ __forceinline__ bool delta_at(const float *__restrict__ d, int H, int W, int dx, int dy, int64_t i,
+                                         float *out) {
+    // index space: first the (H - dy) * W vertical deltas, then the H * (W - dx) horizontal ones
+    const int64_t ny = dy > 0 ? static_cast<int64_t>(H - dy) * W : 0;
+    if (i < ny) {
+        *out = fabsf(__fsub_rn(d[i + static_cast<int64_t>(dy) * W], d[i]));
+        return true;
+    }
+    const int64_t j = i - ny;
+    const int wx = W - dx;
+    if (dx > 0 && j < static_cast<int64_t>(H) * wx) {
+        const int r = static_cast<int>(j / wx), c = static_cast<int>(j % wx);
+        const int64_t p = static_cast<int64_t>(r) * W + c;
+        *out = fabsf(__fsub_rn(d[p + dx], d[p]));
+        return true;
+    }
+    return false;
+}
+
+// pass p in {0,1,2}: digit widths 11, 11, 10 bits from the top
+__device__ __forceinline__ void digit_layout(int pass, int *shift, uint32_t *nbins, uint32_t *hi_mask) {
+    if (pass == 0) {
+        *shift = 21;
+        *nbins = 2048;
+        *hi_mask = 0u;
+    } else if (pass == 1) {
+        *shift = 10;
+        *nbins = 2048;
+        *hi_mask = 0xFFE00000u;
+    } else {
+        *shift = 0;
+        *nbins = 1024;
+        *hi_mask = 0xFFFFFC00u;
+    }
+}
+
+__global__ void shadow_hist_kernel(const float *__restrict__ depth, int H, int W, int dx, int dy, int pass,
+                                   const SelectState *__restrict__ st, uint32_t *__restrict__ hist) {
+    int shift;
+    uint32_t nbins, hi_mask;
+    digit_layout(pass, &shift, &nbins, &hi_mask);
+    const int64_t n = (dy > 0 ? static_cast<int64_t>(H - dy) * W : 0) + (dx > 0 ? static_cast<int64_t>(H) * (W - dx) : 0);
+    const uint32_t p0 = pass ? st->prefix[0] : 0u, p1 = pass ? st->prefix[1] : 0u;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float v;
+        if (!delta_at(depth, H, W, dx, dy, i, &v) || !(v > 0.0f)) continue;  // delta_values[delta_values > 0]
+        const uint32_t bits = __float_as_uint(v);
+        const uint32_t digit = (bits >> shift) & (nbins - 1);
+        if ((bits & hi_mask) == p0) atomicAdd(hist + digit, 1u);
+        if ((bits & hi_mask) == p1) atomicAdd(hist + 2048 + digit, 1u);
+    }
+}
+
+// one block: walk the two histograms, fix the next digit of both ranks, clear the histograms
+__global__ void shadow_pick_kernel(int pass, SelectState *st, uint32_t *hist) {
+    int shift;
+    uint32_t nbins, hi_mask;
+    digit_layout(pass, &shift, &nbins, &hi_mask);
+    if (threadIdx.x == 0) {
+        if (pass == 0) {
+            uint32_t total = 0;
+            for (uint32_t b = 0; b < nbins; ++b) total += hist[b];
+            st->total = total;
+            st->rank[0] = total ? (total - 1) / 2 : 0;  // numpy median: mean of elements (n-1)//2 and n//2
+            st->rank[1] = total / 2;
+            st->prefix[0] = st->prefix[1] = 0;
+        }
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t *h = hist + 2048 * k;
+            uint32_t r = st->rank[k], b = 0;
+            while (b + 1 < nbins && r >= h[b]) {
+                r -= h[b];
+                ++b;
+            }
+            st->rank[k] = r;
+            st->prefix[k] |= b << shift;
+        }
+        if (pass == 2) {
+            const float a = __uint_as_float(st->prefix[0]), b = __uint_as_float(st->prefix[1]);
+            // np.median -> mean of the two middle values in float32; then float32(1.4826) * mad; then 3 * sigma
+            const float mad = st->total ? __fmul_rn(__fadd_rn(a, b), 0.5f) : __uint_as_float(0x7FC00000u);
+            st->threshold = __fmul_rn(3.0f, __fmul_rn(1.4826f, mad));
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
+}
+
+__global__ void shadow_mask_kernel(const float *__restrict__ depth, int H, int W, int dx, int dy, float fill,
+                                   const SelectState *__restrict__ st, float *__restrict__ out) {
+    const int64_t n = static_cast<int64_t>(H) * W;
+    const float thr = st->threshold;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / W), c = static_cast<int>(i % W);
+        const float d = depth[i];
+        bool m = false;
+        if (dy > 0) {
+            if (r >= dy) m |= fabsf(__fsub_rn(d, depth[i - static_cast<int64_t>(dy) * W])) > thr;
+            if (r < H - dy) m |= fabsf(__fsub_rn(depth[i + static_cast<int64_t>(dy) * W], d)) > thr;
+        }
+        if (dx > 0) {
+            if (c >= dx) m |= fabsf(__fsub_rn(d, depth[i - dx])) > thr;
+            if (c < W - dx) m |= fabsf(__fsub_rn(depth[i + dx], d)) > thr;
+        }
+        out[i] = m ? fill : d;
+    }
+}
+
+// scratch: sizeof(SelectState) + 4096 * 4 bytes of device memory, zero-initialised by the caller once
+cudaError_t launch_filter_shadow_points(const float *depth, int H, int W, int dx, int dy, float fill, float *out,
+                                        void *scratch, cudaStream_t stream) {
+    SelectState *st = static_cast<SelectState *>(scratch);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) + 64);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 64 + 4096 * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    for (int pass = 0; pass < 3; ++pass) {
+        shadow_hist_kernel<<<296, 256, 0, stream>>>(depth, H, W, dx, dy, pass, st, hist);
+        shadow_pick_kernel<<<1, 256, 0, stream>>>(pass, st, hist);
+    }
+    shadow_mask_kernel<<<296, 256, 0, stream>>>(depth, H, W, dx, dy, fill, st, out);
+    return cudaGetLastError();
+}
+
+}  // namespace b2v

@@ -286,6 +286,22 @@ class B200TsdfVolume:
         return PointCloud(P.astype(np.float64), Cc.astype(np.float64))
 
 
+def filter_shadow_points(depth, delta_depth=None, delta_x=2, delta_y=2, fill_value=-1, device=0):
+    """GPU version of `pyslam.utilities.depth.filter_shadow_points` (depth.py:103-146) for the default
+    `delta_depth=None` (median-based threshold).  depth float32 [H,W] -> filtered copy."""
+    if delta_depth is not None:
+        raise NotImplementedError("only the median-based threshold (delta_depth=None) is implemented")
+    d = np.ascontiguousarray(depth, dtype=np.float32)
+    if d.ndim != 2:
+        raise RuntimeError("depth must be a 2D array")
+    out = np.empty_like(d)
+    rc = _lib.load().b2v_filter_shadow_points(d.ctypes.data, d.shape[0], d.shape[1], int(delta_x), int(delta_y),
+                                             float(fill_value), out.ctypes.data, int(device))
+    if rc != _lib.B2V_OK:
+        raise RuntimeError(f"b2v_filter_shadow_points failed (status {rc})")
+    return out
+
+
 class CameraFrustrum:
     """Mirror of `volumetric.CameraFrustrum(fx, fy, cx, cy, width, height, T_cw, depth_max, depth_min)`
     (cpp/volumetric/camera_frustrum.h:36-48): the arguments of carve / frustum queries."""
@@ -393,11 +409,13 @@ class VoxelBlockGrid:
                     "b2v_grid_integrate")
         self._check(self._L.b2v_grid_synchronize(self._h), "b2v_grid_synchronize")
 
-    def integrate_rgbd(self, depth, color, K, Twc, max_depth=np.inf, min_depth=0.0):
+    def integrate_rgbd(self, depth, color, K, Twc, max_depth=np.inf, min_depth=0.0, filter_shadow_points=False):
         """Fused front-end of `VolumetricIntegratorVoxelGrid.volume_integration`
         (volumetric_integrator_voxel_grid.py:247-300): `depth2pointcloud(depth, color, fx, fy, cx, cy,
         max_depth)` + `Twc` transform + `integrate(points, colors)` in one GPU call.  depth float32 [H,W]
-        metres, color uint8 RGB [H,W,3], Twc = inv_T(pose) 4x4 float64."""
+        metres, color uint8 RGB [H,W,3], Twc = inv_T(pose) 4x4 float64.  `filter_shadow_points=True` applies
+        the reference's shadow-point filter first (kVolumetricIntegrationVoxelGridShadowPointsFilter,
+        voxel_grid.py:236-245)."""
         d = np.ascontiguousarray(depth, dtype=np.float32)
         c = np.ascontiguousarray(color)
         if d.ndim != 2 or c.shape != d.shape + (3,) or c.dtype != np.uint8:
@@ -406,7 +424,8 @@ class VoxelBlockGrid:
         T = np.ascontiguousarray(np.asarray(Twc, np.float64).reshape(4, 4)).reshape(16)
         mx = float(np.finfo(np.float32).max) if not np.isfinite(max_depth) else float(max_depth)
         self._check(self._L.b2v_grid_integrate_rgbd(self._h, d.ctypes.data, c.ctypes.data, d.shape[0], d.shape[1],
-                                                    K4.ctypes.data, T.ctypes.data, mx, float(min_depth)),
+                                                    K4.ctypes.data, T.ctypes.data, mx, float(min_depth),
+                                                    1 if filter_shadow_points else 0),
                     "b2v_grid_integrate_rgbd")
         self._check(self._L.b2v_grid_synchronize(self._h), "b2v_grid_synchronize")
 

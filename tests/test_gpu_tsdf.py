@@ -339,3 +339,54 @@ def test_fused_batch_equals_frame_by_frame_and_oracle():
         orc.integrate(d, c, cfg.K, t)
     _assert_same_volume(fused, orc)
     assert np.array_equal(sorted_keys(fused.last_touched_keys()), sorted_keys(orc.last_touched()))
+
+
+def test_mixed_call_patterns_stay_consistent_with_the_oracle():
+    """Interleave every entry path (single frames from host / device memory, fused and un-fused batches of
+    odd lengths, resets, mesh extraction in between) on one volume: the stream / event choreography must
+    never change the result."""
+    import torch
+    cfg = S.CONFIGS["T0"]
+    rng = np.random.default_rng(11)
+    frames = [S.render_frame(cfg, i) for i in range(24)]
+    vol, orc = _pair(cfg, capacity=8192)
+    pos = 0
+
+    def take(n):
+        nonlocal pos
+        idx = [(pos + k) % len(frames) for k in range(n)]
+        pos += n
+        return idx
+
+    for round_ in range(3):
+        for step in range(10):
+            mode = int(rng.integers(0, 5))
+            if mode == 0:                                   # single frame, host memory
+                (i,) = take(1)
+                vol.integrate(*frames[i][:2], cfg.K, frames[i][2])
+            elif mode == 1:                                 # single frame, device memory
+                (i,) = take(1)
+                vol.integrate(torch.from_numpy(frames[i][0]).cuda(), torch.from_numpy(frames[i][1]).cuda(),
+                              cfg.K, frames[i][2])
+            elif mode in (2, 3):                            # batch (fused unless mode 3) of odd length
+                idx = take(int(rng.integers(2, 20)))
+                vol.set_fusion(mode == 2)
+                D = np.stack([frames[i][0] for i in idx])
+                Cc = np.stack([frames[i][1] for i in idx])
+                T = np.stack([frames[i][2] for i in idx])
+                if rng.integers(0, 2):
+                    vol.integrate_batch(torch.from_numpy(D).cuda(), torch.from_numpy(Cc).cuda(), cfg.K, T)
+                else:
+                    vol.integrate_batch(D, Cc, cfg.K, T)
+                for i in idx:
+                    orc.integrate(*frames[i][:2], cfg.K, frames[i][2])
+                continue
+            else:                                           # an extraction in the middle of the stream
+                vol.extract_mesh()
+                continue
+            orc.integrate(*frames[i][:2], cfg.K, frames[i][2])
+        _assert_same_volume(vol, orc)
+        if round_ == 1:
+            vol.reset()
+            orc.reset()
+    torch.cuda.synchronize()
