@@ -60,6 +60,18 @@ const char *b2v_last_error(const b2v_volume *v);
  * with DEVICE image pointers; NULL uses the library's own streams. */
 int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
                   int32_t width, const double K[4], const double Tcw[16], void *stream);
+/* Rectification on the GPU (volumetric_integrator_base.py:1017-1054): with maps installed, the frames given
+ * to b2v_integrate / b2v_integrate_batch are the RAW (distorted) images; colour is remapped like
+ * cv2.remap(..., INTER_LINEAR), depth like cv2.remap(..., INTER_NEAREST) (bit-exact with OpenCV's fixed-point
+ * arithmetic, constant zero border) before allocation.  map_x / map_y: float32 [height*width] as produced by
+ * cv2.initUndistortRectifyMap(..., CV_32FC1) (host); NULL maps remove the stage.  swap_rb != 0 also converts
+ * BGR input to RGB (cv2.cvtColor(COLOR_BGR2RGB), base.py:1054).  Synchronises. */
+int b2v_set_rectification(b2v_volume *v, const float *map_x, const float *map_y, int32_t height,
+                          int32_t width, int32_t swap_rb);
+/* stand-alone cv2.remap equivalents on host arrays (tests, other callers): kind 0 = uint8 x3 bilinear,
+ * kind 1 = 32-bit pixels (float32 depth / int32 labels) nearest */
+int b2v_remap(const void *src, int32_t kind, int32_t height, int32_t width, const float *map_x,
+              const float *map_y, void *dst, int32_t swap_rb, int32_t device);
 /* n frames back to back (the rebuild(map) bulk path, base.py:1242-1318): depth [n*H*W],
  * color [n*H*W*3], Tcw [n*16]; same K for all.  By default groups of up to 8 frames are FUSED: a block
  * is read once, updated by the frames of the group in frame order, and written once - bit-identical

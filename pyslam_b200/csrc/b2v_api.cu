@@ -103,6 +103,11 @@ struct b2v_volume {
     cudaEvent_t ev_galloc[2] = {}, ev_group_done[2] = {};
     int last_group_buf = -1, last_group_count = 0;  // most recent frame came from a fused group
     int64_t prof_frames = 0, prof_int_launches = 0;
+    // optional rectification stage (b2v_set_rectification)
+    float *d_mapx = nullptr, *d_mapy = nullptr;
+    int rect_H = 0, rect_W = 0, rect_swap = 0;
+    float *d_rdepth[kStage] = {};    // rectified frames (same slot layout as the raw staging)
+    uint8_t *d_rcolor[kStage] = {};
     // TMA descriptors are cached per image address (encoding costs ~1 us of host time each)
     std::unordered_map<uintptr_t, FrameMaps> map_cache;
     int map_H = 0, map_W = 0;
@@ -245,6 +250,10 @@ extern "C" int b2v_destroy(b2v_volume *v) {
         if (v->ev_free[s]) cudaEventDestroy(v->ev_free[s]);
     }
     cudaFree(v->d_lambda);
+    cudaFree(v->d_mapx);
+    cudaFree(v->d_mapy);
+    cudaFree(v->d_rdepth[0]);
+    cudaFree(v->d_rcolor[0]);
     for (float4 *t : v->d_gtex) cudaFree(t);
     for (int b = 0; b < 2; ++b) {
         if (v->ev_galloc[b]) cudaEventDestroy(v->ev_galloc[b]);
@@ -380,6 +389,9 @@ static const FrameMaps *frame_maps(b2v_volume *v, const float *d_depth, const ui
     return &res.first->second;
 }
 
+static int rectify_frame(b2v_volume *v, const float **d_depth, const uint8_t **d_color, int H, int W, int slot,
+                         cudaStream_t stream);
+
 static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
                            int32_t width, const double K[4], const double Tcw[16], void *stream,
                            int dev_hint = -1) {
@@ -439,6 +451,10 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
         // allocate(f) recycles the ring slot / texel buffer last read by integrate(f - 3) .. (f - 4)
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_int_done[(v->frame_id - 3) % kActiveRing], 0));
     }
+    {
+        const int rc = rectify_frame(v, &d_depth, &d_color, height, width, s, as);
+        if (rc != B2V_OK) return rc;
+    }
     FrameParams P;
     fill_frame_params(&P, K, Tcw, height, width, v->cfg.depth_stride, v->cfg.voxel_size, v->cfg.sdf_trunc,
                       v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank, v->cfg.shard_count);
@@ -486,6 +502,91 @@ extern "C" int b2v_integrate(b2v_volume *v, const float *depth, const uint8_t *c
                              int32_t width, const double K[4], const double Tcw[16], void *stream) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
     return integrate_frame(v, depth, color, height, width, K, Tcw, stream);
+}
+
+extern "C" int b2v_set_rectification(b2v_volume *v, const float *map_x, const float *map_y, int32_t height,
+                                     int32_t width, int32_t swap_rb) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    const int rc = read_counters(v);  // drains every stream
+    if (rc == B2V_ERR_CUDA) return rc;
+    cudaFree(v->d_mapx);
+    cudaFree(v->d_mapy);
+    cudaFree(v->d_rdepth[0]);
+    cudaFree(v->d_rcolor[0]);
+    v->d_mapx = v->d_mapy = nullptr;
+    for (int s = 0; s < kStage; ++s) {
+        v->d_rdepth[s] = nullptr;
+        v->d_rcolor[s] = nullptr;
+    }
+    v->rect_H = v->rect_W = 0;
+    v->rect_swap = swap_rb;
+    v->map_cache.clear();
+    if (!map_x || !map_y) return B2V_OK;
+    if (height <= 0 || width <= 0) {
+        v->err = "b2v_set_rectification: bad image size";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    const size_t pixels = static_cast<size_t>(height) * width;
+    B2V_CUDA(v, cudaMalloc(&v->d_mapx, pixels * sizeof(float)));
+    B2V_CUDA(v, cudaMalloc(&v->d_mapy, pixels * sizeof(float)));
+    B2V_CUDA(v, cudaMemcpy(v->d_mapx, map_x, pixels * sizeof(float), cudaMemcpyHostToDevice));
+    B2V_CUDA(v, cudaMemcpy(v->d_mapy, map_y, pixels * sizeof(float), cudaMemcpyHostToDevice));
+    float *dbase = nullptr;
+    uint8_t *cbase = nullptr;
+    B2V_CUDA(v, cudaMalloc(&dbase, pixels * sizeof(float) * kStage));
+    B2V_CUDA(v, cudaMalloc(&cbase, pixels * 3 * kStage));
+    for (int s = 0; s < kStage; ++s) {
+        v->d_rdepth[s] = dbase + pixels * s;
+        v->d_rcolor[s] = cbase + pixels * 3 * s;
+    }
+    v->rect_H = height;
+    v->rect_W = width;
+    return B2V_OK;
+}
+
+extern "C" int b2v_remap(const void *src, int32_t kind, int32_t height, int32_t width, const float *map_x,
+                         const float *map_y, void *dst, int32_t swap_rb, int32_t device) {
+    if (!src || !dst || !map_x || !map_y || height <= 0 || width <= 0 || (kind != 0 && kind != 1))
+        return B2V_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) return B2V_ERR_CUDA;
+    const size_t pixels = static_cast<size_t>(height) * width;
+    const size_t bytes = pixels * (kind == 0 ? 3 : 4);
+    void *d_src = nullptr, *d_dst = nullptr;
+    float *d_mx = nullptr, *d_my = nullptr;
+    cudaError_t e = cudaMalloc(&d_src, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_dst, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_mx, pixels * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_my, pixels * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_src, src, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_mx, map_x, pixels * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_my, map_y, pixels * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = kind == 0 ? launch_remap_u8c3_linear(static_cast<const uint8_t *>(d_src), height, width, d_mx, d_my,
+                                                 static_cast<uint8_t *>(d_dst), swap_rb, nullptr)
+                      : launch_remap_b32_nearest(d_src, height, width, d_mx, d_my, d_dst, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(dst, d_dst, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_src);
+    cudaFree(d_dst);
+    cudaFree(d_mx);
+    cudaFree(d_my);
+    return e == cudaSuccess ? B2V_OK : B2V_ERR_CUDA;
+}
+
+// rectify one frame (raw staging or caller device buffers -> rectified slot), on the allocate stream
+static int rectify_frame(b2v_volume *v, const float **d_depth, const uint8_t **d_color, int H, int W, int slot,
+                         cudaStream_t as) {
+    if (!v->d_mapx) return B2V_OK;
+    if (H != v->rect_H || W != v->rect_W) {
+        v->err = "rectification maps were installed for a different image size";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    B2V_CUDA(v, launch_remap_b32_nearest(*d_depth, H, W, v->d_mapx, v->d_mapy, v->d_rdepth[slot], as));
+    B2V_CUDA(v, launch_remap_u8c3_linear(*d_color, H, W, v->d_mapx, v->d_mapy, v->d_rcolor[slot], v->rect_swap, as));
+    *d_depth = v->d_rdepth[slot];
+    *d_color = v->d_rcolor[slot];
+    v->launches += 2;
+    return B2V_OK;
 }
 
 static int ensure_group_buffers(b2v_volume *v, size_t pixels) {
@@ -602,8 +703,6 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
             aargs.depth[k] = d_depth;
             aargs.color[k] = d_color;
             aargs.tex[k] = tex;
-            const FrameMaps *fm = frame_maps(v, d_depth, d_color, height, width);
-            if (fm) aargs.maps[k] = *fm; else aargs.use_tma = 0;
             IntFrame &F = args.f[k];
             std::memcpy(F.E, P.E, sizeof(F.E));
             F.fxf = P.fxf;
@@ -621,6 +720,15 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         if (staged) {
             B2V_CUDA(v, cudaEventRecord(v->ev_ready[buf], v->copy));  // all frames of the group uploaded
             B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_ready[buf], 0));
+        }
+        for (int k = 0; k < count; ++k) {  // optional rectification, then the TMA descriptors of the final images
+            const int rrc = rectify_frame(v, &aargs.depth[k], &aargs.color[k], height, width, buf * kMaxGroup + k, as);
+            if (rrc != B2V_OK) {
+                v->inputs_fenced = false;
+                return rrc;
+            }
+            const FrameMaps *fm = frame_maps(v, aargs.depth[k], aargs.color[k], height, width);
+            if (fm) aargs.maps[k] = *fm; else aargs.use_tma = 0;
         }
         cudaEvent_t *pe = nullptr;
         if (v->prof_enabled) {

@@ -192,6 +192,12 @@ constexpr size_t kShadowScratchBytes = 64 + 4096 * sizeof(uint32_t);
 cudaError_t launch_filter_shadow_points(const float *depth, int H, int W, int dx, int dy, float fill, float *out,
                                         void *scratch, cudaStream_t stream);
 
+// cv2.remap equivalents (bit-exact fixed-point bilinear for 8-bit x3, nearest for 32-bit pixels)
+cudaError_t launch_remap_u8c3_linear(const uint8_t *src, int H, int W, const float *mapx, const float *mapy,
+                                     uint8_t *dst, int swap_rb, cudaStream_t stream);
+cudaError_t launch_remap_b32_nearest(const void *src, int H, int W, const float *mapx, const float *mapy, void *dst,
+                                     cudaStream_t stream);
+
 // Spatial queries / carving over the existing blocks (voxel_block_grid.hpp:822-1195, 1334-1540;
 // voxel_grid_carving.h:47-80; camera_frustrum.cpp:174-196).  mode 0: axis-aligned box, mode 1: camera
 // frustum.  A voxel qualifies if count >= min_count, its key lies in [min_key, max_key] and its mean

@@ -144,4 +144,65 @@ cudaError_t launch_filter_shadow_points(const float *depth, int H, int W, int dx
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// undistort / rectify: cv2.remap with the precomputed maps of initUndistortRectifyMap
+// (pyslam/dense/volumetric_integrator_base.py:1017-1054: colour INTER_LINEAR, depth and labels
+// INTER_NEAREST, constant zero border).  OpenCV's fixed-point arithmetic is reproduced exactly:
+//   linear (8-bit): sx = round_half_even(mapx * 32), pixel = sx >> 5, fraction a = sx & 31;
+//                   weights (32-ay)(32-ax)*32, ... (sum 32768); out = (sum w*p + 16384) >> 15
+//   nearest:        pixel = round_half_even(mapx)
+// ------------------------------------------------------------------------------------------------
+__global__ void remap_u8c3_linear_kernel(const uint8_t *__restrict__ src, int H, int W,
+                                         const float *__restrict__ mapx, const float *__restrict__ mapy,
+                                         uint8_t *__restrict__ dst, int swap_rb) {
+    const int64_t n = static_cast<int64_t>(H) * W;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int sx = __float2int_rn(__fmul_rn(mapx[i], 32.0f)), sy = __float2int_rn(__fmul_rn(mapy[i], 32.0f));
+        const int x0 = sx >> 5, y0 = sy >> 5, ax = sx & 31, ay = sy & 31;
+        const int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32, w10 = ay * (32 - ax) * 32,
+                  w11 = ay * ax * 32;
+        int acc[3] = {16384, 16384, 16384};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int x = x0 + (t & 1), y = y0 + (t >> 1);
+            const int w = t == 0 ? w00 : (t == 1 ? w01 : (t == 2 ? w10 : w11));
+            if (x >= 0 && x < W && y >= 0 && y < H && w) {  // BORDER_CONSTANT, value 0
+                const uint8_t *p = src + (static_cast<int64_t>(y) * W + x) * 3;
+                acc[0] += w * p[0];
+                acc[1] += w * p[1];
+                acc[2] += w * p[2];
+            }
+        }
+        uint8_t *o = dst + i * 3;
+        o[swap_rb ? 2 : 0] = static_cast<uint8_t>(acc[0] >> 15);
+        o[1] = static_cast<uint8_t>(acc[1] >> 15);
+        o[swap_rb ? 0 : 2] = static_cast<uint8_t>(acc[2] >> 15);
+    }
+}
+
+__global__ void remap_b32_nearest_kernel(const uint32_t *__restrict__ src, int H, int W,
+                                         const float *__restrict__ mapx, const float *__restrict__ mapy,
+                                         uint32_t *__restrict__ dst) {
+    const int64_t n = static_cast<int64_t>(H) * W;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int x = __float2int_rn(mapx[i]), y = __float2int_rn(mapy[i]);
+        dst[i] = (x >= 0 && x < W && y >= 0 && y < H) ? src[static_cast<int64_t>(y) * W + x] : 0u;
+    }
+}
+
+cudaError_t launch_remap_u8c3_linear(const uint8_t *src, int H, int W, const float *mapx, const float *mapy,
+                                     uint8_t *dst, int swap_rb, cudaStream_t stream) {
+    remap_u8c3_linear_kernel<<<296, 256, 0, stream>>>(src, H, W, mapx, mapy, dst, swap_rb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_remap_b32_nearest(const void *src, int H, int W, const float *mapx, const float *mapy, void *dst,
+                                     cudaStream_t stream) {
+    remap_b32_nearest_kernel<<<296, 256, 0, stream>>>(static_cast<const uint32_t *>(src), H, W, mapx, mapy,
+                                                      static_cast<uint32_t *>(dst));
+    return cudaGetLastError();
+}
+
 }  // namespace b2v

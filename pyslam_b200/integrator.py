@@ -35,6 +35,8 @@ DEFAULT_PARAMETERS = {
     "kVolumetricIntegrationTsdfExtractMesh": True,
     "kVolumetricIntegrationB200CapacityBlocks": 1 << 19,
     "kVolumetricIntegrationB200Device": 0,
+    # undistort + BGR->RGB on the GPU (b2v_set_rectification) instead of the base class's cv2.remap / cvtColor
+    "kVolumetricIntegrationB200GpuRectify": True,
 }
 
 
@@ -107,6 +109,29 @@ def make_integrator_class(Base, api):
                 device=int(p["kVolumetricIntegrationB200Device"]))
             self.last_output = None
             self.last_integrated_id = -1
+            # rectification on the GPU: the maps the base class computed (base.py:766-778) go to the device once
+            self._gpu_rectify = False
+            m1, m2 = getattr(self, "calib_map1", None), getattr(self, "calib_map2", None)
+            if (p["kVolumetricIntegrationB200GpuRectify"] and m1 is not None and m2 is not None
+                    and getattr(self, "depth_estimator", None) is None):  # estimated depth needs the CPU path
+                self.volume.set_rectification(m1, m2, swap_rb=True)
+                self._gpu_rectify = True
+
+        def _prepare_frame(self, kd):
+            """(color RGB or raw BGR when the GPU rectifies, depth float32).  With GPU rectification and no
+            depth estimator the raw images go straight to the device: remap + channel swap happen there,
+            bit-identically to cv2.remap / cvtColor (base.py:1017-1054)."""
+            if self._gpu_rectify and kd.depth is not None and kd.depth.size and kd.img is not None:
+                depth = kd.depth
+                if depth.dtype != np.float32:  # base.py:1008-1015
+                    depth = depth.astype(np.float32)
+                    if getattr(api, "USE_CPP", False):
+                        depth = depth * np.float32(getattr(self, "depth_factor", 1.0))
+                return kd.img, depth
+            if self._gpu_rectify:
+                return None, None
+            rect = self.estimate_depth_if_needed_and_rectify(kd)
+            return rect[0], rect[1]
 
         def _intrinsics(self):
             if hasattr(self, "get_camera_intrinsics_for_depth"):
@@ -147,8 +172,7 @@ def make_integrator_class(Base, api):
                         ttype = self.last_input_task.task_type
                         if ttype == TaskType.INTEGRATE:
                             kd = self.last_input_task.keyframe_data
-                            rect = self.estimate_depth_if_needed_and_rectify(kd)
-                            color, depth = rect[0], rect[1]
+                            color, depth = self._prepare_frame(kd)
                             if color is not None and depth is not None:
                                 fx, fy, cx, cy = self._intrinsics()
                                 # north_star call: integrate(depth, color, K, pose = Tcw)

@@ -128,19 +128,28 @@ class StandaloneIntegratorBase:
 
     def init(self, camera, environment_type, sensor_type, parameters_dict, constructor_kwargs):
         self.depth_factor = 1.0  # base.py:713
-        self.calib_map1 = self.calib_map2 = None  # no lens distortion in the stand-in
+        # base.py:766-778 computes these with cv2.initUndistortRectifyMap from camera.D; the stand-in takes
+        # ready-made maps (`calib_maps=(map1, map2)`) so that it does not need OpenCV
+        maps = (constructor_kwargs or {}).get("calib_maps")
+        self.calib_map1, self.calib_map2 = (maps if maps is not None else (None, None))
+        self.depth_estimator = None
 
     def get_camera_intrinsics_for_depth(self):
         c = self.camera
         return c.fx, c.fy, c.cx, c.cy
 
     def estimate_depth_if_needed_and_rectify(self, kd):
-        """depth -> float32 metres; colour BGR -> RGB (base.py:1008-1017,1054).  Undistortion
-        (cv2.remap) is a SURVEY.md §8(f) 'next' row and is not done here."""
+        """depth -> float32 metres; undistortion with cv2.remap when maps exist (base.py:1017-1047; the CPU
+        path the plugin's GPU rectification replaces); colour BGR -> RGB (base.py:1054)."""
         if kd.depth is None or kd.depth.size == 0:
             return None, None, None, None, None
         depth = kd.depth if kd.depth.dtype == np.float32 else kd.depth.astype(np.float32)
-        color = np.ascontiguousarray(kd.img[..., ::-1])
+        color = kd.img
+        if self.calib_map1 is not None and self.calib_map2 is not None:
+            import cv2  # only this CPU leg of the stand-in needs OpenCV
+            color = cv2.remap(color, self.calib_map1, self.calib_map2, interpolation=cv2.INTER_LINEAR)
+            depth = cv2.remap(depth, self.calib_map1, self.calib_map2, interpolation=cv2.INTER_NEAREST)
+        color = np.ascontiguousarray(color[..., ::-1])
         return color, depth, None, kd.semantic_img, kd.semantic_instances_img
 
     # -- front-end API --

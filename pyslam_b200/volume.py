@@ -222,6 +222,21 @@ class B200TsdfVolume:
         """integrate_batch: fuse groups of up to 8 frames per block visit (default) or go frame by frame."""
         self._check(self._L.b2v_set_fusion(self._h, 1 if enable else 0), "b2v_set_fusion")
 
+    def set_rectification(self, map_x, map_y, swap_rb: bool = False):
+        """Install the undistortion maps of `cv2.initUndistortRectifyMap(K, D, None, new_K, (w, h), CV_32FC1)`
+        (volumetric_integrator_base.py:766-778): integrate() then takes the RAW images and rectifies them on the
+        GPU exactly like `cv2.remap` (colour bilinear, depth nearest; base.py:1034-1039).  `swap_rb=True` also
+        converts BGR input to RGB (base.py:1054).  `None` maps remove the stage."""
+        if map_x is None or map_y is None:
+            self._check(self._L.b2v_set_rectification(self._h, None, None, 0, 0, 0), "b2v_set_rectification")
+            return
+        mx = np.ascontiguousarray(map_x, np.float32)
+        my = np.ascontiguousarray(map_y, np.float32)
+        if mx.ndim != 2 or mx.shape != my.shape:
+            raise RuntimeError("map_x and map_y must be float32 [H,W] arrays of the same shape")
+        self._check(self._L.b2v_set_rectification(self._h, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1],
+                                                  1 if swap_rb else 0), "b2v_set_rectification")
+
     def set_overlap(self, enable: bool):
         """Run allocate(f+1) concurrently with integrate(f) (default) or serialise them."""
         self._check(self._L.b2v_set_overlap(self._h, 1 if enable else 0), "b2v_set_overlap")
@@ -299,6 +314,29 @@ def filter_shadow_points(depth, delta_depth=None, delta_x=2, delta_y=2, fill_val
                                              float(fill_value), out.ctypes.data, int(device))
     if rc != _lib.B2V_OK:
         raise RuntimeError(f"b2v_filter_shadow_points failed (status {rc})")
+    return out
+
+
+def remap(src, map_x, map_y, interpolation="linear", swap_rb=False, device=0):
+    """GPU `cv2.remap(src, map_x, map_y, interpolation)` for the two cases the dense front-end uses
+    (volumetric_integrator_base.py:1017-1047): uint8 [H,W,3] with INTER_LINEAR, and float32 / int32 [H,W] with
+    INTER_NEAREST; constant zero border.  Bit-exact with OpenCV's fixed-point arithmetic."""
+    a = np.ascontiguousarray(src)
+    mx = np.ascontiguousarray(map_x, np.float32)
+    my = np.ascontiguousarray(map_y, np.float32)
+    if a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3 and interpolation == "linear":
+        kind = 0
+    elif a.dtype in (np.float32, np.int32) and a.ndim == 2 and interpolation == "nearest":
+        kind = 1
+    else:
+        raise RuntimeError("remap supports uint8 [H,W,3] + 'linear' and float32/int32 [H,W] + 'nearest'")
+    if mx.shape != a.shape[:2] or my.shape != a.shape[:2]:
+        raise RuntimeError("maps must have the image's height and width")
+    out = np.empty_like(a)
+    rc = _lib.load().b2v_remap(a.ctypes.data, kind, a.shape[0], a.shape[1], mx.ctypes.data, my.ctypes.data,
+                              out.ctypes.data, 1 if swap_rb else 0, int(device))
+    if rc != _lib.B2V_OK:
+        raise RuntimeError(f"b2v_remap failed (status {rc})")
     return out
 
 

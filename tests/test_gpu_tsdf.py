@@ -390,3 +390,70 @@ def test_mixed_call_patterns_stay_consistent_with_the_oracle():
             vol.reset()
             orc.reset()
     torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------
+# rectification row: GPU remap == cv2.remap, bit for bit (tests/golden/remap_T0.npz)
+# ---------------------------------------------------------------------------------------------------
+def test_remap_equals_opencv_golden():
+    from pyslam_b200 import remap
+    g = np.load(os.path.join(GOLDEN, "remap_T0.npz"))
+    col = remap(g["bgr"], g["map1"], g["map2"], "linear")
+    assert np.array_equal(col, g["color_u"])
+    assert np.array_equal(remap(g["bgr"], g["map1"], g["map2"], "linear", swap_rb=True), g["rgb_u"])
+    dep = remap(g["depth"], g["map1"], g["map2"], "nearest")
+    assert np.array_equal(dep, g["depth_u"])
+    lab = remap(g["labels"], g["map1"], g["map2"], "nearest")
+    assert np.array_equal(lab, g["labels_u"])
+    assert (g["depth_u"] == 0).sum() > 50          # the zero border is exercised
+    with pytest.raises(RuntimeError):
+        remap(g["depth"], g["map1"], g["map2"], "linear")
+    with pytest.raises(RuntimeError):
+        remap(g["bgr"], g["map1"][:10], g["map2"][:10], "linear")
+
+
+def test_volume_with_rectification_equals_prerectified_input():
+    """set_rectification + raw frames == cv2-rectified frames fed directly, on the per-frame path and on the
+    fused batch path (19 frames: two full groups + a ragged one)."""
+    g = np.load(os.path.join(GOLDEN, "remap_T0.npz"))
+    cfg = S.CONFIGS["T0"]
+    K = (float(g["new_K"][0, 0]), float(g["new_K"][1, 1]), float(g["new_K"][0, 2]), float(g["new_K"][1, 2]))
+    n = 19
+    frames = [S.render_frame(cfg, i) for i in range(n)]
+    raw_d = np.stack([f[0] for f in frames])
+    raw_bgr = np.stack([np.ascontiguousarray(f[1][..., ::-1]) for f in frames])
+    Ts = np.stack([f[2] for f in frames])
+    from pyslam_b200 import remap
+    rect_d = np.stack([remap(d, g["map1"], g["map2"], "nearest") for d in raw_d])
+    rect_rgb = np.stack([remap(c, g["map1"], g["map2"], "linear", swap_rb=True) for c in raw_bgr])
+    assert np.array_equal(rect_d[2], g["depth_u"]) and np.array_equal(rect_rgb[2], g["rgb_u"])
+
+    def run(batch, rectify):
+        vol = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=1 << 13)
+        if rectify:
+            vol.set_rectification(g["map1"], g["map2"], swap_rb=True)
+        d, c = (raw_d, raw_bgr) if rectify else (rect_d, rect_rgb)
+        if batch:
+            vol.integrate_batch(d, c, K, Ts)
+        else:
+            for i in range(n):
+                vol.integrate(d[i], c[i], K, Ts[i])
+        out = sort_dump(vol.dump_blocks())
+        vol.close()
+        return out
+
+    ref = run(False, False)
+    assert len(ref["keys"]) > 50
+    for batch in (False, True):
+        got = run(batch, True)
+        for k in ("keys", "vox"):
+            assert np.array_equal(got[k], ref[k]), (batch, k)
+    # removing the maps restores the plain path; a wrong image size is an argument error
+    vol = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=1 << 13)
+    vol.set_rectification(g["map1"][:-8], g["map2"][:-8])
+    with pytest.raises(RuntimeError):
+        vol.integrate(raw_d[0], raw_bgr[0], K, Ts[0])
+    vol.set_rectification(None, None)
+    vol.integrate(rect_d[0], rect_rgb[0], K, Ts[0])
+    assert vol.num_blocks() > 0
+    vol.close()

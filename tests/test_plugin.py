@@ -139,3 +139,63 @@ def test_adapter_end_to_end_on_gpu(tmp_path):
     integ.step()
     assert os.path.getsize(os.path.join(tmp_path, "dense_map.ply")) > 15 * len(ref["vertices"])
     integ.quit()
+
+
+def test_adapter_gpu_rectification_hands_raw_frames_to_the_volume(monkeypatch):
+    """With calibration maps the adapter installs them on the volume (swap_rb=True) and passes the RAW BGR
+    image and float32 depth; with the option off it goes through the base class's CPU remap."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "remap_T0.npz"))
+
+    class _RectVolume(_FakeVolume):
+        def set_rectification(self, m1, m2, swap_rb=False):
+            self.calls.append(("rect", m1.shape, bool(swap_rb)))
+
+    monkeypatch.setattr(I, "B200TsdfVolume", _RectVolume)
+    Cls = P.standalone_integrator_class()
+    cfg = S.CONFIGS["T0"]
+    integ = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_TSDF",
+                calib_maps=(g["map1"], g["map2"]))
+    assert integ.volume.calls[0] == ("rect", g["map1"].shape, True)
+    kd = P.VolumetricIntegrationKeyframeData(id=1, pose=g["Tcw"], img=g["bgr"], depth=g["depth"])
+    integ.add_keyframe_data(kd)
+    integ.step()
+    call = [c for c in integ.volume.calls if c[0] == "integrate"][-1]
+    assert np.array_equal(call[3], g["bgr"][0, 0])   # raw BGR, untouched
+    cv2 = pytest.importorskip("cv2")
+    del cv2
+    integ2 = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_TSDF",
+                 calib_maps=(g["map1"], g["map2"]), kVolumetricIntegrationB200GpuRectify=False)
+    assert not any(c[0] == "rect" for c in integ2.volume.calls)
+    integ2.add_keyframe_data(kd)
+    integ2.step()
+    call = [c for c in integ2.volume.calls if c[0] == "integrate"][-1]
+    assert np.array_equal(call[3], g["rgb_u"][0, 0])  # CPU-rectified RGB
+
+
+@pytest.mark.gpu
+def test_adapter_gpu_rectification_equals_cpu_rectification():
+    pytest.importorskip("cv2")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "remap_T0.npz"))
+    Cls = P.standalone_integrator_class()
+    cfg = S.CONFIGS["T0"]
+    nk = g["new_K"]
+    cam = SimpleNamespace(fx=float(nk[0, 0]), fy=float(nk[1, 1]), cx=float(nk[0, 2]), cy=float(nk[1, 2]),
+                          width=cfg.width, height=cfg.height, D=None)
+    dumps = []
+    for gpu_rect in (True, False):
+        integ = Cls(cam, P.DatasetEnvironmentType.INDOOR, None, "B200_TSDF",
+                    calib_maps=(g["map1"], g["map2"]), kVolumetricIntegrationB200GpuRectify=gpu_rect,
+                    kVolumetricIntegrationVoxelLength=cfg.voxel_size,
+                    kVolumetricIntegrationTSdfTrunc=cfg.sdf_trunc,
+                    kVolumetricIntegrationB200CapacityBlocks=4096)
+        for i in range(4):
+            d, c, T = S.render_frame(cfg, i)
+            integ.add_keyframe_data(P.VolumetricIntegrationKeyframeData(
+                id=i, pose=T, img=np.ascontiguousarray(c[..., ::-1]), depth=d))
+        integ.run_pending()
+        from tests._util import sort_dump
+        dumps.append(sort_dump(integ.volume.dump_blocks()))
+        integ.quit()
+    assert len(dumps[0]["keys"]) > 20
+    assert np.array_equal(dumps[0]["keys"], dumps[1]["keys"])
+    assert np.array_equal(dumps[0]["vox"], dumps[1]["vox"])
