@@ -171,6 +171,53 @@ int64_t b2v_grid_get_voxels_in_bb(b2v_grid *g, const double bbox[6], int32_t min
 int64_t b2v_grid_dump_blocks(b2v_grid *g, int32_t *keys, uint64_t *hashes, int32_t *count,
                              float *pos_sum, float *col_sum);
 
+/* ---- semantic voxel-block grids -------------------------------------------
+ * Drop-in for volumetric.VoxelBlockSemanticGrid (voting) and volumetric.VoxelBlockSemanticProbabilisticGrid
+ * (cpp/volumetric/voxel_block_semantic_grid.h:59-121; pybind: volumetric_grid_module.h), for
+ *   integrate(points, colors, class_ids, instance_ids, depths)   voxel_block_grid.hpp:12-112
+ *   get_voxels(min_count, min_confidence)                        voxel_block_grid.hpp:717-819
+ *   set_depth_threshold / set_depth_decay_rate                   voxel_block_semantic_grid.hpp:22-36
+ *   remove_low_count_voxels, remove_low_confidence_segments, merge_segments, remove_segment
+ *                                                                voxel_block_grid.hpp:625-647, semantic_grid.hpp:101-183
+ * Observations reach a voxel in input order, like the reference's sequential build: counts, float64 position
+ * sums, float32 colour sums, labels and log-evidence are bit-identical.  The depth threshold / decay rate are
+ * per grid here (class-static, i.e. process-wide, in the reference: voxel_data_semantic.h:107-108, 251-254). */
+typedef struct b2v_sgrid b2v_sgrid;
+#define B2V_SEM_VOTING 0         /* VoxelSemanticData: (object, class, counter), voxel_data_semantic.h:106-199 */
+#define B2V_SEM_PROBABILISTIC 1  /* VoxelSemanticDataProbabilistic: joint log-evidence per pair, :249-672 */
+#define B2V_SEM_MAX_LABELS 8     /* label pairs kept per Bayesian voxel (the reference's map is unbounded) */
+int b2v_sgrid_create(double voxel_size, int32_t block_size, uint32_t capacity_blocks, int32_t kind,
+                     int32_t device, b2v_sgrid **out);
+int b2v_sgrid_destroy(b2v_sgrid *g);
+const char *b2v_sgrid_last_error(const b2v_sgrid *g);
+int b2v_sgrid_clear(b2v_sgrid *g);
+int b2v_sgrid_set_depth_threshold(b2v_sgrid *g, float depth_threshold);
+int b2v_sgrid_set_depth_decay_rate(b2v_sgrid *g, float depth_decay_rate);
+/* points: float32 or float64 [n][3] (points_f64); colors: NULL, float32 [n][3] in [0,1] or uint8 [n][3]
+ * (colors_u8); class_ids / instance_ids / depths: NULL or [n].  Without colours only positions are integrated
+ * and without instance ids the object id is 0, as in the reference (voxel_block_grid.hpp:228-231, 259-286).
+ * Host or device pointers; synchronous (the inputs are free when the call returns). */
+int b2v_sgrid_integrate(b2v_sgrid *g, int64_t n, const void *points, int32_t points_f64, const void *colors,
+                        int32_t colors_u8, const int32_t *class_ids, const int32_t *instance_ids,
+                        const float *depths);
+int64_t b2v_sgrid_num_blocks(b2v_sgrid *g);
+/* two-step read-out: get_voxels returns the count (or -1), copy_voxels fills caller arrays (any may be NULL):
+ * points f64 [n][3], colors f32 [n][3], class_ids / object_ids i32 [n], confidences f32 [n] */
+int64_t b2v_sgrid_get_voxels(b2v_sgrid *g, int32_t min_count, float min_confidence);
+int b2v_sgrid_copy_voxels(b2v_sgrid *g, double *points, float *colors, int32_t *class_ids, int32_t *object_ids,
+                          float *confidences);
+int b2v_sgrid_remove_low_count_voxels(b2v_sgrid *g, int32_t min_count);
+int b2v_sgrid_remove_low_confidence_segments(b2v_sgrid *g, int32_t min_confidence);
+int b2v_sgrid_merge_segments(b2v_sgrid *g, int32_t object_id1, int32_t object_id2);
+int b2v_sgrid_remove_segment(b2v_sgrid *g, int32_t object_id);
+/* number of label pairs dropped because a Bayesian voxel saw more than B2V_SEM_MAX_LABELS distinct pairs */
+int b2v_sgrid_label_overflows(b2v_sgrid *g, uint64_t *out);
+/* parity hook: arrays [nb][512]...; aux = voting counter / number of label pairs; lab_* [nb][512][K] in
+ * ascending (object, class) order padded with (-1, -1, -inf); any output may be NULL */
+int64_t b2v_sgrid_dump_blocks(b2v_sgrid *g, int32_t *keys, uint64_t *hashes, int32_t *count, double *pos_sum,
+                              float *col_sum, int32_t *object_id, int32_t *class_id, float *confidence,
+                              int32_t *aux, int32_t K, int32_t *lab_obj, int32_t *lab_cls, float *lab_logp);
+
 /* library / device info */
 int b2v_version(void);
 int b2v_device_sm_count(int32_t device);

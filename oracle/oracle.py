@@ -381,3 +381,135 @@ def numpy_integrate_block(vox, key, depth, color, K, Tcw, voxel_size, sdf_trunc,
         out[2 + k] = np.where(ok, (out[2 + k] * w + rgb[:, k]) / wn, out[2 + k])
     out[1] = np.where(ok, wn, w)
     return out, ok
+
+
+# ---------------------------------------------------------------------------------------------
+# compiled reference: semantic voxel-block grids
+# ---------------------------------------------------------------------------------------------
+_SEM_SO = os.path.join(_DIR, "_ref", "libref_semantic.so")
+_sem_lib = None
+
+
+def have_ref_semantic() -> bool:
+    return os.path.exists(_SEM_SO)
+
+
+def _sem():
+    global _sem_lib
+    if _sem_lib is None:
+        if not have_ref_semantic():
+            raise RuntimeError("oracle/_ref/libref_semantic.so missing (needs /root/reference to build)")
+        L = C.CDLL(_SEM_SO)
+        vp = C.c_void_p
+        L.refsem_create.restype = vp
+        L.refsem_create.argtypes = [C.c_int, C.c_double, C.c_int]
+        L.refsem_destroy.argtypes = [vp]
+        L.refsem_clear.argtypes = [vp]
+        L.refsem_set_depth_threshold.argtypes = [C.c_int, C.c_float]
+        L.refsem_set_depth_decay_rate.argtypes = [C.c_float]
+        L.refsem_get_depth_threshold.restype = C.c_float
+        L.refsem_get_depth_threshold.argtypes = [C.c_int]
+        L.refsem_get_depth_decay_rate.restype = C.c_float
+        L.refsem_integrate.argtypes = [vp, _f64p, C.c_int64, vp, vp, vp, vp]
+        L.refsem_integrate_f32.argtypes = [vp, _f32p, C.c_int64, vp, vp, vp, vp]
+        L.refsem_num_blocks.restype = C.c_int64
+        L.refsem_num_blocks.argtypes = [vp]
+        L.refsem_dump_blocks.restype = C.c_int64
+        L.refsem_dump_blocks.argtypes = [vp] * 10 + [C.c_int] + [vp] * 3
+        L.refsem_get_voxels.restype = C.c_int64
+        L.refsem_get_voxels.argtypes = [vp, C.c_int, C.c_float, vp, vp, vp, vp, vp]
+        L.refsem_remove_low_count_voxels.argtypes = [vp, C.c_int]
+        L.refsem_remove_low_confidence_segments.argtypes = [vp, C.c_int]
+        L.refsem_merge_segments.argtypes = [vp, C.c_int, C.c_int]
+        L.refsem_remove_segment.argtypes = [vp, C.c_int]
+        _sem_lib = L
+    return _sem_lib
+
+
+class RefSemanticGrid:
+    """The unmodified reference `VoxelBlockSemanticGrid` (kind="voting") or
+    `VoxelBlockSemanticProbabilisticGrid` (kind="probabilistic"), sequential branch.  The depth threshold
+    and decay rate are class-static in the reference (process-wide): set them right before use."""
+
+    KINDS = {"voting": 0, "probabilistic": 1}
+
+    def __init__(self, voxel_size: float, kind: str = "voting", block_size: int = 8):
+        self._L = _sem()
+        self.kind = self.KINDS[kind]
+        self._h = self._L.refsem_create(self.kind, float(voxel_size), int(block_size))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.refsem_destroy(self._h)
+            self._h = None
+
+    def set_depth_threshold(self, v):
+        self._L.refsem_set_depth_threshold(self.kind, float(v))
+
+    def set_depth_decay_rate(self, v):
+        self._L.refsem_set_depth_decay_rate(float(v))
+
+    def integrate(self, points, colors=None, class_ids=None, instance_ids=None, depths=None):
+        """float32 points take the reference's float overload (keys computed in float32), anything else float64."""
+        f32 = np.asarray(points).dtype == np.float32
+        pts = np.ascontiguousarray(points, np.float32 if f32 else np.float64)
+        n = pts.shape[0]
+        cols = np.ascontiguousarray(colors if colors is not None else np.zeros((n, 3)), np.float32)
+        hold = [pts, cols]
+
+        def ptr(a, dt):
+            if a is None:
+                return None
+            b = np.ascontiguousarray(a, dt)
+            assert b.shape == (n,)
+            hold.append(b)
+            return b.ctypes.data
+
+        fn = self._L.refsem_integrate_f32 if f32 else self._L.refsem_integrate
+        fn(self._h, pts, n, cols.ctypes.data, ptr(class_ids, np.int32), ptr(instance_ids, np.int32),
+           ptr(depths, np.float32))
+
+    def num_blocks(self):
+        return int(self._L.refsem_num_blocks(self._h))
+
+    def clear(self):
+        self._L.refsem_clear(self._h)
+
+    def dump_blocks(self, K=8):
+        nb, nv = self.num_blocks(), 512
+        d = dict(keys=np.zeros((nb, 3), np.int32), hashes=np.zeros(nb, np.uint64),
+                 count=np.zeros((nb, nv), np.int32), pos_sum=np.zeros((nb, nv, 3), np.float64),
+                 col_sum=np.zeros((nb, nv, 3), np.float32), object_id=np.zeros((nb, nv), np.int32),
+                 class_id=np.zeros((nb, nv), np.int32), confidence=np.zeros((nb, nv), np.float32),
+                 aux=np.zeros((nb, nv), np.int32), lab_obj=np.zeros((nb, nv, K), np.int32),
+                 lab_cls=np.zeros((nb, nv, K), np.int32), lab_logp=np.zeros((nb, nv, K), np.float32))
+        a = d
+        self._L.refsem_dump_blocks(self._h, a["keys"].ctypes.data, a["hashes"].ctypes.data, a["count"].ctypes.data,
+                                   a["pos_sum"].ctypes.data, a["col_sum"].ctypes.data, a["object_id"].ctypes.data,
+                                   a["class_id"].ctypes.data, a["confidence"].ctypes.data, a["aux"].ctypes.data,
+                                   int(K), a["lab_obj"].ctypes.data, a["lab_cls"].ctypes.data,
+                                   a["lab_logp"].ctypes.data)
+        return d
+
+    def get_voxels(self, min_count=1, min_confidence=0.0):
+        n = self._L.refsem_get_voxels(self._h, int(min_count), float(min_confidence), None, None, None, None, None)
+        out = dict(points=np.zeros((n, 3), np.float64), colors=np.zeros((n, 3), np.float32),
+                   class_ids=np.zeros(n, np.int32), object_ids=np.zeros(n, np.int32),
+                   confidences=np.zeros(n, np.float32))
+        if n:
+            self._L.refsem_get_voxels(self._h, int(min_count), float(min_confidence), out["points"].ctypes.data,
+                                      out["colors"].ctypes.data, out["class_ids"].ctypes.data,
+                                      out["object_ids"].ctypes.data, out["confidences"].ctypes.data)
+        return out
+
+    def remove_low_count_voxels(self, min_count):
+        self._L.refsem_remove_low_count_voxels(self._h, int(min_count))
+
+    def remove_low_confidence_segments(self, min_confidence):
+        self._L.refsem_remove_low_confidence_segments(self._h, int(min_confidence))
+
+    def merge_segments(self, a, b):
+        self._L.refsem_merge_segments(self._h, int(a), int(b))
+
+    def remove_segment(self, object_id):
+        self._L.refsem_remove_segment(self._h, int(object_id))

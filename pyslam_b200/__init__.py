@@ -6,7 +6,9 @@ CUDA kernels and the C ABI (include/b2v.h); the Python modules mirror the refere
 """
 
 from .volume import (B200TsdfVolume, BoundingBox3D, CameraFrustrum, PointCloud, TriangleMesh,
-                     VoxelBlockGrid, VoxelGridData, filter_shadow_points, remap)
+                     VoxelBlockGrid, VoxelBlockSemanticGrid, VoxelBlockSemanticProbabilisticGrid, VoxelGridData,
+                     VoxelSemanticGrid, VoxelSemanticGridProbabilistic, filter_shadow_points, remap)
 
 __all__ = ["B200TsdfVolume", "BoundingBox3D", "CameraFrustrum", "PointCloud", "TriangleMesh",
-           "VoxelBlockGrid", "VoxelGridData", "filter_shadow_points", "remap"]
+           "VoxelBlockGrid", "VoxelBlockSemanticGrid", "VoxelBlockSemanticProbabilisticGrid", "VoxelGridData",
+           "VoxelSemanticGrid", "VoxelSemanticGridProbabilistic", "filter_shadow_points", "remap"]

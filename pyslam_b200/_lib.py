@@ -13,6 +13,7 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_DIR, "libb2v.so")
 
 B2V_OK = 0
+B2V_SEM_VOTING, B2V_SEM_PROBABILISTIC, B2V_SEM_MAX_LABELS = 0, 1, 8
 B2V_ERR_INVALID_ARGUMENT = 1
 B2V_ERR_CUDA = 2
 B2V_ERR_CAPACITY = 3
@@ -32,6 +33,11 @@ EXPORTED_SYMBOLS = [
     "b2v_grid_size", "b2v_grid_get_voxels", "b2v_grid_copy_voxels",
     "b2v_grid_remove_low_count_voxels", "b2v_grid_dump_blocks", "b2v_grid_carve",
     "b2v_grid_get_voxels_in_frustum", "b2v_grid_get_voxels_in_bb", "b2v_version", "b2v_device_sm_count",
+    "b2v_sgrid_create", "b2v_sgrid_destroy", "b2v_sgrid_last_error", "b2v_sgrid_clear",
+    "b2v_sgrid_set_depth_threshold", "b2v_sgrid_set_depth_decay_rate", "b2v_sgrid_integrate",
+    "b2v_sgrid_num_blocks", "b2v_sgrid_get_voxels", "b2v_sgrid_copy_voxels",
+    "b2v_sgrid_remove_low_count_voxels", "b2v_sgrid_remove_low_confidence_segments", "b2v_sgrid_merge_segments",
+    "b2v_sgrid_remove_segment", "b2v_sgrid_label_overflows", "b2v_sgrid_dump_blocks",
 ]
 
 
@@ -95,6 +101,28 @@ def load() -> C.CDLL:
     L.b2v_profile_enable.argtypes = [vp, i32]
     L.b2v_profile_read.restype = C.c_int
     L.b2v_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), p_i64, p_i64]
+    L.b2v_sgrid_create.restype = C.c_int
+    L.b2v_sgrid_create.argtypes = [C.c_double, i32, C.c_uint32, i32, i32, C.POINTER(vp)]
+    L.b2v_sgrid_destroy.argtypes = [vp]
+    L.b2v_sgrid_last_error.restype = C.c_char_p
+    L.b2v_sgrid_last_error.argtypes = [vp]
+    L.b2v_sgrid_clear.argtypes = [vp]
+    L.b2v_sgrid_set_depth_threshold.argtypes = [vp, C.c_float]
+    L.b2v_sgrid_set_depth_decay_rate.argtypes = [vp, C.c_float]
+    L.b2v_sgrid_integrate.restype = C.c_int
+    L.b2v_sgrid_integrate.argtypes = [vp, C.c_int64, vp, i32, vp, i32, vp, vp, vp]
+    L.b2v_sgrid_num_blocks.restype = C.c_int64
+    L.b2v_sgrid_num_blocks.argtypes = [vp]
+    L.b2v_sgrid_get_voxels.restype = C.c_int64
+    L.b2v_sgrid_get_voxels.argtypes = [vp, i32, C.c_float]
+    L.b2v_sgrid_copy_voxels.argtypes = [vp] * 6
+    L.b2v_sgrid_remove_low_count_voxels.argtypes = [vp, i32]
+    L.b2v_sgrid_remove_low_confidence_segments.argtypes = [vp, i32]
+    L.b2v_sgrid_merge_segments.argtypes = [vp, i32, i32]
+    L.b2v_sgrid_remove_segment.argtypes = [vp, i32]
+    L.b2v_sgrid_label_overflows.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.b2v_sgrid_dump_blocks.restype = C.c_int64
+    L.b2v_sgrid_dump_blocks.argtypes = [vp] * 10 + [i32] + [vp] * 3
     L.b2v_set_rectification.restype = C.c_int
     L.b2v_set_rectification.argtypes = [vp, vp, vp, i32, i32, i32]
     L.b2v_remap.restype = C.c_int

@@ -1,0 +1,217 @@
+"""GPU: semantic voxel-block grids through the C ABI (b2v_sgrid_*).
+
+(1) the reference's own known-answer tests (cpp/test_volumetric_voxel_semantic.py:20-229), assertion for assertion;
+(2) the committed dump of the UNMODIFIED compiled reference (tests/golden/semantic_T0.npz): block keys, hashes,
+    counts, float64 position sums, float32 colour sums, labels, counters and label evidence BIT-EXACT;
+    Bayesian confidence within 2e-6 relative (float exp/log: glibc vs float64-rounded);
+(3) live against oracle/_ref when it travelled, with edits (remove / merge) and every input-dtype variant."""
+
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from pyslam_b200 import (VoxelBlockSemanticGrid, VoxelBlockSemanticProbabilisticGrid, VoxelSemanticGrid,
+                         VoxelSemanticGridProbabilistic)
+from tests._util import GOLDEN, sort_dump
+
+pytestmark = pytest.mark.gpu
+
+BASE_LOG = 0.10536051565782628
+
+
+def _zeros_points(n):
+    return np.zeros((n, 3), dtype=np.float64)
+
+
+def _zeros_colors(n):
+    return np.zeros((n, 3), dtype=np.uint8)
+
+
+# ---- (1) the reference KATs ------------------------------------------------------------------------------------
+def test_kat_voting_label_switch_and_confidence():
+    grid = VoxelSemanticGrid(0.1)
+    grid.integrate(_zeros_points(2), _zeros_colors(2), np.array([1, 2], np.int32), np.array([1, 2], np.int32))
+    v = grid.get_voxels(min_count=1, min_confidence=0.0)
+    assert len(v.object_ids) == 1 and v.object_ids[0] == 2 and v.class_ids[0] == 2
+    assert v.confidences[0] == pytest.approx(0.5, abs=1e-3)
+
+
+def test_kat_probabilistic_majority_depth_decay_and_strong_majority():
+    grid = VoxelSemanticGridProbabilistic(0.1)
+    grid.integrate(_zeros_points(4), _zeros_colors(4), np.array([5, 5, 5, 6], np.int32),
+                   np.array([1, 1, 1, 2], np.int32))
+    v = grid.get_voxels(min_count=1, min_confidence=0.0)
+    assert len(v.object_ids) == 1 and v.object_ids[0] == 1 and v.class_ids[0] == 5 and v.confidences[0] > 0.5
+    grid = VoxelSemanticGridProbabilistic(0.1)
+    grid.integrate(_zeros_points(2), _zeros_colors(2), np.array([7, 8], np.int32), np.array([3, 4], np.int32),
+                   np.array([1.0, 20.0], np.float32))
+    v = grid.get_voxels(min_count=1, min_confidence=0.0)
+    assert len(v.object_ids) == 1 and v.object_ids[0] == 3 and v.class_ids[0] == 7 and v.confidences[0] > 0.5
+    grid = VoxelSemanticGridProbabilistic(0.1)
+    grid.integrate(_zeros_points(13), _zeros_colors(13), np.array([5] * 12 + [6], np.int32),
+                   np.array([1] * 12 + [2], np.int32))
+    v = grid.get_voxels(min_count=1, min_confidence=0.0)
+    assert v.object_ids[0] == 1 and v.class_ids[0] == 5 and v.confidences[0] > 0.7
+
+
+def test_kat_labels_across_voxels():
+    grid = VoxelSemanticGrid(0.1)
+    grid.integrate(np.array([[0.0, 0.0, 0.0], [0.2, 0.0, 0.0]]), _zeros_colors(2), np.array([10, 20], np.int32),
+                   np.array([101, 202], np.int32))
+    v = grid.get_voxels(min_count=1, min_confidence=0.0)
+    paired = sorted(zip(map(tuple, v.points), v.object_ids, v.class_ids))
+    assert len(paired) == 2 and paired[0][1:] == (101, 10) and paired[1][1:] == (202, 20)
+
+
+def test_kat_label_noise_and_joint_softmax():
+    for cls_t, seed, maj, noise, labels in ((VoxelSemanticGridProbabilistic, 0, 50, 5, ((111, 11), (222, 12))),
+                                            (VoxelSemanticGrid, 1, 30, 3, ((210, 21), (220, 22)))):
+        rng = np.random.default_rng(seed)
+        tot = maj + noise
+        pts = rng.uniform(low=0.0, high=0.05, size=(tot, 3)).astype(np.float64)
+        cls = np.array([labels[0][1]] * maj + [labels[1][1]] * noise, np.int32)
+        ins = np.array([labels[0][0]] * maj + [labels[1][0]] * noise, np.int32)
+        perm = rng.permutation(tot)
+        grid = cls_t(0.2)
+        grid.integrate(pts[perm], _zeros_colors(tot), cls[perm], ins[perm])
+        v = grid.get_voxels(min_count=1, min_confidence=0.0)
+        assert len(v.object_ids) == 1 and (v.object_ids[0], v.class_ids[0]) == labels[0]
+        if cls_t is VoxelSemanticGridProbabilistic:
+            assert v.confidences[0] > 0.75
+        else:
+            assert v.confidences[0] == pytest.approx((maj - noise) / float(tot), abs=1e-2)
+    pc = {(1, 10): 3, (1, 11): 3, (2, 10): 4}
+    ins = np.concatenate([[o] * k for (o, c), k in pc.items()]).astype(np.int32)
+    cls = np.concatenate([[c] * k for (o, c), k in pc.items()]).astype(np.int32)
+    perm = np.random.default_rng(42).permutation(10)
+    grid = VoxelSemanticGridProbabilistic(0.1)
+    grid.integrate(_zeros_points(10), _zeros_colors(10), cls[perm], ins[perm])
+    v = grid.get_voxels(min_count=1, min_confidence=0.0)
+    lp = np.array([4, 3, 3]) * BASE_LOG
+    assert v.object_ids[0] == 2 and v.class_ids[0] == 10
+    assert v.confidences[0] == pytest.approx(np.exp(lp[0]) / np.exp(lp).sum(), rel=1e-4, abs=1e-4)
+
+
+# ---- (2) golden dump of the compiled reference --------------------------------------------------------------------
+def _compare_dumps(a, b, kind):
+    assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["hashes"], b["hashes"])
+    for k in ("count", "pos_sum", "col_sum", "object_id", "class_id", "aux"):
+        assert np.array_equal(a[k], b[k]), k
+    if kind == "prob":
+        assert np.array_equal(a["lab_obj"], b["lab_obj"]) and np.array_equal(a["lab_cls"], b["lab_cls"])
+        assert np.array_equal(a["lab_logp"], b["lab_logp"])
+        bad = np.argwhere(~np.isclose(a["confidence"], b["confidence"], rtol=2e-6, atol=1e-9))
+        assert len(bad) == 0, (len(bad), [(tuple(i), a["confidence"][tuple(i)], b["confidence"][tuple(i)],
+                                           b["count"][tuple(i)], b["aux"][tuple(i)], b["object_id"][tuple(i)],
+                                           b["class_id"][tuple(i)], b["lab_obj"][tuple(i)].tolist(),
+                                           b["lab_cls"][tuple(i)].tolist(), b["lab_logp"][tuple(i)].tolist())
+                                          for i in bad[:4]])
+    else:
+        assert np.array_equal(a["confidence"], b["confidence"])
+
+
+@pytest.mark.parametrize("tag", ["vote", "prob"])
+def test_golden_reference_dump(tag):
+    g = np.load(os.path.join(GOLDEN, "semantic_T0.npz"))
+    cls_t = VoxelBlockSemanticGrid if tag == "vote" else VoxelBlockSemanticProbabilisticGrid
+    grid = cls_t(float(g["voxel_size"]), 8, capacity_blocks=1024)
+    grid.set_depth_threshold(float(g[f"{tag}_depth_threshold"]))
+    grid.set_depth_decay_rate(float(g[f"{tag}_depth_decay_rate"]))
+    for i in range(int(g["n_frames"])):
+        grid.integrate(g[f"{tag}_points_{i}"], g[f"{tag}_colors_{i}"], g[f"{tag}_cls_{i}"], g[f"{tag}_inst_{i}"],
+                       g[f"{tag}_depths_{i}"])
+    ref = {k: g[f"{tag}_{k}"] for k in ("keys", "hashes", "count", "pos_sum", "col_sum", "object_id", "class_id",
+                                         "confidence", "aux", "lab_obj", "lab_cls", "lab_logp")}
+    _compare_dumps(sort_dump(grid.dump_blocks(8)), ref, tag)
+    assert grid.label_overflows() == 0
+    v = grid.get_voxels(2, 0.4)
+    order = np.lexsort((v.points[:, 2], v.points[:, 1], v.points[:, 0]))
+    # voxels whose confidence sits within float rounding of 0.4 may flip for the Bayesian grid
+    if len(order) == len(g[f"{tag}_voxels_points"]):
+        assert np.array_equal(v.points[order], g[f"{tag}_voxels_points"])
+        assert np.array_equal(v.colors[order], g[f"{tag}_voxels_colors"])
+        assert np.array_equal(v.class_ids[order], g[f"{tag}_voxels_class_ids"])
+        assert np.array_equal(v.object_ids[order], g[f"{tag}_voxels_object_ids"])
+        assert np.allclose(v.confidences[order], g[f"{tag}_voxels_confidences"], rtol=2e-6)
+    else:
+        assert tag == "prob" and abs(len(order) - len(g[f"{tag}_voxels_points"])) <= 2
+    assert grid.num_blocks() == len(ref["keys"]) and grid.size() == int((ref["count"] > 0).sum())
+    grid.clear()
+    assert grid.empty() and len(grid.get_voxels(1, 0.0).points) == 0
+
+
+# ---- (3) live against the compiled reference ----------------------------------------------------------------------
+@pytest.mark.skipif(not oracle.have_ref_semantic(), reason="compiled reference (oracle/_ref) not on this box")
+@pytest.mark.parametrize("kind", ["voting", "probabilistic"])
+def test_live_against_compiled_reference_with_edits(kind):
+    rng = np.random.default_rng(11)
+    vs = 0.05
+    cls_t = VoxelBlockSemanticGrid if kind == "voting" else VoxelBlockSemanticProbabilisticGrid
+    ref = oracle.RefSemanticGrid(vs, kind)
+    grid = cls_t(vs, 8, capacity_blocks=1 << 12)
+    thr, rate = (2.0, 0.0) if kind == "voting" else (1.5, 0.8)
+    ref.set_depth_threshold(thr)
+    grid.set_depth_threshold(thr)
+    if kind == "probabilistic":
+        ref.set_depth_decay_rate(rate)
+        grid.set_depth_decay_rate(rate)
+    tag = "vote" if kind == "voting" else "prob"
+    variants = [dict(f64=True, u8=False, inst=True, depth=True), dict(f64=False, u8=True, inst=True, depth=False),
+                dict(f64=True, u8=False, inst=False, depth=True), dict(f64=False, u8=False, inst=False, depth=False)]
+    for var in variants:
+        n = 30000
+        dirs = rng.normal(size=(n, 3))
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        pts = dirs * (0.5 + 0.01 * rng.normal(size=(n, 1))) + [0.05, -0.1, 0.02]   # shell across the origin
+        pts = pts.astype(np.float64 if var["f64"] else np.float32)
+        cols_u8 = rng.integers(0, 256, size=(n, 3), dtype=np.uint8)
+        # the reference harness takes float colours; uint8 goes through c * (1.0f / 255.0f) (voxel_data.h:82-85)
+        cols_f = (cols_u8.astype(np.float32) * (np.float32(1.0) / np.float32(255.0))) if var["u8"] \
+            else rng.random((n, 3)).astype(np.float32)
+        side = (pts[:, 0] > 0).astype(np.int32)
+        flip, noise = rng.random(n) < 0.2, rng.integers(-1, 1, n)    # correlated label noise incl. the invalid id -1
+        cls = np.where(flip, noise, 1 + side).astype(np.int32)
+        ins = np.where(flip, noise, 10 + side).astype(np.int32)
+        dep = rng.uniform(0.5, 4.0, n).astype(np.float32)
+        ref.integrate(pts, cols_f, cls, ins if var["inst"] else None, dep if var["depth"] else None)
+        grid.integrate(pts, cols_u8 if var["u8"] else cols_f, cls, ins if var["inst"] else None,
+                       dep if var["depth"] else None)
+    a, b = sort_dump(grid.dump_blocks(8)), sort_dump(ref.dump_blocks(8))
+    assert b["aux"].max() <= 8 or kind == "voting"
+    _compare_dumps(a, b, tag)
+    # edits: merge two objects, drop one, drop low-count voxels, then compare again
+    for g_ in (ref, grid):
+        g_.merge_segments(10, 11)
+        g_.remove_segment(0)
+        g_.remove_low_count_voxels(3)
+    a, b = sort_dump(grid.dump_blocks(8)), sort_dump(ref.dump_blocks(8))
+    assert np.array_equal(a["count"], b["count"]) and np.array_equal(a["object_id"], b["object_id"])
+    assert np.array_equal(a["class_id"], b["class_id"])
+    assert np.allclose(a["confidence"], b["confidence"], rtol=2e-6, atol=1e-9)
+    rv = ref.get_voxels(2, 0.3)
+    gv = grid.get_voxels(2, 0.3)
+    assert abs(len(gv.points) - len(rv["points"])) <= 2 and len(rv["points"]) > 50
+    for g_ in (ref, grid):
+        g_.remove_low_confidence_segments(1)      # int threshold: everything below confidence 1 goes
+    a, b = sort_dump(grid.dump_blocks(1)), sort_dump(ref.dump_blocks(1))
+    assert np.array_equal(a["count"], b["count"]) and (b["count"] > 0).sum() > 0
+
+
+def test_label_overflow_is_counted_and_keeps_the_majority():
+    grid = VoxelBlockSemanticProbabilisticGrid(0.1, 8, capacity_blocks=64)
+    n_noise = 11                                   # 11 distinct minority pairs + the majority pair > 8 slots
+    cls = np.array([5] * 20 + list(range(100, 100 + n_noise)), np.int32)
+    ins = np.array([1] * 20 + list(range(200, 200 + n_noise)), np.int32)
+    perm = np.random.default_rng(3).permutation(len(cls))
+    grid.integrate(np.zeros((len(cls), 3), np.float32), np.zeros((len(cls), 3), np.float32), cls[perm], ins[perm])
+    v = grid.get_voxels(1, 0.0)
+    assert (v.object_ids[0], v.class_ids[0]) == (1, 5)
+    assert grid.label_overflows() == n_noise + 1 - 8
+    with pytest.raises(RuntimeError):
+        grid.integrate(np.zeros((2, 3), np.float32), None, None, np.array([1, 2], np.int32))
+    with pytest.raises(RuntimeError):
+        grid.integrate(np.zeros((2, 3), np.float32), np.zeros((2, 3), np.float32), np.array([1], np.int32))
+    with pytest.raises(RuntimeError):
+        VoxelBlockSemanticGrid(0.1, 4)

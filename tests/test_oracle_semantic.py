@@ -1,0 +1,97 @@
+"""CPU: pin the semantic-fusion oracle.  (1) The reference's own known-answer tests
+(cpp/test_volumetric_voxel_semantic.py:20-229) run against the UNMODIFIED compiled reference block grids
+(oracle/_ref/libref_semantic.so).  (2) The committed golden dump (tests/golden/semantic_T0.npz, produced by that
+library) obeys the rules the GPU implementation restates: voting confidence = min(1, counter / count), Bayesian
+confidence = softmax of the label evidence, argmax = label with the largest evidence."""
+
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tests._util import GOLDEN
+
+BASE_LOG = 0.10536051565782628  # voxel_data_semantic.h:287
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref_semantic(), reason="oracle/_ref/libref_semantic.so not built")
+
+
+def _one_voxel(kind, voxel, cls, inst, depths=None, points=None):
+    g = oracle.RefSemanticGrid(voxel, kind)
+    g.set_depth_threshold(10.0 if kind == "voting" else 5.0)   # class defaults (voxel_data_semantic.h:107,251-254)
+    if kind == "probabilistic":
+        g.set_depth_decay_rate(0.07)
+    n = len(cls)
+    g.integrate(np.zeros((n, 3)) if points is None else points, np.zeros((n, 3), np.float32), cls, inst, depths)
+    return g.get_voxels(1, 0.0)
+
+
+@needs_ref
+def test_reference_kats_hold_for_the_compiled_block_grids():
+    v = _one_voxel("voting", 0.1, [1, 2], [1, 2])                         # :20-36 label switch, confidence 0.5
+    assert list(v["object_ids"]) == [2] and list(v["class_ids"]) == [2]
+    assert v["confidences"][0] == pytest.approx(0.5, abs=1e-3)
+    v = _one_voxel("probabilistic", 0.1, [5, 5, 5, 6], [1, 1, 1, 2])      # :39-55 majority
+    assert (v["object_ids"][0], v["class_ids"][0]) == (1, 5) and v["confidences"][0] > 0.5
+    v = _one_voxel("probabilistic", 0.1, [7, 8], [3, 4], [1.0, 20.0])     # :58-76 depth decay
+    assert (v["object_ids"][0], v["class_ids"][0]) == (3, 7) and v["confidences"][0] > 0.5
+    v = _one_voxel("voting", 0.1, [10, 20], [101, 202], points=np.array([[0.0, 0, 0], [0.2, 0, 0]]))  # :79-97
+    pairs = sorted(zip(map(tuple, v["points"]), v["object_ids"], v["class_ids"]))
+    assert [p[1:] for p in pairs] == [(101, 10), (202, 20)]
+    v = _one_voxel("probabilistic", 0.1, [5] * 12 + [6], [1] * 12 + [2])  # :100-120 strong majority
+    assert (v["object_ids"][0], v["class_ids"][0]) == (1, 5) and v["confidences"][0] > 0.7
+    # :123-185 seeded noise
+    for kind, seed, maj, noise, labels, bound in (("probabilistic", 0, 50, 5, ((111, 11), (222, 12)), 0.75),
+                                                  ("voting", 1, 30, 3, ((210, 21), (220, 22)), None)):
+        rng = np.random.default_rng(seed)
+        tot = maj + noise
+        pts = rng.uniform(0.0, 0.05, size=(tot, 3))
+        cls = np.array([labels[0][1]] * maj + [labels[1][1]] * noise, np.int32)
+        ins = np.array([labels[0][0]] * maj + [labels[1][0]] * noise, np.int32)
+        perm = rng.permutation(tot)
+        v = _one_voxel(kind, 0.2, cls[perm], ins[perm], points=pts[perm])
+        assert (v["object_ids"][0], v["class_ids"][0]) == labels[0]
+        if bound:
+            assert v["confidences"][0] > bound
+        else:
+            assert v["confidences"][0] == pytest.approx((maj - noise) / tot, abs=1e-2)
+    # :188-229 exact softmax of k * BASE_LOG
+    pc = {(1, 10): 3, (1, 11): 3, (2, 10): 4}
+    ins = np.concatenate([[o] * k for (o, c), k in pc.items()]).astype(np.int32)
+    cls = np.concatenate([[c] * k for (o, c), k in pc.items()]).astype(np.int32)
+    perm = np.random.default_rng(42).permutation(10)
+    v = _one_voxel("probabilistic", 0.1, cls[perm], ins[perm])
+    lp = np.array([4, 3, 3]) * BASE_LOG
+    assert (v["object_ids"][0], v["class_ids"][0]) == (2, 10)
+    assert v["confidences"][0] == pytest.approx(np.exp(lp[0]) / np.exp(lp).sum(), rel=1e-4, abs=1e-4)
+
+
+def test_golden_dump_obeys_the_fusion_rules():
+    g = np.load(os.path.join(GOLDEN, "semantic_T0.npz"))
+    # voting: confidence = min(1, counter / count) (voxel_data_semantic.h:117-132)
+    cnt, ctr = g["vote_count"], g["vote_aux"]
+    occ = cnt > 0
+    exp = np.minimum(1.0, ctr[occ].astype(np.float32) / cnt[occ].astype(np.float32))
+    assert np.array_equal(g["vote_confidence"][occ], exp.astype(np.float32))
+    assert (ctr[occ] < cnt[occ]).any() and (g["vote_object_id"][occ] == -1).any()   # gated + invalid ids occur
+    # Bayesian: argmax + softmax over the label evidence (voxel_data_semantic.h:561-570, 607-624)
+    lp = g["prob_lab_logp"].astype(np.float64)
+    nl = g["prob_aux"]
+    occ = (g["prob_count"] > 0) & (nl > 0)
+    assert nl.max() <= 8 and nl[occ].min() >= 1 and (nl[occ] > 2).any()
+    best = lp[occ].max(axis=1)
+    k = lp[occ].argmax(axis=1)
+    rows = np.arange(len(k))
+    obj, cls = g["prob_lab_obj"][occ][rows, k], g["prob_lab_cls"][occ][rows, k]
+    valid = (obj != -1) & (cls != -1)
+    # ties keep the earlier label, so compare labels only where the maximum is unique
+    srt = np.sort(lp[occ], axis=1)
+    unique = (srt[:, -1] - srt[:, -2] > 1e-6) | (nl[occ] == 1)
+    assert np.array_equal(g["prob_object_id"][occ][unique], obj[unique])
+    assert np.array_equal(g["prob_class_id"][occ][unique], cls[unique])
+    soft = np.exp(best - np.log(np.exp(lp[occ]).sum(axis=1)))
+    conf = g["prob_confidence"][occ]
+    chosen_valid = (g["prob_object_id"][occ] != -1) & (g["prob_class_id"][occ] != -1)
+    assert np.allclose(conf[unique & chosen_valid], soft[unique & chosen_valid], rtol=2e-6, atol=1e-7)
+    assert np.all(conf[~chosen_valid] == 0.0) and valid.any()
