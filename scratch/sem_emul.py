@@ -66,3 +66,13 @@ for b in range(len(keys)):
             if nbad<5: print("conf mismatch",k,c,rc,st["labs"],st["ml"],st["mlp"], list(zip(d["lab_obj"][b,li],d["lab_cls"][b,li],d["lab_logp"][b,li]))[:6])
         worst=max(worst,r)
 print("voxels",tot,"worst rel",worst,"bad",nbad)
+nd=0
+for b in range(len(keys)):
+    for li in np.where(d["count"][b]>0)[0]:
+        lx,ly,lz=li&7,(li>>3)&7,li>>6
+        k=(keys[b,0]*8+lx,keys[b,1]*8+ly,keys[b,2]*8+lz)
+        st=vox[k]
+        mine=[st["labs"][p] for p in sorted(st["labs"])]
+        refl=list(d["lab_logp"][b,li][:len(mine)])
+        if any(float(x)!=float(y) for x,y in zip(mine,refl)): nd+=1
+print("voxels with logp differing (correctly-rounded exp vs glibc):", nd)
