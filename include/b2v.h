@@ -200,6 +200,15 @@ int b2v_sgrid_set_depth_decay_rate(b2v_sgrid *g, float depth_decay_rate);
 int b2v_sgrid_integrate(b2v_sgrid *g, int64_t n, const void *points, int32_t points_f64, const void *colors,
                         int32_t colors_u8, const int32_t *class_ids, const int32_t *instance_ids,
                         const float *depths);
+/* Fused front-end of the semantic integrator (volumetric_integrator_voxel_semantic_grid.py:332-461): optional
+ * shadow-point filter, depth2pointcloud (depth.py:45-85) with class / object-id images, camera->world transform
+ * (Twc, float64 then float32) and integrate, without materialising the point cloud.  Points reach a voxel in
+ * row-major pixel order, the order of the reference's point arrays.  class_image / object_image: NULL or int32
+ * [H][W]; use_depths: weight the evidence by camera depth (kVolumetricSemanticProbabilisticIntegrationUseDepth). */
+int b2v_sgrid_integrate_rgbd(b2v_sgrid *g, const float *depth, const uint8_t *color, const int32_t *class_image,
+                             const int32_t *object_image, int32_t height, int32_t width, const double K[4],
+                             const double Twc[16], float max_depth, float min_depth, int32_t use_depths,
+                             int32_t filter_shadow_points);
 int64_t b2v_sgrid_num_blocks(b2v_sgrid *g);
 /* two-step read-out: get_voxels returns the count (or -1), copy_voxels fills caller arrays (any may be NULL):
  * points f64 [n][3], colors f32 [n][3], class_ids / object_ids i32 [n], confidences f32 [n] */

@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = [
     "b2v_grid_get_voxels_in_frustum", "b2v_grid_get_voxels_in_bb", "b2v_version", "b2v_device_sm_count",
     "b2v_sgrid_create", "b2v_sgrid_destroy", "b2v_sgrid_last_error", "b2v_sgrid_clear",
     "b2v_sgrid_set_depth_threshold", "b2v_sgrid_set_depth_decay_rate", "b2v_sgrid_integrate",
+    "b2v_sgrid_integrate_rgbd",
     "b2v_sgrid_num_blocks", "b2v_sgrid_get_voxels", "b2v_sgrid_copy_voxels",
     "b2v_sgrid_remove_low_count_voxels", "b2v_sgrid_remove_low_confidence_segments", "b2v_sgrid_merge_segments",
     "b2v_sgrid_remove_segment", "b2v_sgrid_label_overflows", "b2v_sgrid_dump_blocks",
@@ -111,6 +112,8 @@ def load() -> C.CDLL:
     L.b2v_sgrid_set_depth_decay_rate.argtypes = [vp, C.c_float]
     L.b2v_sgrid_integrate.restype = C.c_int
     L.b2v_sgrid_integrate.argtypes = [vp, C.c_int64, vp, i32, vp, i32, vp, vp, vp]
+    L.b2v_sgrid_integrate_rgbd.restype = C.c_int
+    L.b2v_sgrid_integrate_rgbd.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, C.c_float, C.c_float, i32, i32]
     L.b2v_sgrid_num_blocks.restype = C.c_int64
     L.b2v_sgrid_num_blocks.argtypes = [vp]
     L.b2v_sgrid_get_voxels.restype = C.c_int64

@@ -72,11 +72,11 @@ template <> struct PointKey<double> {  // get_voxel_key_inv<double, double>: the
 // ---- 1. make sure every point's block exists ---------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-sem_insert_kernel(const T *__restrict__ pts, const int64_t n, const float inv_vs, const HashTable H,
-                  const SemGrid G) {
+sem_insert_kernel(const T *__restrict__ pts, const uint8_t *__restrict__ valid, const int64_t n,
+                  const float inv_vs, const HashTable H, const SemGrid G) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool have = i < n;
+    const bool have = i < n && (valid == nullptr || valid[i]);
     int bx = 0, by = 0, bz = 0;
     if (have) {
         bx = block_coord(PointKey<T>::coord(pts[3 * i + 0], inv_vs));
@@ -116,14 +116,16 @@ sem_insert_kernel(const T *__restrict__ pts, const int64_t n, const float inv_vs
 // ---- 2. sort keys --------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-sem_keys_kernel(const T *__restrict__ pts, const int64_t n, const float inv_vs, const HashTable H, const SemGrid G,
-                uint32_t *__restrict__ vid, uint32_t *__restrict__ order) {
+sem_keys_kernel(const T *__restrict__ pts, const uint8_t *__restrict__ valid, const int64_t n, const float inv_vs,
+                const HashTable H, const SemGrid G, uint32_t *__restrict__ vid, uint32_t *__restrict__ order) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int vx = PointKey<T>::coord(pts[3 * i + 0], inv_vs), vy = PointKey<T>::coord(pts[3 * i + 1], inv_vs),
               vz = PointKey<T>::coord(pts[3 * i + 2], inv_vs);
     uint32_t key = kBadVid;
-    const uint32_t slot = table_find(H, block_coord(vx), block_coord(vy), block_coord(vz));
+    const uint32_t slot = (valid == nullptr || valid[i])
+                              ? table_find(H, block_coord(vx), block_coord(vy), block_coord(vz))
+                              : kEmpty;
     if (slot != kEmpty) {
         const uint32_t idx = H.entries[slot].w;
         if (idx < G.capacity)
@@ -131,6 +133,39 @@ sem_keys_kernel(const T *__restrict__ pts, const int64_t n, const float inv_vs, 
     }
     vid[i] = key;
     order[i] = static_cast<uint32_t>(i);
+}
+
+// ---- fused front-end: depth2pointcloud + world transform of one labelled RGBD frame ------------------------
+// (pyslam/utilities/depth.py:45-85; pyslam/dense/volumetric_integrator_voxel_semantic_grid.py:392-453).  One
+// thread per pixel writes the point record the reference front-end would have produced for it; invalid pixels
+// are masked instead of compacted - their sort key is kBadVid, so the per-voxel order of the valid ones is the
+// row-major pixel order, i.e. the reference's point order.
+__global__ void __launch_bounds__(256)
+sem_rgbd_points_kernel(const RgbdParams P, const float *__restrict__ depth, const uint8_t *__restrict__ rgb,
+                       const int32_t *__restrict__ class_img, const int32_t *__restrict__ object_img,
+                       float *__restrict__ pts, float *__restrict__ cols, int32_t *__restrict__ cls,
+                       int32_t *__restrict__ inst, float *__restrict__ depths, uint8_t *__restrict__ valid) {
+    const int64_t n = static_cast<int64_t>(P.H) * P.W;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float d = depth[i];
+    const bool ok = d > P.min_depth && d < P.max_depth;  // depth.py:62
+    valid[i] = ok ? 1 : 0;
+    if (!ok) return;
+    const int row = static_cast<int>(i / P.W), col = static_cast<int>(i % P.W);
+    const double z = static_cast<double>(d);
+    const double x = __dmul_rn(__dmul_rn(__dsub_rn(static_cast<double>(col), P.cx), z), P.fx_inv);  // depth.py:72
+    const double y = __dmul_rn(__dmul_rn(__dsub_rn(static_cast<double>(row), P.cy), z), P.fy_inv);  // depth.py:73
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {  // semantic_grid.py:411-415 in float64, then ascontiguousarray(float32) :434-436
+        pts[3 * i + a] = __double2float_rn(__dadd_rn(
+            __dadd_rn(__dadd_rn(__dmul_rn(x, P.R[3 * a]), __dmul_rn(y, P.R[3 * a + 1])), __dmul_rn(z, P.R[3 * a + 2])),
+            P.t[a]));
+        cols[3 * i + a] = __double2float_rn(__ddiv_rn(static_cast<double>(rgb[3 * i + a]), 255.0));  // depth.py:76
+    }
+    if (class_img) cls[i] = class_img[i];
+    if (object_img) inst[i] = object_img[i];
+    depths[i] = d;  // points[:, 2] narrowed back to float32 (:408-409) is the depth itself
 }
 
 // ---- 4. per-voxel sequential update ------------------------------------------------------------------------
@@ -448,6 +483,12 @@ struct b2v_sgrid {
     uint32_t *d_vid[2] = {nullptr, nullptr}, *d_ord[2] = {nullptr, nullptr};
     void *d_sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0, stage_points = 0;
+    // fused RGBD front-end
+    float *d_img_depth = nullptr, *d_img_filtered = nullptr;
+    uint8_t *d_img_rgb = nullptr, *d_valid = nullptr;
+    int32_t *d_img_cls = nullptr, *d_img_obj = nullptr;
+    void *d_shadow_scratch = nullptr;
+    size_t img_pixels = 0;
     // read-out
     uint32_t *d_sums = nullptr, *d_offs = nullptr, *d_total = nullptr;
     uint32_t scan_cap = 0;
@@ -544,7 +585,8 @@ extern "C" int b2v_sgrid_destroy(b2v_sgrid *g) {
                     g->G.cls, g->G.counter, g->G.ml_logp, g->G.conf, g->G.lab_obj, g->G.lab_cls, g->G.lab_logp,
                     g->d_pts, g->d_cols, g->d_cls, g->d_inst, g->d_depths, g->d_vid[0], g->d_vid[1], g->d_ord[0],
                     g->d_ord[1], g->d_sort_tmp, g->d_sums, g->d_offs, g->d_total, g->d_out_pts, g->d_out_cols,
-                    g->d_out_conf, g->d_out_cls, g->d_out_obj};
+                    g->d_out_conf, g->d_out_cls, g->d_out_obj, g->d_img_depth, g->d_img_filtered, g->d_img_rgb,
+                    g->d_valid, g->d_img_cls, g->d_img_obj, g->d_shadow_scratch};
     for (void *p : ptrs) cudaFree(p);
     cudaFreeHost(g->h_counters);
     if (g->stream) cudaStreamDestroy(g->stream);
@@ -620,6 +662,30 @@ static int sgrid_ensure_stage(b2v_sgrid *g, size_t n) {
     return B2V_OK;
 }
 
+// insert -> keys -> sort -> runs over the staged point records (valid: optional per-point mask)
+static int sgrid_fuse_staged(b2v_sgrid *g, int64_t n, const SemInputs &in, const uint8_t *valid) {
+    cudaStream_t s = g->stream;
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (in.pts_f64) {
+        sem_insert_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double *>(in.pts), valid, n,
+                                                       g->inv_voxel_size, g->table, g->G);
+        sem_keys_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double *>(in.pts), valid, n, g->inv_voxel_size,
+                                                     g->table, g->G, g->d_vid[0], g->d_ord[0]);
+    } else {
+        sem_insert_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(in.pts), valid, n, g->inv_voxel_size,
+                                                      g->table, g->G);
+        sem_keys_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(in.pts), valid, n, g->inv_voxel_size,
+                                                    g->table, g->G, g->d_vid[0], g->d_ord[0]);
+    }
+    SG_CUDA(g, cudaGetLastError());
+    size_t tmp = g->sort_tmp_bytes;  // all 32 key bits: kBadVid (points without storage) must sort last
+    SG_CUDA(g, cub::DeviceRadixSort::SortPairs(g->d_sort_tmp, tmp, g->d_vid[0], g->d_vid[1], g->d_ord[0], g->d_ord[1],
+                                               n, 0, 32, s));
+    sem_runs_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(g->d_vid[1], g->d_ord[1], n, in, g->G);
+    SG_CUDA(g, cudaGetLastError());
+    return B2V_OK;
+}
+
 extern "C" int b2v_sgrid_integrate(b2v_sgrid *g, int64_t n, const void *points, int32_t points_f64,
                                    const void *colors, int32_t colors_u8, const int32_t *class_ids,
                                    const int32_t *instance_ids, const float *depths) {
@@ -645,22 +711,6 @@ extern "C" int b2v_sgrid_integrate(b2v_sgrid *g, int64_t n, const void *points, 
     if (class_ids) SG_CUDA(g, cudaMemcpyAsync(g->d_cls, class_ids, m * sizeof(int32_t), cudaMemcpyDefault, s));
     if (instance_ids) SG_CUDA(g, cudaMemcpyAsync(g->d_inst, instance_ids, m * sizeof(int32_t), cudaMemcpyDefault, s));
     if (depths) SG_CUDA(g, cudaMemcpyAsync(g->d_depths, depths, m * sizeof(float), cudaMemcpyDefault, s));
-    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
-    if (points_f64) {
-        sem_insert_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double *>(g->d_pts), n, g->inv_voxel_size,
-                                                       g->table, g->G);
-        sem_keys_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double *>(g->d_pts), n, g->inv_voxel_size,
-                                                     g->table, g->G, g->d_vid[0], g->d_ord[0]);
-    } else {
-        sem_insert_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(g->d_pts), n, g->inv_voxel_size,
-                                                      g->table, g->G);
-        sem_keys_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(g->d_pts), n, g->inv_voxel_size,
-                                                    g->table, g->G, g->d_vid[0], g->d_ord[0]);
-    }
-    SG_CUDA(g, cudaGetLastError());
-    size_t tmp = g->sort_tmp_bytes;  // all 32 key bits: kBadVid (points without storage) must sort last
-    SG_CUDA(g, cub::DeviceRadixSort::SortPairs(g->d_sort_tmp, tmp, g->d_vid[0], g->d_vid[1], g->d_ord[0], g->d_ord[1],
-                                               n, 0, 32, s));
     SemInputs in{};
     in.pts = g->d_pts;
     in.cols = colors ? g->d_cols : nullptr;
@@ -669,9 +719,85 @@ extern "C" int b2v_sgrid_integrate(b2v_sgrid *g, int64_t n, const void *points, 
     in.depths = depths ? g->d_depths : nullptr;
     in.pts_f64 = points_f64 ? 1 : 0;
     in.cols_u8 = colors_u8 ? 1 : 0;
-    sem_runs_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(g->d_vid[1], g->d_ord[1], n, in, g->G);
-    SG_CUDA(g, cudaGetLastError());
+    rc = sgrid_fuse_staged(g, n, in, nullptr);
+    if (rc != B2V_OK) return rc;
     return sgrid_read_counters(g);  // also the completion fence: the inputs are free when this returns
+}
+
+extern "C" int b2v_sgrid_integrate_rgbd(b2v_sgrid *g, const float *depth, const uint8_t *color,
+                                        const int32_t *class_image, const int32_t *object_image, int32_t height,
+                                        int32_t width, const double K[4], const double Twc[16], float max_depth,
+                                        float min_depth, int32_t use_depths, int32_t filter_shadow_points) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    if (!depth || !color || !K || !Twc || height <= 0 || width <= 0 || (object_image && !class_image)) {
+        g->err = "b2v_sgrid_integrate_rgbd: bad arguments";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    SG_CUDA(g, cudaSetDevice(g->device));
+    const size_t pixels = static_cast<size_t>(height) * width;
+    int rc = sgrid_ensure_stage(g, pixels);
+    if (rc != B2V_OK) return rc;
+    if (pixels > g->img_pixels) {
+        SG_CUDA(g, cudaStreamSynchronize(g->stream));
+        void **bufs[] = {reinterpret_cast<void **>(&g->d_img_depth), reinterpret_cast<void **>(&g->d_img_filtered),
+                         reinterpret_cast<void **>(&g->d_img_rgb), reinterpret_cast<void **>(&g->d_img_cls),
+                         reinterpret_cast<void **>(&g->d_img_obj), reinterpret_cast<void **>(&g->d_valid),
+                         &g->d_shadow_scratch};
+        for (void **b : bufs) {
+            cudaFree(*b);
+            *b = nullptr;
+        }
+        SG_CUDA(g, cudaMalloc(&g->d_img_depth, pixels * sizeof(float)));
+        SG_CUDA(g, cudaMalloc(&g->d_img_filtered, pixels * sizeof(float)));
+        SG_CUDA(g, cudaMalloc(&g->d_img_rgb, pixels * 3));
+        SG_CUDA(g, cudaMalloc(&g->d_img_cls, pixels * sizeof(int32_t)));
+        SG_CUDA(g, cudaMalloc(&g->d_img_obj, pixels * sizeof(int32_t)));
+        SG_CUDA(g, cudaMalloc(&g->d_valid, pixels));
+        SG_CUDA(g, cudaMalloc(&g->d_shadow_scratch, kShadowScratchBytes));
+        g->img_pixels = pixels;
+    }
+    cudaStream_t s = g->stream;
+    SG_CUDA(g, cudaMemcpyAsync(g->d_img_depth, depth, pixels * sizeof(float), cudaMemcpyDefault, s));
+    SG_CUDA(g, cudaMemcpyAsync(g->d_img_rgb, color, pixels * 3, cudaMemcpyDefault, s));
+    if (class_image) SG_CUDA(g, cudaMemcpyAsync(g->d_img_cls, class_image, pixels * sizeof(int32_t), cudaMemcpyDefault, s));
+    if (object_image) SG_CUDA(g, cudaMemcpyAsync(g->d_img_obj, object_image, pixels * sizeof(int32_t), cudaMemcpyDefault, s));
+    const float *d_depth = g->d_img_depth;
+    if (filter_shadow_points) {  // semantic_grid.py:332-341: everything downstream sees the filtered depth
+        if (height <= 2 || width <= 2) {
+            g->err = "b2v_sgrid_integrate_rgbd: image too small for the shadow filter";
+            return B2V_ERR_INVALID_ARGUMENT;
+        }
+        SG_CUDA(g, launch_filter_shadow_points(d_depth, height, width, 2, 2, -1.0f, g->d_img_filtered,
+                                               g->d_shadow_scratch, s));
+        d_depth = g->d_img_filtered;
+    }
+    RgbdParams P;
+    P.fx_inv = 1.0 / K[0];
+    P.fy_inv = 1.0 / K[1];
+    P.cx = K[2];
+    P.cy = K[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) P.R[3 * i + j] = Twc[4 * i + j];
+        P.t[i] = Twc[4 * i + 3];
+    }
+    P.min_depth = min_depth;
+    P.max_depth = max_depth;
+    P.H = height;
+    P.W = width;
+    const int64_t n = static_cast<int64_t>(pixels);
+    sem_rgbd_points_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
+        P, d_depth, g->d_img_rgb, class_image ? g->d_img_cls : nullptr, object_image ? g->d_img_obj : nullptr,
+        static_cast<float *>(g->d_pts), static_cast<float *>(g->d_cols), g->d_cls, g->d_inst, g->d_depths, g->d_valid);
+    SG_CUDA(g, cudaGetLastError());
+    SemInputs in{};
+    in.pts = g->d_pts;
+    in.cols = g->d_cols;
+    in.cls = class_image ? g->d_cls : nullptr;
+    in.inst = object_image ? g->d_inst : nullptr;
+    in.depths = use_depths ? g->d_depths : nullptr;
+    rc = sgrid_fuse_staged(g, n, in, g->d_valid);
+    if (rc != B2V_OK) return rc;
+    return sgrid_read_counters(g);
 }
 
 extern "C" int64_t b2v_sgrid_num_blocks(b2v_sgrid *g) {

@@ -648,6 +648,36 @@ class VoxelBlockSemanticGrid:
         self._check(self._L.b2v_sgrid_integrate(self._h, n, pts.ctypes.data, 1 if pts.dtype == np.float64 else 0,
                                                 cp, cu8, ci, ii, di), "b2v_sgrid_integrate")
 
+    def integrate_rgbd(self, depth, color, K, Twc, class_image=None, object_image=None, max_depth=np.inf,
+                       min_depth=0.0, use_depths=True, filter_shadow_points=False):
+        """The reference integrator's per-frame front-end fused on the GPU
+        (volumetric_integrator_voxel_semantic_grid.py:332-461): optional `filter_shadow_points`, `depth2pointcloud`
+        with the class / object-id images, world transform by `Twc` (camera -> world), `integrate`.  `use_depths`
+        mirrors kVolumetricSemanticProbabilisticIntegrationUseDepth.  color is RGB uint8."""
+        d = np.ascontiguousarray(depth, np.float32)
+        c = np.ascontiguousarray(color, np.uint8)
+        if d.ndim != 2 or c.shape != d.shape + (3,):
+            raise RuntimeError("depth must be [H,W] float32 and color [H,W,3] uint8")
+        hold = [d, c]
+
+        def img(a, name):
+            if a is None or np.asarray(a).size == 0:
+                return None
+            b = np.ascontiguousarray(a, np.int32)
+            if b.shape != d.shape:
+                raise RuntimeError(f"{name} must have the depth image's shape")
+            hold.append(b)
+            return b.ctypes.data
+
+        ci, oi = img(class_image, "class_image"), img(object_image, "object_image")
+        K4 = _as_K4(K)
+        T = np.ascontiguousarray(np.asarray(Twc, np.float64).reshape(16))
+        md = float(np.finfo(np.float32).max) if not np.isfinite(max_depth) else float(max_depth)
+        self._check(self._L.b2v_sgrid_integrate_rgbd(self._h, d.ctypes.data, c.ctypes.data, ci, oi, d.shape[0],
+                                                     d.shape[1], K4.ctypes.data, T.ctypes.data, md, float(min_depth),
+                                                     1 if use_depths else 0, 1 if filter_shadow_points else 0),
+                    "b2v_sgrid_integrate_rgbd")
+
     # ---- read-outs ----
     def get_voxels(self, min_count: int = 1, min_confidence: float = 0.0) -> VoxelGridData:
         n = self._L.b2v_sgrid_get_voxels(self._h, int(min_count), float(min_confidence))
