@@ -276,7 +276,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     F, H, W = depth.shape
     capacity = args.capacity
     vol = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=capacity,
-                         device=local_rank, shard_rank=rank, shard_count=world)
+                         device=local_rank, shard_rank=rank,
+                         shard_count=args.shard_of if (world == 1 and args.shard_of > 1) else world)
     # a dedicated (non-default) stream: the legacy default stream has handle 0, which the C ABI reads
     # as "use the library's own stream" and which torch events would not observe
     stream = torch.cuda.Stream()
@@ -457,12 +458,16 @@ def run_gpu_arm(args, rank, world, local_rank):
             "block_visits_per_update": situ["visits"] / max(situ["updates"], 1),
             "measured": "in situ: CUDA events around every launch in the timed-region schedule "
                         "(allocate kernels of the next group run beside it)",
+            "allocate_group_kernel_avg_us_in_situ": 1e3 * situ["alloc_ms"] / max(situ["launches"], 1),
             "per_frame_kernel": {
                 "kernel": "integrate_kernel (one frame per launch, b2v_set_fusion 0, b2v_set_overlap 0)",
                 "bound": "hbm", "achieved": iso["gbs"], "frac": iso["gbs"] / peak if peak else None,
                 "avg_launch_us": 1e3 * iso["integ_ms"] / max(iso["launches"], 1),
                 "allocate_kernel_avg_us": 1e3 * iso["alloc_ms"] / max(iso["frames"], 1)}},
         "clocks": clocks,
+        **({"diagnostic": f"--shard-of {args.shard_of}: this process is rank 0 of a {args.shard_of}-way sharded job "
+                          f"(value = that job's per-rank rate = its whole-job rate, ranks share nothing)"}
+           if (world == 1 and args.shard_of > 1) else {}),
         "mesh": mesh_info,
         "cpu_baseline": cpu,
         **extra,
@@ -483,6 +488,9 @@ def main():
     ap.add_argument("--capacity", type=int, default=1 << 19, help="block-pool capacity (10 KiB each)")
     ap.add_argument("--cpu-frames", type=int, default=32, help="frames in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shard-of", type=int, default=0,
+                    help="diagnostic (N=1 only): act as rank 0 of a --shard-of-way sharded job on one GPU; ranks share "
+                         "nothing, so this is the per-rank work of that job")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -69,7 +69,7 @@ void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], 
 namespace {
 
 constexpr int kFrameStage = 4;                       // staging ring of the frame-by-frame path
-constexpr int kGroupStage = 2 * kMaxGroup;           // two group buffers x kMaxGroup frames
+constexpr int kGroupStage = kGroupBufs * kMaxGroup;  // group buffers x kMaxGroup frames
 constexpr int kStage = kGroupStage + kFrameStage;    // raw-frame staging slots (device copies of host frames)
 
 uint32_t next_pow2(uint64_t v) {
@@ -97,10 +97,10 @@ struct b2v_volume {
     bool use_tma = true;                 // stage image tiles with TMA when the layout allows it
     bool inputs_fenced = false;          // batch call: device inputs already ordered before the alloc stream
     bool fuse = true;                    // b2v_integrate_batch fuses groups of up to kMaxGroup frames
-    float4 *d_gtex[2 * kMaxGroup] = {};  // texel images of the two group buffers
+    float4 *d_gtex[kGroupBufs * kMaxGroup] = {};  // texel images of the group buffers
     size_t gtex_pixels = 0;
     uint32_t group_id = 0;
-    cudaEvent_t ev_galloc[2] = {}, ev_group_done[2] = {};
+    cudaEvent_t ev_galloc[kGroupBufs] = {}, ev_group_done[kGroupBufs] = {};
     int last_group_buf = -1, last_group_count = 0;  // most recent frame came from a fused group
     int64_t prof_frames = 0, prof_int_launches = 0;
     // optional rectification stage (b2v_set_rectification)
@@ -153,7 +153,7 @@ static int volume_clear_device(b2v_volume *v) {
     const size_t tcap = static_cast<size_t>(v->table.mask) + 1;
     B2V_CUDA(v, cudaMemsetAsync(v->table.entries, 0xFF, tcap * sizeof(uint4), v->compute));
     B2V_CUDA(v, cudaMemsetAsync(v->table.stamp, 0, tcap * sizeof(uint32_t), v->compute));
-    B2V_CUDA(v, cudaMemsetAsync(v->meta.group_mask, 0, tcap * 2 * sizeof(uint32_t), v->compute));
+    B2V_CUDA(v, cudaMemsetAsync(v->meta.group_mask, 0, tcap * kGroupBufs * sizeof(uint32_t), v->compute));
     B2V_CUDA(v, cudaMemsetAsync(v->meta.counters, 0, kNumCounters * sizeof(uint32_t), v->compute));
     return B2V_OK;
 }
@@ -195,7 +195,7 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     if (const char *e = std::getenv("B2V_OVERLAP")) v->overlap = std::atoi(e) != 0;
     if (const char *e = std::getenv("B2V_TMA")) v->use_tma = std::atoi(e) != 0;
     if (const char *e = std::getenv("B2V_FUSE")) v->fuse = std::atoi(e) != 0;
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kGroupBufs; ++b) {
         B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_galloc[b], cudaEventDisableTiming));
         B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_group_done[b], cudaEventDisableTiming));
     }
@@ -213,8 +213,8 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     B2V_CUDA(v, cudaMalloc(&v->meta.block_keys, static_cast<size_t>(cap) * sizeof(int4)));
     B2V_CUDA(v, cudaMalloc(&v->meta.counters, kNumCounters * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMalloc(&v->meta.active_slots, static_cast<size_t>(cap) * kActiveRing * sizeof(uint32_t)));
-    B2V_CUDA(v, cudaMalloc(&v->meta.group_mask, static_cast<size_t>(tcap) * 2 * sizeof(uint32_t)));
-    B2V_CUDA(v, cudaMalloc(&v->meta.union_slots, static_cast<size_t>(cap) * 2 * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMalloc(&v->meta.group_mask, static_cast<size_t>(tcap) * kGroupBufs * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMalloc(&v->meta.union_slots, static_cast<size_t>(cap) * kGroupBufs * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMallocHost(&v->h_counters, kNumCounters * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMallocHost(&v->h_totals, 2 * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMemsetAsync(v->meta.pool, 0, static_cast<size_t>(cap) * kBlockFloats * sizeof(float),
@@ -255,7 +255,7 @@ extern "C" int b2v_destroy(b2v_volume *v) {
     cudaFree(v->d_rdepth[0]);
     cudaFree(v->d_rcolor[0]);
     for (float4 *t : v->d_gtex) cudaFree(t);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kGroupBufs; ++b) {
         if (v->ev_galloc[b]) cudaEventDestroy(v->ev_galloc[b]);
         if (v->ev_group_done[b]) cudaEventDestroy(v->ev_group_done[b]);
     }
@@ -352,7 +352,8 @@ static int ensure_staging(b2v_volume *v, size_t pixels) {
     for (int s = 0; s < kStage; ++s) {
         v->d_depth[s] = dbase + pixels * s;
         v->d_color[s] = cbase + pixels * 3 * s;
-        B2V_CUDA(v, cudaMalloc(&v->d_texel[s], pixels * sizeof(float4)));
+        if (s >= kGroupStage)  // texel images of the per-frame path (the group buffers have their own)
+            B2V_CUDA(v, cudaMalloc(&v->d_texel[s], pixels * sizeof(float4)));
     }
     cudaFree(v->d_lambda);
     v->d_lambda = nullptr;
@@ -651,14 +652,10 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
     const bool staged = dev_hint != 1;
     for (int32_t g0 = 0; g0 < n_frames; g0 += kMaxGroup) {
         const int count = std::min<int32_t>(kMaxGroup, n_frames - g0);
-        const int buf = static_cast<int>(v->group_id % 2);
-        // the group buffer (masks, union list, texel images) was last used by group id - 2
+        const int buf = static_cast<int>(v->group_id % kGroupBufs);
+        // the group buffer (masks, union list, texel images) was last used by group id - kGroupBufs
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_group_done[buf], 0));
-        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + kCtrUnion0 + buf, 0, sizeof(uint32_t), as));
-        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + kCtrGroupNext0 + buf, 0, sizeof(uint32_t), as));
-        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + kCtrGroupNew0 + buf, 0, sizeof(uint32_t), as));
-        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + kCtrGroupTouched0 + buf * kMaxGroup, 0,
-                                    kMaxGroup * sizeof(uint32_t), as));
+        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + group_ctr(buf, 0), 0, kGroupCtrStride * sizeof(uint32_t), as));
         static thread_local GroupAllocArgs aargs;  // 5.5 KB: keep it off the stack
         GroupArgs args;
         std::memset(&args, 0, sizeof(args));
@@ -667,7 +664,7 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         aargs.count = count;
         aargs.use_tma = 1;
         if (staged) {
-            // the raw staging slots of this buffer were consumed by the allocate launch of group id - 2;
+            // the raw staging slots of this buffer were consumed by the allocate launch of group id - kGroupBufs;
             // the group's frames are contiguous on both sides: one H2D copy per image type
             B2V_CUDA(v, cudaStreamWaitEvent(v->copy, v->ev_galloc[buf], 0));
             const int s0 = buf * kMaxGroup;
@@ -786,7 +783,7 @@ extern "C" int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int6
         if (v->frame_id == 0)
             *touched_blocks = 0;
         else if (v->last_group_buf >= 0)
-            *touched_blocks = v->h_counters[kCtrGroupTouched0 + v->last_group_buf * kMaxGroup + v->last_group_count - 1];
+            *touched_blocks = v->h_counters[group_ctr(v->last_group_buf, kGcTouched0) + v->last_group_count - 1];
         else
             *touched_blocks = v->h_counters[kCtrActive0 + ring];
     }
@@ -794,7 +791,7 @@ extern "C" int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int6
         if (v->frame_id == 0)
             *new_blocks = 0;
         else if (v->last_group_buf >= 0)  // after a fused batch: blocks allocated by the last group
-            *new_blocks = v->h_counters[kCtrGroupNew0 + v->last_group_buf];
+            *new_blocks = v->h_counters[group_ctr(v->last_group_buf, kGcNew)];
         else
             *new_blocks = v->h_counters[kCtrNew0 + ring];
     }
@@ -941,7 +938,7 @@ extern "C" int64_t b2v_last_touched_keys(b2v_volume *v, int32_t *keys, int64_t m
     if (v->frame_id == 0) return 0;
     const int ring = static_cast<int>((v->frame_id - 1) % kActiveRing);
     const bool grp = v->last_group_buf >= 0;  // after a fused batch: the last group's union of touched blocks
-    uint32_t n = grp ? v->h_counters[kCtrUnion0 + v->last_group_buf] : v->h_counters[kCtrActive0 + ring];
+    uint32_t n = grp ? v->h_counters[group_ctr(v->last_group_buf, kGcUnion)] : v->h_counters[kCtrActive0 + ring];
     if (n > v->meta.capacity) n = v->meta.capacity;
     if (!keys) return n;
     if (static_cast<int64_t>(n) > max_keys) n = static_cast<uint32_t>(max_keys);

@@ -35,6 +35,9 @@ struct FrameParams {
 // Fused group integration: up to kMaxGroup consecutive frames are applied to a block while it is
 // resident in registers.  Per-frame constants of the projective update only.
 constexpr int kMaxGroup = 8;
+// group state (masks, union list, texel images, counters) is kGroupBufs-deep: the allocation of group g+3 may
+// run while group g is still being integrated
+constexpr int kGroupBufs = 4;
 struct IntFrame {
     float E[12];
     float fxf, fyf, cxh, cyh, safe_w, safe_h, tau, inv_tau;
@@ -53,8 +56,8 @@ struct PoolMeta {
     int4 *block_keys;         // [capacity] key of pool block i (w unused)
     uint32_t *counters;       // device counters, see Counter
     uint32_t *active_slots;   // [kActiveRing][capacity] table slots touched by a frame
-    uint32_t *group_mask;     // [2][table capacity] bit k: the slot is touched by frame k of the group
-    uint32_t *union_slots;    // [2][capacity] slots touched by any frame of the group
+    uint32_t *group_mask;     // [kGroupBufs][table capacity] bit k: the slot is touched by frame k of the group
+    uint32_t *union_slots;    // [kGroupBufs][capacity] slots touched by any frame of the group
     uint32_t capacity;
 };
 
@@ -65,15 +68,26 @@ enum Counter : int {
     kCtrUpdatesHi = 3,
     kCtrActive0 = 4,         // [kActiveRing] per-frame counts of touched blocks
     kCtrNew0 = 8,            // [kActiveRing] per-frame counts of newly allocated blocks
-    kCtrUnion0 = 12,         // [2] group buffers: number of slots in the group's union list
-    kCtrVisitsLo = 14,       // 64-bit total of block visits (one block read + written) since reset
-    kCtrVisitsHi = 15,
-    kCtrGroupTouched0 = 16,  // [2][kMaxGroup] blocks touched by frame k of the group
-    kCtrGroupNext0 = 32,     // [2] work-stealing cursor of the fused kernel
-    kCtrGroupNew0 = 34,      // [2] blocks newly allocated by the group
-    kNumCounters = 40
+    kCtrVisitsLo = 12,       // 64-bit total of block visits (one block read + written) since reset
+    kCtrVisitsHi = 13,
+    kCtrGroup0 = 16,         // [kGroupBufs][kGroupCtrStride] per-group-buffer counters, contiguous so that ONE
+                             // memset re-arms a buffer: see GroupCounter
+    kNumCounters = 16 + 4 * 12
 };
+// offsets inside one group buffer's counter block (M.counters + kCtrGroup0 + buf * kGroupCtrStride)
+enum GroupCounter : int {
+    kGcUnion = 0,    // number of slots in the group's union list
+    kGcNext = 1,     // work-stealing cursor of the fused kernel
+    kGcNew = 2,      // blocks newly allocated by the group
+    kGcTouched0 = 4  // [kMaxGroup] blocks touched by frame k of the group
+};
+constexpr int kGroupCtrStride = 12;
+__host__ __device__ __forceinline__ constexpr int group_ctr(int buf, int which) {
+    return kCtrGroup0 + buf * kGroupCtrStride + which;
+}
 constexpr int kActiveRing = 4;
+static_assert(kGcTouched0 + kMaxGroup <= kGroupCtrStride && kCtrGroup0 + kGroupBufs * kGroupCtrStride <= kNumCounters,
+              "counter layout");
 
 void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], int H, int W,
                        int stride, float vs, float tau, float depth_trunc, uint32_t frame_id,

@@ -61,7 +61,7 @@ __device__ __forceinline__ void touch_key(const FrameParams &P, const HashTable 
             s_new[pos] = slot;
         } else {  // list overflow: assign directly
             assign_block(T, M, slot, atomicAdd(M.counters + kCtrPool, 1u));
-            atomicAdd(P.group_bit >= 0 ? M.counters + kCtrGroupNew0 + P.group_buf : M.counters + kCtrNew0 + ring, 1u);
+            atomicAdd(P.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcNew) : M.counters + kCtrNew0 + ring, 1u);
         }
     }
     bool first;
@@ -76,7 +76,7 @@ __device__ __forceinline__ void touch_key(const FrameParams &P, const HashTable 
         if (pos < kListCap) {
             s_act[pos] = slot;
         } else if (P.group_bit >= 0) {
-            const uint32_t g = atomicAdd(M.counters + kCtrUnion0 + P.group_buf, 1u);
+            const uint32_t g = atomicAdd(M.counters + group_ctr(P.group_buf, kGcUnion), 1u);
             if (g < M.capacity) M.union_slots[static_cast<size_t>(P.group_buf) * M.capacity + g] = slot;
         } else {
             const uint32_t g = atomicAdd(M.counters + kCtrActive0 + ring, 1u);
@@ -364,10 +364,10 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
     const uint32_t n_new = min(s_n_new, static_cast<uint32_t>(kListCap));
     const uint32_t n_act = min(s_n_act, static_cast<uint32_t>(kListCap));
     if (tid == 0) s_base_new = n_new ? atomicAdd(M.counters + kCtrPool, n_new) : 0u;
-    uint32_t *list_count = P.group_bit >= 0 ? M.counters + kCtrUnion0 + P.group_buf : M.counters + kCtrActive0 + ring;
+    uint32_t *list_count = P.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcUnion) : M.counters + kCtrActive0 + ring;
     if (tid == 32) s_base_act = n_act ? atomicAdd(list_count, n_act) : 0u;
     if (tid == 64 && n_new)
-        atomicAdd(P.group_bit >= 0 ? M.counters + kCtrGroupNew0 + P.group_buf : M.counters + kCtrNew0 + ring, n_new);
+        atomicAdd(P.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcNew) : M.counters + kCtrNew0 + ring, n_new);
     __syncthreads();
     for (uint32_t k = tid; k < n_new; k += kAllocThreads) assign_block(T, M, s_new[k], s_base_new + k);
     uint32_t *active_out = P.group_bit >= 0 ? M.union_slots + static_cast<size_t>(P.group_buf) * M.capacity
@@ -388,7 +388,7 @@ allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint
 
 // blockIdx.z = frame of the group: one launch allocates for up to kMaxGroup frames
 template <bool kTma>
-__global__ void __launch_bounds__(kAllocThreads, 4)
+__global__ void __launch_bounds__(kAllocThreads, 8)
 allocate_group_kernel(const __grid_constant__ GroupAllocArgs A, const float *__restrict__ lam,
                       const HashTable T, const PoolMeta M) {
     const int k = blockIdx.z;
@@ -593,10 +593,10 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
     __shared__ IntFrame s_f[kMaxGroup];   // per-frame constants (dynamic indexing by frame bit)
     __shared__ float s_rcp[256];          // correctly rounded 1/n for the small integer weights
     __shared__ uint32_t s_next;           // work-stealing: next list position of this CTA
-    const uint32_t n = min(M.counters[kCtrUnion0 + gbuf], M.capacity);
+    const uint32_t n = min(M.counters[group_ctr(gbuf, kGcUnion)], M.capacity);
     const uint32_t *__restrict__ list = M.union_slots + static_cast<size_t>(gbuf) * M.capacity;
     const uint32_t *__restrict__ mask = M.group_mask + static_cast<size_t>(gbuf) * (static_cast<size_t>(T.mask) + 1);
-    uint32_t *cursor = M.counters + kCtrGroupNext0 + gbuf;
+    uint32_t *cursor = M.counters + group_ctr(gbuf, kGcNext);
     const int t = threadIdx.x;
     const int lx0 = (t & 1) * 4, ly = (t >> 1) & 7, lz = t >> 4;
     {
@@ -712,7 +712,7 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
         __syncthreads();  // s_next is rewritten at the top of the next iteration
     }
     if (t < kMaxGroup && my_cnt) {
-        atomicAdd(M.counters + kCtrGroupTouched0 + gbuf * kMaxGroup + t, my_cnt);
+        atomicAdd(M.counters + group_ctr(gbuf, kGcTouched0) + t, my_cnt);
         atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrUpdatesLo),
                   static_cast<unsigned long long>(my_cnt));
     }
@@ -720,7 +720,7 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
 
 // clears the membership masks of a finished group (its buffer is reused two groups later)
 __global__ void group_clear_kernel(const HashTable T, const PoolMeta M, const int gbuf) {
-    const uint32_t n = min(M.counters[kCtrUnion0 + gbuf], M.capacity);
+    const uint32_t n = min(M.counters[group_ctr(gbuf, kGcUnion)], M.capacity);
     uint32_t *mask = M.group_mask + static_cast<size_t>(gbuf) * (static_cast<size_t>(T.mask) + 1);
     const uint32_t *list = M.union_slots + static_cast<size_t>(gbuf) * M.capacity;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mask[list[i]] = 0u;
