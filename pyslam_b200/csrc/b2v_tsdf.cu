@@ -718,7 +718,7 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
     }
 }
 
-// clears the membership masks of a finished group (its buffer is reused two groups later)
+// clears the membership masks of a finished group (its buffer is reused kGroupBufs groups later)
 __global__ void group_clear_kernel(const HashTable T, const PoolMeta M, const int gbuf) {
     const uint32_t n = min(M.counters[group_ctr(gbuf, kGcUnion)], M.capacity);
     uint32_t *mask = M.group_mask + static_cast<size_t>(gbuf) * (static_cast<size_t>(T.mask) + 1);
