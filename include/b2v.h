@@ -219,6 +219,25 @@ int b2v_sgrid_remove_low_count_voxels(b2v_sgrid *g, int32_t min_count);
 int b2v_sgrid_remove_low_confidence_segments(b2v_sgrid *g, int32_t min_confidence);
 int b2v_sgrid_merge_segments(b2v_sgrid *g, int32_t object_id1, int32_t object_id2);
 int b2v_sgrid_remove_segment(b2v_sgrid *g, int32_t object_id);
+/* carve (voxel_block_grid.hpp:616-622; voxel_grid_carving.h:47-80) on a semantic grid: K = {fx, fy, cx, cy} float,
+ * Tcw row-major 4x4, depth float32 [height][width] (host or device) */
+int b2v_sgrid_carve(b2v_sgrid *g, const float K[4], int32_t width, int32_t height, const double Tcw[16],
+                    float depth_max, float depth_min, const float *depth, float depth_threshold);
+/* assign_object_ids_to_instance_ids (voxel_block_semantic_grid.h:67-71; voxel_semantic_data_association.h:69-373):
+ * voxels in the frustum whose class equals the pixel's class and that lie on the observed surface vote
+ * "2-D instance id -> 3-D object id"; returns the number of (instance, object) pairs of the resulting map, or -1;
+ * b2v_sgrid_copy_instance_map copies them out (ascending instance id; object id -1 = no confident match).
+ * class_image / instance_image: int32 [height][width]; depth_image: float32 or NULL.  New object ids come from a
+ * per-grid counter (process-wide in the reference, voxel_semantic_shared_data.h:27-33) handed out in ascending
+ * instance-id order (block-iteration order in the reference): maps agree up to that renumbering. */
+int64_t b2v_sgrid_assign_object_ids_to_instance_ids(b2v_sgrid *g, const float K[4], int32_t width, int32_t height,
+                                                    const double Tcw[16], float depth_max, float depth_min,
+                                                    const int32_t *class_image, const int32_t *instance_image,
+                                                    const float *depth_image, float depth_threshold,
+                                                    int32_t do_carving, float min_vote_ratio, int32_t min_votes);
+int b2v_sgrid_copy_instance_map(b2v_sgrid *g, int32_t *instance_ids, int32_t *object_ids);
+int b2v_sgrid_set_next_object_id(b2v_sgrid *g, int32_t next_object_id);
+int32_t b2v_sgrid_get_next_object_id(const b2v_sgrid *g);
 /* number of label pairs dropped because a Bayesian voxel saw more than B2V_SEM_MAX_LABELS distinct pairs */
 int b2v_sgrid_label_overflows(b2v_sgrid *g, uint64_t *out);
 /* parity hook: arrays [nb][512]...; aux = voting counter / number of label pairs; lab_* [nb][512][K] in

@@ -418,6 +418,12 @@ def _sem():
         L.refsem_dump_blocks.argtypes = [vp] * 10 + [C.c_int] + [vp] * 3
         L.refsem_get_voxels.restype = C.c_int64
         L.refsem_get_voxels.argtypes = [vp, C.c_int, C.c_float, vp, vp, vp, vp, vp]
+        L.refsem_assign_object_ids.restype = C.c_int64
+        L.refsem_assign_object_ids.argtypes = [vp, _f32p, C.c_int, C.c_int, _f64p, C.c_float, C.c_float, _i32p, _i32p,
+                                               vp, C.c_float, C.c_int, C.c_float, C.c_int, _i32p, _i32p, C.c_int64]
+        L.refsem_carve.argtypes = [vp, _f32p, C.c_int, C.c_int, _f64p, C.c_float, C.c_float, _f32p, C.c_float]
+        L.refsem_set_next_object_id.argtypes = [C.c_int32]
+        L.refsem_get_next_object_id.restype = C.c_int32
         L.refsem_remove_low_count_voxels.argtypes = [vp, C.c_int]
         L.refsem_remove_low_confidence_segments.argtypes = [vp, C.c_int]
         L.refsem_merge_segments.argtypes = [vp, C.c_int, C.c_int]
@@ -501,6 +507,36 @@ class RefSemanticGrid:
                                       out["colors"].ctypes.data, out["class_ids"].ctypes.data,
                                       out["object_ids"].ctypes.data, out["confidences"].ctypes.data)
         return out
+
+    def assign_object_ids_to_instance_ids(self, K, width, height, Tcw, depth_max, depth_min, class_image,
+                                          instance_image, depth_image=None, depth_threshold=0.1, do_carving=False,
+                                          min_vote_ratio=0.5, min_votes=3):
+        """-> dict instance id -> object id (voxel_semantic_data_association.h:69-373)."""
+        K4 = np.ascontiguousarray(K, np.float32)
+        T = np.ascontiguousarray(np.asarray(Tcw, np.float64).reshape(16))
+        ci = np.ascontiguousarray(class_image, np.int32)
+        ii = np.ascontiguousarray(instance_image, np.int32)
+        di = None if depth_image is None else np.ascontiguousarray(depth_image, np.float32)
+        ids, objs = np.zeros(4096, np.int32), np.zeros(4096, np.int32)
+        n = self._L.refsem_assign_object_ids(self._h, K4, int(width), int(height), T, float(depth_max),
+                                             float(depth_min), ci, ii, None if di is None else di.ctypes.data,
+                                             float(depth_threshold), int(bool(do_carving)), float(min_vote_ratio),
+                                             int(min_votes), ids, objs, 4096)
+        assert n <= 4096
+        return {int(i): int(o) for i, o in zip(ids[:n], objs[:n])}
+
+    def carve(self, K, width, height, Tcw, depth_max, depth_min, depth_image, depth_threshold):
+        self._L.refsem_carve(self._h, np.ascontiguousarray(K, np.float32), int(width), int(height),
+                             np.ascontiguousarray(np.asarray(Tcw, np.float64).reshape(16)), float(depth_max),
+                             float(depth_min), np.ascontiguousarray(depth_image, np.float32), float(depth_threshold))
+
+    @staticmethod
+    def set_next_object_id(v):
+        _sem().refsem_set_next_object_id(int(v))
+
+    @staticmethod
+    def get_next_object_id():
+        return int(_sem().refsem_get_next_object_id())
 
     def remove_low_count_voxels(self, min_count):
         self._L.refsem_remove_low_count_voxels(self._h, int(min_count))

@@ -37,6 +37,10 @@ struct ISem {
                          float *lab_logp) const = 0;
     virtual int64_t get_voxels(int min_count, float min_conf, double *pts, float *cols, int32_t *cls, int32_t *obj,
                                float *conf) const = 0;
+    virtual int64_t assign(const volumetric::CameraFrustrum &fr, const cv::Mat &cls, const cv::Mat &inst,
+                           const cv::Mat &depth, float thr, bool carve, float ratio, int min_votes, int32_t *ids,
+                           int32_t *objs, int64_t cap) = 0;
+    virtual void carve(const volumetric::CameraFrustrum &fr, const cv::Mat &depth, float thr) = 0;
     virtual void remove_low_count(int min_count) = 0;
     virtual void remove_low_confidence(int min_confidence) = 0;
     virtual void merge_segments(int a, int b) = 0;
@@ -132,6 +136,23 @@ template <typename Grid, typename V> struct Sem final : ISem {
         if (conf) std::memcpy(conf, out.confidences.data(), sizeof(float) * n);
         return n;
     }
+    int64_t assign(const volumetric::CameraFrustrum &fr, const cv::Mat &cls, const cv::Mat &inst, const cv::Mat &depth,
+                   float thr, bool carve, float ratio, int min_votes, int32_t *ids, int32_t *objs,
+                   int64_t cap) override {
+        const auto m = g.assign_object_ids_to_instance_ids(fr, cls, inst, depth, thr, carve, ratio, min_votes);
+        int64_t k = 0;
+        for (const auto &[i, o] : m) {
+            if (k < cap) {
+                ids[k] = i;
+                objs[k] = o;
+            }
+            ++k;
+        }
+        return k;
+    }
+    void carve(const volumetric::CameraFrustrum &fr, const cv::Mat &depth, float thr) override {
+        g.carve(fr, depth, thr);
+    }
     void remove_low_count(int min_count) override { g.remove_low_count_voxels(min_count); }
     void remove_low_confidence(int min_confidence) override { g.remove_low_confidence_segments(min_confidence); }
     void merge_segments(int a, int b) override { g.merge_segments(a, b); }
@@ -191,6 +212,42 @@ int64_t refsem_get_voxels(void *h, int min_count, float min_conf, double *pts, f
                           int32_t *obj, float *conf) {
     return static_cast<ISem *>(h)->get_voxels(min_count, min_conf, pts, cols, cls, obj, conf);
 }
+
+static volumetric::CameraFrustrum sem_frustum(const float *K, int width, int height, const double *Tcw,
+                                              float depth_max, float depth_min) {
+    Eigen::Matrix4d T;
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) T(r, c) = Tcw[4 * r + c];
+    return volumetric::CameraFrustrum(K[0], K[1], K[2], K[3], width, height, T, depth_max, depth_min);
+}
+
+// VoxelBlockSemanticGridT::assign_object_ids_to_instance_ids (voxel_block_semantic_grid.hpp; the algorithm is
+// voxel_semantic_data_association.h:69-373).  Images are row-major int32 / float32 HxW; depth may be NULL.
+// Returns the number of (instance id -> object id) pairs; the first `cap` are written.
+int64_t refsem_assign_object_ids(void *h, const float *K, int width, int height, const double *Tcw, float depth_max,
+                                 float depth_min, const int32_t *class_image, const int32_t *instance_image,
+                                 const float *depth_image, float depth_threshold, int do_carving,
+                                 float min_vote_ratio, int min_votes, int32_t *ids, int32_t *objs, int64_t cap) {
+    const auto fr = sem_frustum(K, width, height, Tcw, depth_max, depth_min);
+    cv::Mat cls(height, width, CV_MAKETYPE(CV_32S, 1), const_cast<int32_t *>(class_image));
+    cv::Mat inst(height, width, CV_MAKETYPE(CV_32S, 1), const_cast<int32_t *>(instance_image));
+    cv::Mat depth;
+    if (depth_image) depth = cv::Mat(height, width, CV_32FC1, const_cast<float *>(depth_image));
+    return static_cast<ISem *>(h)->assign(fr, cls, inst, depth, depth_threshold, do_carving != 0, min_vote_ratio,
+                                          min_votes, ids, objs, cap);
+}
+
+// VoxelBlockGridT::carve (voxel_block_grid.hpp:616-622; voxel_grid_carving.h:47-80) on a semantic grid
+void refsem_carve(void *h, const float *K, int width, int height, const double *Tcw, float depth_max, float depth_min,
+                  const float *depth_image, float depth_threshold) {
+    const auto fr = sem_frustum(K, width, height, Tcw, depth_max, depth_min);
+    cv::Mat depth(height, width, CV_32FC1, const_cast<float *>(depth_image));
+    static_cast<ISem *>(h)->carve(fr, depth, depth_threshold);
+}
+
+// process-wide object-id allocator (voxel_semantic_shared_data.h:27-33)
+void refsem_set_next_object_id(int32_t v) { volumetric::VoxelSemanticSharedData::next_object_id.store(v); }
+int32_t refsem_get_next_object_id(void) { return volumetric::VoxelSemanticSharedData::next_object_id.load(); }
 
 void refsem_remove_low_count_voxels(void *h, int min_count) { static_cast<ISem *>(h)->remove_low_count(min_count); }
 void refsem_remove_low_confidence_segments(void *h, int min_confidence) {

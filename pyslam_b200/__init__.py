@@ -7,8 +7,10 @@ CUDA kernels and the C ABI (include/b2v.h); the Python modules mirror the refere
 
 from .volume import (B200TsdfVolume, BoundingBox3D, CameraFrustrum, PointCloud, TriangleMesh,
                      VoxelBlockGrid, VoxelBlockSemanticGrid, VoxelBlockSemanticProbabilisticGrid, VoxelGridData,
-                     VoxelSemanticGrid, VoxelSemanticGridProbabilistic, filter_shadow_points, remap)
+                     VoxelSemanticGrid, VoxelSemanticGridProbabilistic, filter_shadow_points, remap,
+                     remap_instance_ids)
 
 __all__ = ["B200TsdfVolume", "BoundingBox3D", "CameraFrustrum", "PointCloud", "TriangleMesh",
            "VoxelBlockGrid", "VoxelBlockSemanticGrid", "VoxelBlockSemanticProbabilisticGrid", "VoxelGridData",
-           "VoxelSemanticGrid", "VoxelSemanticGridProbabilistic", "filter_shadow_points", "remap"]
+           "VoxelSemanticGrid", "VoxelSemanticGridProbabilistic", "filter_shadow_points", "remap",
+           "remap_instance_ids"]

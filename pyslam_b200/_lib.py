@@ -38,7 +38,9 @@ EXPORTED_SYMBOLS = [
     "b2v_sgrid_integrate_rgbd",
     "b2v_sgrid_num_blocks", "b2v_sgrid_get_voxels", "b2v_sgrid_copy_voxels",
     "b2v_sgrid_remove_low_count_voxels", "b2v_sgrid_remove_low_confidence_segments", "b2v_sgrid_merge_segments",
-    "b2v_sgrid_remove_segment", "b2v_sgrid_label_overflows", "b2v_sgrid_dump_blocks",
+    "b2v_sgrid_remove_segment", "b2v_sgrid_label_overflows", "b2v_sgrid_dump_blocks", "b2v_sgrid_carve",
+    "b2v_sgrid_assign_object_ids_to_instance_ids", "b2v_sgrid_copy_instance_map", "b2v_sgrid_set_next_object_id",
+    "b2v_sgrid_get_next_object_id",
 ]
 
 
@@ -114,6 +116,15 @@ def load() -> C.CDLL:
     L.b2v_sgrid_integrate.argtypes = [vp, C.c_int64, vp, i32, vp, i32, vp, vp, vp]
     L.b2v_sgrid_integrate_rgbd.restype = C.c_int
     L.b2v_sgrid_integrate_rgbd.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, C.c_float, C.c_float, i32, i32]
+    L.b2v_sgrid_carve.restype = C.c_int
+    L.b2v_sgrid_carve.argtypes = [vp, vp, i32, i32, vp, C.c_float, C.c_float, vp, C.c_float]
+    L.b2v_sgrid_assign_object_ids_to_instance_ids.restype = C.c_int64
+    L.b2v_sgrid_assign_object_ids_to_instance_ids.argtypes = [vp, vp, i32, i32, vp, C.c_float, C.c_float, vp, vp, vp,
+                                                             C.c_float, i32, C.c_float, i32]
+    L.b2v_sgrid_copy_instance_map.argtypes = [vp, vp, vp]
+    L.b2v_sgrid_set_next_object_id.argtypes = [vp, i32]
+    L.b2v_sgrid_get_next_object_id.restype = i32
+    L.b2v_sgrid_get_next_object_id.argtypes = [vp]
     L.b2v_sgrid_num_blocks.restype = C.c_int64
     L.b2v_sgrid_num_blocks.argtypes = [vp]
     L.b2v_sgrid_get_voxels.restype = C.c_int64

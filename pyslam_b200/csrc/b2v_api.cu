@@ -1363,8 +1363,8 @@ static void fill_key_bounds(GridQuery *q, float inv_vs) {
     }
 }
 
-static void fill_frustum_query(GridQuery *q, const float K[4], int W, int H, const double Tcw[16],
-                               float depth_max, float depth_min, int min_count, float inv_vs) {
+void b2v::fill_frustum_query(GridQuery *q, const float K[4], int W, int H, const double Tcw[16],
+                             float depth_max, float depth_min, int min_count, float inv_vs) {
     std::memset(q, 0, sizeof(*q));
     q->mode = 1;
     q->min_count = min_count;

@@ -224,6 +224,9 @@ struct GridQuery {
     float fx, fy, cx, cy, depth_min, depth_max;
     int32_t W, H;
 };
+// frustum -> GridQuery: world AABB of the frustum corners -> voxel key bounds (b2v_api.cu)
+void fill_frustum_query(GridQuery *q, const float K[4], int W, int H, const double Tcw[16], float depth_max,
+                        float depth_min, int min_count, float inv_vs);
 cudaError_t launch_grid_query_count(const GridMeta &meta, uint32_t n_blocks, const GridQuery &q,
                                     uint32_t *sums, uint32_t *offs, uint32_t *total, cudaStream_t stream);
 cudaError_t launch_grid_query_emit(const GridMeta &meta, uint32_t n_blocks, const GridQuery &q,

@@ -26,6 +26,7 @@
 
 #include <climits>
 #include <limits>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -452,6 +453,147 @@ __global__ void __launch_bounds__(kVox) sem_edit_kernel(const SemGrid G, const i
     }
 }
 
+// ---- frustum iteration: carve and instance -> object association ------------------------------------------
+struct SemImagePoint {
+    float u, v, depth;
+};
+
+// iterate_voxels_in_camera_frustrum's per-voxel chain (voxel_block_grid.hpp:1336-1460, min_count 1, min_confidence
+// 0) + CameraFrustrum::contains (camera_frustrum.cpp:174-196) on the voxel's float64 mean position
+__device__ __forceinline__ bool sem_voxel_in_frustum(const SemGrid &G, const GridQuery &Q, uint32_t b, int t,
+                                                     SemImagePoint *ip) {
+    const uint32_t v = b * kVox + t;
+    const int c = G.count[v];
+    if (c < 1) return false;
+    const int4 key = G.block_keys[b];
+    const int vk[3] = {key.x * kB + (t & 7), key.y * kB + ((t >> 3) & 7), key.z * kB + (t >> 6)};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (vk[a] < Q.min_key[a] || vk[a] > Q.max_key[a]) return false;
+    const double dc = static_cast<double>(c);
+    double p[3], pc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p[a] = __ddiv_rn(G.pos[3 * static_cast<size_t>(v) + a], dc);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        pc[a] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(Q.R[3 * a], p[0]), __dmul_rn(Q.R[3 * a + 1], p[1])),
+                                    __dmul_rn(Q.R[3 * a + 2], p[2])),
+                          Q.t[a]);
+    const float depth = static_cast<float>(pc[2]);
+    if (!(depth >= Q.depth_min && depth <= Q.depth_max)) return false;
+    ip->u = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(Q.fx), __ddiv_rn(pc[0], pc[2])),
+                                         static_cast<double>(Q.cx)));
+    ip->v = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(Q.fy), __ddiv_rn(pc[1], pc[2])),
+                                         static_cast<double>(Q.cy)));
+    ip->depth = depth;
+    return ip->u >= 0.0f && ip->u < static_cast<float>(Q.W) && ip->v >= 0.0f && ip->v < static_cast<float>(Q.H);
+}
+
+__device__ __forceinline__ bool sem_block_in_range(const GridQuery &Q, const int4 key) {
+    const int k[3] = {key.x, key.y, key.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (k[a] < block_coord(Q.min_key[a]) || k[a] > block_coord(Q.max_key[a])) return false;
+    return true;
+}
+
+// set_object_id (voxel_data_semantic.h:135, 455-460): the Bayesian voxel collapses onto the forced pair
+__device__ __forceinline__ void sem_set_object_id(const SemGrid &G, uint32_t v, int32_t id) {
+    G.obj[v] = id;
+    if (G.kind == B2V_SEM_PROBABILISTIC) {
+        const int32_t cl = G.cls[v];
+        if (id >= 0 && cl >= 0) {
+            G.counter[v] = 1;
+            G.lab_obj[static_cast<size_t>(v) * kSemLabels] = id;
+            G.lab_cls[static_cast<size_t>(v) * kSemLabels] = cl;
+            G.lab_logp[static_cast<size_t>(v) * kSemLabels] = 0.0f;
+            G.ml_logp[v] = 0.0f;
+            G.conf[v] = 1.0f;
+        } else {
+            G.counter[v] = 0;
+            G.ml_logp[v] = __uint_as_float(0xFF800000u);
+            G.conf[v] = 0.0f;
+        }
+    }
+}
+
+// carve (voxel_grid_carving.h:47-80): reset voxels in front of the observed surface by more than the threshold;
+// the depth image is indexed with truncated pixel coordinates, like at<float>(v, u)
+__global__ void __launch_bounds__(kVox)
+sem_carve_kernel(const SemGrid G, const GridQuery Q, const float *__restrict__ depth, const float thr) {
+    const uint32_t b = blockIdx.x;
+    if (!sem_block_in_range(Q, G.block_keys[b])) return;
+    SemImagePoint ip;
+    if (!sem_voxel_in_frustum(G, Q, b, threadIdx.x, &ip)) return;
+    const float image_depth = depth[static_cast<size_t>(static_cast<int>(ip.v)) * Q.W + static_cast<int>(ip.u)];
+    if (image_depth <= 0.0f || !isfinite(image_depth)) return;
+    if (ip.depth < image_depth - thr) sem_reset_voxel(G, b * kVox + threadIdx.x);
+}
+
+// process_point of assign_object_ids_to_instance_ids (voxel_semantic_data_association.h:171-229): every voxel in
+// the frustum whose class equals the pixel's class and that lies on the observed surface votes
+// "image instance id -> my object id".  Voxels without an object id are recorded as pending (pend[v] = instance
+// id); the host turns the vote records into the instance -> object map.
+constexpr int32_t kAssocPending = INT_MIN;
+__global__ void __launch_bounds__(kVox)
+sem_assoc_kernel(const SemGrid G, const GridQuery Q, const int32_t *__restrict__ class_img,
+                 const int32_t *__restrict__ inst_img, const float *__restrict__ depth_img, const float thr,
+                 const int do_carving, int32_t *__restrict__ pend, int2 *__restrict__ records,
+                 uint32_t *__restrict__ n_records, const uint32_t cap_records) {
+    const uint32_t b = blockIdx.x;
+    if (!sem_block_in_range(Q, G.block_keys[b])) return;
+    SemImagePoint ip;
+    if (!sem_voxel_in_frustum(G, Q, b, threadIdx.x, &ip)) return;
+    const uint32_t v = b * kVox + threadIdx.x;
+    const size_t px = static_cast<size_t>(static_cast<int>(ip.v)) * Q.W + static_cast<int>(ip.u);
+    const int32_t image_class = class_img[px];
+    if (image_class < 0) return;
+    const int32_t point_class = G.cls[v];
+    if (point_class < 0 || point_class != image_class) return;
+    const int32_t image_instance = inst_img[px];
+    if (image_instance < 0) return;
+    int32_t point_object = G.obj[v];
+    if (depth_img != nullptr) {
+        const float image_depth = depth_img[px];
+        if (image_depth <= 0.0f || !isfinite(image_depth)) return;
+        if (do_carving && ip.depth < image_depth - thr) {
+            sem_reset_voxel(G, v);
+            return;
+        }
+        if (ip.depth > image_depth + thr) return;
+    }
+    if (point_object < 0) {
+        if (image_instance == 0) {
+            point_object = 0;
+            sem_set_object_id(G, v, 0);
+        } else {
+            point_object = kAssocPending;  // one new object id per instance id, handed out by the host
+            pend[v] = image_instance;
+        }
+    }
+    const uint32_t r = atomicAdd(n_records, 1u);
+    if (r < cap_records) records[r] = make_int2(image_instance, point_object);
+}
+
+// deferred assignment (voxel_semantic_data_association.h:354-370): pending voxels take their instance's final id
+__global__ void __launch_bounds__(kVox)
+sem_assoc_apply_kernel(const SemGrid G, const int32_t *__restrict__ pend, const int32_t *__restrict__ map_inst,
+                       const int32_t *__restrict__ map_obj, const int n_map) {
+    const uint32_t v = blockIdx.x * kVox + threadIdx.x;
+    const int32_t inst = pend[v];
+    if (inst < 0) return;
+    int lo = 0, hi = n_map - 1;
+    while (lo <= hi) {  // map_inst is sorted
+        const int mid = (lo + hi) >> 1;
+        const int32_t m = map_inst[mid];
+        if (m == inst) {
+            if (map_obj[mid] >= 0) sem_set_object_id(G, v, map_obj[mid]);
+            return;
+        }
+        if (m < inst) lo = mid + 1; else hi = mid - 1;
+    }
+}
+
 __global__ void sem_fill_kernel(const SemGrid G, const size_t n_vox) {
     for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < n_vox;
          v += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -489,6 +631,13 @@ struct b2v_sgrid {
     int32_t *d_img_cls = nullptr, *d_img_obj = nullptr;
     void *d_shadow_scratch = nullptr;
     size_t img_pixels = 0;
+    // instance -> object association
+    int32_t *d_pend = nullptr;
+    int2 *d_records = nullptr;
+    uint32_t *d_n_records = nullptr;
+    size_t records_cap = 0;
+    int32_t next_object_id = 1;  // VoxelSemanticSharedData::next_object_id (process-wide in the reference)
+    std::vector<int32_t> map_inst, map_obj;
     // read-out
     uint32_t *d_sums = nullptr, *d_offs = nullptr, *d_total = nullptr;
     uint32_t scan_cap = 0;
@@ -586,7 +735,8 @@ extern "C" int b2v_sgrid_destroy(b2v_sgrid *g) {
                     g->d_pts, g->d_cols, g->d_cls, g->d_inst, g->d_depths, g->d_vid[0], g->d_vid[1], g->d_ord[0],
                     g->d_ord[1], g->d_sort_tmp, g->d_sums, g->d_offs, g->d_total, g->d_out_pts, g->d_out_cols,
                     g->d_out_conf, g->d_out_cls, g->d_out_obj, g->d_img_depth, g->d_img_filtered, g->d_img_rgb,
-                    g->d_valid, g->d_img_cls, g->d_img_obj, g->d_shadow_scratch};
+                    g->d_valid, g->d_img_cls, g->d_img_obj, g->d_shadow_scratch, g->d_pend, g->d_records,
+                    g->d_n_records};
     for (void *p : ptrs) cudaFree(p);
     cudaFreeHost(g->h_counters);
     if (g->stream) cudaStreamDestroy(g->stream);
@@ -997,4 +1147,192 @@ extern "C" int64_t b2v_sgrid_dump_blocks(b2v_sgrid *g, int32_t *keys, uint64_t *
         }
     }
     return nb;
+}
+
+
+// ---- carve / instance -> object association -------------------------------------------------------------------------
+static int sgrid_upload_image(b2v_sgrid *g, const void *src, size_t bytes, void **tmp, const void **out) {
+    cudaPointerAttributes attr{};
+    const bool on_device = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (on_device) {
+        *out = src;
+        return B2V_OK;
+    }
+    SG_CUDA(g, cudaMalloc(tmp, bytes));
+    SG_CUDA(g, cudaMemcpyAsync(*tmp, src, bytes, cudaMemcpyHostToDevice, g->stream));
+    *out = *tmp;
+    return B2V_OK;
+}
+
+extern "C" int b2v_sgrid_carve(b2v_sgrid *g, const float K[4], int32_t width, int32_t height, const double Tcw[16],
+                               float depth_max, float depth_min, const float *depth, float depth_threshold) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    if (!K || !Tcw || !depth || width <= 0 || height <= 0) {
+        g->err = "b2v_sgrid_carve: bad arguments";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    const int64_t nb = b2v_sgrid_num_blocks(g);
+    if (nb < 0) return B2V_ERR_CUDA;
+    if (nb == 0) return B2V_OK;
+    void *tmp = nullptr;
+    const void *d_depth = nullptr;
+    int rc = sgrid_upload_image(g, depth, static_cast<size_t>(width) * height * sizeof(float), &tmp, &d_depth);
+    if (rc == B2V_OK) {
+        GridQuery q;
+        fill_frustum_query(&q, K, width, height, Tcw, depth_max, depth_min, 1, g->inv_voxel_size);
+        sem_carve_kernel<<<static_cast<unsigned>(nb), kVox, 0, g->stream>>>(g->G, q, static_cast<const float *>(d_depth),
+                                                                             depth_threshold);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+        if (e != cudaSuccess) {
+            g->err = std::string("b2v_sgrid_carve: ") + cudaGetErrorString(e);
+            rc = B2V_ERR_CUDA;
+        }
+    }
+    cudaFree(tmp);
+    return rc;
+}
+
+extern "C" int b2v_sgrid_set_next_object_id(b2v_sgrid *g, int32_t next_object_id) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    g->next_object_id = next_object_id;
+    return B2V_OK;
+}
+
+extern "C" int32_t b2v_sgrid_get_next_object_id(const b2v_sgrid *g) { return g ? g->next_object_id : -1; }
+
+extern "C" int64_t b2v_sgrid_assign_object_ids_to_instance_ids(
+    b2v_sgrid *g, const float K[4], int32_t width, int32_t height, const double Tcw[16], float depth_max,
+    float depth_min, const int32_t *class_image, const int32_t *instance_image, const float *depth_image,
+    float depth_threshold, int32_t do_carving, float min_vote_ratio, int32_t min_votes) {
+    if (!g) return -1;
+    g->map_inst.clear();
+    g->map_obj.clear();
+    if (!K || !Tcw || !class_image || !instance_image || width <= 0 || height <= 0) {
+        g->err = "b2v_sgrid_assign_object_ids_to_instance_ids: bad arguments";
+        return -1;
+    }
+    const int64_t nb = b2v_sgrid_num_blocks(g);
+    if (nb < 0) return -1;
+    const size_t pixels = static_cast<size_t>(width) * height;
+    const size_t nv = static_cast<size_t>(nb) * kVox;
+    auto fail = [&](const char *what, cudaError_t e) {
+        g->err = std::string("b2v_sgrid_assign_object_ids_to_instance_ids: ") + what + ": " + cudaGetErrorString(e);
+        return static_cast<int64_t>(-1);
+    };
+    // host copies of the label images: the map must cover every (instance >= 0, class >= 0) pixel (:322-352)
+    std::vector<int32_t> h_cls(pixels), h_inst(pixels);
+    cudaError_t e = cudaMemcpy(h_cls.data(), class_image, pixels * sizeof(int32_t), cudaMemcpyDefault);
+    if (e == cudaSuccess) e = cudaMemcpy(h_inst.data(), instance_image, pixels * sizeof(int32_t), cudaMemcpyDefault);
+    if (e != cudaSuccess) return fail("label images", e);
+
+    std::vector<int2> rec;
+    if (nb > 0) {
+        void *t_cls = nullptr, *t_inst = nullptr, *t_depth = nullptr;
+        const void *d_cls = nullptr, *d_inst = nullptr, *d_depth = nullptr;
+        int rc = sgrid_upload_image(g, class_image, pixels * sizeof(int32_t), &t_cls, &d_cls);
+        if (rc == B2V_OK) rc = sgrid_upload_image(g, instance_image, pixels * sizeof(int32_t), &t_inst, &d_inst);
+        if (rc == B2V_OK && depth_image)
+            rc = sgrid_upload_image(g, depth_image, pixels * sizeof(float), &t_depth, &d_depth);
+        if (rc == B2V_OK && nv > g->records_cap) {
+            cudaFree(g->d_pend);
+            cudaFree(g->d_records);
+            g->d_pend = nullptr;
+            g->d_records = nullptr;
+            g->records_cap = 0;
+            e = cudaMalloc(&g->d_pend, nv * sizeof(int32_t));
+            if (e == cudaSuccess) e = cudaMalloc(&g->d_records, nv * sizeof(int2));
+            if (e == cudaSuccess && !g->d_n_records) e = cudaMalloc(&g->d_n_records, sizeof(uint32_t));
+            if (e != cudaSuccess) rc = B2V_ERR_CUDA; else g->records_cap = nv;
+        }
+        uint32_t n_rec = 0;
+        if (rc == B2V_OK) {
+            GridQuery q;
+            fill_frustum_query(&q, K, width, height, Tcw, depth_max, depth_min, 1, g->inv_voxel_size);
+            e = cudaMemsetAsync(g->d_pend, 0xFF, nv * sizeof(int32_t), g->stream);
+            if (e == cudaSuccess) e = cudaMemsetAsync(g->d_n_records, 0, sizeof(uint32_t), g->stream);
+            if (e == cudaSuccess) {
+                sem_assoc_kernel<<<static_cast<unsigned>(nb), kVox, 0, g->stream>>>(
+                    g->G, q, static_cast<const int32_t *>(d_cls), static_cast<const int32_t *>(d_inst),
+                    static_cast<const float *>(d_depth), depth_threshold, (do_carving && depth_image) ? 1 : 0, g->d_pend,
+                    g->d_records, g->d_n_records, static_cast<uint32_t>(nv));
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&n_rec, g->d_n_records, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+            if (e == cudaSuccess && n_rec) {
+                rec.resize(n_rec);
+                e = cudaMemcpy(rec.data(), g->d_records, n_rec * sizeof(int2), cudaMemcpyDeviceToHost);
+            }
+            if (e != cudaSuccess) rc = B2V_ERR_CUDA;
+        }
+        cudaFree(t_cls);
+        cudaFree(t_inst);
+        cudaFree(t_depth);
+        if (rc != B2V_OK) return e != cudaSuccess ? fail("device pass", e) : -1;
+    }
+
+    // votes: instance id -> (object id -> count); pending voxels vote for their instance's NEW object id, handed
+    // out here in ascending instance-id order (the reference hands them out in block-iteration order, :118-141)
+    std::map<int32_t, std::map<int32_t, int>> votes;
+    std::map<int32_t, int32_t> new_id;
+    for (const int2 &r : rec)
+        if (r.y == kAssocPending) new_id.emplace(r.x, 0);
+    for (auto &kv : new_id) kv.second = g->next_object_id++;
+    for (const int2 &r : rec) votes[r.x][r.y == kAssocPending ? new_id[r.x] : r.y] += 1;
+    std::map<int32_t, int32_t> result;
+    for (const auto &[inst, ov] : votes) {  // :287-320
+        int max_votes = 0, winner = -1, total = 0;
+        for (const auto &[obj, cnt] : ov) {
+            total += cnt;
+            if (cnt > max_votes) {
+                max_votes = cnt;
+                winner = obj;
+            }
+        }
+        if (total < min_votes || static_cast<float>(max_votes) / static_cast<float>(total) < min_vote_ratio)
+            result[inst] = -1;
+        else
+            result[inst] = winner;
+    }
+    for (size_t i = 0; i < pixels; ++i) {  // :322-352: every labelled instance of the image gets an entry
+        const int32_t inst = h_inst[i];
+        if (inst < 0 || h_cls[i] < 0) continue;
+        if (inst == 0)
+            result[0] = 0;
+        else
+            result.emplace(inst, -1);
+    }
+    for (const auto &[inst, obj] : result) {
+        g->map_inst.push_back(inst);
+        g->map_obj.push_back(obj);
+    }
+    if (!new_id.empty() && nb > 0) {  // deferred assignment of the pending voxels
+        int32_t *d_mi = nullptr, *d_mo = nullptr;
+        const size_t m = g->map_inst.size();
+        e = cudaMalloc(&d_mi, m * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&d_mo, m * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_mi, g->map_inst.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_mo, g->map_obj.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream);
+        if (e == cudaSuccess) {
+            sem_assoc_apply_kernel<<<static_cast<unsigned>(nb), kVox, 0, g->stream>>>(g->G, g->d_pend, d_mi, d_mo,
+                                                                                       static_cast<int>(m));
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+        cudaFree(d_mi);
+        cudaFree(d_mo);
+        if (e != cudaSuccess) return fail("apply", e);
+    }
+    return static_cast<int64_t>(g->map_inst.size());
+}
+
+extern "C" int b2v_sgrid_copy_instance_map(b2v_sgrid *g, int32_t *instance_ids, int32_t *object_ids) {
+    if (!g) return B2V_ERR_INVALID_ARGUMENT;
+    for (size_t i = 0; i < g->map_inst.size(); ++i) {
+        if (instance_ids) instance_ids[i] = g->map_inst[i];
+        if (object_ids) object_ids[i] = g->map_obj[i];
+    }
+    return B2V_OK;
 }

@@ -738,6 +738,54 @@ class VoxelBlockSemanticGrid:
     def remove_segment(self, object_id: int):
         self._check(self._L.b2v_sgrid_remove_segment(self._h, int(object_id)), "remove_segment")
 
+    def carve(self, camera_frustrum, depth_image, depth_threshold: float = 1e-2):
+        """carve(camera_frustrum, depth_image, depth_threshold) (voxel_block_grid.hpp:616-622); a wrongly sized
+        image is a soft failure like in the reference (voxel_grid_carving.h:51-58)."""
+        d = np.asarray(depth_image)
+        if d.size == 0 or d.shape != (camera_frustrum.height, camera_frustrum.width):
+            print("volumetric::carve: depth image is empty or has the wrong size")
+            return
+        d = np.ascontiguousarray(d, dtype=np.float32)
+        K, T = camera_frustrum._args()
+        self._check(self._L.b2v_sgrid_carve(self._h, K.ctypes.data, camera_frustrum.width, camera_frustrum.height,
+                                            T.ctypes.data, camera_frustrum.depth_max, camera_frustrum.depth_min,
+                                            d.ctypes.data, float(depth_threshold)), "b2v_sgrid_carve")
+
+    def assign_object_ids_to_instance_ids(self, camera_frustrum, class_ids_image, semantic_instances_image,
+                                          depth_image=None, depth_threshold: float = 0.1, do_carving: bool = False,
+                                          min_vote_ratio: float = 0.5, min_votes: int = 3) -> dict:
+        """`MapInstanceIdToObjectId` of the frame (voxel_block_semantic_grid.h:67-71;
+        voxel_semantic_data_association.h:69-373): 2-D instance id -> 3-D object id (-1: no confident match).
+        Soft failures (empty / wrongly sized label images) return an empty map like the reference (:80-103)."""
+        hw = (camera_frustrum.height, camera_frustrum.width)
+        ci, ii = np.asarray(class_ids_image), np.asarray(semantic_instances_image)
+        if ci.size == 0 or ii.size == 0 or ci.shape != hw or ii.shape != hw:
+            print("volumetric::assign_object_ids_to_instance_ids: label images are empty or have the wrong size")
+            return {}
+        ci = np.ascontiguousarray(ci, np.int32)
+        ii = np.ascontiguousarray(ii, np.int32)
+        dp, d = None, None
+        if depth_image is not None and np.asarray(depth_image).size and np.asarray(depth_image).shape == hw:
+            d = np.ascontiguousarray(depth_image, np.float32)
+            dp = d.ctypes.data
+        K, T = camera_frustrum._args()
+        n = self._L.b2v_sgrid_assign_object_ids_to_instance_ids(
+            self._h, K.ctypes.data, camera_frustrum.width, camera_frustrum.height, T.ctypes.data,
+            camera_frustrum.depth_max, camera_frustrum.depth_min, ci.ctypes.data, ii.ctypes.data, dp,
+            float(depth_threshold), 1 if do_carving else 0, float(min_vote_ratio), int(min_votes))
+        if n < 0:
+            raise RuntimeError(self._L.b2v_sgrid_last_error(self._h).decode())
+        ids, objs = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(self._L.b2v_sgrid_copy_instance_map(self._h, ids.ctypes.data, objs.ctypes.data),
+                    "b2v_sgrid_copy_instance_map")
+        return {int(i): int(o) for i, o in zip(ids, objs)}
+
+    def set_next_object_id(self, next_object_id: int):
+        self._check(self._L.b2v_sgrid_set_next_object_id(self._h, int(next_object_id)), "set_next_object_id")
+
+    def get_next_object_id(self) -> int:
+        return int(self._L.b2v_sgrid_get_next_object_id(self._h))
+
     def label_overflows(self) -> int:
         out = C.c_uint64(0)
         self._check(self._L.b2v_sgrid_label_overflows(self._h, C.byref(out)), "b2v_sgrid_label_overflows")
@@ -768,6 +816,25 @@ class VoxelBlockSemanticProbabilisticGrid(VoxelBlockSemanticGrid):
     over joint (object, class) pairs with depth-decayed evidence (voxel_data_semantic.h:249-672)."""
 
     KIND = _lib.B2V_SEM_PROBABILISTIC
+
+
+def remap_instance_ids(instance_ids, instance_to_object: dict, invalid_instance_id: int = -1):
+    """`volumetric.remap_instance_ids(instance_ids_image, map)` (cpp/volumetric/image_utils.h:69-163): every pixel's
+    instance id is replaced by its object id; ids missing from the map - and everything when the map is empty -
+    become `invalid_instance_id`."""
+    img = np.ascontiguousarray(instance_ids, np.int32)
+    if img.size == 0:
+        return img
+    out = np.full(img.shape, invalid_instance_id, np.int32)
+    if instance_to_object:
+        keys = np.fromiter(instance_to_object.keys(), np.int64, len(instance_to_object))
+        vals = np.fromiter(instance_to_object.values(), np.int64, len(instance_to_object))
+        order = np.argsort(keys)
+        keys, vals = keys[order], vals[order]
+        pos = np.clip(np.searchsorted(keys, img), 0, len(keys) - 1)
+        hit = keys[pos] == img
+        out[hit] = vals[pos][hit]
+    return out
 
 
 # The direct (non-block) grids of the reference's known-answer tests (cpp/test_volumetric_voxel_semantic.py) hold

@@ -304,3 +304,62 @@ def test_replica_shape_frame_split_equals_whole():
         assert whole.label_overflows() == 0
         whole.close()
         halves.close()
+
+
+@pytest.mark.parametrize("tag", ["vote", "prob"])
+def test_instance_association_pipeline_matches_the_reference(tag):
+    """The reference integrator's loop body (assign_object_ids_to_instance_ids with carving -> remap_instance_ids ->
+    integrate) replayed over 4 frames whose 2-D instance ids change every frame, against the maps and the final
+    grid of the UNMODIFIED compiled reference (tests/golden/semantic_assoc_T0.npz).  New object ids are handed out
+    in a different order (ascending instance id here, block-iteration order there), so ids are compared through
+    the bijection the maps themselves define."""
+    from pyslam_b200 import CameraFrustrum, remap_instance_ids
+    from pyslam_b200 import synthetic as S
+    g = np.load(os.path.join(GOLDEN, "semantic_assoc_T0.npz"))
+    cls_t = VoxelBlockSemanticGrid if tag == "vote" else VoxelBlockSemanticProbabilisticGrid
+    grid = cls_t(float(g["voxel_size"]), 8, capacity_blocks=1024)
+    grid.set_depth_threshold(10.0)
+    K = g["K"]
+    phi = {-1: -1, 0: 0}           # reference object id -> our object id
+    for i in range(int(g["n_frames"])):
+        d, c, T = g[f"depth_{i}"], g[f"color_{i}"], g[f"Tcw_{i}"]
+        cls_img, inst_img = g[f"class_image_{i}"], g[f"instance_image_{i}"]
+        h, w = d.shape
+        fr = CameraFrustrum(K[0], K[1], K[2], K[3], w, h, T, depth_max=float(g["param_depth_max"]),
+                            depth_min=float(g["param_depth_min"]))
+        m = grid.assign_object_ids_to_instance_ids(fr, cls_img, inst_img, d, float(g["param_depth_threshold"]),
+                                                   bool(g["param_do_carving"]), float(g["param_min_vote_ratio"]),
+                                                   int(g["param_min_votes"]))
+        ref = dict(zip(g[f"{tag}_map_inst_{i}"].tolist(), g[f"{tag}_map_obj_{i}"].tolist()))
+        assert sorted(m) == sorted(ref), (i, m, ref)
+        for k, ro in ref.items():
+            assert phi.setdefault(ro, m[k]) == m[k], (i, k, ro, m[k], phi)
+        obj_img = remap_instance_ids(inst_img, m)
+        Twc = S.inv_T(T)
+        valid = (d > 0) & (d < float(g["max_depth"]))
+        z = d[valid].astype(np.float64)
+        rows, cols = np.where(valid)
+        x, y = (cols - K[2]) * z * (1.0 / K[0]), (rows - K[3]) * z * (1.0 / K[1])
+        pw = np.stack([x * Twc[r, 0] + y * Twc[r, 1] + z * Twc[r, 2] + Twc[r, 3] for r in range(3)],
+                      axis=1).astype(np.float32)
+        grid.integrate(pw, (c[valid] / 255.0).astype(np.float32), cls_img[valid], obj_img[valid], d[valid])
+    assert len(set(phi.values())) == len(phi)                      # a bijection
+    assert grid.get_next_object_id() == int(g[f"{tag}_next_object_id"])
+    dmp = sort_dump(grid.dump_blocks(1))
+    assert np.array_equal(dmp["keys"], g[f"{tag}_keys"])
+    # carving compares float depths against the image: a voxel within rounding of the threshold may flip
+    same = dmp["count"] == g[f"{tag}_count"]
+    assert int((~same).sum()) <= 4, int((~same).sum())
+    lut = np.vectorize(lambda o: phi.get(int(o), -12345))
+    occ = same & (g[f"{tag}_count"] > 0)
+    assert np.array_equal(dmp["object_id"][occ], lut(g[f"{tag}_object_id"][occ]))
+    assert np.array_equal(dmp["class_id"][occ], g[f"{tag}_class_id"][occ])
+    assert np.allclose(dmp["confidence"][occ], g[f"{tag}_confidence"][occ], rtol=2e-6, atol=1e-9)
+    assert (g[f"{tag}_object_id"][occ] > 0).sum() > 200           # objects really were associated
+    # soft failures and argument checks
+    assert grid.assign_object_ids_to_instance_ids(fr, cls_img[:5], inst_img) == {}
+    grid.carve(fr, d[:5])                                          # wrong size: no-op
+    before = sort_dump(grid.dump_blocks(1))["count"]
+    grid.carve(fr, d + 0.5, depth_threshold=0.05)                  # the surface moved back: carve what is in front
+    after = sort_dump(grid.dump_blocks(1))["count"]
+    assert (after > 0).sum() < (before > 0).sum()
