@@ -204,3 +204,8 @@ API = SimpleNamespace(
 def standalone_integrator_class():
     from .integrator import make_integrator_class
     return make_integrator_class(StandaloneIntegratorBase, API)
+
+
+def standalone_semantic_integrator_class():
+    from .integrator_semantic import make_semantic_integrator_class
+    return make_semantic_integrator_class(StandaloneIntegratorBase, API)

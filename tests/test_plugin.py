@@ -199,3 +199,131 @@ def test_adapter_gpu_rectification_equals_cpu_rectification():
     assert len(dumps[0]["keys"]) > 20
     assert np.array_equal(dumps[0]["keys"], dumps[1]["keys"])
     assert np.array_equal(dumps[0]["vox"], dumps[1]["vox"])
+
+
+# ---- semantic backend ------------------------------------------------------------------------------------------
+class _FakeSemanticGrid:
+    def __init__(self, **kw):
+        self.kw = kw
+        self.calls = []
+
+    def set_depth_threshold(self, v):
+        self.calls.append(("thr", v))
+
+    def set_depth_decay_rate(self, v):
+        self.calls.append(("rate", v))
+
+    def assign_object_ids_to_instance_ids(self, fr, cls, inst, depth, **kw):
+        self.calls.append(("assign", np.asarray(fr.T_cw).copy(), kw))
+        return {0: 0, 7: 3, 9: -1}
+
+    def carve(self, fr, depth, thr):
+        self.calls.append(("carve", thr))
+
+    def integrate_rgbd(self, depth, color, K, Twc, class_image=None, object_image=None, **kw):
+        self.calls.append(("rgbd", tuple(K), np.asarray(Twc).copy(), None if object_image is None else
+                           object_image.copy(), kw))
+
+    def get_voxels(self, min_count=1, min_confidence=0.0):
+        self.calls.append(("voxels", min_count, min_confidence))
+        return SimpleNamespace(points=np.zeros((2, 3)), colors=np.ones((2, 3), np.float32),
+                               class_ids=np.array([1, 2], np.int32), object_ids=np.array([3, -1], np.int32),
+                               confidences=np.ones(2, np.float32))
+
+    def reset(self):
+        self.calls.append(("reset",))
+
+    def close(self):
+        self.calls.append(("close",))
+
+
+def test_semantic_adapter_flow_with_fake_grid(monkeypatch, tmp_path):
+    from pyslam_b200 import integrator_semantic as IS
+    monkeypatch.setattr(IS, "VoxelBlockSemanticGrid", _FakeSemanticGrid)
+    monkeypatch.setattr(IS, "VoxelBlockSemanticProbabilisticGrid", _FakeSemanticGrid)
+    monkeypatch.setattr(IS, "filter_shadow_points", lambda d: d)
+    Cls = P.standalone_semantic_integrator_class()
+    cfg = S.CONFIGS["T0"]
+    integ = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_SEMANTIC",
+                use_semantic_probabilistic=True, kVolumetricIntegrationVoxelGridUseCarving=True)
+    assert integ.volume.calls[:2] == [("thr", 5.0), ("rate", 0.1)]          # indoor defaults (config :370-375)
+    d, c, T = S.render_frame(cfg, 0)
+    inst = np.full(d.shape, 7, np.int32)
+    inst[:, :10] = 9
+    inst[:, 10:20] = 0
+    kd = P.VolumetricIntegrationKeyframeData(id=3, pose=T, img=np.ascontiguousarray(c[..., ::-1]), depth=d,
+                                             semantic_img=np.ones(d.shape, np.int32), semantic_instances_img=inst)
+    integ.add_keyframe_data(kd)
+    integ.step()
+    names = [x[0] for x in integ.volume.calls]
+    assert "assign" in names and "carve" not in names                        # carving rides on the association
+    rgbd = [x for x in integ.volume.calls if x[0] == "rgbd"][0]
+    assert np.allclose(rgbd[2] @ T, np.eye(4), atol=1e-9)                    # Twc = inv(Tcw)
+    assert set(np.unique(rgbd[3])) == {-1, 0, 3}                             # instance ids remapped to object ids
+    assert rgbd[4]["filter_shadow_points"] is True and rgbd[4]["use_depths"] is True
+    out = integ.pop_output()
+    assert out.point_cloud.semantics.tolist() == [1, 2] and out.point_cloud.object_ids.tolist() == [3, -1]
+    assert ("voxels", 3, 0.6) in integ.volume.calls
+    # no instance image: plain carve + integrate without object ids
+    integ2 = Cls(_camera(cfg), P.DatasetEnvironmentType.OUTDOOR, None, "B200_SEMANTIC",
+                 kVolumetricIntegrationVoxelGridUseCarving=True)
+    assert integ2.volume.calls[:2] == [("thr", 10.0), ("rate", 0.05)]
+    integ2.add_keyframe_data(P.VolumetricIntegrationKeyframeData(
+        id=4, pose=T, img=np.ascontiguousarray(c[..., ::-1]), depth=d, semantic_img=np.ones(d.shape, np.int32)))
+    integ2.step()
+    names = [x[0] for x in integ2.volume.calls]
+    assert "carve" in names and "assign" not in names
+    assert [x for x in integ2.volume.calls if x[0] == "rgbd"][0][3] is None
+    integ2.save(str(tmp_path))
+    integ2.step()
+    assert os.path.exists(os.path.join(tmp_path, "dense_map.ply"))
+    integ2.reset()
+    integ2.add_update_output_task()
+    integ2.step()
+    assert ("reset",) in integ2.volume.calls
+
+
+@pytest.mark.gpu
+def test_semantic_adapter_end_to_end_on_gpu():
+    """The plugin class driving the real GPU grid == the same calls made by hand."""
+    from pyslam_b200 import CameraFrustrum, VoxelBlockSemanticProbabilisticGrid, remap_instance_ids
+    from tests._util import GOLDEN, sort_dump
+    g = np.load(os.path.join(GOLDEN, "semantic_assoc_T0.npz"))
+    cfg = S.CONFIGS["T0"]
+    kw = dict(kVolumetricIntegrationVoxelLength=float(g["voxel_size"]), kVolumetricIntegrationVoxelGridUseCarving=True,
+              kVolumetricIntegrationVoxelGridShadowPointsFilter=False,
+              kVolumetricIntegrationVoxelGridCarvingDepthThreshold=0.08,
+              kVolumetricIntegrationB200CapacityBlocks=1024, use_semantic_probabilistic=True)
+    Cls = P.standalone_semantic_integrator_class()
+    integ = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_SEMANTIC", **kw)
+    manual = VoxelBlockSemanticProbabilisticGrid(float(g["voxel_size"]), 8, capacity_blocks=1024)
+    manual.set_depth_threshold(5.0)
+    manual.set_depth_decay_rate(0.1)
+    K = g["K"]
+    for i in range(int(g["n_frames"])):
+        d, c, T = g[f"depth_{i}"], g[f"color_{i}"], g[f"Tcw_{i}"]
+        cls_img, inst_img = g[f"class_image_{i}"], g[f"instance_image_{i}"]
+        integ.add_keyframe_data(P.VolumetricIntegrationKeyframeData(
+            id=i, pose=T, img=np.ascontiguousarray(c[..., ::-1]), depth=d, semantic_img=cls_img,
+            semantic_instances_img=inst_img))
+        integ.step()
+        fr = CameraFrustrum(K[0], K[1], K[2], K[3], d.shape[1], d.shape[0], T, depth_max=8.0, depth_min=1e-2)
+        m = manual.assign_object_ids_to_instance_ids(fr, cls_img, inst_img, d, depth_threshold=0.08, do_carving=True,
+                                                     min_vote_ratio=0.5, min_votes=3)
+        assert m == integ.last_instance_map
+        manual.integrate_rgbd(d, c, K, np.linalg.inv(T), cls_img, remap_instance_ids(inst_img, m), max_depth=4.0,
+                              use_depths=True, filter_shadow_points=False)
+    a, b = sort_dump(integ.volume.dump_blocks(8)), sort_dump(manual.dump_blocks(8))
+    for k in ("keys", "count", "pos_sum", "col_sum", "object_id", "class_id", "confidence", "lab_logp"):
+        assert np.array_equal(a[k], b[k]), k
+    assert (a["object_id"] > 0).sum() > 200
+    integ.add_update_output_task()
+    integ.step()
+    out = None
+    while True:
+        o = integ.pop_output()
+        if o is None:
+            break
+        out = o
+    assert out.point_cloud.points.shape[1] == 3 and len(out.point_cloud.semantics) == len(out.point_cloud.points)
+    integ.quit()
