@@ -107,6 +107,10 @@ int64_t b2v_dump_blocks(b2v_volume *v, int32_t *keys, uint64_t *hashes, float *v
  * blocks are overwritten.  The reference's load() is a stub (base.py:595-604); this is the restore
  * half of b2v_dump_blocks, also used to gather shards onto one GPU and by the tests. */
 int b2v_upload_blocks(b2v_volume *v, int64_t n_blocks, const int32_t *keys, const float *voxels);
+/* the same exchange with DEVICE buffers (multi-GPU mesh gather): d_keys4 int32 [n][4] = {x, y, z, 0},
+ * d_voxels float32 [n][5][512].  export returns the block count (with both pointers NULL: just the count). */
+int64_t b2v_export_blocks_device(b2v_volume *v, int32_t *d_keys4, float *d_voxels, int64_t max_blocks);
+int b2v_import_blocks_device(b2v_volume *v, int64_t n_blocks, const int32_t *d_keys4, const float *d_voxels);
 /* keys int32[n*3] of the blocks touched by the most recent frame; returns n or <0 */
 int64_t b2v_last_touched_keys(b2v_volume *v, int32_t *keys, int64_t max_keys);
 

@@ -932,6 +932,53 @@ extern "C" int b2v_upload_blocks(b2v_volume *v, int64_t n_blocks, const int32_t 
     return read_counters(v);
 }
 
+// Device-to-device block exchange (multi-GPU mesh gather): keys as int32 x 4 {x, y, z, 0}
+extern "C" int64_t b2v_export_blocks_device(b2v_volume *v, int32_t *d_keys4, float *d_voxels, int64_t max_blocks) {
+    if (!v) return -1;
+    if (read_counters(v) == B2V_ERR_CUDA) return -1;
+    const uint32_t nb = block_count(v);
+    if (!d_keys4 && !d_voxels) return nb;
+    if (static_cast<int64_t>(nb) > max_blocks) {
+        v->err = "b2v_export_blocks_device: destination too small";
+        return -1;
+    }
+    if (nb == 0) return 0;
+    cudaError_t e = cudaSuccess;
+    if (d_keys4) e = cudaMemcpyAsync(d_keys4, v->meta.block_keys, nb * sizeof(int4), cudaMemcpyDeviceToDevice, v->compute);
+    if (e == cudaSuccess && d_voxels)
+        e = cudaMemcpyAsync(d_voxels, v->meta.pool, static_cast<size_t>(nb) * kBlockFloats * sizeof(float),
+                            cudaMemcpyDeviceToDevice, v->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->compute);
+    if (e != cudaSuccess) {
+        v->err = std::string("b2v_export_blocks_device: ") + cudaGetErrorString(e);
+        return -1;
+    }
+    return nb;
+}
+
+extern "C" int b2v_import_blocks_device(b2v_volume *v, int64_t n_blocks, const int32_t *d_keys4, const float *d_voxels) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    if (n_blocks < 0 || (n_blocks > 0 && (!d_keys4 || !d_voxels))) {
+        v->err = "b2v_import_blocks_device: bad arguments";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    if (n_blocks == 0) return B2V_OK;
+    B2V_CUDA(v, cudaSetDevice(v->cfg.device));
+    uint32_t *d_i = nullptr;
+    cudaError_t e = cudaMalloc(&d_i, static_cast<size_t>(n_blocks) * sizeof(uint32_t));
+    if (e == cudaSuccess)
+        e = launch_upload_blocks(reinterpret_cast<const int4 *>(d_keys4), d_voxels, static_cast<uint32_t>(n_blocks), d_i,
+                                 v->table, v->meta, v->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->compute);
+    cudaFree(d_i);
+    v->launches += 2;
+    if (e != cudaSuccess) {
+        v->err = std::string("b2v_import_blocks_device: ") + cudaGetErrorString(e);
+        return B2V_ERR_CUDA;
+    }
+    return read_counters(v);
+}
+
 extern "C" int64_t b2v_last_touched_keys(b2v_volume *v, int32_t *keys, int64_t max_keys) {
     if (!v) return -1;
     if (read_counters(v) == B2V_ERR_CUDA) return -1;

@@ -4,8 +4,8 @@ One process per GPU.  A block belongs to rank `BlockKeyHash(key) % world` — th
 (`cpp/volumetric/voxel_hashing.h:106-113`), so ownership is reproducible from the keys alone.  The
 integrate path needs no collective: every rank sees every frame and keeps the keys it owns
 (`b2v_config.shard_rank / shard_count`).  Mesh extraction needs the +1-voxel halos of blocks that
-may live on another rank; `gather_blocks` collects all shards on one rank (torch.distributed:
-NCCL on GPUs, gloo in the CPU tests), which then meshes the union.
+may live on another rank; `gather_blocks_device` collects all shards on one rank GPU-to-GPU over NCCL
+(`gather_blocks` is the host-array variant used with gloo in the CPU tests), which then meshes the union.
 """
 
 from __future__ import annotations
@@ -65,21 +65,58 @@ def gather_blocks(keys, vox, dst: int = 0, group=None, device=None):
     return out_k, out_v
 
 
+def gather_blocks_device(volume, dst: int = 0, group=None):
+    """Device-resident gather over NCCL: every rank exports its blocks device-to-device
+    (`b2v_export_blocks_device`), the payloads travel GPU to GPU (NVLink), nothing touches host memory.
+    Returns (keys int32 [n,4], vox float32 [n,5,512]) CUDA tensors on dst, (None, None) elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    keys, vox = volume.export_blocks_torch()
+    n = torch.tensor([keys.shape[0]], dtype=torch.int64, device=keys.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    nmax = max(max(sizes), 1)
+    k = torch.zeros((nmax, 4), dtype=torch.int32, device=keys.device)
+    v = torch.zeros((nmax,) + tuple(vox.shape[1:]), dtype=torch.float32, device=keys.device)
+    k[:keys.shape[0]] = keys
+    v[:vox.shape[0]] = vox
+    ks = [torch.zeros_like(k) for _ in range(world)] if rank == dst else None
+    vs = [torch.zeros_like(v) for _ in range(world)] if rank == dst else None
+    dist.gather(k, ks, dst=dst, group=group)
+    dist.gather(v, vs, dst=dst, group=group)
+    if rank != dst:
+        return None, None
+    return (torch.cat([ks[r][:sizes[r]] for r in range(world)]).contiguous(),
+            torch.cat([vs[r][:sizes[r]] for r in range(world)]).contiguous())
+
+
 def extract_mesh_distributed(volume, dst: int = 0, group=None, device=None, capacity_blocks=None):
-    """Mesh of a sharded volume: gather all shards on `dst`, upload them into a scratch single-GPU
+    """Mesh of a sharded volume: gather all shards on `dst`, load them into a scratch single-GPU
     volume there and run the marching-cubes kernels on the union.  Returns a TriangleMesh on dst,
-    None elsewhere."""
+    None elsewhere.  With the NCCL backend the blocks stay on the GPUs (`gather_blocks_device`); any other
+    backend (gloo in the CPU tests) goes through host arrays (`gather_blocks`)."""
     import torch.distributed as dist
     from .volume import B200TsdfVolume
 
-    d = volume.dump_blocks()
-    keys, vox = gather_blocks(d["keys"], d["vox"], dst=dst, group=group, device=device)
+    on_device = dist.get_backend(group) == "nccl"
+    if on_device:
+        keys, vox = gather_blocks_device(volume, dst=dst, group=group)
+    else:
+        d = volume.dump_blocks()
+        keys, vox = gather_blocks(d["keys"], d["vox"], dst=dst, group=group, device=device)
     if dist.get_rank(group) != dst:
         return None
     cap = capacity_blocks or max(2 * len(keys), 1024)
     scratch = B200TsdfVolume(volume.voxel_length, volume.sdf_trunc, volume.depth_trunc,
                              capacity_blocks=cap, device=volume.device)
-    scratch.upload_blocks(keys, vox)
+    if on_device:
+        scratch.import_blocks_torch(keys, vox)
+    else:
+        scratch.upload_blocks(keys, vox)
     mesh = scratch.extract_mesh()
     scratch.close()
     return mesh

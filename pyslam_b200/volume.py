@@ -277,6 +277,31 @@ class B200TsdfVolume:
         self._check(self._L.b2v_upload_blocks(self._h, k.shape[0], k.ctypes.data, x.ctypes.data),
                     "b2v_upload_blocks")
 
+    def export_blocks_torch(self):
+        """(keys int32 [n,4] = {x,y,z,0}, vox float32 [n,5,512]) as torch CUDA tensors on this volume's device:
+        device-to-device copies of the block keys and the block pool (multi-GPU mesh gather)."""
+        import torch
+        n = self._L.b2v_export_blocks_device(self._h, None, None, 0)
+        if n < 0:
+            raise RuntimeError(self._L.b2v_last_error(self._h).decode())
+        dev = torch.device("cuda", self.device)
+        keys = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        vox = torch.empty((n, VOXEL_PLANES, BLOCK_VOXELS), dtype=torch.float32, device=dev)
+        if n:
+            got = self._L.b2v_export_blocks_device(self._h, keys.data_ptr(), vox.data_ptr(), n)
+            if got != n:
+                raise RuntimeError(self._L.b2v_last_error(self._h).decode())
+        return keys, vox
+
+    def import_blocks_torch(self, keys, vox):
+        """Inverse of export_blocks_torch: contiguous torch CUDA tensors on this volume's device."""
+        if keys.shape[0] == 0:
+            return
+        if not (keys.is_cuda and vox.is_cuda and keys.is_contiguous() and vox.is_contiguous()):
+            raise RuntimeError("keys and vox must be contiguous CUDA tensors")
+        self._check(self._L.b2v_import_blocks_device(self._h, int(keys.shape[0]), keys.data_ptr(), vox.data_ptr()),
+                    "b2v_import_blocks_device")
+
     # ---- outputs ----
     def extract_mesh(self) -> TriangleMesh:
         """north_star `extract_mesh()` == Open3D `extract_triangle_mesh()` (tsdf.py:239,260)."""

@@ -457,3 +457,34 @@ def test_volume_with_rectification_equals_prerectified_input():
     vol.integrate(rect_d[0], rect_rgb[0], K, Ts[0])
     assert vol.num_blocks() > 0
     vol.close()
+
+
+def test_device_block_export_import_round_trip():
+    """b2v_export_blocks_device / b2v_import_blocks_device (the multi-GPU mesh gather's device path): a volume
+    rebuilt from another volume's device-resident blocks has the same blocks and the same mesh."""
+    import torch
+    cfg = S.CONFIGS["T0"]
+    a = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=4096)
+    for i in range(3):
+        d, c, T = S.render_frame(cfg, i)
+        a.integrate(d, c, cfg.K, T)
+    keys, vox = a.export_blocks_torch()
+    assert keys.is_cuda and keys.shape == (a.num_blocks(), 4) and vox.shape == (a.num_blocks(), 5, 512)
+    b = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=4096)
+    perm = torch.randperm(keys.shape[0], device=keys.device)        # block order must not matter
+    b.import_blocks_torch(keys[perm].contiguous(), vox[perm].contiguous())
+    da, db = sort_dump(a.dump_blocks()), sort_dump(b.dump_blocks())
+    assert np.array_equal(da["keys"], db["keys"]) and np.array_equal(da["vox"], db["vox"])
+    ma, mb = a.extract_mesh(), b.extract_mesh()
+    ca = oracle.canonical_mesh(ma.vertices.astype(np.float32), ma.vertex_colors.astype(np.float32), ma.edge_ids,
+                               ma.triangles)
+    cb = oracle.canonical_mesh(mb.vertices.astype(np.float32), mb.vertex_colors.astype(np.float32), mb.edge_ids,
+                               mb.triangles)
+    for n in ("edges", "triangles", "vertices", "colors"):
+        assert np.array_equal(ca[n], cb[n]), n
+    empty = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=64)
+    k0, v0 = empty.export_blocks_torch()
+    assert k0.shape[0] == 0 and v0.shape[0] == 0
+    empty.import_blocks_torch(k0, v0)
+    for v in (a, b, empty):
+        v.close()
