@@ -488,3 +488,28 @@ def test_device_block_export_import_round_trip():
     empty.import_blocks_torch(k0, v0)
     for v in (a, b, empty):
         v.close()
+
+
+def test_sharded_fused_batches_equal_the_unsharded_volume():
+    """4-way hash-sharded volumes fed through the fused batch path (what a rank of `bench.py --gpus 4` runs): the
+    union of the shards must equal the unsharded volume and the oracle bit for bit."""
+    cfg = S.CONFIGS["C1"]
+    n = 19
+    frames = [S.render_frame(cfg, i) for i in range(n)]
+    D, Cc, T = (np.stack([f[k] for f in frames]) for k in range(3))
+    full, orc = _pair(cfg, capacity=1 << 16)
+    full.integrate_batch(D, Cc, cfg.K, T)
+    for d, c, t in frames:
+        orc.integrate(d, c, cfg.K, t)
+    _assert_same_volume(full, orc)
+    parts = []
+    for r in range(4):
+        s = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=1 << 15, shard_rank=r,
+                           shard_count=4)
+        s.integrate_batch(D, Cc, cfg.K, T)
+        parts.append(s.dump_blocks())
+        s.close()
+    merged = sort_dump({k: np.concatenate([p[k] for p in parts]) for k in ("keys", "hashes", "vox")})
+    ref = sort_dump(full.dump_blocks())
+    for name in ("keys", "hashes", "vox"):
+        assert np.array_equal(merged[name], ref[name]), name
