@@ -1,6 +1,10 @@
 """Timing of the semantic row: one 640x480 frame worth of labelled points per call (C3-style), GPU vs the compiled
 reference on this host.  Not a bench.py line; numbers go to DESIGN.md."""
+import os
+import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
