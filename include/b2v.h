@@ -219,6 +219,12 @@ int64_t b2v_sgrid_num_blocks(b2v_sgrid *g);
 int64_t b2v_sgrid_get_voxels(b2v_sgrid *g, int32_t min_count, float min_confidence);
 int b2v_sgrid_copy_voxels(b2v_sgrid *g, double *points, float *colors, int32_t *class_ids, int32_t *object_ids,
                           float *confidences);
+/* spatial read-outs, same two-step pattern (voxel_block_grid.hpp:822-1016 get_voxels_in_bb, bbox = min xyz, max xyz;
+ * :1019-1195 get_voxels_in_camera_frustrum) */
+int64_t b2v_sgrid_get_voxels_in_bb(b2v_sgrid *g, const double bbox[6], int32_t min_count, float min_confidence);
+int64_t b2v_sgrid_get_voxels_in_frustum(b2v_sgrid *g, const float K[4], int32_t width, int32_t height,
+                                        const double Tcw[16], float depth_max, float depth_min, int32_t min_count,
+                                        float min_confidence);
 int b2v_sgrid_remove_low_count_voxels(b2v_sgrid *g, int32_t min_count);
 int b2v_sgrid_remove_low_confidence_segments(b2v_sgrid *g, int32_t min_confidence);
 int b2v_sgrid_merge_segments(b2v_sgrid *g, int32_t object_id1, int32_t object_id2);

@@ -421,6 +421,9 @@ def _sem():
         L.refsem_assign_object_ids.restype = C.c_int64
         L.refsem_assign_object_ids.argtypes = [vp, _f32p, C.c_int, C.c_int, _f64p, C.c_float, C.c_float, _i32p, _i32p,
                                                vp, C.c_float, C.c_int, C.c_float, C.c_int, _i32p, _i32p, C.c_int64]
+        L.refsem_query.restype = C.c_int64
+        L.refsem_query.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_float, C.c_float, vp, C.c_int, C.c_float, vp, vp,
+                                   vp, vp, vp]
         L.refsem_carve.argtypes = [vp, _f32p, C.c_int, C.c_int, _f64p, C.c_float, C.c_float, _f32p, C.c_float]
         L.refsem_set_next_object_id.argtypes = [C.c_int32]
         L.refsem_get_next_object_id.restype = C.c_int32
@@ -524,6 +527,37 @@ class RefSemanticGrid:
                                              int(min_votes), ids, objs, 4096)
         assert n <= 4096
         return {int(i): int(o) for i, o in zip(ids[:n], objs[:n])}
+
+    def _query(self, K, width, height, Tcw, depth_max, depth_min, bbox, min_count, min_confidence):
+        kp = tp = bp = None
+        hold = []
+        if K is not None:
+            K4 = np.ascontiguousarray(K, np.float32)
+            T = np.ascontiguousarray(np.asarray(Tcw, np.float64).reshape(16))
+            hold += [K4, T]
+            kp, tp = K4.ctypes.data, T.ctypes.data
+        else:
+            bb = np.ascontiguousarray(bbox, np.float64).reshape(6)
+            hold.append(bb)
+            bp = bb.ctypes.data
+        args = (self._h, kp, int(width), int(height), tp, float(depth_max), float(depth_min), bp, int(min_count),
+                float(min_confidence))
+        n = self._L.refsem_query(*args, None, None, None, None, None)
+        out = dict(points=np.zeros((n, 3), np.float64), colors=np.zeros((n, 3), np.float32),
+                   class_ids=np.zeros(n, np.int32), object_ids=np.zeros(n, np.int32),
+                   confidences=np.zeros(n, np.float32))
+        if n:
+            self._L.refsem_query(*args, out["points"].ctypes.data, out["colors"].ctypes.data,
+                                 out["class_ids"].ctypes.data, out["object_ids"].ctypes.data,
+                                 out["confidences"].ctypes.data)
+        return out
+
+    def get_voxels_in_camera_frustrum(self, K, width, height, Tcw, depth_max, depth_min, min_count=1,
+                                      min_confidence=0.0):
+        return self._query(K, width, height, Tcw, depth_max, depth_min, None, min_count, min_confidence)
+
+    def get_voxels_in_bb(self, bbox, min_count=1, min_confidence=0.0):
+        return self._query(None, 0, 0, None, 0.0, 0.0, bbox, min_count, min_confidence)
 
     def carve(self, K, width, height, Tcw, depth_max, depth_min, depth_image, depth_threshold):
         self._L.refsem_carve(self._h, np.ascontiguousarray(K, np.float32), int(width), int(height),

@@ -41,6 +41,8 @@ struct ISem {
                            const cv::Mat &depth, float thr, bool carve, float ratio, int min_votes, int32_t *ids,
                            int32_t *objs, int64_t cap) = 0;
     virtual void carve(const volumetric::CameraFrustrum &fr, const cv::Mat &depth, float thr) = 0;
+    virtual int64_t query(const volumetric::CameraFrustrum *fr, const double *bb, int min_count, float min_conf,
+                          double *pts, float *cols, int32_t *cls, int32_t *obj, float *conf) const = 0;
     virtual void remove_low_count(int min_count) = 0;
     virtual void remove_low_confidence(int min_confidence) = 0;
     virtual void merge_segments(int a, int b) = 0;
@@ -153,6 +155,21 @@ template <typename Grid, typename V> struct Sem final : ISem {
     void carve(const volumetric::CameraFrustrum &fr, const cv::Mat &depth, float thr) override {
         g.carve(fr, depth, thr);
     }
+    int64_t query(const volumetric::CameraFrustrum *fr, const double *bb, int min_count, float min_conf, double *pts,
+                  float *cols, int32_t *cls, int32_t *obj, float *conf) const override {
+        // IncludeSemantics = true: the variant that also returns labels (voxel_block_grid.h:125-137)
+        const auto out =
+            fr ? g.template get_voxels_in_camera_frustrum<true>(*fr, min_count, min_conf)
+               : g.template get_voxels_in_bb<true>(volumetric::BoundingBox3D(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5]),
+                                                   min_count, min_conf);
+        const int64_t n = static_cast<int64_t>(out.points.size());
+        if (pts) std::memcpy(pts, out.points.data(), sizeof(double) * 3 * n);
+        if (cols) std::memcpy(cols, out.colors.data(), sizeof(float) * 3 * n);
+        if (cls) std::memcpy(cls, out.class_ids.data(), sizeof(int) * n);
+        if (obj) std::memcpy(obj, out.object_ids.data(), sizeof(int) * n);
+        if (conf) std::memcpy(conf, out.confidences.data(), sizeof(float) * n);
+        return n;
+    }
     void remove_low_count(int min_count) override { g.remove_low_count_voxels(min_count); }
     void remove_low_confidence(int min_confidence) override { g.remove_low_confidence_segments(min_confidence); }
     void merge_segments(int a, int b) override { g.merge_segments(a, b); }
@@ -243,6 +260,17 @@ void refsem_carve(void *h, const float *K, int width, int height, const double *
     const auto fr = sem_frustum(K, width, height, Tcw, depth_max, depth_min);
     cv::Mat depth(height, width, CV_32FC1, const_cast<float *>(depth_image));
     static_cast<ISem *>(h)->carve(fr, depth, depth_threshold);
+}
+
+// get_voxels_in_camera_frustrum / get_voxels_in_bb (voxel_block_grid.hpp:1019-1195, 822-1016); K == NULL selects the box
+int64_t refsem_query(void *h, const float *K, int width, int height, const double *Tcw, float depth_max,
+                     float depth_min, const double *bbox, int min_count, float min_conf, double *pts, float *cols,
+                     int32_t *cls, int32_t *obj, float *conf) {
+    if (K) {
+        const auto fr = sem_frustum(K, width, height, Tcw, depth_max, depth_min);
+        return static_cast<ISem *>(h)->query(&fr, nullptr, min_count, min_conf, pts, cols, cls, obj, conf);
+    }
+    return static_cast<ISem *>(h)->query(nullptr, bbox, min_count, min_conf, pts, cols, cls, obj, conf);
 }
 
 // process-wide object-id allocator (voxel_semantic_shared_data.h:27-33)

@@ -36,7 +36,8 @@ EXPORTED_SYMBOLS = [
     "b2v_sgrid_create", "b2v_sgrid_destroy", "b2v_sgrid_last_error", "b2v_sgrid_clear",
     "b2v_sgrid_set_depth_threshold", "b2v_sgrid_set_depth_decay_rate", "b2v_sgrid_integrate",
     "b2v_sgrid_integrate_rgbd",
-    "b2v_sgrid_num_blocks", "b2v_sgrid_get_voxels", "b2v_sgrid_copy_voxels",
+    "b2v_sgrid_num_blocks", "b2v_sgrid_get_voxels", "b2v_sgrid_copy_voxels", "b2v_sgrid_get_voxels_in_bb",
+    "b2v_sgrid_get_voxels_in_frustum",
     "b2v_sgrid_remove_low_count_voxels", "b2v_sgrid_remove_low_confidence_segments", "b2v_sgrid_merge_segments",
     "b2v_sgrid_remove_segment", "b2v_sgrid_label_overflows", "b2v_sgrid_dump_blocks", "b2v_sgrid_carve",
     "b2v_sgrid_assign_object_ids_to_instance_ids", "b2v_sgrid_copy_instance_map", "b2v_sgrid_set_next_object_id",
@@ -130,6 +131,10 @@ def load() -> C.CDLL:
     L.b2v_sgrid_get_voxels.restype = C.c_int64
     L.b2v_sgrid_get_voxels.argtypes = [vp, i32, C.c_float]
     L.b2v_sgrid_copy_voxels.argtypes = [vp] * 6
+    L.b2v_sgrid_get_voxels_in_bb.restype = C.c_int64
+    L.b2v_sgrid_get_voxels_in_bb.argtypes = [vp, vp, i32, C.c_float]
+    L.b2v_sgrid_get_voxels_in_frustum.restype = C.c_int64
+    L.b2v_sgrid_get_voxels_in_frustum.argtypes = [vp, vp, i32, i32, vp, C.c_float, C.c_float, i32, C.c_float]
     L.b2v_sgrid_remove_low_count_voxels.argtypes = [vp, i32]
     L.b2v_sgrid_remove_low_confidence_segments.argtypes = [vp, i32]
     L.b2v_sgrid_merge_segments.argtypes = [vp, i32, i32]

@@ -25,6 +25,8 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <climits>
+#include <cmath>
+#include <cstring>
 #include <limits>
 #include <map>
 #include <new>
@@ -382,45 +384,6 @@ __device__ __forceinline__ void sem_reset_voxel(const SemGrid &G, uint32_t v) { 
     }
 }
 
-__global__ void __launch_bounds__(kVox)
-sem_count_kernel(const SemGrid G, const int min_count, const float min_conf, uint32_t *__restrict__ sums) {
-    __shared__ uint32_t s_warp[16];
-    const uint32_t v = blockIdx.x * kVox + threadIdx.x;
-    const int t = threadIdx.x;
-    const int c = G.count[v];
-    const bool keep = c >= min_count && sem_confidence(G, v, c) >= min_conf;  // voxel_block_grid.hpp:797-803
-    const uint32_t x = __reduce_add_sync(0xffffffffu, keep ? 1u : 0u);
-    if ((t & 31) == 0) s_warp[t >> 5] = x;
-    __syncthreads();
-    if (t == 0) {
-        uint32_t s = 0;
-        for (int k = 0; k < 16; ++k) s += s_warp[k];
-        sums[blockIdx.x] = s;
-    }
-}
-
-__global__ void __launch_bounds__(kVox)
-sem_emit_kernel(const SemGrid G, const int min_count, const float min_conf, const uint32_t *__restrict__ offs,
-                double *__restrict__ out_pts, float *__restrict__ out_cols, int32_t *__restrict__ out_cls,
-                int32_t *__restrict__ out_obj, float *__restrict__ out_conf) {
-    __shared__ uint32_t s_warp[16];
-    const uint32_t v = blockIdx.x * kVox + threadIdx.x;
-    const int c = G.count[v];
-    const float conf = sem_confidence(G, v, c);
-    const bool keep = c >= min_count && conf >= min_conf;
-    const size_t pos = offs[blockIdx.x] + block_excl_scan_512(keep ? 1u : 0u, s_warp);
-    if (!keep) return;
-    const double dc = static_cast<double>(c);
-    const float fc = static_cast<float>(c);
-    for (int a = 0; a < 3; ++a) {  // voxel_data.h:58-69, 98-109: sum / (T)count, zero for an empty voxel
-        out_pts[3 * pos + a] = c ? __ddiv_rn(G.pos[3 * static_cast<size_t>(v) + a], dc) : 0.0;
-        out_cols[3 * pos + a] = c ? __fdiv_rn(G.col[3 * static_cast<size_t>(v) + a], fc) : 0.0f;
-    }
-    out_cls[pos] = G.cls[v];
-    out_obj[pos] = G.obj[v];
-    out_conf[pos] = conf;
-}
-
 // op 0: remove_low_count_voxels(a)  1: remove_low_confidence_segments(a)  2: remove_segment(a)
 // op 3: merge_segments(a, b)  (voxel_block_grid.hpp:625-647; voxel_block_semantic_grid.hpp:101-183)
 __global__ void __launch_bounds__(kVox) sem_edit_kernel(const SemGrid G, const int op, const int a, const int b) {
@@ -495,6 +458,72 @@ __device__ __forceinline__ bool sem_block_in_range(const GridQuery &Q, const int
     for (int a = 0; a < 3; ++a)
         if (k[a] < block_coord(Q.min_key[a]) || k[a] > block_coord(Q.max_key[a])) return false;
     return true;
+}
+
+// spatial filter of a read-out: mode 0 = every voxel (get_voxels), 1 = bounding box (get_voxels_in_bb,
+// voxel_block_grid.hpp:822-1016), 2 = camera frustum (get_voxels_in_camera_frustrum, :1019-1195)
+__device__ __forceinline__ bool sem_keep(const SemGrid &G, const GridQuery &Q, uint32_t b, int t, int min_count,
+                                         float min_conf, float *conf_out) {
+    const uint32_t v = b * kVox + t;
+    const int c = G.count[v];
+    const float conf = sem_confidence(G, v, c);
+    *conf_out = conf;
+    if (!(c >= min_count && conf >= min_conf)) return false;  // voxel_block_grid.hpp:797-803
+    if (Q.mode == 0) return true;
+    const int4 key = G.block_keys[b];
+    if (!sem_block_in_range(Q, key)) return false;
+    if (Q.mode == 2) {
+        SemImagePoint ip;
+        return sem_voxel_in_frustum(G, Q, b, t, &ip);
+    }
+    const int vk[3] = {key.x * kB + (t & 7), key.y * kB + ((t >> 3) & 7), key.z * kB + (t >> 6)};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (vk[a] < Q.min_key[a] || vk[a] > Q.max_key[a]) return false;
+    if (c == 0) return false;
+    const double dc = static_cast<double>(c);
+    const double x = __ddiv_rn(G.pos[3 * static_cast<size_t>(v) + 0], dc), y = __ddiv_rn(G.pos[3 * static_cast<size_t>(v) + 1], dc),
+                 z = __ddiv_rn(G.pos[3 * static_cast<size_t>(v) + 2], dc);
+    return x >= Q.bb[0] && x <= Q.bb[3] && y >= Q.bb[1] && y <= Q.bb[4] && z >= Q.bb[2] && z <= Q.bb[5];
+}
+
+__global__ void __launch_bounds__(kVox)
+sem_count_kernel(const SemGrid G, const GridQuery Q, const int min_count, const float min_conf,
+                 uint32_t *__restrict__ sums) {
+    __shared__ uint32_t s_warp[16];
+    const int t = threadIdx.x;
+    float conf;
+    const bool keep = sem_keep(G, Q, blockIdx.x, t, min_count, min_conf, &conf);
+    const uint32_t x = __reduce_add_sync(0xffffffffu, keep ? 1u : 0u);
+    if ((t & 31) == 0) s_warp[t >> 5] = x;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t s = 0;
+        for (int k = 0; k < 16; ++k) s += s_warp[k];
+        sums[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kVox)
+sem_emit_kernel(const SemGrid G, const GridQuery Q, const int min_count, const float min_conf,
+                const uint32_t *__restrict__ offs, double *__restrict__ out_pts, float *__restrict__ out_cols,
+                int32_t *__restrict__ out_cls, int32_t *__restrict__ out_obj, float *__restrict__ out_conf) {
+    __shared__ uint32_t s_warp[16];
+    const uint32_t v = blockIdx.x * kVox + threadIdx.x;
+    float conf;
+    const bool keep = sem_keep(G, Q, blockIdx.x, threadIdx.x, min_count, min_conf, &conf);
+    const size_t pos = offs[blockIdx.x] + block_excl_scan_512(keep ? 1u : 0u, s_warp);
+    if (!keep) return;
+    const int c = G.count[v];
+    const double dc = static_cast<double>(c);
+    const float fc = static_cast<float>(c);
+    for (int a = 0; a < 3; ++a) {  // voxel_data.h:58-69, 98-109: sum / (T)count, zero for an empty voxel
+        out_pts[3 * pos + a] = c ? __ddiv_rn(G.pos[3 * static_cast<size_t>(v) + a], dc) : 0.0;
+        out_cols[3 * pos + a] = c ? __fdiv_rn(G.col[3 * static_cast<size_t>(v) + a], fc) : 0.0f;
+    }
+    out_cls[pos] = G.cls[v];
+    out_obj[pos] = G.obj[v];
+    out_conf[pos] = conf;
 }
 
 // set_object_id (voxel_data_semantic.h:135, 455-460): the Bayesian voxel collapses onto the forced pair
@@ -968,18 +997,17 @@ extern "C" int b2v_sgrid_label_overflows(b2v_sgrid *g, uint64_t *out) {
     return B2V_OK;
 }
 
-extern "C" int64_t b2v_sgrid_get_voxels(b2v_sgrid *g, int32_t min_count, float min_confidence) {
-    if (!g) return -1;
+static int64_t sgrid_run_readout(b2v_sgrid *g, const GridQuery &q, int32_t min_count, float min_confidence) {
     const int64_t nb64 = b2v_sgrid_num_blocks(g);
     if (nb64 < 0) {
-        g->err = "b2v_sgrid_get_voxels: device error";
+        g->err = "semantic read-out: device error";
         return -1;
     }
     const uint32_t nb = static_cast<uint32_t>(nb64);
     g->last_n = 0;
     if (nb == 0) return 0;
     auto fail = [&](cudaError_t e) {
-        g->err = std::string("b2v_sgrid_get_voxels: ") + cudaGetErrorString(e);
+        g->err = std::string("semantic read-out: ") + cudaGetErrorString(e);
         return static_cast<int64_t>(-1);
     };
     cudaError_t e;
@@ -991,7 +1019,7 @@ extern "C" int64_t b2v_sgrid_get_voxels(b2v_sgrid *g, int32_t min_count, float m
         if ((e = cudaMalloc(&g->d_offs, static_cast<size_t>(nb) * 2 * sizeof(uint32_t))) != cudaSuccess) return fail(e);
         g->scan_cap = nb * 2;
     }
-    sem_count_kernel<<<nb, kVox, 0, g->stream>>>(g->G, min_count, min_confidence, g->d_sums);
+    sem_count_kernel<<<nb, kVox, 0, g->stream>>>(g->G, q, min_count, min_confidence, g->d_sums);
     exclusive_scan_kernel<<<1, 1024, 0, g->stream>>>(g->d_sums, g->d_offs, g->d_total, nb);
     uint32_t total = 0;
     if ((e = cudaMemcpyAsync(&total, g->d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream)) != cudaSuccess)
@@ -1003,6 +1031,7 @@ extern "C" int64_t b2v_sgrid_get_voxels(b2v_sgrid *g, int32_t min_count, float m
         g->d_out_pts = nullptr;
         g->d_out_cols = g->d_out_conf = nullptr;
         g->d_out_cls = g->d_out_obj = nullptr;
+        g->out_cap = 0;
         const size_t cap = static_cast<size_t>(total) + total / 4 + 1024;
         if ((e = cudaMalloc(&g->d_out_pts, cap * 3 * sizeof(double))) != cudaSuccess) return fail(e);
         if ((e = cudaMalloc(&g->d_out_cols, cap * 3 * sizeof(float))) != cudaSuccess) return fail(e);
@@ -1012,12 +1041,43 @@ extern "C" int64_t b2v_sgrid_get_voxels(b2v_sgrid *g, int32_t min_count, float m
         g->out_cap = cap;
     }
     if (total) {
-        sem_emit_kernel<<<nb, kVox, 0, g->stream>>>(g->G, min_count, min_confidence, g->d_offs, g->d_out_pts,
+        sem_emit_kernel<<<nb, kVox, 0, g->stream>>>(g->G, q, min_count, min_confidence, g->d_offs, g->d_out_pts,
                                                     g->d_out_cols, g->d_out_cls, g->d_out_obj, g->d_out_conf);
         if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
     }
     g->last_n = total;
     return total;
+}
+
+extern "C" int64_t b2v_sgrid_get_voxels(b2v_sgrid *g, int32_t min_count, float min_confidence) {
+    if (!g) return -1;
+    GridQuery q;
+    std::memset(&q, 0, sizeof(q));
+    return sgrid_run_readout(g, q, min_count, min_confidence);
+}
+
+extern "C" int64_t b2v_sgrid_get_voxels_in_bb(b2v_sgrid *g, const double bbox[6], int32_t min_count,
+                                              float min_confidence) {
+    if (!g || !bbox) return -1;
+    GridQuery q;
+    std::memset(&q, 0, sizeof(q));
+    q.mode = 1;
+    for (int a = 0; a < 6; ++a) q.bb[a] = bbox[a];
+    for (int a = 0; a < 3; ++a) {  // voxel_block_grid.hpp:828-831: keys in double with the float inverse voxel size
+        q.min_key[a] = static_cast<int32_t>(std::floor(bbox[a] * static_cast<double>(g->inv_voxel_size)));
+        q.max_key[a] = static_cast<int32_t>(std::floor(bbox[3 + a] * static_cast<double>(g->inv_voxel_size)));
+    }
+    return sgrid_run_readout(g, q, min_count, min_confidence);
+}
+
+extern "C" int64_t b2v_sgrid_get_voxels_in_frustum(b2v_sgrid *g, const float K[4], int32_t width, int32_t height,
+                                                   const double Tcw[16], float depth_max, float depth_min,
+                                                   int32_t min_count, float min_confidence) {
+    if (!g || !K || !Tcw || width <= 0 || height <= 0) return -1;
+    GridQuery q;
+    fill_frustum_query(&q, K, width, height, Tcw, depth_max, depth_min, min_count, g->inv_voxel_size);
+    q.mode = 2;
+    return sgrid_run_readout(g, q, min_count, min_confidence);
 }
 
 extern "C" int b2v_sgrid_copy_voxels(b2v_sgrid *g, double *points, float *colors, int32_t *class_ids,

@@ -705,7 +705,21 @@ class VoxelBlockSemanticGrid:
 
     # ---- read-outs ----
     def get_voxels(self, min_count: int = 1, min_confidence: float = 0.0) -> VoxelGridData:
-        n = self._L.b2v_sgrid_get_voxels(self._h, int(min_count), float(min_confidence))
+        return self._collect(self._L.b2v_sgrid_get_voxels(self._h, int(min_count), float(min_confidence)))
+
+    def get_voxels_in_bb(self, bbox, min_count: int = 1, min_confidence: float = 0.0) -> VoxelGridData:
+        bb = np.ascontiguousarray(getattr(bbox, "bounds", bbox), np.float64).reshape(6)
+        return self._collect(self._L.b2v_sgrid_get_voxels_in_bb(self._h, bb.ctypes.data, int(min_count),
+                                                                float(min_confidence)))
+
+    def get_voxels_in_camera_frustrum(self, camera_frustrum, min_count: int = 1,
+                                      min_confidence: float = 0.0) -> VoxelGridData:
+        K, T = camera_frustrum._args()
+        return self._collect(self._L.b2v_sgrid_get_voxels_in_frustum(
+            self._h, K.ctypes.data, camera_frustrum.width, camera_frustrum.height, T.ctypes.data,
+            camera_frustrum.depth_max, camera_frustrum.depth_min, int(min_count), float(min_confidence)))
+
+    def _collect(self, n) -> VoxelGridData:
         if n < 0:
             raise RuntimeError(self._L.b2v_sgrid_last_error(self._h).decode())
         out = VoxelGridData(np.zeros((n, 3), np.float64), np.zeros((n, 3), np.float32))

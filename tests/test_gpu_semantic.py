@@ -363,3 +363,47 @@ def test_instance_association_pipeline_matches_the_reference(tag):
     grid.carve(fr, d + 0.5, depth_threshold=0.05)                  # the surface moved back: carve what is in front
     after = sort_dump(grid.dump_blocks(1))["count"]
     assert (after > 0).sum() < (before > 0).sum()
+
+
+@pytest.mark.skipif(not oracle.have_ref_semantic(), reason="compiled reference (oracle/_ref) not on this box")
+@pytest.mark.parametrize("tag", ["vote", "prob"])
+def test_spatial_read_outs_match_the_compiled_reference(tag):
+    """get_voxels_in_camera_frustrum / get_voxels_in_bb (with labels) against the compiled reference fed the same
+    stream (tests/golden/semantic_T0.npz inputs).  Compared as sets ordered by position; a voxel whose projection
+    or mean lies within float rounding of a bound, or whose Bayesian confidence lies within rounding of the
+    threshold, may flip (<= 3 voxels)."""
+    from pyslam_b200 import BoundingBox3D, CameraFrustrum
+    g = np.load(os.path.join(GOLDEN, "semantic_T0.npz"))
+    a = np.load(os.path.join(GOLDEN, "semantic_assoc_T0.npz"))
+    kind = "voting" if tag == "vote" else "probabilistic"
+    cls_t = VoxelBlockSemanticGrid if tag == "vote" else VoxelBlockSemanticProbabilisticGrid
+    ref = oracle.RefSemanticGrid(float(g["voxel_size"]), kind)
+    grid = cls_t(float(g["voxel_size"]), 8, capacity_blocks=1024)
+    for g_ in (ref, grid):
+        g_.set_depth_threshold(float(g[f"{tag}_depth_threshold"]))
+        g_.set_depth_decay_rate(float(g[f"{tag}_depth_decay_rate"]))
+    for i in range(int(g["n_frames"])):
+        args = [g[f"{tag}_{n}_{i}"] for n in ("points", "colors", "cls", "inst", "depths")]
+        ref.integrate(*args)
+        grid.integrate(*args)
+    K = np.array(a["K"], np.float32)
+    T = a["Tcw_2"]
+
+    def same(out, r):
+        assert abs(len(out.points) - len(r["points"])) <= 3 and len(r["points"]) > 20
+        if len(out.points) != len(r["points"]):
+            return
+        o1 = np.lexsort((out.points[:, 2], out.points[:, 1], out.points[:, 0]))
+        o2 = np.lexsort((r["points"][:, 2], r["points"][:, 1], r["points"][:, 0]))
+        assert np.array_equal(out.points[o1], r["points"][o2])
+        assert np.array_equal(out.colors[o1], r["colors"][o2])
+        assert np.array_equal(out.class_ids[o1], r["class_ids"][o2])
+        assert np.array_equal(out.object_ids[o1], r["object_ids"][o2])
+        assert np.allclose(out.confidences[o1], r["confidences"][o2], rtol=2e-6, atol=1e-9)
+
+    fr = CameraFrustrum(K[0], K[1], K[2], K[3], 96, 72, T, depth_max=3.0, depth_min=0.05)
+    same(grid.get_voxels_in_camera_frustrum(fr, 2, 0.3), ref.get_voxels_in_camera_frustrum(K, 96, 72, T, 3.0, 0.05, 2, 0.3))
+    pts = ref.get_voxels(1, 0.0)["points"]
+    box = np.concatenate([np.quantile(pts, 0.2, axis=0), np.quantile(pts, 0.8, axis=0)])
+    same(grid.get_voxels_in_bb(BoundingBox3D(*box), 1, 0.2), ref.get_voxels_in_bb(box, 1, 0.2))
+    same(grid.get_voxels(1, 0.0), ref.get_voxels(1, 0.0))
