@@ -310,7 +310,7 @@ def test_execution_variants_are_bit_identical(env, monkeypatch):
 
 def test_fused_batch_equals_frame_by_frame_and_oracle():
     """integrate_batch fuses groups of 8 frames per block visit; 19 frames = 8 + 8 + 3 exercises full and
-    partial groups and the double-buffered group state.  Bit-identical to frame-by-frame and the oracle."""
+    partial groups and the rotation of the group buffers.  Bit-identical to frame-by-frame and the oracle."""
     cfg = S.CONFIGS["C1"]
     n = 19
     frames = [S.render_frame(cfg, i) for i in range(n)]
