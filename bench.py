@@ -406,6 +406,26 @@ def run_gpu_arm(args, rank, world, local_rank):
                      "note": "b2v_extract_mesh on the populated map: neighbours, classify, scan, vertices, "
                              "triangles kernels + a 8-byte size read-back; arrays stay on the device"}
 
+    # ---- secondary e2e figure: the same frames as RAW 16-bit depth (TUM-style payload, 5000 units per metre) ----
+    e2e_u16 = None
+    if world == 1:
+        scale = np.float32(1.0 / 5000.0)
+        raw16 = torch.from_numpy(np.round(depth * 5000.0).astype(np.uint16)).pin_memory()
+        raw16_np = raw16.numpy()
+        for _ in range(2):
+            vol.integrate_batch(raw16_np, c_pin_np, K, Tcw, depth_scale=scale)
+        vol.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            vol.integrate_batch(raw16_np, c_pin_np, K, Tcw, depth_scale=scale)
+            vol.synchronize()
+        dt16 = time.perf_counter() - t0
+        e2e_u16 = {"value": args.steps * F / dt16, "unit": UNIT, "h2d_bytes_per_step": int(F * H * W * 5),
+                   "d2h_bytes_per_step": 256,
+                   "api": "B200TsdfVolume.integrate_batch(depths uint16, colors, K, poses, depth_scale) -> "
+                          "b2v_integrate_batch_u16: raw 16-bit depth over PCIe, widened to float32 metres on the GPU "
+                          "(bit-identical to depth.astype(float32) * depth_factor on the host)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -443,6 +463,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * H * W * 7),
                 "d2h_bytes_per_step": 256, "timing": "wall clock around a full device sync",
                 "api": "B200TsdfVolume.integrate_batch(depths, colors, K, poses) -> b2v_integrate_batch (pinned host frames)"},
+        **({"e2e_u16_depth": e2e_u16} if e2e_u16 else {}),
         "gpu_launches": int(launches1 - launches0),
         "roofline": {
             "kernel": "integrate_group_kernel (up to 8 frames applied per block visit)", "bound": "hbm",

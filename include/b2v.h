@@ -79,6 +79,15 @@ int b2v_remap(const void *src, int32_t kind, int32_t height, int32_t width, cons
 int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float *depth, const uint8_t *color,
                         int32_t height, int32_t width, const double K[4], const double *Tcw,
                         void *stream);
+/* The same two calls for RAW 16-bit depth (TUM / ScanNet style PNG payloads): `depth` is uint16 [height][width]
+ * (per frame), uploaded as is - 2 instead of 4 bytes per pixel over PCIe - and widened on the device to
+ * float32(depth) * depth_scale in float32 arithmetic, the value numpy's `depth.astype(np.float32) * depth_factor`
+ * produces in the reference (volumetric_integrator_base.py:1008-1015).  Everything else as above. */
+int b2v_integrate_u16(b2v_volume *v, const uint16_t *depth, float depth_scale, const uint8_t *color, int32_t height,
+                      int32_t width, const double K[4], const double Tcw[16], void *stream);
+int b2v_integrate_batch_u16(b2v_volume *v, int32_t n_frames, const uint16_t *depth, float depth_scale,
+                            const uint8_t *color, int32_t height, int32_t width, const double K[4], const double *Tcw,
+                            void *stream);
 /* wait for all enqueued work; returns B2V_ERR_CAPACITY if a frame overflowed the pool */
 int b2v_synchronize(b2v_volume *v);
 

@@ -113,6 +113,10 @@ struct b2v_volume {
     int map_H = 0, map_W = 0;
     const float *map_lam = nullptr;
     cudaEvent_t ev_in = nullptr, ev_alloc_done[kActiveRing] = {}, ev_int_done[kActiveRing] = {};
+    // raw 16-bit depth input (b2v_integrate_u16 / b2v_integrate_batch_u16): uploaded as is, widened on the device
+    uint16_t *d_depth16[kStage] = {};   // same slot layout as d_depth; allocated on first use
+    size_t stage16_pixels = 0;
+    float in_u16_scale = 0.0f;          // > 0 while a *_u16 entry point runs: `depth` pointers are uint16_t
     float *d_depth[kStage] = {};
     uint8_t *d_color[kStage] = {};
     float4 *d_texel[kStage] = {};   // packed {depth, lambda, rgbx} frames read by integrate_kernel
@@ -254,6 +258,7 @@ extern "C" int b2v_destroy(b2v_volume *v) {
     cudaFree(v->d_mapy);
     cudaFree(v->d_rdepth[0]);
     cudaFree(v->d_rcolor[0]);
+    cudaFree(v->d_depth16[0]);
     for (float4 *t : v->d_gtex) cudaFree(t);
     for (int b = 0; b < kGroupBufs; ++b) {
         if (v->ev_galloc[b]) cudaEventDestroy(v->ev_galloc[b]);
@@ -393,6 +398,22 @@ static const FrameMaps *frame_maps(b2v_volume *v, const float *d_depth, const ui
 static int rectify_frame(b2v_volume *v, const float **d_depth, const uint8_t **d_color, int H, int W, int slot,
                          cudaStream_t stream);
 
+// raw uint16 staging, one contiguous allocation carved into the same slots as the float staging
+static int ensure_staging16(b2v_volume *v, size_t pixels) {
+    if (pixels <= v->stage16_pixels) return B2V_OK;
+    B2V_CUDA(v, cudaStreamSynchronize(v->compute));
+    B2V_CUDA(v, cudaStreamSynchronize(v->copy));
+    B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
+    if (v->last_stream) B2V_CUDA(v, cudaStreamSynchronize(v->last_stream));
+    cudaFree(v->d_depth16[0]);
+    for (int s = 0; s < kStage; ++s) v->d_depth16[s] = nullptr;
+    uint16_t *base = nullptr;
+    B2V_CUDA(v, cudaMalloc(&base, pixels * sizeof(uint16_t) * kStage));
+    for (int s = 0; s < kStage; ++s) v->d_depth16[s] = base + pixels * s;
+    v->stage16_pixels = pixels;
+    return B2V_OK;
+}
+
 static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *color, int32_t height,
                            int32_t width, const double K[4], const double Tcw[16], void *stream,
                            int dev_hint = -1) {
@@ -425,15 +446,21 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
     const float *d_depth = depth;
     const uint8_t *d_color = color;
     const bool staged = !(dev_depth && dev_color);
+    const bool u16 = v->in_u16_scale > 0.0f;  // `depth` is really const uint16_t *
     {
-        const int rc = ensure_staging(v, pixels);
+        int rc = ensure_staging(v, pixels);
+        if (rc == B2V_OK && u16) rc = ensure_staging16(v, pixels);
         if (rc != B2V_OK) return rc;
     }
     if (staged) {
         B2V_CUDA(v, cudaStreamWaitEvent(v->copy, v->ev_free[s], 0));
         if (!dev_depth) {
-            B2V_CUDA(v, cudaMemcpyAsync(v->d_depth[s], depth, pixels * sizeof(float),
-                                        cudaMemcpyHostToDevice, v->copy));
+            if (u16)
+                B2V_CUDA(v, cudaMemcpyAsync(v->d_depth16[s], depth, pixels * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                                            v->copy));
+            else
+                B2V_CUDA(v, cudaMemcpyAsync(v->d_depth[s], depth, pixels * sizeof(float),
+                                            cudaMemcpyHostToDevice, v->copy));
             d_depth = v->d_depth[s];
         }
         if (!dev_color) {
@@ -451,6 +478,12 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
     if (v->overlap && v->frame_id >= 3) {
         // allocate(f) recycles the ring slot / texel buffer last read by integrate(f - 3) .. (f - 4)
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_int_done[(v->frame_id - 3) % kActiveRing], 0));
+    }
+    if (u16) {  // widen the raw depth into the float staging slot: float(u16) * scale, one rounding
+        const uint16_t *src = dev_depth ? reinterpret_cast<const uint16_t *>(depth) : v->d_depth16[s];
+        B2V_CUDA(v, launch_depth_u16_to_f32(src, v->d_depth[s], pixels, v->in_u16_scale, as));
+        d_depth = v->d_depth[s];
+        v->launches += 1;
     }
     {
         const int rc = rectify_frame(v, &d_depth, &d_color, height, width, s, as);
@@ -480,7 +513,7 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
     float4 *tex = v->d_texel[s];
     B2V_CUDA(v, launch_allocate(P, d_depth, d_color, v->d_lambda, tex, v->table, v->meta, ring,
                                 frame_maps(v, d_depth, d_color, height, width), as));
-    if (staged) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], as));  // the raw frame is consumed by allocate only
+    if (staged || u16) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], as));  // the raw frame is consumed by allocate only
     v->launches += 1;
     v->frame_id += 1;
     if (v->prof_enabled) v->prof_frames += 1;
@@ -625,15 +658,19 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         v->inputs_fenced = true;
     }
     int rc = B2V_OK;
+    const bool u16 = v->in_u16_scale > 0.0f;  // `depth` is really const uint16_t *
+    const uint16_t *depth16 = reinterpret_cast<const uint16_t *>(depth);
     if (!v->fuse || n_frames < 2) {
         for (int32_t f = 0; f < n_frames && rc == B2V_OK; ++f)
-            rc = integrate_frame(v, depth + pixels * f, color + pixels * 3 * f, height, width, K,
-                                 Tcw + 16 * static_cast<size_t>(f), stream, dev_hint);
+            rc = integrate_frame(v, u16 ? reinterpret_cast<const float *>(depth16 + pixels * f) : depth + pixels * f,
+                                 color + pixels * 3 * f, height, width, K, Tcw + 16 * static_cast<size_t>(f), stream,
+                                 dev_hint);
         v->inputs_fenced = false;
         return rc;
     }
     rc = ensure_group_buffers(v, pixels);
     if (rc == B2V_OK) rc = ensure_staging(v, pixels);
+    if (rc == B2V_OK && u16) rc = ensure_staging16(v, pixels);
     if (rc != B2V_OK) {
         v->inputs_fenced = false;
         return rc;
@@ -668,20 +705,21 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
             // the group's frames are contiguous on both sides: one H2D copy per image type
             B2V_CUDA(v, cudaStreamWaitEvent(v->copy, v->ev_galloc[buf], 0));
             const int s0 = buf * kMaxGroup;
-            B2V_CUDA(v, cudaMemcpyAsync(v->d_depth[s0], depth + pixels * g0, pixels * sizeof(float) * count,
-                                        cudaMemcpyHostToDevice, v->copy));
+            if (u16)
+                B2V_CUDA(v, cudaMemcpyAsync(v->d_depth16[s0], depth16 + pixels * g0, pixels * sizeof(uint16_t) * count,
+                                            cudaMemcpyHostToDevice, v->copy));
+            else
+                B2V_CUDA(v, cudaMemcpyAsync(v->d_depth[s0], depth + pixels * g0, pixels * sizeof(float) * count,
+                                            cudaMemcpyHostToDevice, v->copy));
             B2V_CUDA(v, cudaMemcpyAsync(v->d_color[s0], color + pixels * 3 * g0, pixels * 3 * count,
                                         cudaMemcpyHostToDevice, v->copy));
         }
         for (int k = 0; k < count; ++k) {
             const size_t f = static_cast<size_t>(g0 + k);
-            const float *d_depth = depth + pixels * f;
+            const float *d_depth = u16 ? nullptr : depth + pixels * f;
             const uint8_t *d_color = color + pixels * 3 * f;
-            if (staged) {
-                const int s = buf * kMaxGroup + k;
-                d_depth = v->d_depth[s];
-                d_color = v->d_color[s];
-            }
+            if (staged || u16) d_depth = v->d_depth[buf * kMaxGroup + k];  // (widened) float staging slot
+            if (staged) d_color = v->d_color[buf * kMaxGroup + k];
             FrameParams &P = aargs.P[k];
             fill_frame_params(&P, K, Tcw + 16 * f, height, width, v->cfg.depth_stride, v->cfg.voxel_size,
                               v->cfg.sdf_trunc, v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank,
@@ -718,6 +756,11 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
             B2V_CUDA(v, cudaEventRecord(v->ev_ready[buf], v->copy));  // all frames of the group uploaded
             B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_ready[buf], 0));
         }
+        if (u16) {  // widen the group's raw depth into its (contiguous) float staging slots in one launch
+            const uint16_t *src = staged ? v->d_depth16[buf * kMaxGroup] : depth16 + pixels * g0;
+            B2V_CUDA(v, launch_depth_u16_to_f32(src, v->d_depth[buf * kMaxGroup], pixels * count, v->in_u16_scale, as));
+            v->launches += 1;
+        }
         for (int k = 0; k < count; ++k) {  // optional rectification, then the TMA descriptors of the final images
             const int rrc = rectify_frame(v, &aargs.depth[k], &aargs.color[k], height, width, buf * kMaxGroup + k, as);
             if (rrc != B2V_OK) {
@@ -752,6 +795,38 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
     }
     v->inputs_fenced = false;
     return B2V_OK;
+}
+
+// Raw 16-bit depth (e.g. TUM / ScanNet PNGs): uploaded as uint16 (2 instead of 4 bytes per pixel over PCIe) and
+// widened on the device to float(u16) * depth_scale in float32 - the value numpy's
+// `depth.astype(np.float32) * depth_factor` produces (volumetric_integrator_base.py:1008-1015).
+extern "C" int b2v_integrate_batch_u16(b2v_volume *v, int32_t n_frames, const uint16_t *depth, float depth_scale,
+                                       const uint8_t *color, int32_t height, int32_t width, const double K[4],
+                                       const double *Tcw, void *stream) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    if (!(depth_scale > 0.0f)) {
+        v->err = "b2v_integrate_batch_u16: depth_scale must be positive";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    v->in_u16_scale = depth_scale;
+    const int rc = b2v_integrate_batch(v, n_frames, reinterpret_cast<const float *>(depth), color, height, width, K,
+                                       Tcw, stream);
+    v->in_u16_scale = 0.0f;
+    return rc;
+}
+
+extern "C" int b2v_integrate_u16(b2v_volume *v, const uint16_t *depth, float depth_scale, const uint8_t *color,
+                                 int32_t height, int32_t width, const double K[4], const double Tcw[16],
+                                 void *stream) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    if (!(depth_scale > 0.0f)) {
+        v->err = "b2v_integrate_u16: depth_scale must be positive";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    v->in_u16_scale = depth_scale;
+    const int rc = integrate_frame(v, reinterpret_cast<const float *>(depth), color, height, width, K, Tcw, stream);
+    v->in_u16_scale = 0.0f;
+    return rc;
 }
 
 extern "C" int b2v_set_fusion(b2v_volume *v, int32_t enable) {

@@ -201,6 +201,9 @@ cudaError_t launch_grid_integrate_rgbd(const RgbdParams &p, const float *depth, 
                                        float inv_vs, const HashTable &table, const GridMeta &meta,
                                        cudaStream_t stream);
 
+// raw uint16 depth -> float32 metres (b2v_prep.cu)
+cudaError_t launch_depth_u16_to_f32(const uint16_t *src, float *dst, size_t n, float scale, cudaStream_t stream);
+
 // filter_shadow_points (pyslam/utilities/depth.py:103-146) on the device; scratch: 64 + 16384 bytes
 constexpr size_t kShadowScratchBytes = 64 + 4096 * sizeof(uint32_t);
 cudaError_t launch_filter_shadow_points(const float *depth, int H, int W, int dx, int dy, float fill, float *out,

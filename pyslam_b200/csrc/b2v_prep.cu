@@ -192,6 +192,20 @@ __global__ void remap_b32_nearest_kernel(const uint32_t *__restrict__ src, int H
     }
 }
 
+// raw 16-bit depth -> metres: float(u16) * scale, one float32 rounding (numpy: depth.astype(float32) * factor)
+__global__ void depth_u16_to_f32_kernel(const uint16_t *__restrict__ src, float *__restrict__ dst, const size_t n,
+                                        const float scale) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = __fmul_rn(static_cast<float>(src[i]), scale);
+}
+
+cudaError_t launch_depth_u16_to_f32(const uint16_t *src, float *dst, size_t n, float scale, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    depth_u16_to_f32_kernel<<<1184, 256, 0, stream>>>(src, dst, n, scale);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_remap_u8c3_linear(const uint8_t *src, int H, int W, const float *mapx, const float *mapy,
                                      uint8_t *dst, int swap_rb, cudaStream_t stream) {
     remap_u8c3_linear_kernel<<<296, 256, 0, stream>>>(src, H, W, mapx, mapy, dst, swap_rb);

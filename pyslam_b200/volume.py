@@ -114,12 +114,14 @@ class B200TsdfVolume:
             raise RuntimeError(f"{what} failed (status {rc}): {self._L.b2v_last_error(self._h).decode()}")
 
     # ---- integrate ----
-    def integrate(self, depth, color=None, K=None, pose=None, stream=None):
+    def integrate(self, depth, color=None, K=None, pose=None, stream=None, depth_scale=None):
         """north_star: `integrate(depth, color, K, pose)` with depth float32 [H,W] metres, colour
         uint8 RGB [H,W,3], K = (fx,fy,cx,cy) | 3x3, pose = Tcw 4x4 float64.
         Open3D style (tsdf.py:223): `integrate(rgbd, intrinsic, extrinsic)` where `rgbd` has
         `.color` / `.depth`.  Inputs may be numpy arrays or CUDA torch tensors.  Asynchronous.
-        `stream`: optional cudaStream_t handle (int) to launch on; device inputs only."""
+        `stream`: optional cudaStream_t handle (int) to launch on; device inputs only.
+        `depth_scale`: given with a RAW uint16 depth image (numpy) - it is uploaded as 16-bit and widened on the
+        GPU to float32(depth) * float32(depth_scale), like `depth.astype(np.float32) * depth_factor`."""
         if hasattr(depth, "depth") and hasattr(depth, "color"):
             rgbd, K, pose = depth, color, K
             depth, color = rgbd.depth, rgbd.color
@@ -148,11 +150,24 @@ class B200TsdfVolume:
                 raise RuntimeError("color must be [H,W,3] with the depth image's size")
             if c.dtype != np.uint8:
                 raise RuntimeError("color must be uint8 RGB")
-            d = np.ascontiguousarray(d, dtype=np.float32)  # reference: depth.astype(float32), base.py:1008-1017
+            raw16 = depth_scale is not None and d.dtype == np.uint16
+            if depth_scale is not None and not raw16:
+                raise RuntimeError("depth_scale goes with a uint16 depth image")
+            # reference: depth.astype(float32), base.py:1008-1017 (raw uint16 is widened on the GPU instead)
+            d = np.ascontiguousarray(d) if raw16 else np.ascontiguousarray(d, dtype=np.float32)
             c = np.ascontiguousarray(c)
             H, W = d.shape
             dp, cp = d.ctypes.data, c.ctypes.data
             self._keepalive.append((d, c))
+            if raw16:
+                rc = self._L.b2v_integrate_u16(self._h, dp, float(depth_scale), cp, H, W, K4.ctypes.data,
+                                               T.ctypes.data, None)
+                self._check(rc, "b2v_integrate_u16")
+                if len(self._keepalive) > 8:
+                    del self._keepalive[:-8]
+                return
+        if depth_scale is not None:
+            raise RuntimeError("depth_scale is supported for host (numpy) uint16 depth images")
         rc = self._L.b2v_integrate(self._h, dp, cp, H, W, K4.ctypes.data, T.ctypes.data,
                                    C.c_void_p(stream) if stream else None)
         self._check(rc, "b2v_integrate")
@@ -160,28 +175,38 @@ class B200TsdfVolume:
             # staging ring is 4 deep: anything older has been consumed by the copy engine
             del self._keepalive[:-8]
 
-    def integrate_batch(self, depths, colors, K, poses, stream=None):
+    def integrate_batch(self, depths, colors, K, poses, stream=None, depth_scale=None):
         """n frames back to back (the rebuild(map) bulk path, base.py:1242-1318): depths [n,H,W] f32,
-        colors [n,H,W,3] u8, poses [n,4,4] Tcw.  One C call enqueues every frame."""
+        colors [n,H,W,3] u8, poses [n,4,4] Tcw.  One C call enqueues every frame.  With `depth_scale`, depths
+        is RAW uint16 [n,H,W] (numpy, or a CUDA uint16 / int16 tensor) widened on the GPU."""
         K4 = _as_K4(K)
         T = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 16))
         n = T.shape[0]
+        raw16 = depth_scale is not None
         if _is_torch_cuda(depths):
             if not (depths.is_contiguous() and colors.is_contiguous()):
                 raise RuntimeError("depths and colors must be contiguous")
+            if raw16 and depths.element_size() != 2:
+                raise RuntimeError("depth_scale goes with 16-bit depth images")
             H, W = int(depths.shape[1]), int(depths.shape[2])
             dp, cp = depths.data_ptr(), colors.data_ptr()
             hold = (depths, colors)
         else:
-            d = np.ascontiguousarray(depths, dtype=np.float32)
+            if raw16 and np.asarray(depths).dtype != np.uint16:
+                raise RuntimeError("depth_scale goes with uint16 depth images")
+            d = np.ascontiguousarray(depths) if raw16 else np.ascontiguousarray(depths, dtype=np.float32)
             c = np.ascontiguousarray(colors, dtype=np.uint8)
             if d.ndim != 3 or c.shape != d.shape + (3,) or d.shape[0] != n:
                 raise RuntimeError("depths must be [n,H,W], colors [n,H,W,3], poses [n,4,4]")
             H, W = d.shape[1:]
             dp, cp = d.ctypes.data, c.ctypes.data
             hold = (d, c)
-        rc = self._L.b2v_integrate_batch(self._h, n, dp, cp, H, W, K4.ctypes.data, T.ctypes.data,
-                                         C.c_void_p(stream) if stream else None)
+        if raw16:
+            rc = self._L.b2v_integrate_batch_u16(self._h, n, dp, float(depth_scale), cp, H, W, K4.ctypes.data,
+                                                 T.ctypes.data, C.c_void_p(stream) if stream else None)
+        else:
+            rc = self._L.b2v_integrate_batch(self._h, n, dp, cp, H, W, K4.ctypes.data, T.ctypes.data,
+                                             C.c_void_p(stream) if stream else None)
         self._check(rc, "b2v_integrate_batch")
         self._keepalive = [hold]
 

@@ -513,3 +513,51 @@ def test_sharded_fused_batches_equal_the_unsharded_volume():
     ref = sort_dump(full.dump_blocks())
     for name in ("keys", "hashes", "vox"):
         assert np.array_equal(merged[name], ref[name]), name
+
+
+def test_raw_uint16_depth_equals_host_converted_float_depth():
+    """b2v_integrate_u16 / b2v_integrate_batch_u16: raw 16-bit depth widened on the GPU == the reference's host
+    conversion depth.astype(float32) * depth_factor (volumetric_integrator_base.py:1008-1015) fed as float32,
+    bit for bit, on the fused batch path, the frame-by-frame path and with device-resident input."""
+    import torch
+    cfg = S.CONFIGS["C1"]
+    n = 19
+    frames = [S.render_frame(cfg, i) for i in range(n)]
+    D, Cc, T = (np.stack([f[k] for f in frames]) for k in range(3))
+    raw = np.round(D * 5000.0).astype(np.uint16)                 # TUM convention: 5000 units per metre
+    scale = 1.0 / 5000.0
+    Df = raw.astype(np.float32) * np.float32(scale)              # what the reference computes on the host
+    ref, _ = _pair(cfg, capacity=1 << 16)
+    ref.integrate_batch(Df, Cc, cfg.K, T)
+    want = sort_dump(ref.dump_blocks())
+
+    def check(vol):
+        got = sort_dump(vol.dump_blocks())
+        for name in ("keys", "hashes", "vox"):
+            assert np.array_equal(got[name], want[name]), name
+        vol.close()
+
+    a, _ = _pair(cfg, capacity=1 << 16)
+    a.integrate_batch(raw, Cc, cfg.K, T, depth_scale=scale)      # fused groups, host staging
+    check(a)
+    b, _ = _pair(cfg, capacity=1 << 16)
+    for i in range(n):                                           # frame by frame
+        b.integrate(raw[i], Cc[i], cfg.K, T[i], depth_scale=scale)
+    check(b)
+    c, _ = _pair(cfg, capacity=1 << 16)
+    c.set_fusion(False)
+    c.integrate_batch(raw, Cc, cfg.K, T, depth_scale=scale)      # un-fused batch
+    check(c)
+    d, _ = _pair(cfg, capacity=1 << 16)
+    raw_dev = torch.from_numpy(raw.view(np.int16)).cuda()        # device-resident raw depth (same 16 bits)
+    col_dev = torch.from_numpy(Cc).cuda()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        d.integrate_batch(raw_dev, col_dev, cfg.K, T, stream=st.cuda_stream, depth_scale=scale)
+    torch.cuda.synchronize()
+    check(d)
+    with pytest.raises(RuntimeError):
+        ref.integrate(Df[0], Cc[0], cfg.K, T[0], depth_scale=scale)   # a scale goes with uint16 input only
+    with pytest.raises(RuntimeError):
+        ref.integrate_batch(raw, Cc, cfg.K, T, depth_scale=0.0)       # non-positive scale
+    ref.close()
