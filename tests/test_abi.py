@@ -59,3 +59,24 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "pyslam_b200", "does_not_exist.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_no_gpu_means_an_error_not_a_fallback():
+    """Without a CUDA device every product entry point must fail loudly - there is no CPU path to fall back to."""
+    from tests._util import has_gpu
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    import numpy as np
+    import pyslam_b200 as P
+    with pytest.raises(RuntimeError):
+        P.B200TsdfVolume(0.01, 0.04, 4.0, capacity_blocks=64)
+    with pytest.raises(RuntimeError):
+        P.VoxelBlockGrid(0.05, 8, capacity_blocks=64)
+    with pytest.raises(RuntimeError):
+        P.VoxelBlockSemanticGrid(0.05, 8, capacity_blocks=64)
+    with pytest.raises(RuntimeError):
+        P.VoxelBlockSemanticProbabilisticGrid(0.05, 8, capacity_blocks=64)
+    with pytest.raises(RuntimeError):
+        P.filter_shadow_points(np.ones((8, 8), np.float32))
+    with pytest.raises(RuntimeError):
+        P.remap(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32))
