@@ -23,7 +23,7 @@ import traceback
 import numpy as np
 
 from .integrator import write_ply_points
-from .volume import (CameraFrustrum, VoxelBlockSemanticGrid, VoxelBlockSemanticProbabilisticGrid,
+from .volume import (CameraFrustrum, VoxelBlockGrid, VoxelBlockSemanticGrid, VoxelBlockSemanticProbabilisticGrid,
                      filter_shadow_points, remap_instance_ids)
 
 # defaults of pyslam/config_parameters.py:311-380 (overridable through parameters_dict / constructor kwargs)
@@ -213,6 +213,68 @@ def make_semantic_integrator_class(Base, api):
                 self.volume.close()
 
     return VolumetricIntegratorB200SemanticGrid
+
+
+def make_voxel_grid_integrator_class(Base, api):
+    """The point-average backend (`VolumetricIntegratorVoxelGrid`, pyslam/dense/volumetric_integrator_voxel_grid.py)
+    on the GPU compat grid.  Same task loop as the semantic class; the loop body is reference :232-300: optional
+    shadow filter -> depth2pointcloud -> world transform -> optional carve (with the UNFILTERED depth, :283-296) ->
+    integrate, all of which `VoxelBlockGrid.carve` / `integrate_rgbd` do on the device."""
+    SemanticCls = make_semantic_integrator_class(Base, api)
+
+    class VolumetricIntegratorB200VoxelGrid(SemanticCls):
+        def init(self, camera, environment_type, sensor_type, parameters_dict, constructor_kwargs):
+            Base.init(self, camera, environment_type, sensor_type, parameters_dict, constructor_kwargs)
+            p = dict(DEFAULT_PARAMETERS)
+            p["kVolumetricIntegrationB200CapacityBlocks"] = 1 << 17
+            if parameters_dict:
+                p.update({k: parameters_dict[k] for k in DEFAULT_PARAMETERS if k in parameters_dict})
+            if constructor_kwargs:
+                p.update({k: v for k, v in constructor_kwargs.items() if k in DEFAULT_PARAMETERS})
+            self.b200_parameters = p
+            indoor = True
+            env_t = getattr(api, "DatasetEnvironmentType", None)
+            if env_t is not None and hasattr(env_t, "INDOOR"):
+                indoor = environment_type == env_t.INDOOR
+            side = "Indoor" if indoor else "Outdoor"
+            self.volumetric_integration_depth_trunc = p[f"kVolumetricIntegrationTsdfDepthTrunc{side}"]
+            self.volume = VoxelBlockGrid(p["kVolumetricIntegrationVoxelLength"], p["kVolumetricIntegrationBlockSize"],
+                                         capacity_blocks=int(p["kVolumetricIntegrationB200CapacityBlocks"]),
+                                         device=int(p["kVolumetricIntegrationB200Device"]))
+            fx, fy, cx, cy = self._intrinsics()
+            self.camera_frustrum = CameraFrustrum(
+                fx, fy, cx, cy, self.camera.width, self.camera.height, np.eye(4),
+                depth_max=p[f"kVolumetricIntegrationVoxelGridCarvingDepthMax{side}"],
+                depth_min=p["kVolumetricIntegrationVoxelGridCarvingDepthMin"])
+            self.last_output = None
+            self.last_integrated_id = -1
+
+        def _integrate_keyframe(self, kd):
+            p = self.b200_parameters
+            rect = self.estimate_depth_if_needed_and_rectify(kd)
+            color, depth = rect[0], rect[1]
+            if color is None or depth is None:
+                return False
+            depth = np.ascontiguousarray(depth, np.float32)
+            if p["kVolumetricIntegrationVoxelGridUseCarving"]:
+                self.camera_frustrum.set_T_cw(kd.pose)
+                self.volume.carve(self.camera_frustrum, depth,
+                                  float(p["kVolumetricIntegrationVoxelGridCarvingDepthThreshold"]))
+            fx, fy, cx, cy = self._intrinsics()
+            Twc = np.linalg.inv(np.asarray(kd.pose, np.float64).reshape(4, 4))
+            self.volume.integrate_rgbd(depth, color, (fx, fy, cx, cy), Twc,
+                                       max_depth=self.volumetric_integration_depth_trunc,
+                                       filter_shadow_points=bool(p["kVolumetricIntegrationVoxelGridShadowPointsFilter"]))
+            self.last_integrated_id = kd.id
+            return True
+
+        def _make_output(self, task_type):
+            v = self.volume.get_voxels(min_count=int(self.b200_parameters["kVolumetricIntegrationVoxelGridMinCount"]))
+            pc = api.VolumetricIntegrationPointCloud(points=np.ascontiguousarray(v.points, np.float32),
+                                                     colors=np.ascontiguousarray(v.colors, np.float32))
+            return api.VolumetricIntegrationOutput(task_type, self.last_integrated_id, pc, None)
+
+    return VolumetricIntegratorB200VoxelGrid
 
 
 def load_pyslam_semantic_plugin():

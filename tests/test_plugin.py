@@ -327,3 +327,42 @@ def test_semantic_adapter_end_to_end_on_gpu():
         out = o
     assert out.point_cloud.points.shape[1] == 3 and len(out.point_cloud.semantics) == len(out.point_cloud.points)
     integ.quit()
+
+
+def test_voxel_grid_adapter_flow_with_fake_grid(monkeypatch, tmp_path):
+    """The point-average backend: carve sees the UNFILTERED depth before the frame is integrated, integrate_rgbd gets
+    Twc and the shadow-filter flag, outputs are plain point clouds (volumetric_integrator_voxel_grid.py:232-370)."""
+    from pyslam_b200 import integrator_semantic as IS
+
+    class _FakeGrid(_FakeSemanticGrid):
+        def __init__(self, voxel_size, block_size, **kw):
+            super().__init__(voxel_size=voxel_size, block_size=block_size, **kw)
+
+        def integrate_rgbd(self, depth, color, K, Twc, **kw):
+            self.calls.append(("rgbd", tuple(K), np.asarray(Twc).copy(), kw))
+
+        def get_voxels(self, min_count=1, min_confidence=0.0):
+            self.calls.append(("voxels", min_count))
+            return SimpleNamespace(points=np.zeros((2, 3)), colors=np.ones((2, 3), np.float32))
+
+    monkeypatch.setattr(IS, "VoxelBlockGrid", _FakeGrid)
+    Cls = P.standalone_voxel_grid_integrator_class()
+    cfg = S.CONFIGS["T0"]
+    integ = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_VOXEL_GRID",
+                kVolumetricIntegrationVoxelGridUseCarving=True, kVolumetricIntegrationVoxelLength=0.02)
+    assert integ.volume.kw["voxel_size"] == 0.02 and integ.volume.kw["capacity_blocks"] == 1 << 17
+    d, c, T = S.render_frame(cfg, 0)
+    integ.add_keyframe_data(P.VolumetricIntegrationKeyframeData(id=5, pose=T, img=np.ascontiguousarray(c[..., ::-1]),
+                                                                depth=d))
+    integ.step()
+    names = [x[0] for x in integ.volume.calls]
+    assert names.index("carve") < names.index("rgbd")
+    rgbd = [x for x in integ.volume.calls if x[0] == "rgbd"][0]
+    assert np.allclose(rgbd[2] @ T, np.eye(4), atol=1e-9) and rgbd[3]["filter_shadow_points"] is True
+    assert rgbd[3]["max_depth"] == 4.0
+    out = integ.pop_output()
+    assert out.id == 5 and out.point_cloud.points.shape == (2, 3) and out.mesh is None
+    assert ("voxels", 3) in integ.volume.calls
+    integ.save(str(tmp_path))
+    integ.step()
+    assert os.path.exists(os.path.join(tmp_path, "dense_map.ply"))
