@@ -366,3 +366,38 @@ def test_voxel_grid_adapter_flow_with_fake_grid(monkeypatch, tmp_path):
     integ.save(str(tmp_path))
     integ.step()
     assert os.path.exists(os.path.join(tmp_path, "dense_map.ply"))
+
+
+@pytest.mark.gpu
+def test_voxel_grid_adapter_end_to_end_on_gpu():
+    """The point-average plugin class on the real GPU grid == the same calls made by hand."""
+    from pyslam_b200 import CameraFrustrum, VoxelBlockGrid
+    from tests._util import sort_dump
+    cfg = S.CONFIGS["T0"]
+    Cls = P.standalone_voxel_grid_integrator_class()
+    integ = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_VOXEL_GRID",
+                kVolumetricIntegrationVoxelLength=0.03, kVolumetricIntegrationVoxelGridUseCarving=True,
+                kVolumetricIntegrationB200CapacityBlocks=4096)
+    manual = VoxelBlockGrid(0.03, 8, capacity_blocks=4096)
+    for i in range(4):
+        d, c, T = S.render_frame(cfg, i)
+        integ.add_keyframe_data(P.VolumetricIntegrationKeyframeData(id=i, pose=T, img=np.ascontiguousarray(c[..., ::-1]),
+                                                                    depth=d))
+        integ.step()
+        fr = CameraFrustrum(cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.width, cfg.height, T, depth_max=8.0, depth_min=1e-2)
+        manual.carve(fr, d, 3e-2)
+        manual.integrate_rgbd(d, c, cfg.K, np.linalg.inv(T), max_depth=4.0, filter_shadow_points=True)
+    a, b = sort_dump(integ.volume.dump_blocks()), sort_dump(manual.dump_blocks())
+    assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["count"], b["count"])
+    assert np.allclose(a["pos_sum"], b["pos_sum"], rtol=1e-5, atol=1e-6)      # float atomics: order differs
+    assert (a["count"] > 0).sum() > 1000
+    integ.add_update_output_task()
+    integ.step()
+    out = None
+    while True:
+        o = integ.pop_output()
+        if o is None:
+            break
+        out = o
+    assert out.point_cloud.points.shape[1] == 3 and len(out.point_cloud.points) > 100
+    integ.quit()
