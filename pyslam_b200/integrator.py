@@ -14,7 +14,6 @@ stand-ins in `plugin_api` that mirror their fields so the adapter can be exercis
 
 from __future__ import annotations
 
-import struct
 import time
 import traceback
 from types import SimpleNamespace
