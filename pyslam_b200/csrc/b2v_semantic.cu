@@ -822,6 +822,7 @@ static int sgrid_ensure_stage(b2v_sgrid *g, size_t n) {
         cudaFree(*b);
         *b = nullptr;
     }
+    g->stage_points = 0;  // stays 0 if an allocation below fails
     const size_t cap = n + n / 4 + 1024;
     SG_CUDA(g, cudaMalloc(&g->d_pts, cap * 3 * sizeof(double)));
     SG_CUDA(g, cudaMalloc(&g->d_cols, cap * 3 * sizeof(float)));
@@ -926,6 +927,7 @@ extern "C" int b2v_sgrid_integrate_rgbd(b2v_sgrid *g, const float *depth, const 
             cudaFree(*b);
             *b = nullptr;
         }
+        g->img_pixels = 0;  // stays 0 if an allocation below fails
         SG_CUDA(g, cudaMalloc(&g->d_img_depth, pixels * sizeof(float)));
         SG_CUDA(g, cudaMalloc(&g->d_img_filtered, pixels * sizeof(float)));
         SG_CUDA(g, cudaMalloc(&g->d_img_rgb, pixels * 3));
