@@ -348,6 +348,7 @@ static int ensure_staging(b2v_volume *v, size_t pixels) {
         v->d_color[s] = nullptr;
         v->d_texel[s] = nullptr;
     }
+    v->stage_pixels = 0;  // stays 0 if an allocation below fails
     float *dbase = nullptr;
     uint8_t *cbase = nullptr;
     B2V_CUDA(v, cudaMalloc(&dbase, pixels * sizeof(float) * kStage));
@@ -407,6 +408,7 @@ static int ensure_staging16(b2v_volume *v, size_t pixels) {
     if (v->last_stream) B2V_CUDA(v, cudaStreamSynchronize(v->last_stream));
     cudaFree(v->d_depth16[0]);
     for (int s = 0; s < kStage; ++s) v->d_depth16[s] = nullptr;
+    v->stage16_pixels = 0;
     uint16_t *base = nullptr;
     B2V_CUDA(v, cudaMalloc(&base, pixels * sizeof(uint16_t) * kStage));
     for (int s = 0; s < kStage; ++s) v->d_depth16[s] = base + pixels * s;
@@ -626,6 +628,7 @@ static int rectify_frame(b2v_volume *v, const float **d_depth, const uint8_t **d
 static int ensure_group_buffers(b2v_volume *v, size_t pixels) {
     if (pixels <= v->gtex_pixels) return B2V_OK;
     B2V_CUDA(v, cudaDeviceSynchronize());
+    v->gtex_pixels = 0;  // stays 0 if an allocation below fails
     for (float4 *&t : v->d_gtex) {
         cudaFree(t);
         t = nullptr;
