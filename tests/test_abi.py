@@ -80,3 +80,31 @@ def test_no_gpu_means_an_error_not_a_fallback():
         P.filter_shadow_points(np.ones((8, 8), np.float32))
     with pytest.raises(RuntimeError):
         P.remap(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32))
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/b2v.h must be consumable from C (the boundary is a C ABI, no C++ or torch types): a C11 translation
+    unit that takes the address of every declared entry point compiles with -Wall -Werror -pedantic and links
+    against libb2v.so."""
+    import shutil
+    import subprocess
+    from pyslam_b200 import _lib
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    header = open(os.path.join(ROOT, "include", "b2v.h")).read()
+    names = sorted(set(re.findall(r"\b(b2v_[a-z0-9_]+)\s*\(", header)))
+    src = tmp_path / "abi_check.c"
+    body = "\n".join(f"    table[{i}] = (void (*)(void))&{n};" for i, n in enumerate(names))
+    src.write_text('#include "b2v.h"\n#include <stdio.h>\nint main(void) {\n'
+                   f"    void (*table[{len(names)}])(void);\n{body}\n"
+                   f'    printf("%d %d\\n", b2v_version(), table[{len(names) - 1}] != 0);\n    return 0;\n}}\n')
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = [gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic",
+           "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir, "-l:libb2v.so",
+           f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and int(out.stdout.split()[0]) >= 100
