@@ -95,3 +95,52 @@ def test_golden_dump_obeys_the_fusion_rules():
     chosen_valid = (g["prob_object_id"][occ] != -1) & (g["prob_class_id"][occ] != -1)
     assert np.allclose(conf[unique & chosen_valid], soft[unique & chosen_valid], rtol=2e-6, atol=1e-7)
     assert np.all(conf[~chosen_valid] == 0.0) and valid.any()
+
+
+@needs_ref
+@pytest.mark.parametrize("tag", ["vote", "prob"])
+def test_compiled_reference_reproduces_the_semantic_goldens(tag):
+    """The committed dumps are exactly what the compiled reference produces from the committed inputs (so the GPU
+    tests that compare against the .npz compare against the reference itself)."""
+    from tests._util import sort_dump
+    g = np.load(os.path.join(GOLDEN, "semantic_T0.npz"))
+    kind = "voting" if tag == "vote" else "probabilistic"
+    r = oracle.RefSemanticGrid(float(g["voxel_size"]), kind)
+    r.set_depth_threshold(float(g[f"{tag}_depth_threshold"]))
+    if kind == "probabilistic":
+        r.set_depth_decay_rate(float(g[f"{tag}_depth_decay_rate"]))
+    for i in range(int(g["n_frames"])):
+        r.integrate(*[g[f"{tag}_{n}_{i}"] for n in ("points", "colors", "cls", "inst", "depths")])
+    d = sort_dump(r.dump_blocks(8))
+    for k in ("keys", "hashes", "count", "pos_sum", "col_sum", "object_id", "class_id", "confidence", "aux",
+              "lab_obj", "lab_cls", "lab_logp"):
+        assert np.array_equal(d[k], g[f"{tag}_{k}"]), k
+    # the association replay: same maps, same allocator end value
+    a = np.load(os.path.join(GOLDEN, "semantic_assoc_T0.npz"))
+    from pyslam_b200 import remap_instance_ids
+    from pyslam_b200 import synthetic as S
+    oracle.RefSemanticGrid.set_next_object_id(1)
+    r2 = oracle.RefSemanticGrid(float(a["voxel_size"]), kind)
+    r2.set_depth_threshold(10.0)
+    K = a["K"]
+    for i in range(int(a["n_frames"])):
+        dep, col, T = a[f"depth_{i}"], a[f"color_{i}"], a[f"Tcw_{i}"]
+        cls_img, inst_img = a[f"class_image_{i}"], a[f"instance_image_{i}"]
+        m = r2.assign_object_ids_to_instance_ids(np.array(K, np.float32), dep.shape[1], dep.shape[0], T,
+                                                 float(a["param_depth_max"]), float(a["param_depth_min"]), cls_img,
+                                                 inst_img, dep, float(a["param_depth_threshold"]),
+                                                 bool(a["param_do_carving"]), float(a["param_min_vote_ratio"]),
+                                                 int(a["param_min_votes"]))
+        assert m == dict(zip(a[f"{tag}_map_inst_{i}"].tolist(), a[f"{tag}_map_obj_{i}"].tolist()))
+        Twc = S.inv_T(T)
+        valid = (dep > 0) & (dep < float(a["max_depth"]))
+        z = dep[valid].astype(np.float64)
+        rows, cols = np.where(valid)
+        x, y = (cols - K[2]) * z * (1.0 / K[0]), (rows - K[3]) * z * (1.0 / K[1])
+        pw = np.stack([x * Twc[q, 0] + y * Twc[q, 1] + z * Twc[q, 2] + Twc[q, 3] for q in range(3)],
+                      axis=1).astype(np.float32)
+        obj_img = remap_instance_ids(inst_img, m)
+        r2.integrate(pw, (col[valid] / 255.0).astype(np.float32), cls_img[valid], obj_img[valid], dep[valid])
+    assert oracle.RefSemanticGrid.get_next_object_id() == int(a[f"{tag}_next_object_id"])
+    d2 = sort_dump(r2.dump_blocks(1))
+    assert np.array_equal(d2["count"], a[f"{tag}_count"]) and np.array_equal(d2["object_id"], a[f"{tag}_object_id"])
