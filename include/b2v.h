@@ -46,6 +46,12 @@ typedef struct b2v_config {
     int32_t device;          /* CUDA device ordinal                                             */
     int32_t shard_rank;      /* this GPU's shard; a block is owned iff                          */
     int32_t shard_count;     /*   BlockKeyHash(key) % shard_count == shard_rank (1 = own all)   */
+    int32_t unit_resolution; /* Open3D volume_unit_resolution: 16 (0 = default; the reference's value,
+                              * tsdf.py:104-108): allocation by ScalableTSDFVolume::LocateVolumeUnit, every 8^3
+                              * block of a touched 16^3 unit; 8: SURVEY decision D1, allocation by the float32
+                              * pyslam key range (voxel_hashing.h:69-75) of the +-sdf_trunc box               */
+    double voxel_length;     /* the float64 voxel length / truncation Open3D holds (Python floats); 0 = widen  */
+    double sdf_trunc_d;      /*   the float32 fields.  (float)voxel_length must equal voxel_size, same for tau */
 } b2v_config;
 
 /* ---- lifetime: replaces o3d.pipelines.integration.ScalableTSDFVolume(...) (tsdf.py:104-108) ---- */
@@ -125,14 +131,15 @@ int64_t b2v_last_touched_keys(b2v_volume *v, int32_t *keys, int64_t max_keys);
 
 /* ---- mesh: replaces self.volume.extract_triangle_mesh() (tsdf.py:239,260) ----
  * Two-call pattern: b2v_extract_mesh runs the kernels and returns the sizes; b2v_copy_mesh copies
- * the result of the last extraction into HOST arrays vertices f32[nv*3], colors f32[nv*3] in [0,1],
- * edge_ids int32[nv*4] (canonical weld key: voxel x,y,z + axis), triangles int32[nt*3]. */
+ * the result of the last extraction into HOST arrays vertices f64[nv*3], colors f64[nv*3] in [0,1] (float64 like
+ * Open3D's TriangleMesh, computed with Open3D's float64 formulas), edge_ids int32[nv*4] (canonical weld key:
+ * voxel x,y,z + axis), triangles int32[nt*3]. */
 int b2v_extract_mesh(b2v_volume *v, int64_t *n_vertices, int64_t *n_triangles);
-int b2v_copy_mesh(b2v_volume *v, float *vertices, float *colors, int32_t *edge_ids,
+int b2v_copy_mesh(b2v_volume *v, double *vertices, double *colors, int32_t *edge_ids,
                   int32_t *triangles);
 /* replaces self.volume.extract_point_cloud() (tsdf.py:246,267): zero crossings along +x,+y,+z */
 int b2v_extract_points(b2v_volume *v, int64_t *n_points);
-int b2v_copy_points(b2v_volume *v, float *points, float *colors);
+int b2v_copy_points(b2v_volume *v, double *points, double *colors);   /* float64 [n*3], Open3D's formulas */
 
 /* ---- duck type B: pySLAM's own volumetric.VoxelBlockGrid (point-average grid) ----
  * replaces VoxelBlockGridT<VoxelData> (cpp/volumetric/voxel_block_grid.h:61-233) behind the pybind

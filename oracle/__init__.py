@@ -11,11 +11,14 @@ legs may import this package; the product (`pyslam_b200/`) never does.
 * `TsdfOracle`  - C restatement of Open3D's legacy ScalableTSDFVolume under decision D1
                   (oracle/tsdf_oracle.c): truth for tsdf / weight / rgb and the mesh.
                   PARITY UNPINNED against Open3D itself (not installed, not vendored).
+* `Open3DOrderVolume` - ScalableTSDFVolume restated in OPEN3D'S OWN operation order and types (16^3 units,
+                  incremental `p += vl*E[:,2]`, true divisions, float64 colour; oracle/open3d_order.c): the independent
+                  truth the twin above and the kernels are measured against, with the tolerances of SURVEY.md 8c.
 * `numpy_tsdf`  - a second, independent numpy restatement of A.3 used to pin the C oracle.
 """
 
-from .oracle import (RefGrid, RefSemanticGrid, TsdfOracle, build, canonical_mesh, have_ref, have_ref_semantic, numpy_integrate_block,
+from .oracle import (Open3DOrderVolume, RefGrid, RefSemanticGrid, TsdfOracle, build, canonical_mesh, have_ref, have_ref_semantic, numpy_integrate_block,
                      numpy_touched_blocks, ref_block_key_hash, ref_floor_div, ref_keys)
 
-__all__ = ["RefGrid", "RefSemanticGrid", "TsdfOracle", "build", "canonical_mesh", "have_ref", "have_ref_semantic", "numpy_integrate_block",
+__all__ = ["Open3DOrderVolume", "RefGrid", "RefSemanticGrid", "TsdfOracle", "build", "canonical_mesh", "have_ref", "have_ref_semantic", "numpy_integrate_block",
            "numpy_touched_blocks", "ref_block_key_hash", "ref_floor_div", "ref_keys"]

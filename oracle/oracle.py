@@ -55,7 +55,7 @@ def _tsdf():
         L.tsdf_oracle_dump.restype = C.c_int64
         L.tsdf_oracle_dump.argtypes = [C.c_void_p, _i32p, _u64p, _f32p]
         L.tsdf_oracle_extract_mesh.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-        L.tsdf_oracle_mesh_copy.argtypes = [_f32p, _f64p, _f32p, _i32p, _i32p]
+        L.tsdf_oracle_mesh_copy.argtypes = [_f64p, _f64p, _i32p, _i32p]
         L.tsdf_oracle_block_key_hash.restype = C.c_uint64
         L.tsdf_oracle_block_key_hash.argtypes = [C.c_int32] * 3
         L.tsdf_oracle_floor_div.restype = C.c_int64
@@ -64,6 +64,7 @@ def _tsdf():
         L.tsdf_oracle_voxel_coord.argtypes = [C.c_float, C.c_float]
         L.tsdf_oracle_max_threads.restype = C.c_int
         L.tsdf_oracle_set_block.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _f32p]
+        L.tsdf_oracle_set_units.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         _tsdf_lib = L
     return _tsdf_lib
 
@@ -221,13 +222,14 @@ class RefGrid:
 # ---------------------------------------------------------------------------------------------
 
 class TsdfOracle:
-    def __init__(self, voxel_size, sdf_trunc, depth_trunc, block_size=8, stride=4):
+    def __init__(self, voxel_size, sdf_trunc, depth_trunc, block_size=8, stride=4, unit_resolution=16):
         self._L = _tsdf()
         self.block_size = block_size
         self.nvox = block_size ** 3
         self._h = self._L.tsdf_oracle_create(float(np.float32(voxel_size)), int(block_size),
                                              float(np.float32(sdf_trunc)),
                                              float(np.float32(depth_trunc)), int(stride))
+        self.set_units(unit_resolution, voxel_size, sdf_trunc)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -240,6 +242,11 @@ class TsdfOracle:
 
     def reset(self):
         self._L.tsdf_oracle_reset(self._h)
+
+    def set_units(self, unit_resolution, voxel_length, sdf_trunc):
+        """Open3D volume-unit resolution: 16 = the reference's setting (allocation by LocateVolumeUnit), 8 = decision
+        D1 (allocation by the float32 pyslam key range); voxel_length / sdf_trunc as the float64 values Open3D holds."""
+        self._L.tsdf_oracle_set_units(self._h, int(unit_resolution), float(voxel_length), float(sdf_trunc))
 
     def integrate(self, depth, color, K, Tcw, nthreads=1) -> int:
         d = np.ascontiguousarray(depth, np.float32)
@@ -276,13 +283,114 @@ class TsdfOracle:
     def extract_mesh(self):
         nv, nt = C.c_int64(0), C.c_int64(0)
         self._L.tsdf_oracle_extract_mesh(self._h, C.byref(nv), C.byref(nt))
-        V = np.zeros((nv.value, 3), np.float32)
         V64 = np.zeros((nv.value, 3), np.float64)
-        Cc = np.zeros((nv.value, 3), np.float32)
+        Cc = np.zeros((nv.value, 3), np.float64)
         E = np.zeros((nv.value, 4), np.int32)
         T = np.zeros((nt.value, 3), np.int32)
-        self._L.tsdf_oracle_mesh_copy(V, V64, Cc, E, T)
-        return dict(vertices=V, vertices64=V64, colors=Cc, edges=E, triangles=T)
+        self._L.tsdf_oracle_mesh_copy(V64.reshape(-1), Cc.reshape(-1), E.reshape(-1), T.reshape(-1))
+        return dict(vertices=V64, colors=Cc, edges=E, triangles=T)
+
+
+# ---------------------------------------------------------------------------------------------
+# Open3D ScalableTSDFVolume in Open3D's own operation order (oracle/open3d_order.c)
+# ---------------------------------------------------------------------------------------------
+_O3D_SO = os.path.join(_DIR, "libopen3d_order.so")
+_o3d_lib = None
+
+
+def _o3d():
+    global _o3d_lib
+    if _o3d_lib is None:
+        if not os.path.exists(_O3D_SO):
+            build()
+        L = C.CDLL(_O3D_SO)
+        vp = C.c_void_p
+        L.o3d_create.restype = vp
+        L.o3d_create.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+        L.o3d_destroy.argtypes = [vp]
+        L.o3d_reset.argtypes = [vp]
+        L.o3d_num_units.restype = C.c_int64
+        L.o3d_num_units.argtypes = [vp]
+        L.o3d_num_touched.restype = C.c_int64
+        L.o3d_num_touched.argtypes = [vp]
+        L.o3d_prepare_depth.argtypes = [_f32p, _f32p, C.c_int64, C.c_double, C.c_double]
+        L.o3d_multiplier.argtypes = [_f32p, C.c_int, C.c_int, _f64p]
+        L.o3d_integrate.restype = C.c_int64
+        L.o3d_integrate.argtypes = [vp, _f32p, _u8p, _f32p, C.c_int, C.c_int, _f64p, _f64p, C.c_int]
+        L.o3d_last_touched.restype = C.c_int64
+        L.o3d_last_touched.argtypes = [vp, _i32p]
+        L.o3d_dump_blocks.restype = C.c_int64
+        L.o3d_dump_blocks.argtypes = [vp, vp, vp]
+        L.o3d_extract_mesh.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.o3d_mesh_copy.argtypes = [_f64p, _f64p, _i32p, _i32p]
+        _o3d_lib = L
+    return _o3d_lib
+
+
+class Open3DOrderVolume:
+    """`o3d.pipelines.integration.ScalableTSDFVolume(voxel_length, sdf_trunc, RGB8, volume_unit_resolution,
+    depth_sampling_stride)` as the reference constructs it (volumetric_integrator_tsdf.py:104-108), restated in
+    Open3D's own operation order and types.  `integrate` takes what the reference passes at tsdf.py:215-223:
+    a float32 depth in metres (depth_scale 1.0), the depth truncation of create_from_color_and_depth, RGB u8,
+    the intrinsics and the world->camera pose."""
+
+    def __init__(self, voxel_length, sdf_trunc, volume_unit_resolution=16, depth_sampling_stride=4):
+        self._L = _o3d()
+        self.R = int(volume_unit_resolution)
+        assert self.R % 8 == 0
+        self._h = self._L.o3d_create(float(voxel_length), float(sdf_trunc), self.R, int(depth_sampling_stride))
+        self._mult_key, self._mult = None, None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.o3d_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        self._L.o3d_reset(self._h)
+
+    def integrate(self, depth, color, K, Tcw, depth_trunc, depth_scale=1.0, nthreads=1) -> int:
+        d_in = np.ascontiguousarray(depth, np.float32)
+        c = np.ascontiguousarray(color, np.uint8)
+        H, W = d_in.shape
+        assert c.shape == (H, W, 3)
+        d = np.empty_like(d_in)
+        self._L.o3d_prepare_depth(d_in.reshape(-1), d.reshape(-1), d.size, float(depth_scale), float(depth_trunc))
+        K4 = np.ascontiguousarray(K, np.float64).reshape(4)
+        key = (H, W, tuple(K4))
+        if self._mult_key != key:
+            self._mult = np.zeros((H, W), np.float32)
+            self._L.o3d_multiplier(self._mult.reshape(-1), H, W, K4)
+            self._mult_key = key
+        return int(self._L.o3d_integrate(self._h, d.reshape(-1), c.reshape(-1), self._mult.reshape(-1), H, W, K4,
+                                         np.ascontiguousarray(Tcw, np.float64).reshape(16), int(nthreads)))
+
+    def num_units(self) -> int:
+        return int(self._L.o3d_num_units(self._h))
+
+    def last_touched_units(self):
+        n = int(self._L.o3d_num_touched(self._h))
+        idx = np.zeros((n, 3), np.int32)
+        self._L.o3d_last_touched(self._h, idx.reshape(-1))
+        return idx
+
+    def dump_blocks(self):
+        """Every unit as (R/8)^3 blocks in the product's layout: keys int32 [nb,3], vox float64 [nb,5,512]."""
+        nb = self.num_units() * (self.R // 8) ** 3
+        keys = np.zeros((nb, 3), np.int32)
+        vox = np.zeros((nb, 5, 512), np.float64)
+        self._L.o3d_dump_blocks(self._h, keys.ctypes.data, vox.ctypes.data)
+        return dict(keys=keys, vox=vox)
+
+    def extract_triangle_mesh(self):
+        nv, nt = C.c_int64(0), C.c_int64(0)
+        self._L.o3d_extract_mesh(self._h, C.byref(nv), C.byref(nt))
+        V = np.zeros((nv.value, 3), np.float64)
+        Cc = np.zeros((nv.value, 3), np.float64)
+        E = np.zeros((nv.value, 4), np.int32)
+        T = np.zeros((nt.value, 3), np.int32)
+        self._L.o3d_mesh_copy(V.reshape(-1), Cc.reshape(-1), E.reshape(-1), T.reshape(-1))
+        return dict(vertices=V, colors=Cc, edges=E, triangles=T)
 
 
 def canonical_mesh(vertices, colors, edges, triangles):

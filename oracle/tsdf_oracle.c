@@ -2,7 +2,8 @@
  * executed by pyslam_b200/.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load the library built from this file.
  *
- * PARITY UNPINNED for TSDF values / mesh: the reference's TSDF engine is Open3D's legacy
+ * PARITY vs a RUNNING Open3D is unpinned (pinned against oracle/open3d_order.c, the literal restatement of the
+ * upstream source, instead): the reference's TSDF engine is Open3D's legacy
  * ScalableTSDFVolume (called from /root/reference/pyslam/dense/volumetric_integrator_tsdf.py:104-108,
  * 215-223,239,260), an un-vendored dependency (pin 02674268f706be4b004bbbf3d39b95fa9de35f74,
  * /root/reference/scripts/install_open3d_python.sh:114-118; conda open3d-0.19.0) that is absent
@@ -23,13 +24,16 @@
  *   allocate  (A.2) every `stride`-th pixel with 0 < d < depth_trunc: back-project in f64,
  *             p_w = Twc * p_c (rigid inverse of Tcw), touch every block in the key range of
  *             [p_w - tau, p_w + tau]
- *   update    (A.3) voxel centre c = ((float)v + 0.5f) * vs;  p = E*c with E = Tcw as f32:
- *             A = fmaf(E1, c.y, fmaf(E2, c.z, E3)) per x-row, p = fmaf(E0, c.x, A);
- *             u_f = fmaf(p.x*fx, 1/p.z, cx+0.5f) (same for v_f); Open3D's 0.0001 image margin;
- *             sdf = (d - p.z) * lambda(u,v);  if sdf > -tau:  t = min(1, sdf/tau),
- *             r = 1/(w+1), tsdf = fmaf(tsdf,w,t)*r, rgb_k = fmaf(rgb_k,w,RGB_k)*r, w += 1
- *   mesh      (A.4) classic tables; vertex on edge (voxel e, axis a):
- *             base = ((float)e + 0.5f)*vs;  base[a] += (|f0|*vs)/(|f0|+|f1|)
+ *   update    (A.3) OPEN3D'S OPERATION ORDER (contract v3): a block is a sub-block of its R^3 volume unit; voxel
+ *             centre h = (float)((double)(vl/2 + vl*x) + unit*L) (z: the unit's first voxel), p = ((E0*h0 + E1*h1)
+ *             + E2*h2) + E3 without FMA, then p += vl*E[:,2] once per z step from the unit's z = 0;
+ *             u_f = p.x*fx/p.z + cx + 0.5f with true divisions; Open3D's 0.0001 image margin;
+ *             sdf = (d - p.z) * lambda(u,v);  if sdf > -tau:  t = min(1, sdf*(1/tau)),
+ *             tsdf = (tsdf*w + t)/(w+1) (mul, add, div);  w += 1.  In unit-16 mode tsdf and weight are BIT-IDENTICAL
+ *             to oracle/open3d_order.c (tests/test_oracle_open3d.py).  Colour is a float32 running mean
+ *             rgb_k = fmaf(rgb_k,w,RGB_k)*(1/(w+1)) where Open3D keeps float64 (compared with a tolerance).
+ *   mesh      (A.4) classic tables; vertex on edge (voxel e, axis a) in float64 like Open3D:
+ *             pt = vl/2 + vl*e;  pt[a] += |f0|*vl/(|f0|+|f1|);  colour (|f1|*c0/255 + |f0|*c1/255)/(|f0|+|f1|)
  */
 #include <math.h>
 #include <stdint.h>
@@ -60,6 +64,11 @@ typedef struct tsdf_oracle {
     int64_t ntouched, touched_cap;
     int64_t *touched;
     int64_t frame;
+    /* Open3D volume units of R = 8*unit_blocks voxels.  R = 16 (the reference's setting): allocation by
+     * LocateVolumeUnit in float64, every block of a touched unit.  R = 8 (decision D1): allocation by the float32
+     * pyslam key range of the +-tau box; the update arithmetic is Open3D's with 8^3 units. */
+    int unit_blocks;
+    double unit_len, tau_d;
 } tsdf_oracle;
 
 static inline uint64_t mix64(uint64_t h) {
@@ -148,8 +157,20 @@ tsdf_oracle *tsdf_oracle_create(float voxel_size, int block_size, float sdf_trun
     o->B = block_size;
     o->nvox = block_size * block_size * block_size;
     o->stride = stride < 1 ? 1 : stride;
+    o->unit_blocks = 1;
+    o->unit_len = (double)voxel_size * (double)block_size;
+    o->tau_d = (double)sdf_trunc;
     table_rebuild(o, 1 << 12);
     return o;
+}
+
+/* Open3D allocation granularity: unit_resolution voxels per volume-unit side (a multiple of the block side; 16 in
+ * the reference, volumetric_integrator_tsdf.py:104-108; 8 = decision D1), voxel_length / sdf_trunc as the float64
+ * values Open3D holds. */
+void tsdf_oracle_set_units(tsdf_oracle *o, int unit_resolution, double voxel_length, double sdf_trunc) {
+    o->unit_blocks = unit_resolution > o->B ? unit_resolution / o->B : 1;
+    o->unit_len = voxel_length * (double)(o->unit_blocks * o->B);
+    o->tau_d = sdf_trunc;
 }
 
 void tsdf_oracle_destroy(tsdf_oracle *o) {
@@ -194,7 +215,7 @@ static void allocate_frame(tsdf_oracle *o, const float *depth, int H, int W, con
         for (int j = 0; j < 3; ++j) R[i][j] = Tcw[4 * j + i];
     for (int i = 0; i < 3; ++i)
         t[i] = -((R[i][0] * Tcw[3] + R[i][1] * Tcw[7]) + R[i][2] * Tcw[11]);
-    const double tau = (double)o->tau;
+    const double tau = o->unit_blocks > 1 ? o->tau_d : (double)o->tau;
     const int B = o->B;
     for (int i = 0; i < H; i += o->stride) {
         for (int j = 0; j < W; j += o->stride) {
@@ -206,6 +227,13 @@ static void allocate_frame(tsdf_oracle *o, const float *depth, int H, int W, con
             int32_t lo[3], hi[3];
             for (int a = 0; a < 3; ++a) {
                 const double pw = ((R[a][0] * x + R[a][1] * y) + R[a][2] * z) + t[a];
+                if (o->unit_blocks > 1) { /* ScalableTSDFVolume::LocateVolumeUnit: floor(p / unit length), float64 */
+                    const int32_t ulo = (int32_t)floor((pw - tau) / o->unit_len);
+                    const int32_t uhi = (int32_t)floor((pw + tau) / o->unit_len);
+                    lo[a] = ulo * o->unit_blocks;
+                    hi[a] = uhi * o->unit_blocks + o->unit_blocks - 1;
+                    continue;
+                }
                 const int32_t vlo = tsdf_oracle_voxel_coord((float)(pw - tau), o->inv_vs);
                 const int32_t vhi = tsdf_oracle_voxel_coord((float)(pw + tau), o->inv_vs);
                 lo[a] = (int32_t)tsdf_oracle_floor_div(vlo, B);
@@ -221,50 +249,62 @@ static void allocate_frame(tsdf_oracle *o, const float *depth, int H, int W, con
     }
 }
 
-/* A.3: projective update of one block. Returns the number of voxels updated. */
-static int64_t integrate_block(float *vox, key3 key, int B, float vs, float tau, float inv_tau,
-                               float depth_trunc, const float *depth, const uint8_t *rgb, int H,
-                               int W, float fx, float fy, float cxf, float cyf, const float E[12]) {
+/* A.3: projective update of one block, in Open3D's operation order
+ * (UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier) on the voxels of the block:
+ * the block is sub-block (s = key - unit*S) of the volume unit `unit = floor_div(key, S)`; voxel (x,y,z) of the
+ * unit has x = 8*s.x + lx etc.  Returns the number of voxels updated. */
+static int64_t integrate_block(float *vox, key3 key, int B, int S, double unit_len, float vs, float tau,
+                               float depth_trunc, const float *depth, const uint8_t *rgb, int H, int W, float fx,
+                               float fy, float cxf, float cyf, const float E[12]) {
     const int nvox = B * B * B;
-    float *p_tsdf = vox, *p_w = vox + nvox, *p_r = vox + 2 * nvox, *p_g = vox + 3 * nvox,
-          *p_b = vox + 4 * nvox;
+    float *p_tsdf = vox, *p_w = vox + nvox, *p_r = vox + 2 * nvox, *p_g = vox + 3 * nvox, *p_b = vox + 4 * nvox;
     const float inv_fx = 1.0f / fx, inv_fy = 1.0f / fy;
-    const float cxh = cxf + 0.5f, cyh = cyf + 0.5f;
+    const float half = vs * 0.5f, inv_tau = 1.0f / tau;
     const float safe_w = (float)W - 0.0001f, safe_h = (float)H - 0.0001f;
+    const float Es[3] = {E[2] * vs, E[6] * vs, E[10] * vs}; /* extrinsic_scaled_f(:, 2) */
+    int32_t u[3], sb[3];
+    const int32_t k3[3] = {key.x, key.y, key.z};
+    for (int a = 0; a < 3; ++a) {
+        u[a] = (int32_t)tsdf_oracle_floor_div(k3[a], S);
+        sb[a] = k3[a] - u[a] * S;
+    }
+    const double origin[3] = {(double)u[0] * unit_len, (double)u[1] * unit_len, (double)u[2] * unit_len};
     int64_t updated = 0;
-    for (int lz = 0; lz < B; ++lz) {
-        const float cz = ((float)(key.z * B + lz) + 0.5f) * vs;
+    for (int lx = 0; lx < B; ++lx) {
+        const float h0 = (float)((double)(half + vs * (float)(sb[0] * B + lx)) + origin[0]);
         for (int ly = 0; ly < B; ++ly) {
-            const float cy_ = ((float)(key.y * B + ly) + 0.5f) * vs;
-            /* row part of E*c, shared by the voxels of one x-row */
-            const float ax = fmaf(E[1], cy_, fmaf(E[2], cz, E[3]));
-            const float ay = fmaf(E[5], cy_, fmaf(E[6], cz, E[7]));
-            const float az = fmaf(E[9], cy_, fmaf(E[10], cz, E[11]));
-            for (int lx = 0; lx < B; ++lx) {
-                const float cx_ = ((float)(key.x * B + lx) + 0.5f) * vs;
-                const float px = fmaf(E[0], cx_, ax);
-                const float py = fmaf(E[4], cx_, ay);
-                const float pz = fmaf(E[8], cx_, az);
-                if (!(pz > 0.0f)) continue;
-                const float inv_z = 1.0f / pz;
-                const float u_f = fmaf(px * fx, inv_z, cxh);
-                const float v_f = fmaf(py * fy, inv_z, cyh);
+            const float h1 = (float)((double)(half + vs * (float)(sb[1] * B + ly)) + origin[1]);
+            const float h2 = (float)((double)half + origin[2]);
+            float pc[3];
+            for (int r = 0; r < 3; ++r)
+                pc[r] = ((E[4 * r + 0] * h0 + E[4 * r + 1] * h1) + E[4 * r + 2] * h2) + E[4 * r + 3];
+            /* the unit's z loop reaches this block after sb.z * B increments */
+            for (int z = 0; z < sb[2] * B; ++z) {
+                pc[0] += Es[0];
+                pc[1] += Es[1];
+                pc[2] += Es[2];
+            }
+            for (int lz = 0; lz < B; ++lz, pc[0] += Es[0], pc[1] += Es[1], pc[2] += Es[2]) {
+                if (pc[2] <= 0) continue;
+                const float u_f = pc[0] * fx / pc[2] + cxf + 0.5f;
+                const float v_f = pc[1] * fy / pc[2] + cyf + 0.5f;
                 if (!(u_f >= 0.0001f && u_f < safe_w && v_f >= 0.0001f && v_f < safe_h)) continue;
-                const int u = (int)u_f, v = (int)v_f;
-                const float d = depth[(size_t)v * W + u];
+                const int uu = (int)u_f, vv = (int)v_f;
+                const float d = depth[(size_t)vv * W + uu];
                 if (!depth_valid(d, depth_trunc)) continue;
-                const float xx = ((float)u - cxf) * inv_fx;
-                const float yy = ((float)v - cyf) * inv_fy;
-                const float lam = sqrtf(fmaf(xx, xx, fmaf(yy, yy, 1.0f)));
-                const float sdf = (d - pz) * lam;
+                const float xx = ((float)uu - cxf) * inv_fx;
+                const float yy = ((float)vv - cyf) * inv_fy;
+                const float lam = sqrtf(xx * xx + yy * yy + 1.0f);
+                const float sdf = (d - pc[2]) * lam;
                 if (sdf > -tau) {
                     const int idx = lx + ly * B + lz * B * B;
                     const float tval = fminf(1.0f, sdf * inv_tau);
                     const float w = p_w[idx];
                     const float wn = w + 1.0f;
                     const float r = 1.0f / wn;
-                    const uint8_t *c = rgb + ((size_t)v * W + u) * 3;
-                    p_tsdf[idx] = fmaf(p_tsdf[idx], w, tval) * r;
+                    const uint8_t *c = rgb + ((size_t)vv * W + uu) * 3;
+                    p_tsdf[idx] = (p_tsdf[idx] * w + tval) / wn;
+                    /* colour: float32 running mean (Open3D keeps float64; compared with a tolerance) */
                     p_r[idx] = fmaf(p_r[idx], w, (float)c[0]) * r;
                     p_g[idx] = fmaf(p_g[idx], w, (float)c[1]) * r;
                     p_b[idx] = fmaf(p_b[idx], w, (float)c[2]) * r;
@@ -295,7 +335,7 @@ int64_t tsdf_oracle_integrate(tsdf_oracle *o, const float *depth, const uint8_t 
 #endif
     for (int64_t i = 0; i < n; ++i) {
         const int64_t b = o->touched[i];
-        integrate_block(o->vox + bstride * (size_t)b, o->keys[b], o->B, o->vs, o->tau, o->inv_tau,
+        integrate_block(o->vox + bstride * (size_t)b, o->keys[b], o->B, o->unit_blocks, o->unit_len, o->vs, o->tau,
                         o->depth_trunc, depth, rgb, H, W, fx, fy, cx, cy, E);
     }
     return n;
@@ -405,24 +445,20 @@ static int voxel_fetch(const tsdf_oracle *o, int32_t gx, int32_t gy, int32_t gz,
 
 typedef struct {
     int64_t nv, nt, vcap, tcap;
-    float *vert;     /* [nv,3] f32 contract arithmetic */
-    double *vert64;  /* [nv,3] Open3D's f64 formula, for the stated tolerance */
-    float *color;    /* [nv,3] in [0,1] */
+    double *vert64;  /* [nv,3] Open3D's float64 formula */
+    double *color;   /* [nv,3] in [0,1], Open3D's float64 blend of the (float32) voxel colours */
     int32_t *edge;   /* [nv,4] canonical edge id (gx,gy,gz,axis) */
     int32_t *tri;    /* [nt,3] */
 } mesh_out;
 
-static void mesh_push_vertex(mesh_out *m, const float p[3], const double p64[3], const float c[3],
-                             edge4 e) {
+static void mesh_push_vertex(mesh_out *m, const double p64[3], const double c[3], edge4 e) {
     if (m->nv == m->vcap) {
         m->vcap = m->vcap ? m->vcap * 2 : 4096;
-        m->vert = (float *)realloc(m->vert, sizeof(float) * 3 * (size_t)m->vcap);
         m->vert64 = (double *)realloc(m->vert64, sizeof(double) * 3 * (size_t)m->vcap);
-        m->color = (float *)realloc(m->color, sizeof(float) * 3 * (size_t)m->vcap);
+        m->color = (double *)realloc(m->color, sizeof(double) * 3 * (size_t)m->vcap);
         m->edge = (int32_t *)realloc(m->edge, sizeof(int32_t) * 4 * (size_t)m->vcap);
     }
     for (int k = 0; k < 3; ++k) {
-        m->vert[3 * m->nv + k] = p[k];
         m->vert64[3 * m->nv + k] = p64[k];
         m->color[3 * m->nv + k] = c[k];
     }
@@ -437,7 +473,6 @@ static mesh_out g_mesh; /* result of the last extract, copied out by tsdf_oracle
 
 /* Runs A.4 over the whole volume; returns counts via nv/nt. */
 void tsdf_oracle_extract_mesh(const tsdf_oracle *o, int64_t *nv, int64_t *nt) {
-    free(g_mesh.vert);
     free(g_mesh.vert64);
     free(g_mesh.color);
     free(g_mesh.edge);
@@ -446,8 +481,7 @@ void tsdf_oracle_extract_mesh(const tsdf_oracle *o, int64_t *nv, int64_t *nt) {
     edge_map em;
     edge_map_init(&em, 1 << 16);
     const int B = o->B;
-    const float vs = o->vs;
-    const double vs64 = (double)o->vs, h64 = vs64 * 0.5;
+    const double vs64 = o->unit_len / (double)(o->unit_blocks * o->B), h64 = vs64 * 0.5; /* voxel_length_ */
     for (int64_t b = 0; b < o->nb; ++b) {
         const key3 bk = o->keys[b];
         for (int lz = 0; lz < B; ++lz)
@@ -483,22 +517,18 @@ void tsdf_oracle_extract_mesh(const tsdf_oracle *o, int64_t *nv, int64_t *nt) {
                             continue;
                         }
                         const int c0 = MC_EDGE_TO_VERT[e][0], c1 = MC_EDGE_TO_VERT[e][1];
-                        const float f0 = fabsf(f[c0]), f1 = fabsf(f[c1]);
-                        const float fs = f0 + f1;
-                        float p[3] = {((float)ek.x + 0.5f) * vs, ((float)ek.y + 0.5f) * vs,
-                                      ((float)ek.z + 0.5f) * vs};
-                        p[ek.a] = p[ek.a] + (f0 * vs) / fs;
+                        const double f0 = fabs((double)f[c0]), f1 = fabs((double)f[c1]);
                         double p64[3] = {h64 + vs64 * ek.x, h64 + vs64 * ek.y, h64 + vs64 * ek.z};
-                        p64[ek.a] += (double)f0 * vs64 / ((double)f0 + (double)f1);
-                        float cc[3];
+                        p64[ek.a] += f0 * vs64 / (f0 + f1);
+                        double cc[3];
                         for (int k = 0; k < 3; ++k)
-                            cc[k] = (fmaf(f1, col[c0][k], f0 * col[c1][k]) / fs) / 255.0f;
+                            cc[k] = (f1 * ((double)col[c0][k] / 255.0) + f0 * ((double)col[c1][k] / 255.0)) / (f0 + f1);
                         const int64_t s = -r - 1;
                         em.key[s] = ek;
                         em.val[s] = (int32_t)g_mesh.nv;
                         em.n++;
                         vid[e] = (int32_t)g_mesh.nv;
-                        mesh_push_vertex(&g_mesh, p, p64, cc, ek);
+                        mesh_push_vertex(&g_mesh, p64, cc, ek);
                         if (em.n * 2 > em.cap) edge_map_grow(&em);
                     }
                     for (int t = 0; MC_TRI_TABLE[cube][t] != -1 && t < 15; t += 3) {
@@ -521,10 +551,9 @@ void tsdf_oracle_extract_mesh(const tsdf_oracle *o, int64_t *nv, int64_t *nt) {
     *nt = g_mesh.nt;
 }
 
-void tsdf_oracle_mesh_copy(float *vert, double *vert64, float *color, int32_t *edge, int32_t *tri) {
-    if (vert) memcpy(vert, g_mesh.vert, sizeof(float) * 3 * (size_t)g_mesh.nv);
+void tsdf_oracle_mesh_copy(double *vert64, double *color, int32_t *edge, int32_t *tri) {
     if (vert64) memcpy(vert64, g_mesh.vert64, sizeof(double) * 3 * (size_t)g_mesh.nv);
-    if (color) memcpy(color, g_mesh.color, sizeof(float) * 3 * (size_t)g_mesh.nv);
+    if (color) memcpy(color, g_mesh.color, sizeof(double) * 3 * (size_t)g_mesh.nv);
     if (edge) memcpy(edge, g_mesh.edge, sizeof(int32_t) * 4 * (size_t)g_mesh.nv);
     if (tri) memcpy(tri, g_mesh.tri, sizeof(int32_t) * 3 * (size_t)g_mesh.nt);
 }

@@ -56,6 +56,9 @@ class B2VConfig(C.Structure):
         ("device", C.c_int32),
         ("shard_rank", C.c_int32),
         ("shard_count", C.c_int32),
+        ("unit_resolution", C.c_int32),
+        ("voxel_length", C.c_double),
+        ("sdf_trunc_d", C.c_double),
     ]
 
 

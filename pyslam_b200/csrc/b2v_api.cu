@@ -26,8 +26,7 @@ namespace b2v {
 // Host-side pose algebra, same operation order as the oracle (and -ffp-contract=off on the host
 // compiler), so allocation keys agree bit for bit.
 void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], int H, int W,
-                       int stride, float vs, float tau, float depth_trunc, uint32_t frame_id,
-                       int shard_rank, int shard_count) {
+                       const VolumeGeometry &g, uint32_t frame_id) {
     p->fx = K[0];
     p->fy = K[1];
     p->cx = K[2];
@@ -37,37 +36,50 @@ void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], 
     for (int i = 0; i < 3; ++i)
         p->twc[i] = -((p->Rwc[3 * i + 0] * Tcw[3] + p->Rwc[3 * i + 1] * Tcw[7]) +
                       p->Rwc[3 * i + 2] * Tcw[11]);
-    p->tau_d = static_cast<double>(tau);
-    for (int i = 0; i < 12; ++i) p->E[i] = static_cast<float>(Tcw[i]);
-    p->fxf = static_cast<float>(K[0]);
-    p->fyf = static_cast<float>(K[1]);
-    p->cxf = static_cast<float>(K[2]);
-    p->cyf = static_cast<float>(K[3]);
-    p->inv_fx = 1.0f / p->fxf;
-    p->inv_fy = 1.0f / p->fyf;
-    p->cxh = p->cxf + 0.5f;
-    p->cyh = p->cyf + 0.5f;
-    p->safe_w = static_cast<float>(W) - 0.0001f;
-    p->safe_h = static_cast<float>(H) - 0.0001f;
-    p->vs = vs;
-    p->inv_vs = 1.0f / vs;  // voxel_block_grid.hpp:6
-    p->tau = tau;
-    p->inv_tau = 1.0f / tau;
-    p->depth_trunc = depth_trunc;
+    p->tau_d = g.unit_shift > 0 ? g.tau_d : static_cast<double>(g.tau);
+    p->unit_len = g.voxel_length * static_cast<double>(kB << g.unit_shift);
+    IntFrame &I = p->I;
+    for (int i = 0; i < 12; ++i) I.E[i] = static_cast<float>(Tcw[i]);
+    for (int i = 0; i < 3; ++i) I.Es[i] = I.E[4 * i + 2] * g.vs;  // extrinsic_f * voxel_length_f, column 2
+    I.fxf = static_cast<float>(K[0]);
+    I.fyf = static_cast<float>(K[1]);
+    I.cxf = static_cast<float>(K[2]);
+    I.cyf = static_cast<float>(K[3]);
+    I.safe_w = static_cast<float>(W) - 0.0001f;
+    I.safe_h = static_cast<float>(H) - 0.0001f;
+    I.tau = g.tau;
+    I.inv_tau = 1.0f / g.tau;
+    I.W = W;
+    I.tex = nullptr;
+    p->inv_fx = 1.0f / I.fxf;
+    p->inv_fy = 1.0f / I.fyf;
+    p->inv_vs = 1.0f / g.vs;  // voxel_block_grid.hpp:6
+    p->depth_trunc = g.depth_trunc;
+    p->unit_shift = g.unit_shift;
     p->H = H;
     p->W = W;
-    p->stride = stride;
+    p->stride = g.stride;
     p->frame_id = frame_id;
-    p->shard_rank = shard_rank;
-    p->shard_count = shard_count;
+    p->shard_rank = g.shard_rank;
+    p->shard_count = g.shard_count;
     p->group_bit = -1;
     p->group_buf = 0;
+}
+
+VolumeConsts volume_consts(const VolumeGeometry &g) {
+    VolumeConsts c;
+    c.unit_len = g.voxel_length * static_cast<double>(kB << g.unit_shift);
+    c.vs = g.vs;
+    c.half_vs = g.vs * 0.5f;
+    c.unit_shift = g.unit_shift;
+    return c;
 }
 
 }  // namespace b2v
 
 namespace {
 
+static_assert(kCtrNew0 == kCtrActive0 + kActiveRing, "the ring counters are cleared with one memset");
 constexpr int kFrameStage = 4;                       // staging ring of the frame-by-frame path
 constexpr int kGroupStage = kGroupBufs * kMaxGroup;  // group buffers x kMaxGroup frames
 constexpr int kStage = kGroupStage + kFrameStage;    // raw-frame staging slots (device copies of host frames)
@@ -91,12 +103,14 @@ bool is_device_pointer(const void *p) {
 
 struct b2v_volume {
     b2v_config cfg{};
+    VolumeGeometry geo{};
     cudaStream_t compute = nullptr, copy = nullptr, alloc = nullptr;
     cudaStream_t last_stream = nullptr;  // caller stream of the most recent frame (synchronised on reads)
     bool overlap = true;                 // allocate(f+1) on its own stream, concurrent with integrate(f)
     bool use_tma = true;                 // stage image tiles with TMA when the layout allows it
     bool inputs_fenced = false;          // batch call: device inputs already ordered before the alloc stream
     bool fuse = true;                    // b2v_integrate_batch fuses groups of up to kMaxGroup frames
+    bool rings_stale = false;            // a fused batch advanced frame_id: the per-frame ring counters must be re-armed
     float4 *d_gtex[kGroupBufs * kMaxGroup] = {};  // texel images of the group buffers
     size_t gtex_pixels = 0;
     uint32_t group_id = 0;
@@ -177,7 +191,10 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     *out = nullptr;
     if (cfg->block_size != B2V_BLOCK_SIZE || !(cfg->voxel_size > 0.0f) || !(cfg->sdf_trunc > 0.0f) ||
         !(cfg->depth_trunc > 0.0f) || cfg->capacity_blocks == 0 || cfg->shard_count < 1 ||
-        cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count)
+        cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count ||
+        (cfg->unit_resolution != 0 && cfg->unit_resolution != 8 && cfg->unit_resolution != 16) ||
+        static_cast<float>(cfg->voxel_length > 0.0 ? cfg->voxel_length : cfg->voxel_size) != cfg->voxel_size ||
+        static_cast<float>(cfg->sdf_trunc_d > 0.0 ? cfg->sdf_trunc_d : cfg->sdf_trunc) != cfg->sdf_trunc)
         return B2V_ERR_INVALID_ARGUMENT;
     // allocate_kernel packs 21 bits per axis inside one frustum
     if (static_cast<double>(cfg->depth_trunc) / (static_cast<double>(cfg->voxel_size) * kB) > 5.0e5)
@@ -186,6 +203,18 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
     v->cfg = *cfg;
     if (v->cfg.depth_stride < 1) v->cfg.depth_stride = 4;
+    if (v->cfg.unit_resolution == 0) v->cfg.unit_resolution = 16;
+    if (!(v->cfg.voxel_length > 0.0)) v->cfg.voxel_length = static_cast<double>(cfg->voxel_size);
+    if (!(v->cfg.sdf_trunc_d > 0.0)) v->cfg.sdf_trunc_d = static_cast<double>(cfg->sdf_trunc);
+    v->geo.vs = cfg->voxel_size;
+    v->geo.tau = cfg->sdf_trunc;
+    v->geo.depth_trunc = cfg->depth_trunc;
+    v->geo.voxel_length = v->cfg.voxel_length;
+    v->geo.tau_d = v->cfg.sdf_trunc_d;
+    v->geo.unit_shift = v->cfg.unit_resolution == 16 ? 1 : 0;
+    v->geo.stride = v->cfg.depth_stride;
+    v->geo.shard_rank = cfg->shard_rank;
+    v->geo.shard_count = cfg->shard_count;
     *out = v;  // returned even on CUDA failure so the caller can read b2v_last_error and destroy
     B2V_CUDA(v, cudaSetDevice(cfg->device));
     B2V_CUDA(v, cudaStreamCreateWithFlags(&v->compute, cudaStreamNonBlocking));
@@ -327,6 +356,7 @@ extern "C" int b2v_reset(b2v_volume *v) {
     v->frame_id = 0;
     v->group_id = 0;
     v->last_group_buf = -1;
+    v->rings_stale = false;
     v->err.clear();
     B2V_CUDA(v, cudaStreamSynchronize(v->compute));
     return B2V_OK;
@@ -477,7 +507,16 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
         B2V_CUDA(v, cudaEventRecord(v->ev_in, cs));
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_in, 0));
     }
-    if (v->overlap && v->frame_id >= 3) {
+    if (v->rings_stale) {
+        // first single frame after a fused batch: the batch advanced frame_id without passing through the
+        // per-frame rings, so the ring this frame counts into may still hold an old frame's counts (only the
+        // previous per-frame allocate re-arms the next ring).  Rare transition: order it after everything on the
+        // compute stream and clear all ring counters.
+        B2V_CUDA(v, cudaEventRecord(v->ev_in, cs));
+        B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_in, 0));
+        B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + kCtrActive0, 0, 2 * kActiveRing * sizeof(uint32_t), as));
+        v->rings_stale = false;
+    } else if (v->overlap && v->frame_id >= 3) {
         // allocate(f) recycles the ring slot / texel buffer last read by integrate(f - 3) .. (f - 4)
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_int_done[(v->frame_id - 3) % kActiveRing], 0));
     }
@@ -492,8 +531,7 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
         if (rc != B2V_OK) return rc;
     }
     FrameParams P;
-    fill_frame_params(&P, K, Tcw, height, width, v->cfg.depth_stride, v->cfg.voxel_size, v->cfg.sdf_trunc,
-                      v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank, v->cfg.shard_count);
+    fill_frame_params(&P, K, Tcw, height, width, v->geo, v->frame_id + 1);
     if (v->lam_H != height || v->lam_W != width || std::memcmp(v->lam_K, K, sizeof(v->lam_K)) != 0) {
         if (v->overlap) {  // the lambda image is read by allocate kernels that may still be in flight
             B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
@@ -513,6 +551,7 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
         B2V_CUDA(v, cudaEventRecord(pe[0], as));
     }
     float4 *tex = v->d_texel[s];
+    P.I.tex = tex;
     B2V_CUDA(v, launch_allocate(P, d_depth, d_color, v->d_lambda, tex, v->table, v->meta, ring,
                                 frame_maps(v, d_depth, d_color, height, width), as));
     if (staged || u16) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], as));  // the raw frame is consumed by allocate only
@@ -526,7 +565,7 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
         B2V_CUDA(v, cudaStreamWaitEvent(cs, v->ev_alloc_done[ring], 0));
     }
     if (pe) B2V_CUDA(v, cudaEventRecord(pe[2], cs));
-    B2V_CUDA(v, launch_integrate(P, v->d_texel[s], v->table, v->meta, ring, v->grid_ctas, cs));
+    B2V_CUDA(v, launch_integrate(P, volume_consts(v->geo), v->table, v->meta, ring, v->grid_ctas, cs));
     if (pe) B2V_CUDA(v, cudaEventRecord(pe[3], cs));
     if (v->overlap) B2V_CUDA(v, cudaEventRecord(v->ev_int_done[ring], cs));
     v->launches += 1;
@@ -647,12 +686,24 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         return B2V_ERR_INVALID_ARGUMENT;
     }
     if (n_frames == 0) return B2V_OK;
+    if (!(K[0] > 0.0) || !(K[1] > 0.0)) {
+        v->err = "b2v_integrate_batch: focal lengths must be positive";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
     B2V_CUDA(v, cudaSetDevice(v->cfg.device));
     const size_t pixels = static_cast<size_t>(height) * width;
     const bool dd = is_device_pointer(depth), dc = is_device_pointer(color);
     const int dev_hint = dd == dc ? (dd ? 1 : 0) : -1;
+    if (stream != nullptr && dev_hint != 1) {
+        v->err = "b2v_integrate_batch: a caller stream requires device image pointers";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
     cudaStream_t cs = stream ? static_cast<cudaStream_t>(stream) : v->compute;
     cudaStream_t as = v->overlap ? v->alloc : cs;
+    struct FenceGuard {  // every exit path (errors included) drops the batch-wide input fence
+        b2v_volume *v;
+        ~FenceGuard() { v->inputs_fenced = false; }
+    } fence_guard{v};
     if (v->overlap) {
         // one fence for the whole batch: everything enqueued on the caller's stream so far (the inputs'
         // producers, earlier per-frame work) happens before the batch's allocate kernels
@@ -668,26 +719,13 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
             rc = integrate_frame(v, u16 ? reinterpret_cast<const float *>(depth16 + pixels * f) : depth + pixels * f,
                                  color + pixels * 3 * f, height, width, K, Tcw + 16 * static_cast<size_t>(f), stream,
                                  dev_hint);
-        v->inputs_fenced = false;
         return rc;
     }
     rc = ensure_group_buffers(v, pixels);
     if (rc == B2V_OK) rc = ensure_staging(v, pixels);
     if (rc == B2V_OK && u16) rc = ensure_staging16(v, pixels);
-    if (rc != B2V_OK) {
-        v->inputs_fenced = false;
-        return rc;
-    }
-    if (!(K[0] > 0.0) || !(K[1] > 0.0)) {
-        v->err = "b2v_integrate_batch: focal lengths must be positive";
-        v->inputs_fenced = false;
-        return B2V_ERR_INVALID_ARGUMENT;
-    }
-    if (stream != nullptr && dev_hint != 1) {
-        v->err = "b2v_integrate_batch: a caller stream requires device image pointers";
-        v->inputs_fenced = false;
-        return B2V_ERR_INVALID_ARGUMENT;
-    }
+    if (rc != B2V_OK) return rc;
+    v->rings_stale = true;
     v->last_stream = stream ? cs : nullptr;
     const bool staged = dev_hint != 1;
     for (int32_t g0 = 0; g0 < n_frames; g0 += kMaxGroup) {
@@ -699,7 +737,7 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         static thread_local GroupAllocArgs aargs;  // 5.5 KB: keep it off the stack
         GroupArgs args;
         std::memset(&args, 0, sizeof(args));
-        args.vs = v->cfg.voxel_size;
+        args.V = volume_consts(v->geo);
         args.count = count;
         aargs.count = count;
         aargs.use_tma = 1;
@@ -724,9 +762,7 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
             if (staged || u16) d_depth = v->d_depth[buf * kMaxGroup + k];  // (widened) float staging slot
             if (staged) d_color = v->d_color[buf * kMaxGroup + k];
             FrameParams &P = aargs.P[k];
-            fill_frame_params(&P, K, Tcw + 16 * f, height, width, v->cfg.depth_stride, v->cfg.voxel_size,
-                              v->cfg.sdf_trunc, v->cfg.depth_trunc, v->frame_id + 1, v->cfg.shard_rank,
-                              v->cfg.shard_count);
+            fill_frame_params(&P, K, Tcw + 16 * f, height, width, v->geo, v->frame_id + 1);
             P.group_bit = k;
             P.group_buf = buf;
             if (k == 0 && (v->lam_H != height || v->lam_W != width || std::memcmp(v->lam_K, K, sizeof(v->lam_K)) != 0)) {
@@ -741,18 +777,8 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
             aargs.depth[k] = d_depth;
             aargs.color[k] = d_color;
             aargs.tex[k] = tex;
-            IntFrame &F = args.f[k];
-            std::memcpy(F.E, P.E, sizeof(F.E));
-            F.fxf = P.fxf;
-            F.fyf = P.fyf;
-            F.cxh = P.cxh;
-            F.cyh = P.cyh;
-            F.safe_w = P.safe_w;
-            F.safe_h = P.safe_h;
-            F.tau = P.tau;
-            F.inv_tau = P.inv_tau;
-            F.tex = tex;
-            F.W = width;
+            P.I.tex = tex;
+            args.f[k] = P.I;
             v->frame_id += 1;
         }
         if (staged) {
@@ -766,10 +792,7 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         }
         for (int k = 0; k < count; ++k) {  // optional rectification, then the TMA descriptors of the final images
             const int rrc = rectify_frame(v, &aargs.depth[k], &aargs.color[k], height, width, buf * kMaxGroup + k, as);
-            if (rrc != B2V_OK) {
-                v->inputs_fenced = false;
-                return rrc;
-            }
+            if (rrc != B2V_OK) return rrc;
             const FrameMaps *fm = frame_maps(v, aargs.depth[k], aargs.color[k], height, width);
             if (fm) aargs.maps[k] = *fm; else aargs.use_tma = 0;
         }
@@ -796,7 +819,6 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         v->last_group_count = count;
         v->group_id += 1;
     }
-    v->inputs_fenced = false;
     return B2V_OK;
 }
 
@@ -1137,7 +1159,7 @@ static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t
         B2V_CUDA(v, regrow(&v->mb.triangles, nt * 3));
         v->mesh_t_cap = nt;
     }
-    B2V_CUDA(v, launch_mesh_vertices(v->meta, v->mb, v->cfg.voxel_size, cs));
+    B2V_CUDA(v, launch_mesh_vertices(v->meta, v->mb, v->geo.voxel_length, v->geo.unit_shift, !mesh, cs));
     if (mesh) B2V_CUDA(v, launch_mesh_triangles(v->mb, cs));
     B2V_CUDA(v, cudaStreamSynchronize(cs));
     v->launches += mesh ? 6 : 5;
@@ -1153,12 +1175,12 @@ extern "C" int b2v_extract_mesh(b2v_volume *v, int64_t *n_vertices, int64_t *n_t
     return extract_common(v, true, n_vertices, n_triangles);
 }
 
-extern "C" int b2v_copy_mesh(b2v_volume *v, float *vertices, float *colors, int32_t *edge_ids,
+extern "C" int b2v_copy_mesh(b2v_volume *v, double *vertices, double *colors, int32_t *edge_ids,
                              int32_t *triangles) {
     if (!v) return B2V_ERR_INVALID_ARGUMENT;
     const size_t nv = static_cast<size_t>(v->last_nv), nt = static_cast<size_t>(v->last_nt);
-    if (vertices && nv) B2V_CUDA(v, cudaMemcpy(vertices, v->mb.vertices, nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-    if (colors && nv) B2V_CUDA(v, cudaMemcpy(colors, v->mb.colors, nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (vertices && nv) B2V_CUDA(v, cudaMemcpy(vertices, v->mb.vertices, nv * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (colors && nv) B2V_CUDA(v, cudaMemcpy(colors, v->mb.colors, nv * 3 * sizeof(double), cudaMemcpyDeviceToHost));
     if (edge_ids && nv) B2V_CUDA(v, cudaMemcpy(edge_ids, v->mb.edge_ids, nv * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (triangles && nt) B2V_CUDA(v, cudaMemcpy(triangles, v->mb.triangles, nt * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return B2V_OK;
@@ -1169,7 +1191,7 @@ extern "C" int b2v_extract_points(b2v_volume *v, int64_t *n_points) {
     return extract_common(v, false, n_points, nullptr);
 }
 
-extern "C" int b2v_copy_points(b2v_volume *v, float *points, float *colors) {
+extern "C" int b2v_copy_points(b2v_volume *v, double *points, double *colors) {
     return b2v_copy_mesh(v, points, colors, nullptr, nullptr);
 }
 

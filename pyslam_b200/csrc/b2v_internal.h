@@ -10,20 +10,30 @@
 
 namespace b2v {
 
-// Per-frame constants, passed to the kernels by value (kernel-parameter space, no copies).
+// Constants of the projective update of one frame (Open3D UniformTSDFVolume::IntegrateWithDepthToCameraDistance-
+// Multiplier): passed in kernel-parameter space, so the kernels read them as constant-bank operands.
+struct IntFrame {
+    float E[12];     // Tcw rows 0..2 as float32 (extrinsic.cast<float>())
+    float Es[3];     // E[2], E[6], E[10] times voxel_length_f (extrinsic_scaled_f(:, 2)): the per-z-step increment
+    float fxf, fyf, cxf, cyf;
+    float safe_w, safe_h;   // W - 0.0001f, H - 0.0001f
+    float tau, inv_tau;
+    int32_t W;
+    const float4 *tex;      // packed {valid depth | 0, lambda, rgbx, 0} texels of the frame
+};
+
+// Per-frame constants of the allocate kernels (+ the update constants of the frame-by-frame path).
 struct FrameParams {
     // f64 back-projection of the allocation samples (Open3D CreatePointCloudFromFloatDepthImage)
     double fx, fy, cx, cy;
     double Rwc[9];   // rigid inverse of Tcw, row-major
     double twc[3];
-    double tau_d;    // (double)sdf_trunc
-    // f32 projective update (Open3D UniformTSDFVolume::Integrate...)
-    float E[12];     // Tcw rows 0..2 as float32
-    float fxf, fyf, cxf, cyf;
-    float inv_fx, inv_fy;   // 1.0f / fx, 1.0f / fy
-    float cxh, cyh;         // cx + 0.5f, cy + 0.5f
-    float safe_w, safe_h;   // W - 0.0001f, H - 0.0001f
-    float vs, inv_vs, tau, inv_tau, depth_trunc;
+    double tau_d;    // sdf_trunc as float64 (unit mode: the value Open3D holds; D1: (double)sdf_trunc_f)
+    double unit_len; // voxel_length * unit resolution, float64 (volume_unit_length_)
+    IntFrame I;
+    float inv_fx, inv_fy;   // 1.0f / fx, 1.0f / fy (lambda image)
+    float inv_vs, depth_trunc;
+    int32_t unit_shift;     // log2(blocks per unit side): 0 = 8^3 units (D1 allocation), 1 = Open3D's 16^3 units
     int32_t H, W, stride;
     uint32_t frame_id;
     int32_t shard_rank, shard_count;
@@ -32,21 +42,22 @@ struct FrameParams {
     int32_t group_bit, group_buf;
 };
 
+// Volume-wide constants of the update kernels (frame independent).
+struct VolumeConsts {
+    double unit_len;     // float64 volume-unit length
+    float vs, half_vs;   // voxel_length_f, voxel_length_f * 0.5f
+    int32_t unit_shift;
+};
+
 // Fused group integration: up to kMaxGroup consecutive frames are applied to a block while it is
-// resident in registers.  Per-frame constants of the projective update only.
+// resident in registers.
 constexpr int kMaxGroup = 8;
 // group state (masks, union list, texel images, counters) is kGroupBufs-deep: the allocation of group g+3 may
 // run while group g is still being integrated
 constexpr int kGroupBufs = 4;
-struct IntFrame {
-    float E[12];
-    float fxf, fyf, cxh, cyh, safe_w, safe_h, tau, inv_tau;
-    const float4 *tex;
-    int32_t W, pad;
-};
 struct GroupArgs {
     IntFrame f[kMaxGroup];
-    float vs;
+    VolumeConsts V;
     int32_t count;
 };
 
@@ -89,9 +100,15 @@ constexpr int kActiveRing = 4;
 static_assert(kGcTouched0 + kMaxGroup <= kGroupCtrStride && kCtrGroup0 + kGroupBufs * kGroupCtrStride <= kNumCounters,
               "counter layout");
 
+struct VolumeGeometry {   // set once per volume (b2v_create)
+    float vs, tau, depth_trunc;
+    double voxel_length, tau_d;   // float64 values as Open3D holds them
+    int32_t unit_shift, stride;
+    int32_t shard_rank, shard_count;
+};
 void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], int H, int W,
-                       int stride, float vs, float tau, float depth_trunc, uint32_t frame_id,
-                       int shard_rank, int shard_count);
+                       const VolumeGeometry &g, uint32_t frame_id);
+VolumeConsts volume_consts(const VolumeGeometry &g);
 
 // ---- kernels (b2v_tsdf.cu) ----
 // lambda image (Open3D's depth-to-camera-distance multiplier) for the current intrinsics
@@ -115,7 +132,7 @@ cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint
                             const float *lam, float4 *texels, const HashTable &table,
                             const PoolMeta &meta, int ring, const FrameMaps *maps, cudaStream_t stream);
 // projective TSDF + colour update of every block touched by the frame
-cudaError_t launch_integrate(const FrameParams &p, const float4 *texels, const HashTable &table,
+cudaError_t launch_integrate(const FrameParams &p, const VolumeConsts &vc, const HashTable &table,
                              const PoolMeta &meta, int ring, int grid_ctas, cudaStream_t stream);
 // all frames of a group in ONE launch (blockIdx.z = frame): the per-frame latency chains overlap
 struct GroupAllocArgs {
@@ -154,8 +171,8 @@ struct MeshBuffers {
     uint32_t *sums;          // [2][n_blocks] per-block vertex / triangle counts
     uint32_t *offs;          // [2][n_blocks] exclusive scans of sums
     uint32_t *totals;        // [2] total vertices, triangles
-    float *vertices;         // [nv][3]
-    float *colors;           // [nv][3] in [0,1]
+    double *vertices;        // [nv][3] float64, Open3D's formula
+    double *colors;          // [nv][3] in [0,1]
     int32_t *edge_ids;       // [nv][4] canonical weld key (voxel x,y,z, axis)
     int32_t *triangles;      // [nt][3]
 };
@@ -167,8 +184,8 @@ cudaError_t launch_mesh_classify(const PoolMeta &meta, const MeshBuffers &mb, cu
 cudaError_t launch_point_masks(const PoolMeta &meta, const MeshBuffers &mb, cudaStream_t stream);
 // per-block sums + exclusive scans -> offs, totals
 cudaError_t launch_mesh_scan(const MeshBuffers &mb, cudaStream_t stream);
-cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, float vs,
-                                 cudaStream_t stream);
+cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, double voxel_length, int unit_shift,
+                                 bool points, cudaStream_t stream);
 cudaError_t launch_mesh_triangles(const MeshBuffers &mb, cudaStream_t stream);
 
 // ---- point-average grid (b2v_grid.cu) ----

@@ -179,8 +179,14 @@ mesh_block_sums_kernel(const MeshBuffers mb) {
 
 // ---- pass 3a: vertices -----------------------------------------------------------------------
 
+// points = false: ScalableTSDFVolume::ExtractTriangleMesh vertex / colour formulas (float64):
+//     pt = vl/2 + vl * e;  pt[a] += |f0| vl / (|f0| + |f1|);  colour (|f1| c0/255 + |f0| c1/255) / (|f0| + |f1|)
+// points = true: ExtractPointCloud: p0 = (vl/2 + vl * x_in_unit) + unit * L, p1 = p0 + vl on the axis,
+//     p = (p0 r1 + p1 r0) / (r0 + r1) with float32 r0 = |f0|, r1 = |f1| (their sum in float32), colour
+//     ((c0 r1 + c1 r0) / (r0 + r1)) / 255 in float32, widened
+template <bool kPoints>
 __global__ void __launch_bounds__(kVox)
-mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const float vs) {
+mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const double vl, const int unit_shift) {
     __shared__ uint32_t s_warp[16];
     __shared__ int s_nbr[8];
     const uint32_t b = blockIdx.x;
@@ -195,11 +201,23 @@ mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const float vs) {
     const int l[3] = {t & 7, (t >> 3) & 7, t >> 6};
     const int g[3] = {key.x * kB + l[0], key.y * kB + l[1], key.z * kB + l[2]};
     const float *blk = M.pool + static_cast<size_t>(b) * kBlockFloats;
-    const float f0 = fabsf(blk[t]);
+    const float r0 = fabsf(blk[t]);
     const float c0[3] = {blk[2 * kVox + t], blk[3 * kVox + t], blk[4 * kVox + t]};
-    const float ctr[3] = {__fmul_rn(__fadd_rn(static_cast<float>(g[0]), 0.5f), vs),
-                          __fmul_rn(__fadd_rn(static_cast<float>(g[1]), 0.5f), vs),
-                          __fmul_rn(__fadd_rn(static_cast<float>(g[2]), 0.5f), vs)};
+    const double half = __dmul_rn(vl, 0.5);
+    double ctr[3];
+    if (kPoints) {
+        const int kk[3] = {key.x, key.y, key.z};
+        const double L = __dmul_rn(vl, static_cast<double>(kB << unit_shift));  // volume_unit_length_
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int u = kk[a] >> unit_shift;
+            const int x = (kk[a] - (u << unit_shift)) * kB + l[a];
+            ctr[a] = __dadd_rn(__dadd_rn(half, __dmul_rn(vl, static_cast<double>(x))), __dmul_rn(static_cast<double>(u), L));
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) ctr[a] = __dadd_rn(half, __dmul_rn(vl, static_cast<double>(g[a])));
+    }
     uint32_t vid = base;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -209,18 +227,35 @@ mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const float vs) {
         const int pb = s_nbr[(q[0] >> 3) | ((q[1] >> 3) << 1) | ((q[2] >> 3) << 2)];
         const float *nb = M.pool + static_cast<size_t>(pb) * kBlockFloats;
         const int v = (q[0] & 7) + ((q[1] & 7) << 3) + ((q[2] & 7) << 6);
-        const float f1 = fabsf(nb[v]);
-        const float fs = __fadd_rn(f0, f1);
-        float p[3] = {ctr[0], ctr[1], ctr[2]};
-        p[a] = __fadd_rn(p[a], __fdiv_rn(__fmul_rn(f0, vs), fs));
-        mb.vertices[3 * static_cast<size_t>(vid) + 0] = p[0];
-        mb.vertices[3 * static_cast<size_t>(vid) + 1] = p[1];
-        mb.vertices[3 * static_cast<size_t>(vid) + 2] = p[2];
+        const float r1 = fabsf(nb[v]);
+        double p[3] = {ctr[0], ctr[1], ctr[2]};
+        double col[3];
+        if (kPoints) {
+            const float rs = __fadd_rn(r0, r1);
+            const double p1 = __dadd_rn(ctr[a], vl);
+            p[a] = __ddiv_rn(__dadd_rn(__dmul_rn(ctr[a], static_cast<double>(r1)), __dmul_rn(p1, static_cast<double>(r0))),
+                             static_cast<double>(rs));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float c1 = nb[(2 + k) * kVox + v];
+                const float num = __fadd_rn(__fmul_rn(c0[k], r1), __fmul_rn(c1, r0));
+                col[k] = static_cast<double>(__fdiv_rn(__fdiv_rn(num, rs), 255.0f));
+            }
+        } else {
+            const double f0 = static_cast<double>(r0), f1 = static_cast<double>(r1);
+            const double fs = __dadd_rn(f0, f1);
+            p[a] = __dadd_rn(p[a], __ddiv_rn(__dmul_rn(f0, vl), fs));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double d0 = __ddiv_rn(static_cast<double>(c0[k]), 255.0);
+                const double d1 = __ddiv_rn(static_cast<double>(nb[(2 + k) * kVox + v]), 255.0);
+                col[k] = __ddiv_rn(__dadd_rn(__dmul_rn(f1, d0), __dmul_rn(f0, d1)), fs);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float c1 = nb[(2 + k) * kVox + v];
-            const float num = __fmaf_rn(f1, c0[k], __fmul_rn(f0, c1));
-            mb.colors[3 * static_cast<size_t>(vid) + k] = __fdiv_rn(__fdiv_rn(num, fs), 255.0f);
+            mb.vertices[3 * static_cast<size_t>(vid) + k] = p[k];
+            mb.colors[3 * static_cast<size_t>(vid) + k] = col[k];
         }
         reinterpret_cast<int4 *>(mb.edge_ids)[vid] = make_int4(g[0], g[1], g[2], a);
         ++vid;
@@ -292,10 +327,13 @@ cudaError_t launch_mesh_scan(const MeshBuffers &mb, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, float vs,
-                                 cudaStream_t stream) {
+cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, double voxel_length, int unit_shift,
+                                 bool points, cudaStream_t stream) {
     if (mb.n_blocks == 0) return cudaSuccess;
-    mesh_vertices_kernel<<<mb.n_blocks, kVox, 0, stream>>>(meta, mb, vs);
+    if (points)
+        mesh_vertices_kernel<true><<<mb.n_blocks, kVox, 0, stream>>>(meta, mb, voxel_length, unit_shift);
+    else
+        mesh_vertices_kernel<false><<<mb.n_blocks, kVox, 0, stream>>>(meta, mb, voxel_length, unit_shift);
     return cudaGetLastError();
 }
 

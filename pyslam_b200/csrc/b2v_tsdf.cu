@@ -208,10 +208,19 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
                         __dadd_rn(__dadd_rn(__dmul_rn(P.Rwc[3 * a + 0], x), __dmul_rn(P.Rwc[3 * a + 1], y)),
                                   __dmul_rn(P.Rwc[3 * a + 2], z)),
                         P.twc[a]);
-                    const int vlo = voxel_coord(__double2float_rn(__dsub_rn(pw, P.tau_d)), P.inv_vs);
-                    const int vhi = voxel_coord(__double2float_rn(__dadd_rn(pw, P.tau_d)), P.inv_vs);
-                    lo[a] = block_coord(vlo);
-                    n[a] = block_coord(vhi) - lo[a] + 1;
+                    if (P.unit_shift > 0) {
+                        // Open3D ScalableTSDFVolume::LocateVolumeUnit: floor(p / volume_unit_length) in float64;
+                        // every 8^3 block of a touched unit is touched
+                        const int ulo = __double2int_rd(__ddiv_rn(__dsub_rn(pw, P.tau_d), P.unit_len));
+                        const int uhi = __double2int_rd(__ddiv_rn(__dadd_rn(pw, P.tau_d), P.unit_len));
+                        lo[a] = ulo << P.unit_shift;
+                        n[a] = (uhi - ulo + 1) << P.unit_shift;
+                    } else {  // decision D1: pyslam float32 key arithmetic (voxel_hashing.h:69-75, 139-151)
+                        const int vlo = voxel_coord(__double2float_rn(__dsub_rn(pw, P.tau_d)), P.inv_vs);
+                        const int vhi = voxel_coord(__double2float_rn(__dadd_rn(pw, P.tau_d)), P.inv_vs);
+                        lo[a] = block_coord(vlo);
+                        n[a] = block_coord(vhi) - lo[a] + 1;
+                    }
                 }
                 have = true;
             }
@@ -474,28 +483,143 @@ bool encode_frame_maps(FrameMaps *maps, const float *depth, const uint8_t *color
 // projective TSDF + colour update
 // ------------------------------------------------------------------------------------------------
 //
-// One CTA iteration = one touched block: 128 threads x 4 consecutive-x voxels.  A warp reads /
-// writes 512 contiguous bytes per plane (LDG.128 / STG.128), so every block-pool transaction is a
-// full 128-byte line.  The five plane loads of a block are issued first; the projection of the four
-// voxels and their texel gathers (one 16-byte {depth, lambda, rgbx} texel per voxel, packed by
-// allocate_kernel and L2-resident) overlap that HBM latency; the next block's table entry is
-// prefetched one iteration ahead.  Planes are written back only by threads that updated a voxel.
+// Arithmetic = Open3D's UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier in Open3D's own
+// operation order (contract v3; bit-identical in tsdf and weight to oracle/open3d_order.c):
+//   a block is sub-block s = key - (unit << unit_shift) of its volume unit; voxel (x, y, z) of the unit has
+//   x = 8 s.x + lx ...;  centre h = (float)((double)(vl/2 + vl*x) + unit * L) with z taken at the unit's z = 0;
+//   p = ((E0*h0 + E1*h1) + E2*h2) + E3 (no FMA), then p += vl * E[:,2] once per z step (INCREMENTAL);
+//   u_f = p.x*fx / p.z + cx + 0.5 with IEEE divisions; tsdf = (tsdf*w + t) / (w + 1): mul, add, div.
+//
+// One CTA iteration = one touched block: 128 threads, each owning a RUN OF 4 VOXELS ALONG z (so the incremental
+// projection costs three adds per voxel).  A warp's 32 lanes cover lx 0..7 x ly 0..3: every plane access of a
+// warp is one full 128-byte line (LDG.32 / STG.32, coalesced).  The plane loads of a block are issued first; the
+// projections and texel gathers (one 16-byte {depth, lambda, rgbx} texel per voxel, packed by allocate_kernel,
+// L2-resident) overlap that HBM latency.  Planes are written back only by threads that updated a voxel.
 
 constexpr int kIntThreads = 128;
+constexpr int kRun = 4;  // voxels per thread, consecutive in z
+
+// frame-independent geometry of a thread's voxel run
+struct VoxelRun {
+    float h0, h1, h2;  // Open3D voxel-centre coordinates of the column (x, y) and of the UNIT's first z
+    int zskip;         // z steps from the unit's z = 0 to the first voxel of the run
+};
+
+__device__ __forceinline__ VoxelRun voxel_run(const uint4 e, const int t, const VolumeConsts &V) {
+    const int lx = t & 7, ly = (t >> 3) & 7, z0 = (t >> 6) * kRun;
+    const int b[3] = {static_cast<int>(e.x), static_cast<int>(e.y), static_cast<int>(e.z)};
+    int u[3], sb[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        u[a] = b[a] >> V.unit_shift;  // floor division by the blocks per unit side
+        sb[a] = b[a] - (u[a] << V.unit_shift);
+    }
+    VoxelRun r;
+    // float(half_voxel_length_f + voxel_length_f * x + origin_(0)): float product and sum, widened, plus the
+    // float64 unit origin index.cast<double>() * volume_unit_length_, narrowed once
+    r.h0 = __double2float_rn(__dadd_rn(
+        static_cast<double>(__fadd_rn(V.half_vs, __fmul_rn(V.vs, static_cast<float>(sb[0] * kB + lx)))),
+        __dmul_rn(static_cast<double>(u[0]), V.unit_len)));
+    r.h1 = __double2float_rn(__dadd_rn(
+        static_cast<double>(__fadd_rn(V.half_vs, __fmul_rn(V.vs, static_cast<float>(sb[1] * kB + ly)))),
+        __dmul_rn(static_cast<double>(u[1]), V.unit_len)));
+    r.h2 = __double2float_rn(__dadd_rn(static_cast<double>(V.half_vs), __dmul_rn(static_cast<double>(u[2]), V.unit_len)));
+    r.zskip = sb[2] * kB + z0;
+    return r;
+}
+
+// One frame applied to the kRun voxels of a thread.  F lives in kernel-parameter space.
+__device__ __forceinline__ bool apply_frame(const IntFrame &F, const VoxelRun &r, const float *s_rcp, float *ts,
+                                            float *w, float *cr, float *cg, float *cb) {
+    float p0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.E[0], r.h0), __fmul_rn(F.E[1], r.h1)), __fmul_rn(F.E[2], r.h2)), F.E[3]);
+    float p1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.E[4], r.h0), __fmul_rn(F.E[5], r.h1)), __fmul_rn(F.E[6], r.h2)), F.E[7]);
+    float p2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.E[8], r.h0), __fmul_rn(F.E[9], r.h1)), __fmul_rn(F.E[10], r.h2)), F.E[11]);
+    for (int s = 0; s < r.zskip; s += kRun) {  // zskip is a multiple of kRun, uniform across the warp
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) {
+            p0 = __fadd_rn(p0, F.Es[0]);
+            p1 = __fadd_rn(p1, F.Es[1]);
+            p2 = __fadd_rn(p2, F.Es[2]);
+        }
+    }
+    float pz[kRun];
+    int pix[kRun];
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) {
+        pz[k] = p2;
+        pix[k] = -1;
+        if (p2 > 0.0f) {
+            const float u_f = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(p0, F.fxf), p2), F.cxf), 0.5f);
+            const float v_f = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(p1, F.fyf), p2), F.cyf), 0.5f);
+            if (u_f >= 0.0001f && u_f < F.safe_w && v_f >= 0.0001f && v_f < F.safe_h)
+                pix[k] = __float2int_rz(v_f) * F.W + __float2int_rz(u_f);
+        }
+        p0 = __fadd_rn(p0, F.Es[0]);
+        p1 = __fadd_rn(p1, F.Es[1]);
+        p2 = __fadd_rn(p2, F.Es[2]);
+    }
+    float4 tx[kRun];
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) tx[k] = pix[k] >= 0 ? __ldg(F.tex + pix[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bool upd = false;
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) {
+        const float d = tx[k].x;  // 0 where the pixel is invalid (allocate_kernel pre-validates)
+        const float sdf = __fmul_rn(__fsub_rn(d, pz[k]), tx[k].y);
+        if (d > 0.0f && sdf > -F.tau) {
+            const float tv = fminf(1.0f, __fmul_rn(sdf, F.inv_tau));
+            const uint32_t rgbx = __float_as_uint(tx[k].z);
+            const float w0 = w[k];
+            const float wn = __fadd_rn(w0, 1.0f);
+            // colour: float32 running mean with the correctly rounded 1/wn (table for the small integer weights)
+            const float rc = wn < 256.0f ? s_rcp[__float2int_rz(wn)] : __frcp_rn(wn);
+            ts[k] = __fdiv_rn(__fadd_rn(__fmul_rn(ts[k], w0), tv), wn);
+            cr[k] = __fmul_rn(__fmaf_rn(cr[k], w0, static_cast<float>(rgbx & 0xFFu)), rc);
+            cg[k] = __fmul_rn(__fmaf_rn(cg[k], w0, static_cast<float>((rgbx >> 8) & 0xFFu)), rc);
+            cb[k] = __fmul_rn(__fmaf_rn(cb[k], w0, static_cast<float>((rgbx >> 16) & 0xFFu)), rc);
+            w[k] = wn;
+            upd = true;
+        }
+    }
+    return upd;
+}
+
+// plane access of a thread's run: voxel k of the run sits at  base + 64 k  of each 512-float plane
+__device__ __forceinline__ int run_base(const int t) { return (t & 63) + 256 * (t >> 6); }
+
+__device__ __forceinline__ void load_block(const float *blk, float q[kPlanes][kRun]) {
+#pragma unroll
+    for (int c = 0; c < kPlanes; ++c)
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) q[c][k] = blk[c * kVox + 64 * k];
+}
+__device__ __forceinline__ void store_block(float *blk, const float q[kPlanes][kRun]) {
+#pragma unroll
+    for (int c = 0; c < kPlanes; ++c)
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) blk[c * kVox + 64 * k] = q[c][k];
+}
+
+__device__ __forceinline__ void fill_rcp_table(float *s_rcp, int t) {
+    s_rcp[t] = __frcp_rn(static_cast<float>(t));
+    s_rcp[t + 128] = __frcp_rn(static_cast<float>(t + 128));
+}
 
 __global__ void __launch_bounds__(kIntThreads, 8)
-integrate_kernel(const FrameParams P, const float4 *__restrict__ tex, const HashTable T,
+integrate_kernel(const __grid_constant__ IntFrame F, const __grid_constant__ VolumeConsts V, const HashTable T,
                  const PoolMeta M, const int ring) {
+    __shared__ float s_rcp[256];
     const uint32_t n = min(M.counters[kCtrActive0 + ring], M.capacity);
     const uint32_t *__restrict__ act = M.active_slots + static_cast<size_t>(ring) * M.capacity;
     const int t = threadIdx.x;
-    const int lx0 = (t & 1) * 4, ly = (t >> 1) & 7, lz = t >> 4;
+    fill_rcp_table(s_rcp, t);
     if (blockIdx.x == 0 && t == 0) {
         atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrUpdatesLo),
                   static_cast<unsigned long long>(n));
         atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrVisitsLo),
                   static_cast<unsigned long long>(n));
     }
+    __syncthreads();
 
     uint32_t i = blockIdx.x;
     uint4 e = make_uint4(0u, 0u, 0u, kNoBlock);
@@ -506,78 +630,20 @@ integrate_kernel(const FrameParams P, const float4 *__restrict__ tex, const Hash
         if (i_next < n) e_next = T.entries[act[i_next]];  // in flight during this iteration
 
         if (e.w < M.capacity) {  // (>= capacity: the pool overflowed for this key)
-            float *blk = M.pool + static_cast<size_t>(e.w) * kBlockFloats + t * 4;
-            float4 q[kPlanes];
-#pragma unroll
-            for (int c = 0; c < kPlanes; ++c) q[c] = *reinterpret_cast<const float4 *>(blk + c * kVox);
-
-            const int vx0 = static_cast<int>(e.x) * kB + lx0;
-            const float cy = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.y) * kB + ly), 0.5f), P.vs);
-            const float cz = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.z) * kB + lz), 0.5f), P.vs);
-            // row part of E * c, shared by the voxels of one x-row (contract: fmaf(E0, cx, A))
-            const float ax = __fmaf_rn(P.E[1], cy, __fmaf_rn(P.E[2], cz, P.E[3]));
-            const float ay = __fmaf_rn(P.E[5], cy, __fmaf_rn(P.E[6], cz, P.E[7]));
-            const float az = __fmaf_rn(P.E[9], cy, __fmaf_rn(P.E[10], cz, P.E[11]));
-
-            float pzs[4];
-            int pix[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float cx = __fmul_rn(__fadd_rn(static_cast<float>(vx0 + k), 0.5f), P.vs);
-                const float px = __fmaf_rn(P.E[0], cx, ax);
-                const float py = __fmaf_rn(P.E[4], cx, ay);
-                const float pz = __fmaf_rn(P.E[8], cx, az);
-                pzs[k] = pz;
-                pix[k] = -1;
-                if (pz > 0.0f) {
-                    const float inv_z = __frcp_rn(pz);
-                    const float u_f = __fmaf_rn(__fmul_rn(px, P.fxf), inv_z, P.cxh);
-                    const float v_f = __fmaf_rn(__fmul_rn(py, P.fyf), inv_z, P.cyh);
-                    if (u_f >= 0.0001f && u_f < P.safe_w && v_f >= 0.0001f && v_f < P.safe_h)
-                        pix[k] = __float2int_rz(v_f) * P.W + __float2int_rz(u_f);
-                }
-            }
-            float4 tx[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tx[k] = pix[k] >= 0 ? __ldg(tex + pix[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-
-            float *ts = reinterpret_cast<float *>(&q[0]);
-            float *w = reinterpret_cast<float *>(&q[1]);
-            float *cr = reinterpret_cast<float *>(&q[2]);
-            float *cg = reinterpret_cast<float *>(&q[3]);
-            float *cb = reinterpret_cast<float *>(&q[4]);
-            bool upd = false;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float d = tx[k].x;  // 0 where the pixel is invalid (allocate_kernel pre-validates)
-                const float sdf = __fmul_rn(__fsub_rn(d, pzs[k]), tx[k].y);
-                if (d > 0.0f && sdf > -P.tau) {
-                    const float tv = fminf(1.0f, __fmul_rn(sdf, P.inv_tau));
-                    const uint32_t rgbx = __float_as_uint(tx[k].z);
-                    const float w0 = w[k];
-                    const float wn = __fadd_rn(w0, 1.0f);
-                    const float r = __frcp_rn(wn);
-                    ts[k] = __fmul_rn(__fmaf_rn(ts[k], w0, tv), r);
-                    cr[k] = __fmul_rn(__fmaf_rn(cr[k], w0, static_cast<float>(rgbx & 0xFFu)), r);
-                    cg[k] = __fmul_rn(__fmaf_rn(cg[k], w0, static_cast<float>((rgbx >> 8) & 0xFFu)), r);
-                    cb[k] = __fmul_rn(__fmaf_rn(cb[k], w0, static_cast<float>((rgbx >> 16) & 0xFFu)), r);
-                    w[k] = wn;
-                    upd = true;
-                }
-            }
-            if (upd) {
-#pragma unroll
-                for (int c = 0; c < kPlanes; ++c) *reinterpret_cast<float4 *>(blk + c * kVox) = q[c];
-            }
+            float *blk = M.pool + static_cast<size_t>(e.w) * kBlockFloats + run_base(t);
+            float q[kPlanes][kRun];
+            load_block(blk, q);
+            const VoxelRun r = voxel_run(e, t, V);
+            if (apply_frame(F, r, s_rcp, q[0], q[1], q[2], q[3], q[4])) store_block(blk, q);
         }
         e = e_next;
         i = i_next;
     }
 }
 
-cudaError_t launch_integrate(const FrameParams &p, const float4 *texels, const HashTable &table,
+cudaError_t launch_integrate(const FrameParams &p, const VolumeConsts &vc, const HashTable &table,
                              const PoolMeta &meta, int ring, int grid_ctas, cudaStream_t stream) {
-    integrate_kernel<<<grid_ctas, kIntThreads, 0, stream>>>(p, texels, table, meta, ring);
+    integrate_kernel<<<grid_ctas, kIntThreads, 0, stream>>>(p.I, vc, table, meta, ring);
     return cudaGetLastError();
 }
 
@@ -586,70 +652,12 @@ cudaError_t launch_integrate(const FrameParams &p, const float4 *texels, const H
 // frame order while it sits in registers, and it is stored once.  Per voxel the arithmetic is the
 // same sequence as frame-by-frame integration, so results are bit-identical; HBM traffic per frame
 // drops by the group's overlap factor (consecutive keyframes see mostly the same blocks).
+// The per-frame constants are read straight from the kernel-parameter (constant) bank: the frame loop is
+// unrolled over the 8 slots of the group, so every constant is an immediate-offset uniform operand.
 // ------------------------------------------------------------------------------------------------
-// One frame applied to the four voxels of a thread: projection + texel gathers, then the update.  (A variant that
-// kept the NEXT frame's gathers in flight while updating - meant for hash-sharded ranks with few blocks per
-// launch - was measured slower at every shard count, 128 k vs 138 k frames/s per 8-way rank, and was removed.)
-struct GroupTexels {
-    float4 tx[4];
-    float pz[4];
-};
-
-__device__ __forceinline__ void group_project(const IntFrame &F, const float cx[4], float cy, float cz,
-                                              GroupTexels &g) {
-    const float ax = __fmaf_rn(F.E[1], cy, __fmaf_rn(F.E[2], cz, F.E[3]));
-    const float ay = __fmaf_rn(F.E[5], cy, __fmaf_rn(F.E[6], cz, F.E[7]));
-    const float az = __fmaf_rn(F.E[9], cy, __fmaf_rn(F.E[10], cz, F.E[11]));
-    int pix[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float px = __fmaf_rn(F.E[0], cx[k], ax);
-        const float py = __fmaf_rn(F.E[4], cx[k], ay);
-        const float pz = __fmaf_rn(F.E[8], cx[k], az);
-        g.pz[k] = pz;
-        pix[k] = -1;
-        if (pz > 0.0f) {
-            const float inv_z = __frcp_rn(pz);
-            const float u_f = __fmaf_rn(__fmul_rn(px, F.fxf), inv_z, F.cxh);
-            const float v_f = __fmaf_rn(__fmul_rn(py, F.fyf), inv_z, F.cyh);
-            if (u_f >= 0.0001f && u_f < F.safe_w && v_f >= 0.0001f && v_f < F.safe_h)
-                pix[k] = __float2int_rz(v_f) * F.W + __float2int_rz(u_f);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) g.tx[k] = pix[k] >= 0 ? __ldg(F.tex + pix[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-__device__ __forceinline__ bool group_update(const IntFrame &F, const GroupTexels &g, const float *s_rcp, float *ts,
-                                             float *w, float *cr, float *cg, float *cb) {
-    bool upd = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float d = g.tx[k].x;
-        const float sdf = __fmul_rn(__fsub_rn(d, g.pz[k]), g.tx[k].y);
-        if (d > 0.0f && sdf > -F.tau) {
-            const float tv = fminf(1.0f, __fmul_rn(sdf, F.inv_tau));
-            const uint32_t rgbx = __float_as_uint(g.tx[k].z);
-            const float w0 = w[k];
-            const float wn = __fadd_rn(w0, 1.0f);
-            // 1/wn: weights are small integers, so the correctly rounded reciprocal comes
-            // from a table (same value __frcp_rn would give); large weights take the slow path
-            const float r = wn < 256.0f ? s_rcp[__float2int_rz(wn)] : __frcp_rn(wn);
-            ts[k] = __fmul_rn(__fmaf_rn(ts[k], w0, tv), r);
-            cr[k] = __fmul_rn(__fmaf_rn(cr[k], w0, static_cast<float>(rgbx & 0xFFu)), r);
-            cg[k] = __fmul_rn(__fmaf_rn(cg[k], w0, static_cast<float>((rgbx >> 8) & 0xFFu)), r);
-            cb[k] = __fmul_rn(__fmaf_rn(cb[k], w0, static_cast<float>((rgbx >> 16) & 0xFFu)), r);
-            w[k] = wn;
-            upd = true;
-        }
-    }
-    return upd;
-}
-
 __global__ void __launch_bounds__(kIntThreads, 8)
 integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, const PoolMeta M,
                        const int gbuf) {
-    __shared__ IntFrame s_f[kMaxGroup];   // per-frame constants (dynamic indexing by frame bit)
     __shared__ float s_rcp[256];          // correctly rounded 1/n for the small integer weights
     __shared__ uint32_t s_next;           // work-stealing: next list position of this CTA
     const uint32_t n = min(M.counters[group_ctr(gbuf, kGcUnion)], M.capacity);
@@ -657,14 +665,7 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
     const uint32_t *__restrict__ mask = M.group_mask + static_cast<size_t>(gbuf) * (static_cast<size_t>(T.mask) + 1);
     uint32_t *cursor = M.counters + group_ctr(gbuf, kGcNext);
     const int t = threadIdx.x;
-    const int lx0 = (t & 1) * 4, ly = (t >> 1) & 7, lz = t >> 4;
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.f);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(s_f);
-        for (int k = t; k < static_cast<int>(sizeof(IntFrame) * kMaxGroup / 4); k += kIntThreads) dst[k] = src[k];
-        s_rcp[t] = __frcp_rn(static_cast<float>(t));
-        s_rcp[t + 128] = __frcp_rn(static_cast<float>(t + 128));
-    }
+    fill_rcp_table(s_rcp, t);
     if (blockIdx.x == 0 && t == 0)
         atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrVisitsLo),
                   static_cast<unsigned long long>(n));
@@ -694,35 +695,15 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
         if (t < kMaxGroup) my_cnt += (m >> t) & 1u;
 
         if (e.w < M.capacity) {
-            float *blk = M.pool + static_cast<size_t>(e.w) * kBlockFloats + t * 4;
-            float4 q[kPlanes];
-#pragma unroll
-            for (int c = 0; c < kPlanes; ++c) q[c] = *reinterpret_cast<const float4 *>(blk + c * kVox);
-            float *ts = reinterpret_cast<float *>(&q[0]);
-            float *w = reinterpret_cast<float *>(&q[1]);
-            float *cr = reinterpret_cast<float *>(&q[2]);
-            float *cg = reinterpret_cast<float *>(&q[3]);
-            float *cb = reinterpret_cast<float *>(&q[4]);
-
-            // voxel centres are frame independent
-            const int vx0 = static_cast<int>(e.x) * kB + lx0;
-            float cx[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cx[k] = __fmul_rn(__fadd_rn(static_cast<float>(vx0 + k), 0.5f), A.vs);
-            const float cy = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.y) * kB + ly), 0.5f), A.vs);
-            const float cz = __fmul_rn(__fadd_rn(static_cast<float>(static_cast<int>(e.z) * kB + lz), 0.5f), A.vs);
-
+            float *blk = M.pool + static_cast<size_t>(e.w) * kBlockFloats + run_base(t);
+            float q[kPlanes][kRun];
+            load_block(blk, q);
+            const VoxelRun r = voxel_run(e, t, A.V);
             bool upd = false;
-            for (uint32_t mm = m; mm; mm &= mm - 1) {  // ascending bits = frame order
-                const IntFrame &F = s_f[__ffs(mm) - 1];
-                GroupTexels g;
-                group_project(F, cx, cy, cz, g);
-                upd |= group_update(F, g, s_rcp, ts, w, cr, cg, cb);
-            }
-            if (upd) {
 #pragma unroll
-                for (int c = 0; c < kPlanes; ++c) *reinterpret_cast<float4 *>(blk + c * kVox) = q[c];
-            }
+            for (int k = 0; k < kMaxGroup; ++k)  // ascending bits = frame order
+                if ((m >> k) & 1u) upd |= apply_frame(A.f[k], r, s_rcp, q[0], q[1], q[2], q[3], q[4]);
+            if (upd) store_block(blk, q);
         }
         e = e_next;
         m = m_next;
@@ -763,9 +744,10 @@ int integrate_max_resident_ctas_per_sm() {
 __global__ void lambda_kernel(const FrameParams P, float *__restrict__ lam) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
     if (u >= P.W) return;
-    const float xx = __fmul_rn(__fsub_rn(static_cast<float>(u), P.cxf), P.inv_fx);
-    const float yy = __fmul_rn(__fsub_rn(static_cast<float>(v), P.cyf), P.inv_fy);
-    lam[static_cast<size_t>(v) * P.W + u] = __fsqrt_rn(__fmaf_rn(xx, xx, __fmaf_rn(yy, yy, 1.0f)));
+    const float xx = __fmul_rn(__fsub_rn(static_cast<float>(u), P.I.cxf), P.inv_fx);
+    const float yy = __fmul_rn(__fsub_rn(static_cast<float>(v), P.I.cyf), P.inv_fy);
+    lam[static_cast<size_t>(v) * P.W + u] =
+        __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy)), 1.0f));  // Open3D: sqrtf(xx*xx + yy*yy + 1)
 }
 
 cudaError_t launch_lambda(const FrameParams &p, float *lam, cudaStream_t stream) {

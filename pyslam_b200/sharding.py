@@ -112,7 +112,8 @@ def extract_mesh_distributed(volume, dst: int = 0, group=None, device=None, capa
         return None
     cap = capacity_blocks or max(2 * len(keys), 1024)
     scratch = B200TsdfVolume(volume.voxel_length, volume.sdf_trunc, volume.depth_trunc,
-                             capacity_blocks=cap, device=volume.device)
+                             capacity_blocks=cap, device=volume.device,
+                             volume_unit_resolution=volume.volume_unit_resolution)
     if on_device:
         scratch.import_blocks_torch(keys, vox)
     else:

@@ -76,7 +76,11 @@ class B200TsdfVolume:
 
     def __init__(self, voxel_length: float, sdf_trunc: float, depth_trunc: float = 4.0,
                  capacity_blocks: int = 1 << 18, device: int = 0, depth_sampling_stride: int = 4,
-                 block_size: int = BLOCK_SIZE, shard_rank: int = 0, shard_count: int = 1):
+                 block_size: int = BLOCK_SIZE, shard_rank: int = 0, shard_count: int = 1,
+                 volume_unit_resolution: int = 16):
+        """`volume_unit_resolution`: Open3D's parameter of that name.  16 (the reference's value) allocates every
+        8^3 block of each 16^3 unit `ScalableTSDFVolume::LocateVolumeUnit` touches - the same voxels Open3D updates;
+        8 is SURVEY decision D1 (the float32 pyslam key range of the +-sdf_trunc box, ~9 % fewer blocks)."""
         self._L = _lib.load()
         self._h = C.c_void_p()
         self.voxel_length = float(voxel_length)
@@ -86,8 +90,10 @@ class B200TsdfVolume:
         self.capacity_blocks = int(capacity_blocks)
         self.device = int(device)
         self.shard_rank, self.shard_count = int(shard_rank), int(shard_count)
+        self.volume_unit_resolution = int(volume_unit_resolution)
         cfg = B2VConfig(voxel_length, block_size, sdf_trunc, depth_trunc, depth_sampling_stride,
-                        capacity_blocks, device, shard_rank, shard_count)
+                        capacity_blocks, device, shard_rank, shard_count, int(volume_unit_resolution),
+                        float(voxel_length), float(sdf_trunc))
         rc = self._L.b2v_create(C.byref(cfg), C.byref(self._h))
         if rc != _lib.B2V_OK:
             msg = self._L.b2v_last_error(self._h).decode() if self._h else "invalid configuration"
@@ -332,23 +338,23 @@ class B200TsdfVolume:
         """north_star `extract_mesh()` == Open3D `extract_triangle_mesh()` (tsdf.py:239,260)."""
         nv, nt = C.c_int64(0), C.c_int64(0)
         self._check(self._L.b2v_extract_mesh(self._h, C.byref(nv), C.byref(nt)), "b2v_extract_mesh")
-        V = np.zeros((nv.value, 3), np.float32)
-        Cc = np.zeros((nv.value, 3), np.float32)
+        V = np.zeros((nv.value, 3), np.float64)   # float64 like Open3D's TriangleMesh, computed in float64
+        Cc = np.zeros((nv.value, 3), np.float64)
         E = np.zeros((nv.value, 4), np.int32)
         T = np.zeros((nt.value, 3), np.int32)
         self._check(self._L.b2v_copy_mesh(self._h, V.ctypes.data, Cc.ctypes.data, E.ctypes.data,
                                           T.ctypes.data), "b2v_copy_mesh")
-        return TriangleMesh(V.astype(np.float64), T, Cc.astype(np.float64), E)
+        return TriangleMesh(V, T, Cc, E)
 
     extract_triangle_mesh = extract_mesh
 
     def extract_point_cloud(self) -> PointCloud:
         n = C.c_int64(0)
         self._check(self._L.b2v_extract_points(self._h, C.byref(n)), "b2v_extract_points")
-        P = np.zeros((n.value, 3), np.float32)
-        Cc = np.zeros((n.value, 3), np.float32)
+        P = np.zeros((n.value, 3), np.float64)
+        Cc = np.zeros((n.value, 3), np.float64)
         self._check(self._L.b2v_copy_points(self._h, P.ctypes.data, Cc.ctypes.data), "b2v_copy_points")
-        return PointCloud(P.astype(np.float64), Cc.astype(np.float64))
+        return PointCloud(P, Cc)
 
 
 def filter_shadow_points(depth, delta_depth=None, delta_x=2, delta_y=2, fill_value=-1, device=0):

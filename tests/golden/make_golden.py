@@ -1,10 +1,14 @@
 """Regenerate the committed golden fixtures (run in the build container, where /root/reference
 exists):  python tests/golden/make_golden.py
 
-tsdf_T0.npz     inputs (depth, colour, poses of 4 T0 frames) + the C oracle's outputs
-                (sorted block keys, reference BlockKeyHash, voxel planes, per-frame touched sets,
-                canonical welded mesh).  Producer: oracle/tsdf_oracle.c (restatement; Open3D itself
-                is not available -> "parity unpinned" at that boundary).
+tsdf_T0.npz     inputs (depth, colour, poses of 4 T0 frames) + the outputs of BOTH restatements of Open3D's
+                ScalableTSDFVolume(voxel, trunc, RGB8, 16, 4): sorted block keys, reference BlockKeyHash, voxel
+                planes, per-frame touched sets, canonical welded mesh from oracle/tsdf_oracle.c (block based, the
+                kernels' arithmetic contract v3), checked here - before anything is written - to be bit-identical
+                in keys, tsdf, weight, mesh topology and vertex positions to oracle/open3d_order.c (the literal
+                unit-based restatement, whose float64 colours are stored as `o3d_rgb64`).  Open3D itself is not
+                available -> parity vs a RUNNING Open3D stays unpinned.   `python make_golden.py tsdf` remakes
+                this file only.
 refgrid_T0.npz  world-space float32 points / colours derived from the same frames the way the
                 reference front-end does (pyslam/utilities/depth.py:45-85,
                 pyslam/dense/volumetric_integrator_voxel_grid.py:262-281) + the outputs of the
@@ -62,9 +66,24 @@ def main():
     cm = oracle.canonical_mesh(m["vertices"], m["colors"], m["edges"], m["triangles"])
     out.update(mesh_vertices=cm["vertices"], mesh_colors=cm["colors"], mesh_edges=cm["edges"],
                mesh_triangles=cm["triangles"])
+    # the literal Open3D-order restatement must agree before the fixture is written
+    o3 = oracle.Open3DOrderVolume(cfg.voxel_size, cfg.sdf_trunc, 16, 4)
+    for d, c, T in frames:
+        o3.integrate(d, c, cfg.K, T, cfg.depth_trunc)
+    d3 = sort_dump(o3.dump_blocks())
+    assert np.array_equal(d3["keys"], dump["keys"])
+    assert np.array_equal(d3["vox"][:, :2], dump["vox"][:, :2].astype(np.float64)), "tsdf / weight differ"
+    assert np.abs(d3["vox"][:, 2:] - dump["vox"][:, 2:]).max() < 1e-4
+    m3 = o3.extract_triangle_mesh()
+    c3 = oracle.canonical_mesh(m3["vertices"], m3["colors"], m3["edges"], m3["triangles"])
+    assert np.array_equal(c3["edges"], cm["edges"]) and np.array_equal(c3["triangles"], cm["triangles"])
+    assert np.array_equal(c3["vertices"], cm["vertices"]) and np.abs(c3["colors"] - cm["colors"]).max() < 1e-6
+    out.update(o3d_rgb64=d3["vox"][:, 2:], o3d_mesh_colors=c3["colors"], contract=3)
     np.savez_compressed(os.path.join(GOLDEN, "tsdf_T0.npz"), **out)
     print("tsdf_T0:", len(dump["keys"]), "blocks,", len(cm["vertices"]), "vertices,",
           len(cm["triangles"]), "triangles")
+    if len(sys.argv) > 1 and sys.argv[1] == "tsdf":
+        return
 
     assert oracle.have_ref(), "the compiled reference is required to make refgrid_T0.npz"
     g = oracle.RefGrid(cfg.voxel_size, 8)

@@ -48,7 +48,7 @@ def _worker(rank, world, port, q):
             ob = np.lexsort((ref["keys"][:, 2], ref["keys"][:, 1], ref["keys"][:, 0]))
             ok = np.array_equal(gk[oa], ref["keys"][ob]) and np.array_equal(gv[oa], ref["vox"][ob])
             rm = orc.extract_mesh()
-            a = oracle.canonical_mesh(mesh.vertices.astype(np.float32), mesh.vertex_colors.astype(np.float32),
+            a = oracle.canonical_mesh(mesh.vertices, mesh.vertex_colors,
                                       mesh.edge_ids, mesh.triangles)
             b = oracle.canonical_mesh(rm["vertices"], rm["colors"], rm["edges"], rm["triangles"])
             ok = ok and all(np.array_equal(a[n], b[n]) for n in ("edges", "triangles", "vertices", "colors"))

@@ -1,8 +1,8 @@
-"""GPU: parity of the CUDA TSDF path (through the C ABI) against the CPU oracle and the golden
-fixtures.  Bars: block keys, hashes, touched sets, weights, triangle topology and
-canonical edge ids are BIT-EXACT; tsdf / rgb / vertex values are bit-exact against the oracle
-(both sides execute the same IEEE operations), and within the stated float tolerances
-(tsdf 1e-5, rgb 0.5/255, vertices 1e-6 m) of the independent float64 formulas."""
+"""GPU: parity of the CUDA TSDF path (through the C ABI) against the CPU twin (oracle/tsdf_oracle.c) and the
+golden fixtures.  Bars: block keys, hashes, touched sets, weights, tsdf, rgb, triangle topology,
+canonical edge ids and float64 vertex positions / colours are BIT-EXACT against the twin (both sides execute the
+same IEEE operations in Open3D's order).  The comparison with the literal Open3D-order restatement
+(oracle/open3d_order.c) is tests/test_gpu_open3d.py."""
 
 import os
 
@@ -17,10 +17,10 @@ from tests._util import GOLDEN, blocks_checksum, sort_dump, sorted_keys
 pytestmark = pytest.mark.gpu
 
 
-def _pair(cfg, capacity=1 << 15, stride=4):
+def _pair(cfg, capacity=1 << 15, stride=4, unit=16):
     vol = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=capacity,
-                         depth_sampling_stride=stride)
-    orc = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, stride=stride)
+                         depth_sampling_stride=stride, volume_unit_resolution=unit)
+    orc = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, stride=stride, unit_resolution=unit)
     return vol, orc
 
 
@@ -48,7 +48,7 @@ def test_golden_fixture_bit_exact():
     assert np.array_equal(d["hashes"], g["hashes"])
     assert np.array_equal(d["vox"], g["vox"])
     m = vol.extract_mesh()
-    cm = oracle.canonical_mesh(m.vertices.astype(np.float32), m.vertex_colors.astype(np.float32),
+    cm = oracle.canonical_mesh(m.vertices, m.vertex_colors,
                                m.edge_ids, m.triangles)
     assert np.array_equal(cm["edges"], g["mesh_edges"])
     assert np.array_equal(cm["triangles"], g["mesh_triangles"])
@@ -57,17 +57,20 @@ def test_golden_fixture_bit_exact():
     assert m.vertex_normals.shape == (0, 3)
 
 
-@pytest.mark.parametrize("cfg_name,frames,stride", [
-    ("T0", list(range(6)), 4),
-    ("T0", [0, 3], 1),                 # stride-1 superset mode
-    ("C1", [0, 1, 2, 50], 4),          # config 1 shape: 320x240, 1 cm
-    ("C4", [0, 1], 4),                 # ScanNet shape, 4 mm
-    ("C3", [0], 4),                    # Replica shape 1200x680, 5 mm
-    ("C5", [0, 40], 4),                # KITTI shape 1241x376 (W % 16 != 0: plain-load path), 10 cm, tau 0.4
+@pytest.mark.parametrize("cfg_name,frames,stride,unit", [
+    ("T0", list(range(6)), 4, 16),
+    ("T0", list(range(6)), 4, 8),      # decision D1: float32 pyslam key range, 8^3 units
+    ("T0", [0, 3], 1, 16),             # stride-1 superset mode
+    ("C1", [0, 1, 2, 50], 4, 16),      # config 1 shape: 320x240, 1 cm
+    ("C1", [0, 1, 2, 50], 4, 8),
+    ("C4", [0, 1], 4, 16),             # ScanNet shape, 4 mm
+    ("C3", [0], 4, 16),                # Replica shape 1200x680, 5 mm
+    ("C5", [0, 40], 4, 16),            # KITTI shape 1241x376 (W % 16 != 0: plain-load path), 10 cm, tau 0.4
+    ("C5", [0, 40], 4, 8),
 ])
-def test_integrate_matches_oracle(cfg_name, frames, stride):
+def test_integrate_matches_oracle(cfg_name, frames, stride, unit):
     cfg = S.CONFIGS[cfg_name]
-    vol, orc = _pair(cfg, capacity=1 << 16, stride=stride)
+    vol, orc = _pair(cfg, capacity=1 << 16, stride=stride, unit=unit)
     total_new = 0
     for i in frames:
         d, c, T = S.render_frame(cfg, i)
@@ -104,7 +107,7 @@ def test_full_size_tum_frames_match_oracle_and_properties():
     assert np.array_equal(a["hashes"], k[:, 0] ^ (k[:, 1] << np.uint64(1)) ^ (k[:, 2] << np.uint64(2)))
 
 
-def test_mesh_matches_oracle_and_float64_formula():
+def test_mesh_matches_oracle_in_float64():
     cfg = S.CONFIGS["C1"]
     vol, orc = _pair(cfg, capacity=1 << 15)
     for i in (0, 1, 2, 3):
@@ -114,16 +117,15 @@ def test_mesh_matches_oracle_and_float64_formula():
     m = vol.extract_mesh()
     ref = orc.extract_mesh()
     assert len(m.vertices) == len(ref["vertices"]) and len(m.triangles) == len(ref["triangles"]) > 1000
-    a = oracle.canonical_mesh(m.vertices.astype(np.float32), m.vertex_colors.astype(np.float32),
+    a = oracle.canonical_mesh(m.vertices, m.vertex_colors,
                               m.edge_ids, m.triangles)
     b = oracle.canonical_mesh(ref["vertices"], ref["colors"], ref["edges"], ref["triangles"])
     assert np.array_equal(a["edges"], b["edges"])
     assert np.array_equal(a["triangles"], b["triangles"])
     assert np.array_equal(a["vertices"], b["vertices"])
     assert np.array_equal(a["colors"], b["colors"])
-    b64 = oracle.canonical_mesh(ref["vertices64"], ref["colors"], ref["edges"], ref["triangles"])
-    assert np.max(np.abs(a["vertices"].astype(np.float64) - b64["vertices"])) < 1e-6  # metres
-    assert a["colors"].min() >= 0.0 and a["colors"].max() <= 1.0 + 1e-6  # fp32 blend of 255/255
+    assert m.vertices.dtype == np.float64 and m.vertex_colors.dtype == np.float64   # like Open3D's TriangleMesh
+    assert a["colors"].min() >= 0.0 and a["colors"].max() <= 1.0 + 1e-12
     # a second extraction of the same volume is identical (deterministic count -> scan -> emit)
     m2 = vol.extract_mesh()
     assert np.array_equal(m.triangles, m2.triangles) and np.array_equal(m.vertices, m2.vertices)
@@ -164,7 +166,7 @@ def test_upload_dump_round_trip_and_sphere_mesh():
     for k, v in zip(keys, vox):
         orc.set_block(k, v)
     ref = orc.extract_mesh()
-    a = oracle.canonical_mesh(m.vertices.astype(np.float32), m.vertex_colors.astype(np.float32),
+    a = oracle.canonical_mesh(m.vertices, m.vertex_colors,
                               m.edge_ids, m.triangles)
     b = oracle.canonical_mesh(ref["vertices"], ref["colors"], ref["edges"], ref["triangles"])
     for name in ("edges", "triangles", "vertices", "colors"):
@@ -476,9 +478,9 @@ def test_device_block_export_import_round_trip():
     da, db = sort_dump(a.dump_blocks()), sort_dump(b.dump_blocks())
     assert np.array_equal(da["keys"], db["keys"]) and np.array_equal(da["vox"], db["vox"])
     ma, mb = a.extract_mesh(), b.extract_mesh()
-    ca = oracle.canonical_mesh(ma.vertices.astype(np.float32), ma.vertex_colors.astype(np.float32), ma.edge_ids,
+    ca = oracle.canonical_mesh(ma.vertices, ma.vertex_colors, ma.edge_ids,
                                ma.triangles)
-    cb = oracle.canonical_mesh(mb.vertices.astype(np.float32), mb.vertex_colors.astype(np.float32), mb.edge_ids,
+    cb = oracle.canonical_mesh(mb.vertices, mb.vertex_colors, mb.edge_ids,
                                mb.triangles)
     for n in ("edges", "triangles", "vertices", "colors"):
         assert np.array_equal(ca[n], cb[n]), n

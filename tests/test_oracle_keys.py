@@ -88,7 +88,7 @@ def test_reference_grid_block_keys_equal_oracle_allocation_lattice():
     from pyslam_b200 import synthetic as S
     cfg = S.CONFIGS["T0"]
     d, c, T = S.render_frame(cfg, 1)
-    o = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc)
+    o = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, unit_resolution=8)  # decision D1
     o.integrate(d, c, cfg.K, T)
     dump = o.dump_blocks()
     # rebuild the lattice points exactly as the oracle does (float64 -> float32)

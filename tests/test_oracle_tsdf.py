@@ -1,8 +1,9 @@
-"""CPU: pin the C restatement of the TSDF path (oracle/tsdf_oracle.c).
+"""CPU: pin the block-based C restatement of the TSDF path (oracle/tsdf_oracle.c, the kernels' twin).
 
-Open3D itself is absent (PARITY UNPINNED at that boundary), so the C oracle is
-pinned by (1) an independent numpy restatement of Appendix A.2/A.3, (2) analytic properties of the
-marching-cubes output on a sphere SDF, (3) committed golden fixtures."""
+A running Open3D is absent, so the twin is pinned by (0) bit-equality with the literal
+Open3D-order restatement oracle/open3d_order.c (tests/test_oracle_open3d.py), (1) a third, numpy restatement of
+Appendix A.2/A.3 written in plain matrix-vector order, (2) analytic properties of the marching-cubes output on a
+sphere SDF, (3) committed golden fixtures."""
 
 import os
 
@@ -26,8 +27,9 @@ def _run(cfg, frames, stride=4):
 
 @pytest.mark.parametrize("cfg_name,frames", [("T0", [0, 1, 2]), ("C1", [0])])
 def test_touched_sets_match_numpy_restatement(cfg_name, frames):
+    """decision D1 (volume_unit_resolution 8): blocks in the float32 pyslam key range of the +-tau box"""
     cfg = S.CONFIGS[cfg_name]
-    o = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc)
+    o = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, unit_resolution=8)
     for i in frames:
         d, c, T = S.render_frame(cfg, i)
         n = o.integrate(d, c, cfg.K, T)
@@ -37,10 +39,12 @@ def test_touched_sets_match_numpy_restatement(cfg_name, frames):
 
 
 def test_values_match_numpy_restatement_over_three_frames():
-    """tsdf within 1e-5 (SURVEY.md §8c tolerance; 1 ulp of z / tau), rgb within 2e-3 of 255; weights exact.
-    (numpy has no FMA, projects through float64 and uses true divisions.)"""
+    """A third restatement in plain matrix-vector order (numpy, projects through float64): Open3D's own
+    incremental `p += vl*E[:,2]` accumulates up to 16 float32 roundings of p.z (~0.25 um each at 2-4 m), i.e. up to
+    ~1e-4 in tsdf = sdf / 0.04 against exact arithmetic - so this check is 2e-4, weights exact, rgb 2e-3 of 255.
+    The 1e-5 tolerance of SURVEY.md 8c is met (exceeded: bit-equality) against the Open3D-ORDER oracle instead."""
     cfg = S.CONFIGS["T0"]
-    o = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc)
+    o = oracle.TsdfOracle(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, unit_resolution=8)
     state = {}
     for i in range(3):
         d, c, T = S.render_frame(cfg, i)
@@ -56,7 +60,7 @@ def test_values_match_numpy_restatement_over_three_frames():
         ref = state[k]
         # a voxel whose projection lands within float rounding of a pixel boundary may sample the
         # neighbouring pixel in one of the two restatements: count those, require them to be rare
-        bad = (v[1] != ref[1]) | (np.abs(v[0] - ref[0]) > 1e-5) | \
+        bad = (v[1] != ref[1]) | (np.abs(v[0] - ref[0]) > 2e-4) | \
               (np.max(np.abs(v[2:] - ref[2:]), axis=0) > 2e-3)
         n_bad += int(bad.sum())
         n_upd += int((v[1] > 0).sum())
@@ -94,7 +98,7 @@ def test_marching_cubes_sphere_is_closed_oriented_and_accurate():
     o = oracle.TsdfOracle(vs, tau, 4.0)
     _sphere_volume(o, r, vs, tau)
     m = o.extract_mesh()
-    V, T = m["vertices64"], m["triangles"]
+    V, T = m["vertices"], m["triangles"]
     assert len(T) > 5000
     # welded: every edge id is unique
     assert len(np.unique(m["edges"], axis=0)) == len(V)
@@ -118,9 +122,8 @@ def test_marching_cubes_sphere_is_closed_oriented_and_accurate():
     # A.4 winding (i, i+2, i+1): normals point towards positive SDF (outside)
     assert signed_vol > 0
     # colour blend of a constant colour is that colour / 255
-    assert np.allclose(m["colors"], np.array([200, 100, 50]) / 255.0, atol=1e-6)
-    # f32 contract arithmetic vs Open3D's f64 formula
-    assert np.max(np.abs(m["vertices"].astype(np.float64) - V)) < 2e-7
+    assert np.allclose(m["colors"], np.array([200, 100, 50]) / 255.0, atol=1e-12)
+    assert V.dtype == np.float64
 
 
 def test_mesh_skips_cubes_with_unobserved_corners():
@@ -151,7 +154,7 @@ def test_oracle_reproduces_golden_fixture():
     d = sort_dump(o.dump_blocks())
     assert np.array_equal(d["keys"], g["keys"])
     assert np.array_equal(d["hashes"], g["hashes"])
-    assert np.array_equal(d["vox"], g["vox"])  # IEEE arithmetic with explicit fmaf: bit-exact
+    assert np.array_equal(d["vox"], g["vox"])  # IEEE arithmetic, no contraction: bit-exact across machines
     m = o.extract_mesh()
     cm = oracle.canonical_mesh(m["vertices"], m["colors"], m["edges"], m["triangles"])
     assert np.array_equal(cm["edges"], g["mesh_edges"])
