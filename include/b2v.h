@@ -109,6 +109,9 @@ int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches
  * Results are bit-identical either way.  Synchronises. */
 int b2v_set_overlap(b2v_volume *v, int32_t enable);
 int b2v_set_fusion(b2v_volume *v, int32_t enable);
+/* frames per fused group of b2v_integrate_batch: 1..32, default 8.  Larger groups amortise launch and latency costs
+ * (hash-sharded ranks with few blocks each); results do not depend on it.  Synchronises. */
+int b2v_set_group_size(b2v_volume *v, int32_t frames);
 /* Per-kernel device timing (CUDA events on the launching stream around each launch), for the
  * roofline figure: enable, run frames, then read the summed durations (synchronises, resets). */
 int b2v_profile_enable(b2v_volume *v, int32_t enable);

@@ -32,10 +32,10 @@ void fill_frame_params(FrameParams *p, const double K[4], const double Tcw[16], 
     p->cx = K[2];
     p->cy = K[3];
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) p->Rwc[3 * i + j] = Tcw[4 * j + i];
+        for (int j = 0; j < 3; ++j) p->pose.Rwc[3 * i + j] = Tcw[4 * j + i];
     for (int i = 0; i < 3; ++i)
-        p->twc[i] = -((p->Rwc[3 * i + 0] * Tcw[3] + p->Rwc[3 * i + 1] * Tcw[7]) +
-                      p->Rwc[3 * i + 2] * Tcw[11]);
+        p->pose.twc[i] = -((p->pose.Rwc[3 * i + 0] * Tcw[3] + p->pose.Rwc[3 * i + 1] * Tcw[7]) +
+                           p->pose.Rwc[3 * i + 2] * Tcw[11]);
     p->tau_d = g.unit_shift > 0 ? g.tau_d : static_cast<double>(g.tau);
     p->unit_len = g.voxel_length * static_cast<double>(kB << g.unit_shift);
     IntFrame &I = p->I;
@@ -110,6 +110,9 @@ struct b2v_volume {
     bool use_tma = true;                 // stage image tiles with TMA when the layout allows it
     bool inputs_fenced = false;          // batch call: device inputs already ordered before the alloc stream
     bool fuse = true;                    // b2v_integrate_batch fuses groups of up to kMaxGroup frames
+    int group_frames = 8;                // frames per fused group (1..kMaxGroup), b2v_set_group_size
+    LambdaMap lam_map{};
+    bool lam_map_ok = false;
     bool rings_stale = false;            // a fused batch advanced frame_id: the per-frame ring counters must be re-armed
     float4 *d_gtex[kGroupBufs * kMaxGroup] = {};  // texel images of the group buffers
     size_t gtex_pixels = 0;
@@ -228,6 +231,10 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     if (const char *e = std::getenv("B2V_OVERLAP")) v->overlap = std::atoi(e) != 0;
     if (const char *e = std::getenv("B2V_TMA")) v->use_tma = std::atoi(e) != 0;
     if (const char *e = std::getenv("B2V_FUSE")) v->fuse = std::atoi(e) != 0;
+    if (const char *e = std::getenv("B2V_GROUP")) {
+        const int n = std::atoi(e);
+        if (n >= 1 && n <= kMaxGroup) v->group_frames = n;
+    }
     for (int b = 0; b < kGroupBufs; ++b) {
         B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_galloc[b], cudaEventDisableTiming));
         B2V_CUDA(v, cudaEventCreateWithFlags(&v->ev_group_done[b], cudaEventDisableTiming));
@@ -416,11 +423,13 @@ static const FrameMaps *frame_maps(b2v_volume *v, const float *d_depth, const ui
         v->map_H = H;
         v->map_W = W;
         v->map_lam = v->d_lambda;
+        v->lam_map_ok = encode_lambda_map(&v->lam_map, v->d_lambda, H, W, 32);
     }
+    if (!v->lam_map_ok) return nullptr;
     auto it = v->map_cache.find(reinterpret_cast<uintptr_t>(d_depth));
     if (it != v->map_cache.end() && it->second.color_ptr == d_color) return &it->second;
     FrameMaps m;
-    if (!encode_frame_maps(&m, d_depth, d_color, v->d_lambda, H, W, 32)) return nullptr;
+    if (!encode_frame_maps(&m, d_depth, d_color, H, W, 32)) return nullptr;
     m.color_ptr = d_color;
     auto res = v->map_cache.insert_or_assign(reinterpret_cast<uintptr_t>(d_depth), m);
     return &res.first->second;
@@ -553,7 +562,7 @@ static int integrate_frame(b2v_volume *v, const float *depth, const uint8_t *col
     float4 *tex = v->d_texel[s];
     P.I.tex = tex;
     B2V_CUDA(v, launch_allocate(P, d_depth, d_color, v->d_lambda, tex, v->table, v->meta, ring,
-                                frame_maps(v, d_depth, d_color, height, width), as));
+                                frame_maps(v, d_depth, d_color, height, width), &v->lam_map, as));
     if (staged || u16) B2V_CUDA(v, cudaEventRecord(v->ev_free[s], as));  // the raw frame is consumed by allocate only
     v->launches += 1;
     v->frame_id += 1;
@@ -728,14 +737,15 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
     v->rings_stale = true;
     v->last_stream = stream ? cs : nullptr;
     const bool staged = dev_hint != 1;
-    for (int32_t g0 = 0; g0 < n_frames; g0 += kMaxGroup) {
-        const int count = std::min<int32_t>(kMaxGroup, n_frames - g0);
+    const int gsz = std::max(1, std::min(v->group_frames, kMaxGroup));
+    for (int32_t g0 = 0; g0 < n_frames; g0 += gsz) {
+        const int count = std::min<int32_t>(gsz, n_frames - g0);
         const int buf = static_cast<int>(v->group_id % kGroupBufs);
         // the group buffer (masks, union list, texel images) was last used by group id - kGroupBufs
         B2V_CUDA(v, cudaStreamWaitEvent(as, v->ev_group_done[buf], 0));
         B2V_CUDA(v, cudaMemsetAsync(v->meta.counters + group_ctr(buf, 0), 0, kGroupCtrStride * sizeof(uint32_t), as));
-        static thread_local GroupAllocArgs aargs;  // 5.5 KB: keep it off the stack
-        GroupArgs args;
+        static thread_local GroupAllocArgs aargs;  // ~15 KB: keep it off the stack
+        static thread_local GroupArgs args;
         std::memset(&args, 0, sizeof(args));
         args.V = volume_consts(v->geo);
         args.count = count;
@@ -761,10 +771,15 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
             const uint8_t *d_color = color + pixels * 3 * f;
             if (staged || u16) d_depth = v->d_depth[buf * kMaxGroup + k];  // (widened) float staging slot
             if (staged) d_color = v->d_color[buf * kMaxGroup + k];
-            FrameParams &P = aargs.P[k];
+            FrameParams P;
             fill_frame_params(&P, K, Tcw + 16 * f, height, width, v->geo, v->frame_id + 1);
             P.group_bit = k;
             P.group_buf = buf;
+            aargs.pose[k] = P.pose;
+            if (k == 0) {
+                aargs.P = P;
+                aargs.frame_id0 = v->frame_id + 1;
+            }
             if (k == 0 && (v->lam_H != height || v->lam_W != width || std::memcmp(v->lam_K, K, sizeof(v->lam_K)) != 0)) {
                 if (v->overlap) B2V_CUDA(v, cudaStreamSynchronize(v->alloc));
                 B2V_CUDA(v, launch_lambda(P, v->d_lambda, as));
@@ -806,6 +821,7 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
             v->prof_int_launches += 1;
             B2V_CUDA(v, cudaEventRecord(pe[0], as));
         }
+        aargs.lmap = v->lam_map;
         B2V_CUDA(v, launch_allocate_group(aargs, v->d_lambda, v->table, v->meta, as));
         if (pe) B2V_CUDA(v, cudaEventRecord(pe[1], as));
         B2V_CUDA(v, cudaEventRecord(v->ev_galloc[buf], as));
@@ -852,6 +868,18 @@ extern "C" int b2v_integrate_u16(b2v_volume *v, const uint16_t *depth, float dep
     const int rc = integrate_frame(v, reinterpret_cast<const float *>(depth), color, height, width, K, Tcw, stream);
     v->in_u16_scale = 0.0f;
     return rc;
+}
+
+extern "C" int b2v_set_group_size(b2v_volume *v, int32_t frames) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    if (frames < 1 || frames > kMaxGroup) {
+        v->err = "b2v_set_group_size: 1..32 frames";
+        return B2V_ERR_INVALID_ARGUMENT;
+    }
+    const int rc = read_counters(v);
+    if (rc == B2V_ERR_CUDA) return rc;
+    v->group_frames = frames;
+    return B2V_OK;
 }
 
 extern "C" int b2v_set_fusion(b2v_volume *v, int32_t enable) {

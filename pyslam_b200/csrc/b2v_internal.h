@@ -22,12 +22,17 @@ struct IntFrame {
     const float4 *tex;      // packed {valid depth | 0, lambda, rgbx, 0} texels of the frame
 };
 
+// camera -> world of one frame, float64 (allocation samples)
+struct FramePose {
+    double Rwc[9];   // rigid inverse of Tcw, row-major
+    double twc[3];
+};
+
 // Per-frame constants of the allocate kernels (+ the update constants of the frame-by-frame path).
 struct FrameParams {
     // f64 back-projection of the allocation samples (Open3D CreatePointCloudFromFloatDepthImage)
     double fx, fy, cx, cy;
-    double Rwc[9];   // rigid inverse of Tcw, row-major
-    double twc[3];
+    FramePose pose;
     double tau_d;    // sdf_trunc as float64 (unit mode: the value Open3D holds; D1: (double)sdf_trunc_f)
     double unit_len; // voxel_length * unit resolution, float64 (volume_unit_length_)
     IntFrame I;
@@ -51,7 +56,7 @@ struct VolumeConsts {
 
 // Fused group integration: up to kMaxGroup consecutive frames are applied to a block while it is
 // resident in registers.
-constexpr int kMaxGroup = 8;
+constexpr int kMaxGroup = 32;   // frames per fused group (bits of the membership mask); the default group is 8
 // group state (masks, union list, texel images, counters) is kGroupBufs-deep: the allocation of group g+3 may
 // run while group g is still being integrated
 constexpr int kGroupBufs = 4;
@@ -83,7 +88,7 @@ enum Counter : int {
     kCtrVisitsHi = 13,
     kCtrGroup0 = 16,         // [kGroupBufs][kGroupCtrStride] per-group-buffer counters, contiguous so that ONE
                              // memset re-arms a buffer: see GroupCounter
-    kNumCounters = 16 + 4 * 12
+    kNumCounters = 16 + 4 * (4 + 32)
 };
 // offsets inside one group buffer's counter block (M.counters + kCtrGroup0 + buf * kGroupCtrStride)
 enum GroupCounter : int {
@@ -92,7 +97,7 @@ enum GroupCounter : int {
     kGcNew = 2,      // blocks newly allocated by the group
     kGcTouched0 = 4  // [kMaxGroup] blocks touched by frame k of the group
 };
-constexpr int kGroupCtrStride = 12;
+constexpr int kGroupCtrStride = 4 + kMaxGroup;
 __host__ __device__ __forceinline__ constexpr int group_ctr(int buf, int which) {
     return kCtrGroup0 + buf * kGroupCtrStride + which;
 }
@@ -117,32 +122,39 @@ cudaError_t launch_lambda(const FrameParams &p, float *lam, cudaStream_t stream)
 struct FrameMaps {
     alignas(64) CUtensorMap depth;
     alignas(64) CUtensorMap color;
-    alignas(64) CUtensorMap lam;
     const void *color_ptr = nullptr;  // host-side cache validation only
+};
+struct LambdaMap {
+    alignas(64) CUtensorMap lam;
 };
 // TMA tile staging needs 16-byte aligned bases and row pitches (W % 16 == 0) and the 32x32 tile
 bool tma_tiles_usable(int W, int stride, const void *depth, const void *color, const void *lam);
 // returns false if the driver entry point is unavailable or encoding fails
-bool encode_frame_maps(FrameMaps *maps, const float *depth, const uint8_t *color, const float *lam,
-                       int H, int W, int tile);
+bool encode_frame_maps(FrameMaps *maps, const float *depth, const uint8_t *color, int H, int W, int tile);
+bool encode_lambda_map(LambdaMap *map, const float *lam, int H, int W, int tile);
 // frame packing ({valid depth, lambda, rgbx} texels) + allocation + touched-set of one frame;
 // zeroes the next frame's ring counters.  maps != nullptr: the image tiles are staged into shared
 // memory with TMA (cp.async.bulk.tensor.2d); nullptr: plain loads.
 cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint8_t *color,
                             const float *lam, float4 *texels, const HashTable &table,
-                            const PoolMeta &meta, int ring, const FrameMaps *maps, cudaStream_t stream);
+                            const PoolMeta &meta, int ring, const FrameMaps *maps, const LambdaMap *lmap,
+                            cudaStream_t stream);
 // projective TSDF + colour update of every block touched by the frame
 cudaError_t launch_integrate(const FrameParams &p, const VolumeConsts &vc, const HashTable &table,
                              const PoolMeta &meta, int ring, int grid_ctas, cudaStream_t stream);
 // all frames of a group in ONE launch (blockIdx.z = frame): the per-frame latency chains overlap
 struct GroupAllocArgs {
-    FrameParams P[kMaxGroup];
+    FrameParams P;                 // constants shared by the frames of the group (P.pose / P.I unused)
+    FramePose pose[kMaxGroup];
     const float *depth[kMaxGroup];
     const uint8_t *color[kMaxGroup];
     float4 *tex[kMaxGroup];
     FrameMaps maps[kMaxGroup];
+    LambdaMap lmap;
+    uint32_t frame_id0;            // frame id of the group's first frame
     int32_t count, use_tma;
 };
+static_assert(sizeof(GroupAllocArgs) < 32000, "kernel parameter space");
 cudaError_t launch_allocate_group(const GroupAllocArgs &args, const float *lam, const HashTable &table,
                                   const PoolMeta &meta, cudaStream_t stream);
 int integrate_max_resident_ctas_per_sm();

@@ -43,7 +43,12 @@ __device__ __forceinline__ void assign_block(const HashTable &T, const PoolMeta 
 
 // Global find-or-insert of one block key + first-touch detection for this frame.  New slots and
 // first-touched slots are queued in shared-memory lists (flushed with one atomic per CTA).
-__device__ __forceinline__ void touch_key(const FrameParams &P, const HashTable &T, const PoolMeta &M,
+struct FrameSlot {   // which frame this CTA works for
+    int group_bit;       // >= 0: fused group mode (bit of the membership mask); -1: per-frame mode
+    uint32_t frame_id;
+};
+
+__device__ __forceinline__ void touch_key(const FrameParams &P, const FrameSlot &FS, const HashTable &T, const PoolMeta &M,
                                           int ring, int kx, int ky, int kz, uint32_t *s_new,
                                           uint32_t *s_n_new, uint32_t *s_act, uint32_t *s_n_act) {
     if (P.shard_count > 1 &&
@@ -61,21 +66,21 @@ __device__ __forceinline__ void touch_key(const FrameParams &P, const HashTable 
             s_new[pos] = slot;
         } else {  // list overflow: assign directly
             assign_block(T, M, slot, atomicAdd(M.counters + kCtrPool, 1u));
-            atomicAdd(P.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcNew) : M.counters + kCtrNew0 + ring, 1u);
+            atomicAdd(FS.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcNew) : M.counters + kCtrNew0 + ring, 1u);
         }
     }
     bool first;
-    if (P.group_bit >= 0) {  // fused group mode: membership bit; the first frame to touch queues the slot
+    if (FS.group_bit >= 0) {  // fused group mode: membership bit; the first frame to touch queues the slot
         uint32_t *mask = M.group_mask + static_cast<size_t>(P.group_buf) * (static_cast<size_t>(T.mask) + 1);
-        first = atomicOr(mask + slot, 1u << P.group_bit) == 0u;
+        first = atomicOr(mask + slot, 1u << FS.group_bit) == 0u;
     } else {
-        first = atomicExch(T.stamp + slot, P.frame_id) != P.frame_id;
+        first = atomicExch(T.stamp + slot, FS.frame_id) != FS.frame_id;
     }
     if (first) {
         const uint32_t pos = atomicAdd(s_n_act, 1u);
         if (pos < kListCap) {
             s_act[pos] = slot;
-        } else if (P.group_bit >= 0) {
+        } else if (FS.group_bit >= 0) {
             const uint32_t g = atomicAdd(M.counters + group_ctr(P.group_buf, kGcUnion), 1u);
             if (g < M.capacity) M.union_slots[static_cast<size_t>(P.group_buf) * M.capacity + g] = slot;
         } else {
@@ -141,10 +146,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 //           probes in flight - and exchanges the slot's frame stamp (first toucher queues the slot)
 //   flush   one atomic per CTA hands out contiguous pool indices and active-list positions
 template <bool kTma>
-__device__ __forceinline__ void allocate_body(const FrameParams &P, const float *__restrict__ depth,
+__device__ __forceinline__ void allocate_body(const FrameParams &P, const FramePose &pose, const FrameSlot FS,
+                                              const float *__restrict__ depth,
                                               const uint8_t *__restrict__ rgb, const float *__restrict__ lam,
                                               float4 *__restrict__ tex, const HashTable &T, const PoolMeta &M,
-                                              const int ring, const FrameMaps &maps) {
+                                              const int ring, const FrameMaps &maps, const LambdaMap &lmap) {
     // TMA staging buffers of the 32x32-pixel tile (kTma only): depth, lambda (f32) and colour (u8 x3)
     __shared__ alignas(128) float s_td[kTmaTile * kTmaTile];
     __shared__ alignas(128) float s_tl[kTmaTile * kTmaTile];
@@ -168,7 +174,7 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
         s_n_new = 0;
         s_n_act = 0;
         s_ref[3] = 0;
-        if (blockIdx.x == 0 && blockIdx.y == 0 && P.group_bit < 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && FS.group_bit < 0) {
             // the ring slot the NEXT frame will count into (its last user finished 3 frames ago)
             const int nxt = (ring + 1) % kActiveRing;
             M.counters[kCtrActive0 + nxt] = 0;
@@ -185,7 +191,7 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
             mbar_expect_tx(&s_bar, kTmaTile * kTmaTile * (4 + 4 + 3));
             const int x0 = blockIdx.x * kTmaTile, y0 = blockIdx.y * kTmaTile;
             tma_load_2d(s_td, &maps.depth, x0, y0, &s_bar);
-            tma_load_2d(s_tl, &maps.lam, x0, y0, &s_bar);
+            tma_load_2d(s_tl, &lmap.lam, x0, y0, &s_bar);
             tma_load_2d(s_tc, &maps.color, 3 * x0, y0, &s_bar);
         }
     }
@@ -205,9 +211,9 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     const double pw = __dadd_rn(
-                        __dadd_rn(__dadd_rn(__dmul_rn(P.Rwc[3 * a + 0], x), __dmul_rn(P.Rwc[3 * a + 1], y)),
-                                  __dmul_rn(P.Rwc[3 * a + 2], z)),
-                        P.twc[a]);
+                        __dadd_rn(__dadd_rn(__dmul_rn(pose.Rwc[3 * a + 0], x), __dmul_rn(pose.Rwc[3 * a + 1], y)),
+                                  __dmul_rn(pose.Rwc[3 * a + 2], z)),
+                        pose.twc[a]);
                     if (P.unit_shift > 0) {
                         // Open3D ScalableTSDFVolume::LocateVolumeUnit: floor(p / volume_unit_length) in float64;
                         // every 8^3 block of a touched unit is touched
@@ -308,7 +314,7 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
             for (int dx = 0; dx < n[0]; ++dx)
                 for (int dy = 0; dy < n[1]; ++dy)
                     for (int dz = 0; dz < n[2]; ++dz)
-                        touch_key(P, T, M, ring, lo[0] + dx, lo[1] + dy, lo[2] + dz, s_new, &s_n_new, s_act, &s_n_act);
+                        touch_key(P, FS, T, M, ring, lo[0] + dx, lo[1] + dy, lo[2] + dz, s_new, &s_n_new, s_act, &s_n_act);
         }
     }
     __syncthreads();
@@ -351,7 +357,7 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
                         h = (h + 1) & (kKeySet - 1);
                     }
                 }
-                if (!placed) touch_key(P, T, M, ring, kx, ky, kz, s_new, &s_n_new, s_act, &s_n_act);
+                if (!placed) touch_key(P, FS, T, M, ring, kx, ky, kz, s_new, &s_n_new, s_act, &s_n_act);
             }
         }
     }
@@ -362,7 +368,7 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
         const uint32_t nkeys = min(s_n_keys, static_cast<uint32_t>(kListCap));
         for (uint32_t q = tid; q < nkeys; q += kAllocThreads) {
             const uint32_t rk = s_keys[q];
-            touch_key(P, T, M, ring, s_ref[0] + static_cast<int>(rk & 1023u) - 512,
+            touch_key(P, FS, T, M, ring, s_ref[0] + static_cast<int>(rk & 1023u) - 512,
                       s_ref[1] + static_cast<int>((rk >> 10) & 1023u) - 512,
                       s_ref[2] + static_cast<int>((rk >> 20) & 1023u) - 512, s_new, &s_n_new, s_act, &s_n_act);
         }
@@ -373,13 +379,13 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const float 
     const uint32_t n_new = min(s_n_new, static_cast<uint32_t>(kListCap));
     const uint32_t n_act = min(s_n_act, static_cast<uint32_t>(kListCap));
     if (tid == 0) s_base_new = n_new ? atomicAdd(M.counters + kCtrPool, n_new) : 0u;
-    uint32_t *list_count = P.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcUnion) : M.counters + kCtrActive0 + ring;
+    uint32_t *list_count = FS.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcUnion) : M.counters + kCtrActive0 + ring;
     if (tid == 32) s_base_act = n_act ? atomicAdd(list_count, n_act) : 0u;
     if (tid == 64 && n_new)
-        atomicAdd(P.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcNew) : M.counters + kCtrNew0 + ring, n_new);
+        atomicAdd(FS.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcNew) : M.counters + kCtrNew0 + ring, n_new);
     __syncthreads();
     for (uint32_t k = tid; k < n_new; k += kAllocThreads) assign_block(T, M, s_new[k], s_base_new + k);
-    uint32_t *active_out = P.group_bit >= 0 ? M.union_slots + static_cast<size_t>(P.group_buf) * M.capacity
+    uint32_t *active_out = FS.group_bit >= 0 ? M.union_slots + static_cast<size_t>(P.group_buf) * M.capacity
                                             : M.active_slots + static_cast<size_t>(ring) * M.capacity;
     for (uint32_t k = tid; k < n_act; k += kAllocThreads) {
         const uint32_t g = s_base_act + k;
@@ -391,8 +397,9 @@ template <bool kTma>
 __global__ void __launch_bounds__(kAllocThreads, 4)
 allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint8_t *__restrict__ rgb,
                 const float *__restrict__ lam, float4 *__restrict__ tex, const HashTable T,
-                const PoolMeta M, const int ring, const __grid_constant__ FrameMaps maps) {
-    allocate_body<kTma>(P, depth, rgb, lam, tex, T, M, ring, maps);
+                const PoolMeta M, const int ring, const __grid_constant__ FrameMaps maps,
+                const __grid_constant__ LambdaMap lmap) {
+    allocate_body<kTma>(P, P.pose, FrameSlot{-1, P.frame_id}, depth, rgb, lam, tex, T, M, ring, maps, lmap);
 }
 
 // blockIdx.z = frame of the group: one launch allocates for up to kMaxGroup frames
@@ -401,12 +408,13 @@ __global__ void __launch_bounds__(kAllocThreads, 8)
 allocate_group_kernel(const __grid_constant__ GroupAllocArgs A, const float *__restrict__ lam,
                       const HashTable T, const PoolMeta M) {
     const int k = blockIdx.z;
-    allocate_body<kTma>(A.P[k], A.depth[k], A.color[k], lam, A.tex[k], T, M, 0, A.maps[k]);
+    allocate_body<kTma>(A.P, A.pose[k], FrameSlot{k, A.frame_id0 + static_cast<uint32_t>(k)}, A.depth[k], A.color[k], lam,
+                        A.tex[k], T, M, 0, A.maps[k], A.lmap);
 }
 
 cudaError_t launch_allocate_group(const GroupAllocArgs &args, const float *lam, const HashTable &table,
                                   const PoolMeta &meta, cudaStream_t stream) {
-    const FrameParams &p = args.P[0];
+    const FrameParams &p = args.P;
     const int gw = (p.W + p.stride - 1) / p.stride;
     const int gh = (p.H + p.stride - 1) / p.stride;
     const dim3 grid((gw + kAllocTile - 1) / kAllocTile, (gh + kAllocTile - 1) / kAllocTile, args.count);
@@ -419,17 +427,19 @@ cudaError_t launch_allocate_group(const GroupAllocArgs &args, const float *lam, 
 
 cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint8_t *color,
                             const float *lam, float4 *texels, const HashTable &table,
-                            const PoolMeta &meta, int ring, const FrameMaps *maps, cudaStream_t stream) {
+                            const PoolMeta &meta, int ring, const FrameMaps *maps, const LambdaMap *lmap,
+                            cudaStream_t stream) {
     const int gw = (p.W + p.stride - 1) / p.stride;
     const int gh = (p.H + p.stride - 1) / p.stride;
     const dim3 grid((gw + kAllocTile - 1) / kAllocTile, (gh + kAllocTile - 1) / kAllocTile);
-    if (maps != nullptr && p.stride * kAllocTile == kTmaTile) {
+    if (maps != nullptr && lmap != nullptr && p.stride * kAllocTile == kTmaTile) {
         allocate_kernel<true><<<grid, kAllocThreads, 0, stream>>>(p, depth, color, lam, texels, table, meta,
-                                                                 ring, *maps);
+                                                                 ring, *maps, *lmap);
     } else {
         static const FrameMaps dummy{};
+        static const LambdaMap ldummy{};
         allocate_kernel<false><<<grid, kAllocThreads, 0, stream>>>(p, depth, color, lam, texels, table, meta,
-                                                                  ring, dummy);
+                                                                  ring, dummy, ldummy);
     }
     return cudaGetLastError();
 }
@@ -471,12 +481,14 @@ static bool encode_2d(CUtensorMap *m, CUtensorMapDataType dt, const void *base, 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool encode_frame_maps(FrameMaps *maps, const float *depth, const uint8_t *color, const float *lam,
-                       int H, int W, int tile) {
+bool encode_frame_maps(FrameMaps *maps, const float *depth, const uint8_t *color, int H, int W, int tile) {
     return encode_2d(&maps->depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, depth, W, H, static_cast<uint64_t>(W) * 4, tile, tile) &&
-           encode_2d(&maps->lam, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, lam, W, H, static_cast<uint64_t>(W) * 4, tile, tile) &&
            encode_2d(&maps->color, CU_TENSOR_MAP_DATA_TYPE_UINT8, color, static_cast<uint64_t>(W) * 3, H,
                      static_cast<uint64_t>(W) * 3, 3 * tile, tile);
+}
+
+bool encode_lambda_map(LambdaMap *map, const float *lam, int H, int W, int tile) {
+    return encode_2d(&map->lam, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, lam, W, H, static_cast<uint64_t>(W) * 4, tile, tile);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -655,6 +667,8 @@ cudaError_t launch_integrate(const FrameParams &p, const VolumeConsts &vc, const
 // The per-frame constants are read straight from the kernel-parameter (constant) bank: the frame loop is
 // unrolled over the 8 slots of the group, so every constant is an immediate-offset uniform operand.
 // ------------------------------------------------------------------------------------------------
+constexpr int kUnrolledGroup = 8;   // groups up to this size use the fully unrolled frame loop
+template <bool kUnrolled>
 __global__ void __launch_bounds__(kIntThreads, 8)
 integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, const PoolMeta M,
                        const int gbuf) {
@@ -700,9 +714,14 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
             load_block(blk, q);
             const VoxelRun r = voxel_run(e, t, A.V);
             bool upd = false;
+            if constexpr (kUnrolled) {
 #pragma unroll
-            for (int k = 0; k < kMaxGroup; ++k)  // ascending bits = frame order
-                if ((m >> k) & 1u) upd |= apply_frame(A.f[k], r, s_rcp, q[0], q[1], q[2], q[3], q[4]);
+                for (int k = 0; k < kUnrolledGroup; ++k)  // ascending bits = frame order
+                    if ((m >> k) & 1u) upd |= apply_frame(A.f[k], r, s_rcp, q[0], q[1], q[2], q[3], q[4]);
+            } else {
+                for (uint32_t mm = m; mm; mm &= mm - 1u)  // ascending bits = frame order; constants via LDC
+                    upd |= apply_frame(A.f[__ffs(mm) - 1], r, s_rcp, q[0], q[1], q[2], q[3], q[4]);
+            }
             if (upd) store_block(blk, q);
         }
         e = e_next;
@@ -727,7 +746,10 @@ __global__ void group_clear_kernel(const HashTable T, const PoolMeta M, const in
 
 cudaError_t launch_integrate_group(const GroupArgs &args, const HashTable &table, const PoolMeta &meta,
                                    int group_buf, int grid_ctas, cudaStream_t stream) {
-    integrate_group_kernel<<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
+    if (args.count <= kUnrolledGroup)
+        integrate_group_kernel<true><<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
+    else
+        integrate_group_kernel<false><<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
     group_clear_kernel<<<148, 256, 0, stream>>>(table, meta, group_buf);
     return cudaGetLastError();
 }

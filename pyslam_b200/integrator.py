@@ -9,7 +9,7 @@ The reference selects a backend with `volumetric_integrator_factory`
 This module provides that subclass *without importing pySLAM at module import time* (pySLAM does
 not exist on the GPU test box): `make_integrator_class(Base, api)` builds it against whatever base
 class / task / output types it is given — pySLAM's real ones (`load_pyslam_plugin()`), or the small
-stand-ins in `plugin_api` that mirror their fields so the adapter can be exercised stand-alone.
+stand-ins in `tests/plugin_standins.py` that mirror their fields so the adapter can be exercised stand-alone.
 """
 
 from __future__ import annotations
@@ -36,6 +36,11 @@ DEFAULT_PARAMETERS = {
     "kVolumetricIntegrationB200Device": 0,
     # undistort + BGR->RGB on the GPU (b2v_set_rectification) instead of the base class's cv2.remap / cvtColor
     "kVolumetricIntegrationB200GpuRectify": True,
+    # when the input queue holds a backlog (rebuild(map) re-enqueues every keyframe, base.py:1242-1318), up to this
+    # many consecutive INTEGRATE tasks are drained into ONE fused integrate_batch call; 1 = one task per call
+    "kVolumetricIntegrationB200MaxBatch": 32,
+    # Open3D volume_unit_resolution (tsdf.py:104-108 uses 16); 8 = SURVEY decision D1
+    "kVolumetricIntegrationB200UnitResolution": 16,
 }
 
 
@@ -105,9 +110,12 @@ def make_integrator_class(Base, api):
                 sdf_trunc=p["kVolumetricIntegrationTSdfTrunc"],
                 depth_trunc=self.volumetric_integration_depth_trunc,
                 capacity_blocks=int(p["kVolumetricIntegrationB200CapacityBlocks"]),
-                device=int(p["kVolumetricIntegrationB200Device"]))
+                device=int(p["kVolumetricIntegrationB200Device"]),
+                volume_unit_resolution=int(p["kVolumetricIntegrationB200UnitResolution"]))
             self.last_output = None
             self.last_integrated_id = -1
+            self._deferred_task = None      # a non-INTEGRATE task met while draining a backlog: handled next call
+            self._has_deferred = False
             # rectification on the GPU: the maps the base class computed (base.py:766-778) go to the device once
             self._gpu_rectify = False
             m1, m2 = getattr(self, "calib_map1", None), getattr(self, "calib_map2", None)
@@ -117,20 +125,27 @@ def make_integrator_class(Base, api):
                 self._gpu_rectify = True
 
         def _prepare_frame(self, kd):
-            """(color RGB or raw BGR when the GPU rectifies, depth float32).  With GPU rectification and no
+            """(color RGB or raw BGR when the GPU rectifies, depth, depth_scale).  With GPU rectification and no
             depth estimator the raw images go straight to the device: remap + channel swap happen there,
-            bit-identically to cv2.remap / cvtColor (base.py:1017-1054)."""
+            bit-identically to cv2.remap / cvtColor (base.py:1017-1054).  Raw uint16 depth in C++-core mode is
+            passed as is with depth_scale = camera.depth_factor: the GPU widens it to float32(depth) * factor,
+            the value `depth.astype(np.float32) * self.camera.depth_factor` has on the host (base.py:1008-1012)."""
             if self._gpu_rectify and kd.depth is not None and kd.depth.size and kd.img is not None:
-                depth = kd.depth
-                if depth.dtype != np.float32:  # base.py:1008-1015
-                    depth = depth.astype(np.float32)
+                depth, scale = kd.depth, None
+                if depth.dtype != np.float32:  # base.py:1007-1015
                     if getattr(api, "USE_CPP", False):
-                        depth = depth * np.float32(getattr(self, "depth_factor", 1.0))
-                return kd.img, depth
+                        factor = float(getattr(self.camera, "depth_factor", 1.0))
+                        if depth.dtype == np.uint16:
+                            scale = np.float32(factor)
+                        else:
+                            depth = depth.astype(np.float32) * factor
+                    else:
+                        depth = depth.astype(np.float32)
+                return kd.img, depth, scale
             if self._gpu_rectify:
-                return None, None
+                return None, None, None
             rect = self.estimate_depth_if_needed_and_rectify(kd)
-            return rect[0], rect[1]
+            return rect[0], rect[1], None
 
         def _intrinsics(self):
             if hasattr(self, "get_camera_intrinsics_for_depth"):
@@ -164,19 +179,52 @@ def make_integrator_class(Base, api):
                         pass
                     if task is not None and task.task_type == TaskType.RESET:
                         self.volume.reset()
-                    self.last_input_task = q_in.get()  # blocking
+                    if self._has_deferred:
+                        self.last_input_task, self._deferred_task, self._has_deferred = self._deferred_task, None, False
+                    else:
+                        self.last_input_task = q_in.get()  # blocking
                     if self.last_input_task is None:
                         is_running.value = 0  # a None asks the loop to exit
                     else:
                         ttype = self.last_input_task.task_type
                         if ttype == TaskType.INTEGRATE:
-                            kd = self.last_input_task.keyframe_data
-                            color, depth = self._prepare_frame(kd)
-                            if color is not None and depth is not None:
-                                fx, fy, cx, cy = self._intrinsics()
-                                # north_star call: integrate(depth, color, K, pose = Tcw)
-                                self.volume.integrate(depth, color, (fx, fy, cx, cy), kd.pose)
-                                self.last_integrated_id = kd.id
+                            # backlog (rebuild(map), base.py:1242-1318): drain the consecutive INTEGRATE tasks that
+                            # are already queued into one fused batch; anything else waits for the next call
+                            tasks = [self.last_input_task]
+                            max_batch = int(self.b200_parameters["kVolumetricIntegrationB200MaxBatch"])
+                            while len(tasks) < max_batch:
+                                try:
+                                    nxt = q_in.get_nowait()
+                                except Exception:
+                                    break
+                                if nxt is None or nxt.task_type != TaskType.INTEGRATE:
+                                    self._deferred_task, self._has_deferred = nxt, True
+                                    break
+                                tasks.append(nxt)
+                            self.last_input_task = tasks[-1]
+                            frames = []
+                            for t in tasks:
+                                kd = t.keyframe_data
+                                color, depth, scale = self._prepare_frame(kd)
+                                if color is not None and depth is not None:
+                                    frames.append((kd, color, depth, scale))
+                            if frames:
+                                K4 = tuple(self._intrinsics())
+                                same = all(f[1].shape == frames[0][1].shape and f[2].shape == frames[0][2].shape
+                                           and f[2].dtype == frames[0][2].dtype and f[3] == frames[0][3]
+                                           for f in frames)
+                                if len(frames) > 1 and same:
+                                    # one C call: groups of frames fused per block visit (b2v_integrate_batch)
+                                    self.volume.integrate_batch(np.stack([f[2] for f in frames]),
+                                                                np.stack([f[1] for f in frames]), K4,
+                                                                np.stack([np.asarray(f[0].pose, np.float64) for f in frames]),
+                                                                depth_scale=frames[0][3])
+                                else:
+                                    for kd, color, depth, scale in frames:
+                                        # north_star call: integrate(depth, color, K, pose = Tcw)
+                                        self.volume.integrate(depth, color, K4, kd.pose, depth_scale=scale)
+                                self.last_integrated_id = frames[-1][0].id
+                                self.integrated_frames = getattr(self, "integrated_frames", 0) + len(frames)
                                 do_output = True
                                 if self.last_output is not None:
                                     dt = time.perf_counter() - self.last_output.timestamp
@@ -225,8 +273,10 @@ def load_pyslam_plugin():
     from pyslam.config_parameters import Parameters
     from pyslam.dense import volumetric_integrator_base as B
     from pyslam.io.dataset_types import DatasetEnvironmentType
+    from pyslam.slam import USE_CPP   # C++ core: raw depth reaches the integrator unscaled (base.py:29, 1008-1012)
 
     api = SimpleNamespace(
+        USE_CPP=bool(USE_CPP),
         VolumetricIntegrationTaskType=B.VolumetricIntegrationTaskType,
         VolumetricIntegrationOutput=B.VolumetricIntegrationOutput,
         VolumetricIntegrationMesh=B.VolumetricIntegrationMesh,

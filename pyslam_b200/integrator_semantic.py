@@ -2,7 +2,7 @@
 (`VolumetricIntegratorVoxelSemanticGrid`, pyslam/dense/volumetric_integrator_voxel_semantic_grid.py) on the GPU.
 
 Same contract as `integrator.py`: a subclass of `VolumetricIntegratorBase` built against whichever base / task /
-output types it is given (pySLAM's real ones, or the in-process stand-ins of `plugin_api.py`).  The per-frame
+output types it is given (pySLAM's real ones, or the in-process stand-ins of `tests/plugin_standins.py`).  The per-frame
 loop body (reference :326-461) maps one-to-one onto the C ABI:
 
     filter_shadow_points + depth2pointcloud + world transform + integrate  ->  b2v_sgrid_integrate_rgbd

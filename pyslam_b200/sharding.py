@@ -1,11 +1,15 @@
 """Multi-GPU partitioning of the voxel-block hash space.
 
 One process per GPU.  A block belongs to rank `BlockKeyHash(key) % world` — the reference's own hash
-(`cpp/volumetric/voxel_hashing.h:106-113`), so ownership is reproducible from the keys alone.  The
-integrate path needs no collective: every rank sees every frame and keeps the keys it owns
-(`b2v_config.shard_rank / shard_count`).  Mesh extraction needs the +1-voxel halos of blocks that
-may live on another rank; `gather_blocks_device` collects all shards on one rank GPU-to-GPU over NCCL
-(`gather_blocks` is the host-array variant used with gloo in the CPU tests), which then meshes the union.
+(`cpp/volumetric/voxel_hashing.h:106-113`), so ownership is reproducible from the keys alone.  Every rank
+integrates every frame into the blocks it owns (`b2v_config.shard_rank / shard_count`).
+
+* Ingest (`FrameIngest`): a frame crosses PCIe ONCE in the whole job - rank r uploads 1/world of every chunk of
+  frames over its own link and the chunk is completed GPU <-> GPU by an NCCL all-gather over NVLink / NVSwitch on a
+  side stream, overlapped with the kernels of the previous chunk.
+* Mesh extraction needs the +1-voxel halos of blocks that may live on another rank; `gather_blocks_device` collects
+  all shards on one rank GPU-to-GPU over NCCL (`gather_blocks` is the host-array variant used with gloo in the CPU
+  tests), which then meshes the union.
 """
 
 from __future__ import annotations
@@ -29,6 +33,121 @@ def merge_dumps(dumps):
     keys = np.concatenate([d["keys"] for d in dumps])
     order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
     return {name: np.concatenate([d[name] for d in dumps])[order] for name in dumps[0]}
+
+
+def chunk_plan(n_frames: int, world: int, chunk_frames: int):
+    """Split a batch into chunks of <= chunk_frames frames.  -> [(first frame, frame count, q)]: rank r uploads the
+    frames [first + r*q, first + min((r+1)*q, count)) of the chunk (q = ceil(count / world)) into segment r of the
+    chunk buffer, so after the all-gather of the world q-frame segments the chunk's frames are contiguous and in
+    frame order (the last segments of a ragged chunk may be partly or wholly padding)."""
+    plan = []
+    c0 = 0
+    while c0 < n_frames:
+        cnt = min(chunk_frames, n_frames - c0)
+        plan.append((c0, cnt, -(-cnt // world)))
+        c0 += cnt
+    return plan
+
+
+class FrameIngest:
+    """Frame-split ingest of a hash-sharded volume: `integrate_batch(depths, colors, K, poses)` with HOST frames
+    (pinned numpy arrays or torch tensors; every rank passes the same batch) is, per chunk of `chunk_frames`:
+
+        upload stream   H2D of this rank's 1/world share of the chunk (its own PCIe link)
+                        all-gather of the shares (NCCL over NVLink; in place in the chunk buffer)
+        compute stream  volume.integrate_batch(chunk buffer, device pointers)   [allocate + fused update kernels]
+
+    with `buffers` chunk buffers in rotation, so upload + all-gather of chunk c+1 overlap the kernels of chunk c.
+    Frame order is unchanged, so the result is bit-identical to a single-GPU `integrate_batch` of the batch.
+    world = 1 (or no process group) degenerates to a chunked, double-buffered upload.  `depth_scale`: the depths are
+    raw uint16 (2 bytes per pixel over PCIe AND NVLink), widened on the GPU."""
+
+    def __init__(self, volume, group=None, chunk_frames: int = 64, buffers: int = 3, device=None):
+        import torch
+        import torch.distributed as dist
+        self.volume = volume
+        self.group = group
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.chunk_frames = int(chunk_frames)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", volume.device)
+        self.cuda = self.device.type == "cuda"
+        self.n_buffers = int(buffers)
+        self._bufs = None
+        self._shape = None
+        if self.cuda:
+            self.s_up = torch.cuda.Stream(self.device)
+            self.s_int = torch.cuda.Stream(self.device)
+        self.h2d_bytes = 0       # bytes this rank uploaded (accounting for bench.py)
+        self.gather_bytes = 0    # bytes this rank received from its peers
+
+    def _ensure(self, H, W, ddtype):
+        import torch
+        shape = (H, W, ddtype)
+        if self._shape == shape:
+            return
+        if self.cuda and self._bufs is not None:
+            torch.cuda.synchronize(self.device)
+        cap = -(-self.chunk_frames // self.world) * self.world   # room for world equal segments
+        self._bufs = []
+        for _ in range(self.n_buffers):
+            b = dict(depth=torch.empty((cap, H, W), dtype=ddtype, device=self.device),
+                     color=torch.empty((cap, H, W, 3), dtype=torch.uint8, device=self.device))
+            if self.cuda:
+                b["free"] = torch.cuda.Event()
+                b["ready"] = torch.cuda.Event()
+            self._bufs.append(b)
+        self._shape = shape
+
+    def integrate_batch(self, depths, colors, K, poses, depth_scale=None):
+        import contextlib
+        import torch
+        D = depths if torch.is_tensor(depths) else torch.from_numpy(np.ascontiguousarray(depths))
+        Cc = colors if torch.is_tensor(colors) else torch.from_numpy(np.ascontiguousarray(colors))
+        T = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 4, 4))
+        n, H, W = int(D.shape[0]), int(D.shape[1]), int(D.shape[2])
+        if tuple(Cc.shape) != (n, H, W, 3) or T.shape[0] != n:
+            raise RuntimeError("depths must be [n,H,W], colors [n,H,W,3], poses [n,4,4]")
+        if depth_scale is None and D.dtype != torch.float32:
+            raise RuntimeError("depths must be float32 (or uint16 with depth_scale)")
+        self._ensure(H, W, D.dtype)
+        world, r = self.world, self.rank
+        up = torch.cuda.stream(self.s_up) if self.cuda else contextlib.nullcontext()
+        for i, (c0, cnt, q) in enumerate(chunk_plan(n, world, self.chunk_frames)):
+            b = self._bufs[i % self.n_buffers]
+            lo, hi = min(r * q, cnt), min((r + 1) * q, cnt)
+            with up:
+                if self.cuda:
+                    self.s_up.wait_event(b["free"])      # the kernels that read this buffer last are done
+                if hi > lo:
+                    b["depth"][lo:hi].copy_(D[c0 + lo:c0 + hi], non_blocking=True)
+                    b["color"][lo:hi].copy_(Cc[c0 + lo:c0 + hi], non_blocking=True)
+                    self.h2d_bytes += (hi - lo) * H * W * (D.element_size() + 3)
+                if world > 1:
+                    # in place: segment r of the buffer is this rank's contribution
+                    for t in (b["depth"], b["color"]):
+                        if t.dtype == torch.uint16:      # no uint16 in NCCL / gloo: gather the same bytes as uint8
+                            t = t.view(torch.uint8)
+                        self.dist.all_gather_into_tensor(t[:world * q], t[r * q:(r + 1) * q], group=self.group)
+                    self.gather_bytes += (cnt - (hi - lo)) * H * W * (D.element_size() + 3)
+                if self.cuda:
+                    b["ready"].record(self.s_up)
+            if self.cuda:
+                self.s_int.wait_event(b["ready"])
+                self.volume.integrate_batch(b["depth"][:cnt], b["color"][:cnt], K, T[c0:c0 + cnt],
+                                            stream=self.s_int.cuda_stream, depth_scale=depth_scale)
+                b["free"].record(self.s_int)
+            else:   # CPU / gloo (host-logic tests with a stand-in volume)
+                self.volume.integrate_batch(b["depth"][:cnt], b["color"][:cnt], K, T[c0:c0 + cnt],
+                                            depth_scale=depth_scale)
+
+    def synchronize(self):
+        import torch
+        if self.cuda:
+            self.s_up.synchronize()
+            self.s_int.synchronize()
+        self.volume.synchronize()
 
 
 def gather_blocks(keys, vox, dst: int = 0, group=None, device=None):

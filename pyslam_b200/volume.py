@@ -253,6 +253,10 @@ class B200TsdfVolume:
         """integrate_batch: fuse groups of up to 8 frames per block visit (default) or go frame by frame."""
         self._check(self._L.b2v_set_fusion(self._h, 1 if enable else 0), "b2v_set_fusion")
 
+    def set_group_size(self, frames: int):
+        """Frames per fused group of integrate_batch (1..32, default 8); results do not depend on it."""
+        self._check(self._L.b2v_set_group_size(self._h, int(frames)), "b2v_set_group_size")
+
     def set_rectification(self, map_x, map_y, swap_rb: bool = False):
         """Install the undistortion maps of `cv2.initUndistortRectifyMap(K, D, None, new_K, (w, h), CV_32FC1)`
         (volumetric_integrator_base.py:766-778): integrate() then takes the RAW images and rectifies them on the

@@ -202,15 +202,15 @@ API = SimpleNamespace(
 
 
 def standalone_integrator_class():
-    from .integrator import make_integrator_class
+    from pyslam_b200.integrator import make_integrator_class
     return make_integrator_class(StandaloneIntegratorBase, API)
 
 
 def standalone_voxel_grid_integrator_class():
-    from .integrator_semantic import make_voxel_grid_integrator_class
+    from pyslam_b200.integrator_semantic import make_voxel_grid_integrator_class
     return make_voxel_grid_integrator_class(StandaloneIntegratorBase, API)
 
 
 def standalone_semantic_integrator_class():
-    from .integrator_semantic import make_semantic_integrator_class
+    from pyslam_b200.integrator_semantic import make_semantic_integrator_class
     return make_semantic_integrator_class(StandaloneIntegratorBase, API)

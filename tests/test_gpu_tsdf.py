@@ -310,16 +310,21 @@ def test_execution_variants_are_bit_identical(env, monkeypatch):
     _assert_same_volume(var, orc)
 
 
-def test_fused_batch_equals_frame_by_frame_and_oracle():
-    """integrate_batch fuses groups of 8 frames per block visit; 19 frames = 8 + 8 + 3 exercises full and
-    partial groups and the rotation of the group buffers.  Bit-identical to frame-by-frame and the oracle."""
+@pytest.mark.parametrize("group", [8, 3, 16, 32])
+def test_fused_batch_equals_frame_by_frame_and_oracle(group):
+    """integrate_batch fuses groups of `group` frames per block visit (8 by default: the unrolled kernel; larger
+    groups take the constant-indexed loop); 19 or 75 frames exercise full and partial groups and the rotation of
+    the group buffers.  Bit-identical to frame-by-frame and the oracle."""
     cfg = S.CONFIGS["C1"]
-    n = 19
+    n = 19 if group <= 8 else 75
     frames = [S.render_frame(cfg, i) for i in range(n)]
     D, Cc, T = (np.stack([f[k] for f in frames]) for k in range(3))
     fused, orc = _pair(cfg, capacity=1 << 16)
     plain, _ = _pair(cfg, capacity=1 << 16)
     plain.set_fusion(False)
+    fused.set_group_size(group)
+    with pytest.raises(RuntimeError):
+        fused.set_group_size(33)
     fused.integrate_batch(D, Cc, cfg.K, T)
     plain.integrate_batch(D, Cc, cfg.K, T)
     for d, c, t in frames:

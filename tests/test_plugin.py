@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from pyslam_b200 import integrator as I
-from pyslam_b200 import plugin_api as P
+from tests import plugin_standins as P
 from pyslam_b200 import synthetic as S
 
 
@@ -19,9 +19,15 @@ class _FakeVolume:
         self.calls = []
         self.closed = False
 
-    def integrate(self, depth, color, K, pose):
-        assert depth.dtype == np.float32 and color.dtype == np.uint8
+    def integrate(self, depth, color, K, pose, depth_scale=None):
+        assert color.dtype == np.uint8 and (depth.dtype == np.float32 or (depth_scale and depth.dtype == np.uint16))
         self.calls.append(("integrate", tuple(K), np.asarray(pose).copy(), color[0, 0].copy()))
+        self.last_depth, self.last_scale = depth, depth_scale
+
+    def integrate_batch(self, depths, colors, K, poses, depth_scale=None):
+        assert colors.dtype == np.uint8 and depths.shape[0] == colors.shape[0] == poses.shape[0]
+        self.calls.append(("integrate_batch", tuple(K), np.asarray(poses).copy(), int(depths.shape[0])))
+        self.last_depth, self.last_scale = depths, depth_scale
 
     def reset(self):
         self.calls.append(("reset",))
@@ -95,6 +101,45 @@ def test_adapter_task_flow_with_fake_volume(monkeypatch, tmp_path):
     assert integ.volume.closed
 
 
+def test_backlog_is_drained_into_one_fused_batch(monkeypatch):
+    """rebuild(map) re-enqueues every keyframe (base.py:1242-1318): consecutive INTEGRATE tasks already in the queue
+    go to ONE integrate_batch call (bounded); a task of another type met while draining is handled by the next
+    call, in order; output cadence and RESET semantics are unchanged."""
+    monkeypatch.setattr(I, "B200TsdfVolume", _FakeVolume)
+    Cls = P.standalone_integrator_class()
+    cfg = S.CONFIGS["T0"]
+    integ = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_TSDF",
+                kVolumetricIntegrationB200MaxBatch=4)
+    d, c, T = S.render_frame(cfg, 0)
+    bgr = np.ascontiguousarray(c[..., ::-1])
+    poses = []
+    for i in range(6):
+        Ti = T.copy()
+        Ti[0, 3] += 0.01 * i
+        poses.append(Ti)
+        integ.add_keyframe_data(P.VolumetricIntegrationKeyframeData(id=i, pose=Ti, img=bgr, depth=d))
+    integ.add_update_output_task()
+    integ.add_keyframe_data(P.VolumetricIntegrationKeyframeData(id=6, pose=T, img=bgr, depth=d))
+    integ.step()                                   # frames 0..3 (bounded by MaxBatch) in one call
+    name, K, P4, n = integ.volume.calls[0]
+    assert name == "integrate_batch" and n == 4 and np.array_equal(P4, np.stack(poses[:4]))
+    assert integ.pop_output().id == 3              # the first output carries the last integrated id
+    integ.step()                                   # frames 4, 5; the UPDATE_OUTPUT task is met and deferred
+    assert integ.volume.calls[-1][0] == "integrate_batch" and integ.volume.calls[-1][3] == 2
+    assert integ.pop_output() is None              # inside the output interval
+    integ.step()                                   # the deferred UPDATE_OUTPUT, before frame 6
+    assert integ.pop_output().task_type == P.VolumetricIntegrationTaskType.UPDATE_OUTPUT
+    assert [cl[0] for cl in integ.volume.calls if cl[0].startswith("integrate")] == ["integrate_batch"] * 2
+    integ.step()                                   # frame 6 alone: the single-frame call
+    assert integ.volume.calls[-1][0] == "integrate" and integ.integrated_frames == 7
+    # MaxBatch = 1 restores one task per call
+    integ2 = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_TSDF", kVolumetricIntegrationB200MaxBatch=1)
+    for i in range(3):
+        integ2.add_keyframe_data(P.VolumetricIntegrationKeyframeData(id=i, pose=T, img=bgr, depth=d))
+    integ2.run_pending()
+    assert [cl[0] for cl in integ2.volume.calls if cl[0].startswith("integrate")] == ["integrate"] * 3
+
+
 def test_outdoor_depth_trunc_and_point_cloud_mode(monkeypatch):
     monkeypatch.setattr(I, "B200TsdfVolume", _FakeVolume)
     Cls = P.standalone_integrator_class()
@@ -161,6 +206,21 @@ def test_adapter_gpu_rectification_hands_raw_frames_to_the_volume(monkeypatch):
     integ.step()
     call = [c for c in integ.volume.calls if c[0] == "integrate"][-1]
     assert np.array_equal(call[3], g["bgr"][0, 0])   # raw BGR, untouched
+    # raw uint16 depth: python core -> depth.astype(float32) on the host; C++ core (USE_CPP) -> the uint16 image goes
+    # to the GPU with depth_scale = camera.depth_factor (base.py:1007-1015 multiplies by self.camera.depth_factor)
+    raw16 = np.round(g["depth"] * 5000.0).astype(np.uint16)
+    integ.add_keyframe_data(P.VolumetricIntegrationKeyframeData(id=2, pose=g["Tcw"], img=g["bgr"], depth=raw16))
+    integ.step()
+    assert integ.volume.last_depth.dtype == np.float32 and integ.volume.last_scale is None
+    assert np.array_equal(integ.volume.last_depth, raw16.astype(np.float32))
+    api_cpp = SimpleNamespace(**{**vars(P.API), "USE_CPP": True})
+    ClsCpp = I.make_integrator_class(P.StandaloneIntegratorBase, api_cpp)
+    cam = _camera(cfg)
+    cam.depth_factor = 1.0 / 5000.0
+    integ_cpp = ClsCpp(cam, P.DatasetEnvironmentType.INDOOR, None, "B200_TSDF", calib_maps=(g["map1"], g["map2"]))
+    integ_cpp.add_keyframe_data(P.VolumetricIntegrationKeyframeData(id=3, pose=g["Tcw"], img=g["bgr"], depth=raw16))
+    integ_cpp.step()
+    assert integ_cpp.volume.last_depth.dtype == np.uint16 and integ_cpp.volume.last_scale == np.float32(1.0 / 5000.0)
     cv2 = pytest.importorskip("cv2")
     del cv2
     integ2 = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_TSDF",

@@ -87,3 +87,62 @@ def test_hash_and_owner_match_the_reference_hash():
         dict(keys=keys[:100], hashes=h[:100], vox=np.zeros((100, 5, 512), np.float32)),
         dict(keys=keys[100:], hashes=h[100:], vox=np.ones((100, 5, 512), np.float32))])
     assert len(merged["keys"]) == 200 and np.array_equal(sharding.block_key_hash(merged["keys"]), merged["hashes"])
+
+
+class _RecordingVolume:
+    """Stand-in for B200TsdfVolume: records what FrameIngest hands to integrate_batch."""
+    device = 0
+
+    def __init__(self):
+        self.calls = []
+
+    def integrate_batch(self, depths, colors, K, poses, stream=None, depth_scale=None):
+        self.calls.append((depths.clone(), colors.clone(), np.array(poses), depth_scale))
+
+    def synchronize(self):
+        pass
+
+
+def _ingest_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)   # same batch on every rank
+        n, H, W = 23, 6, 8               # ragged: 23 = 2 chunks of 10 + one of 3 (3 frames over 2 ranks: 2 + 1)
+        D = rng.random((n, H, W)).astype(np.float32)
+        Cc = rng.integers(0, 255, (n, H, W, 3), dtype=np.uint8)
+        T = rng.random((n, 4, 4))
+        vol = _RecordingVolume()
+        ing = sharding.FrameIngest(vol, chunk_frames=10, buffers=2, device="cpu")
+        ing.integrate_batch(D, Cc, (1.0, 1.0, 0.0, 0.0), T)
+        ing.integrate_batch(np.round(D * 1000).astype(np.uint16), Cc, (1.0, 1.0, 0.0, 0.0), T, depth_scale=1e-3)
+        got_d = np.concatenate([c[0].numpy() for c in vol.calls[:3]])
+        got_c = np.concatenate([c[1].numpy() for c in vol.calls[:3]])
+        got_t = np.concatenate([c[2] for c in vol.calls[:3]])
+        got16 = np.concatenate([c[0].numpy() for c in vol.calls[3:]])
+        ok = (np.array_equal(got_d, D) and np.array_equal(got_c, Cc) and np.array_equal(got_t, T)
+              and [len(c[0]) for c in vol.calls] == [10, 10, 3, 10, 10, 3]
+              and np.array_equal(got16, np.round(D * 1000).astype(np.uint16)) and vol.calls[3][3] == 1e-3)
+        # every frame was uploaded by exactly one rank
+        t = torch.tensor([float(ing.h2d_bytes)], dtype=torch.float64)
+        dist.all_reduce(t)
+        ok = ok and int(t.item()) == n * H * W * (4 + 3) + n * H * W * (2 + 3)
+        q.put("ok" if ok else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_ingest_splits_uploads_and_gathers_frames_in_order():
+    assert sharding.chunk_plan(23, 2, 10) == [(0, 10, 5), (10, 10, 5), (20, 3, 2)]
+    assert sharding.chunk_plan(8, 8, 64) == [(0, 8, 1)]
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ingest_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert res == ["ok", "ok"]
