@@ -535,6 +535,9 @@ def _sem():
         L.refsem_carve.argtypes = [vp, _f32p, C.c_int, C.c_int, _f64p, C.c_float, C.c_float, _f32p, C.c_float]
         L.refsem_set_next_object_id.argtypes = [C.c_int32]
         L.refsem_get_next_object_id.restype = C.c_int32
+        L.refsem_integrate_segment.argtypes = [vp, _f64p, C.c_int64, _f32p, C.c_int, C.c_int]
+        L.refsem_segments.restype = C.c_int64
+        L.refsem_segments.argtypes = [vp, C.c_int, C.c_int, C.c_float] + [vp] * 8 + [C.POINTER(C.c_int64)]
         L.refsem_remove_low_count_voxels.argtypes = [vp, C.c_int]
         L.refsem_remove_low_confidence_segments.argtypes = [vp, C.c_int]
         L.refsem_merge_segments.argtypes = [vp, C.c_int, C.c_int]
@@ -585,6 +588,37 @@ class RefSemanticGrid:
         fn = self._L.refsem_integrate_f32 if f32 else self._L.refsem_integrate
         fn(self._h, pts, n, cols.ctypes.data, ptr(class_ids, np.int32), ptr(instance_ids, np.int32),
            ptr(depths, np.float32))
+
+    def integrate_segment(self, points, colors, class_id, object_id):
+        pts = np.ascontiguousarray(points, np.float64)
+        cols = np.ascontiguousarray(colors, np.float32)
+        self._L.refsem_integrate_segment(self._h, pts.reshape(-1), pts.shape[0], cols.reshape(-1), int(class_id),
+                                         int(object_id))
+
+    def _segments(self, by_class, min_count, min_confidence):
+        tot = C.c_int64(0)
+        a = (self._h, int(by_class), int(min_count), float(min_confidence))
+        n = self._L.refsem_segments(*a, None, None, None, None, None, None, None, None, C.byref(tot))
+        ids, cls, npts = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int64)
+        cmin, cmax, obb = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros((n, 10), np.float64)
+        pts, cols = np.zeros((tot.value, 3), np.float64), np.zeros((tot.value, 3), np.float32)
+        if n:
+            self._L.refsem_segments(*a, ids.ctypes.data, cls.ctypes.data, npts.ctypes.data, cmin.ctypes.data,
+                                    cmax.ctypes.data, obb.ctypes.data, pts.ctypes.data, cols.ctypes.data, C.byref(tot))
+        out, off = [], 0
+        for k in range(n):
+            m = int(npts[k])
+            out.append(dict(id=int(ids[k]), class_id=int(cls[k]), points=pts[off:off + m], colors=cols[off:off + m],
+                            confidence_min=float(cmin[k]), confidence_max=float(cmax[k]), obb_center=obb[k, 0:3],
+                            obb_size=obb[k, 3:6], obb_quat_wxyz=obb[k, 6:10]))
+            off += m
+        return out
+
+    def get_object_segments(self, min_count=1, min_confidence=0.0):
+        return self._segments(0, min_count, min_confidence)
+
+    def get_class_segments(self, min_count=1, min_confidence=0.0):
+        return self._segments(1, min_count, min_confidence)
 
     def num_blocks(self):
         return int(self._L.refsem_num_blocks(self._h))

@@ -43,6 +43,12 @@ struct ISem {
     virtual void carve(const volumetric::CameraFrustrum &fr, const cv::Mat &depth, float thr) = 0;
     virtual int64_t query(const volumetric::CameraFrustrum *fr, const double *bb, int min_count, float min_conf,
                           double *pts, float *cols, int32_t *cls, int32_t *obj, float *conf) const = 0;
+    virtual void integrate_segment(const double *pts, int64_t n, const float *cols, int cls, int obj) = 0;
+    // flattened get_object_segments (by_class = 0) / get_class_segments (1): per segment {id, class id, n points,
+    // conf min, conf max, OBB centre 3 + size 3 + quaternion wxyz (objects only)}; points / colours concatenated
+    virtual int64_t segments(int by_class, int min_count, float min_conf, int32_t *ids, int32_t *cls, int64_t *npts,
+                             float *conf_min, float *conf_max, double *obb, double *pts, float *cols,
+                             int64_t *total_points) const = 0;
     virtual void remove_low_count(int min_count) = 0;
     virtual void remove_low_confidence(int min_confidence) = 0;
     virtual void merge_segments(int a, int b) = 0;
@@ -170,6 +176,45 @@ template <typename Grid, typename V> struct Sem final : ISem {
         if (conf) std::memcpy(conf, out.confidences.data(), sizeof(float) * n);
         return n;
     }
+    void integrate_segment(const double *pts, int64_t n, const float *cols, int cls, int obj) override {
+        g.template integrate_segment_raw<double, float, int, int>(pts, static_cast<size_t>(n), cols, cls, obj);
+    }
+    int64_t segments(int by_class, int min_count, float min_conf, int32_t *ids, int32_t *cls, int64_t *npts,
+                     float *conf_min, float *conf_max, double *obb, double *pts, float *cols,
+                     int64_t *total_points) const override {
+        int64_t k = 0, off = 0;
+        auto emit = [&](int id, int class_id, const auto &d, const volumetric::OrientedBoundingBox3D *box) {
+            const int64_t n = static_cast<int64_t>(d.points.size());
+            if (ids) ids[k] = id;
+            if (cls) cls[k] = class_id;
+            if (npts) npts[k] = n;
+            if (conf_min) conf_min[k] = d.confidence_min;
+            if (conf_max) conf_max[k] = d.confidence_max;
+            if (obb && box) {
+                for (int a = 0; a < 3; ++a) {
+                    obb[10 * k + a] = box->center[a];
+                    obb[10 * k + 3 + a] = box->size[a];
+                }
+                obb[10 * k + 6] = box->orientation.w();
+                obb[10 * k + 7] = box->orientation.x();
+                obb[10 * k + 8] = box->orientation.y();
+                obb[10 * k + 9] = box->orientation.z();
+            }
+            if (pts) std::memcpy(pts + 3 * off, d.points.data(), sizeof(double) * 3 * n);
+            if (cols) std::memcpy(cols + 3 * off, d.colors.data(), sizeof(float) * 3 * n);
+            off += n;
+            ++k;
+        };
+        if (by_class) {
+            const auto grp = g.get_class_segments(min_count, min_conf);
+            for (const auto &c : grp->class_vector) emit(c->class_id, c->class_id, *c, nullptr);
+        } else {
+            const auto grp = g.get_object_segments(min_count, min_conf);
+            for (const auto &o : grp->object_vector) emit(o->object_id, o->class_id, *o, &o->oriented_bounding_box);
+        }
+        if (total_points) *total_points = off;
+        return k;
+    }
     void remove_low_count(int min_count) override { g.remove_low_count_voxels(min_count); }
     void remove_low_confidence(int min_confidence) override { g.remove_low_confidence_segments(min_confidence); }
     void merge_segments(int a, int b) override { g.merge_segments(a, b); }
@@ -277,6 +322,14 @@ int64_t refsem_query(void *h, const float *K, int width, int height, const doubl
 void refsem_set_next_object_id(int32_t v) { volumetric::VoxelSemanticSharedData::next_object_id.store(v); }
 int32_t refsem_get_next_object_id(void) { return volumetric::VoxelSemanticSharedData::next_object_id.load(); }
 
+void refsem_integrate_segment(void *h, const double *pts, int64_t n, const float *cols, int cls, int obj) {
+    static_cast<ISem *>(h)->integrate_segment(pts, n, cols, cls, obj);
+}
+int64_t refsem_segments(void *h, int by_class, int min_count, float min_conf, int32_t *ids, int32_t *cls, int64_t *npts,
+                        float *conf_min, float *conf_max, double *obb, double *pts, float *cols, int64_t *total_points) {
+    return static_cast<ISem *>(h)->segments(by_class, min_count, min_conf, ids, cls, npts, conf_min, conf_max, obb, pts,
+                                            cols, total_points);
+}
 void refsem_remove_low_count_voxels(void *h, int min_count) { static_cast<ISem *>(h)->remove_low_count(min_count); }
 void refsem_remove_low_confidence_segments(void *h, int min_confidence) {
     static_cast<ISem *>(h)->remove_low_confidence(min_confidence);

@@ -1167,11 +1167,10 @@ static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t
     if (rc != B2V_OK) return rc;
     v->mb.n_blocks = nb;
     cudaStream_t cs = v->compute;
-    B2V_CUDA(v, launch_mesh_neighbors(v->table, v->meta, v->mb, cs));
     if (mesh) {
-        B2V_CUDA(v, launch_mesh_classify(v->meta, v->mb, cs));
+        B2V_CUDA(v, launch_mesh_classify(v->table, v->meta, v->mb, cs));
     } else {
-        B2V_CUDA(v, launch_point_masks(v->meta, v->mb, cs));
+        B2V_CUDA(v, launch_point_masks(v->table, v->meta, v->mb, cs));
     }
     B2V_CUDA(v, launch_mesh_scan(v->mb, cs));
     B2V_CUDA(v, cudaMemcpyAsync(v->h_totals, v->mb.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
@@ -1190,7 +1189,7 @@ static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t
     B2V_CUDA(v, launch_mesh_vertices(v->meta, v->mb, v->geo.voxel_length, v->geo.unit_shift, !mesh, cs));
     if (mesh) B2V_CUDA(v, launch_mesh_triangles(v->mb, cs));
     B2V_CUDA(v, cudaStreamSynchronize(cs));
-    v->launches += mesh ? 6 : 5;
+    v->launches += mesh ? 5 : 4;
     v->last_nv = static_cast<int64_t>(nv);
     v->last_nt = mesh ? static_cast<int64_t>(nt) : 0;
     if (n_vertices) *n_vertices = v->last_nv;

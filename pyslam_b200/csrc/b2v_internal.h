@@ -188,12 +188,13 @@ struct MeshBuffers {
     int32_t *edge_ids;       // [nv][4] canonical weld key (voxel x,y,z, axis)
     int32_t *triangles;      // [nt][3]
 };
-cudaError_t launch_mesh_neighbors(const HashTable &table, const PoolMeta &meta,
-                                  const MeshBuffers &mb, cudaStream_t stream);
-// marching-cubes case per voxel + vertex ownership masks (Open3D ExtractTriangleMesh semantics)
-cudaError_t launch_mesh_classify(const PoolMeta &meta, const MeshBuffers &mb, cudaStream_t stream);
-// zero-crossing masks of Open3D ExtractPointCloud (no cube validity requirement)
-cudaError_t launch_point_masks(const PoolMeta &meta, const MeshBuffers &mb, cudaStream_t stream);
+// neighbour lookup (7 hash probes per block) + marching-cubes case per voxel + vertex ownership masks
+// (Open3D ExtractTriangleMesh semantics)
+cudaError_t launch_mesh_classify(const HashTable &table, const PoolMeta &meta, const MeshBuffers &mb,
+                                 cudaStream_t stream);
+// neighbour lookup + zero-crossing masks of Open3D ExtractPointCloud (no cube validity requirement)
+cudaError_t launch_point_masks(const HashTable &table, const PoolMeta &meta, const MeshBuffers &mb,
+                               cudaStream_t stream);
 // per-block sums + exclusive scans -> offs, totals
 cudaError_t launch_mesh_scan(const MeshBuffers &mb, cudaStream_t stream);
 cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, double voxel_length, int unit_shift,

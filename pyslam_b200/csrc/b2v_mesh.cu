@@ -39,21 +39,15 @@ static cudaError_t upload_tables_once() {
 
 // ---- pass 0: neighbour block indices --------------------------------------------------------
 
-__global__ void mesh_neighbors_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= mb.n_blocks * 8u) return;
-    const uint32_t b = i >> 3, o = i & 7;
+// pool index of the block at +(o&1, o>>1&1, o>>2&1) of block b, -1 if it does not exist; done by the first 8 threads
+// of the classify / point-mask CTAs (the result is kept in mb.nbr for the emit kernels)
+__device__ __forceinline__ int32_t neighbor_block(const HashTable &T, const PoolMeta &M, uint32_t b, uint32_t o) {
+    if (o == 0) return static_cast<int32_t>(b);
     const int4 k = M.block_keys[b];
-    int32_t idx = static_cast<int32_t>(b);
-    if (o != 0) {
-        const uint32_t s = table_find(T, k.x + (o & 1), k.y + ((o >> 1) & 1), k.z + ((o >> 2) & 1));
-        idx = -1;
-        if (s != kEmpty) {
-            const uint32_t w = T.entries[s].w;
-            if (w < M.capacity) idx = static_cast<int32_t>(w);
-        }
-    }
-    mb.nbr[i] = idx;
+    const uint32_t s = table_find(T, k.x + (o & 1), k.y + ((o >> 1) & 1), k.z + ((o >> 2) & 1));
+    if (s == kEmpty) return -1;
+    const uint32_t w = T.entries[s].w;
+    return w < M.capacity ? static_cast<int32_t>(w) : -1;
 }
 
 // owner voxel of cube edge e rooted at local (lx,ly,lz): returns flat index into per-voxel arrays
@@ -71,13 +65,13 @@ __device__ __forceinline__ bool edge_owner(const int *s_nbr, int lx, int ly, int
 // ---- pass 1a: marching-cubes case + vertex ownership (mesh) ---------------------------------
 
 __global__ void __launch_bounds__(kVox)
-mesh_classify_kernel(const PoolMeta M, const MeshBuffers mb) {
+mesh_classify_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) {
     __shared__ float s_f[729];
     __shared__ float s_w[729];
     __shared__ int s_nbr[8];
     const uint32_t b = blockIdx.x;
     const int t = threadIdx.x;
-    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
+    if (t < 8) mb.nbr[b * 8 + t] = s_nbr[t] = neighbor_block(T, M, b, t);
     __syncthreads();
     for (int i = t; i < 729; i += kVox) {
         const int x = i % 9, y = (i / 9) % 9, z = i / 81;
@@ -121,12 +115,12 @@ mesh_classify_kernel(const PoolMeta M, const MeshBuffers mb) {
 // ---- pass 1b: zero-crossing masks (point cloud) ---------------------------------------------
 
 __global__ void __launch_bounds__(kVox)
-point_masks_kernel(const PoolMeta M, const MeshBuffers mb) {
+point_masks_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) {
     __shared__ int s_nbr[8];
     __shared__ uint8_t s_m[kVox];
     const uint32_t b = blockIdx.x;
     const int t = threadIdx.x;
-    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
+    if (t < 8) mb.nbr[b * 8 + t] = s_nbr[t] = neighbor_block(T, M, b, t);
     __syncthreads();
     const float *blk = M.pool + static_cast<size_t>(b) * kBlockFloats;
     const float f0 = blk[t], w0 = blk[kVox + t];
@@ -190,6 +184,7 @@ mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const double vl, co
     __shared__ uint32_t s_warp[16];
     __shared__ int s_nbr[8];
     const uint32_t b = blockIdx.x;
+    if (mb.sums[b] == 0u) return;  // no vertex lives in this block (most blocks: free space / behind the surface)
     const int t = threadIdx.x;
     if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
     const size_t flat = static_cast<size_t>(b) * kVox + t;
@@ -269,6 +264,7 @@ mesh_triangles_kernel(const MeshBuffers mb) {
     __shared__ uint32_t s_warp[16];
     __shared__ int s_nbr[8];
     const uint32_t b = blockIdx.x;
+    if (mb.sums[mb.n_blocks + b] == 0u) return;  // no triangle rooted in this block
     const int t = threadIdx.x;
     if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
     const int cube = mb.cube[static_cast<size_t>(b) * kVox + t];
@@ -297,26 +293,21 @@ mesh_triangles_kernel(const MeshBuffers mb) {
 
 // ---- launchers -------------------------------------------------------------------------------
 
-cudaError_t launch_mesh_neighbors(const HashTable &table, const PoolMeta &meta,
-                                  const MeshBuffers &mb, cudaStream_t stream) {
+cudaError_t launch_mesh_classify(const HashTable &table, const PoolMeta &meta, const MeshBuffers &mb,
+                                 cudaStream_t stream) {
     cudaError_t e = upload_tables_once();
     if (e != cudaSuccess || mb.n_blocks == 0) return e;
-    const uint32_t n = mb.n_blocks * 8u;
-    mesh_neighbors_kernel<<<(n + 255) / 256, 256, 0, stream>>>(table, meta, mb);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_mesh_classify(const PoolMeta &meta, const MeshBuffers &mb, cudaStream_t stream) {
-    if (mb.n_blocks == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(mb.edge_mask, 0, static_cast<size_t>(mb.n_blocks) * kVox, stream);
+    e = cudaMemsetAsync(mb.edge_mask, 0, static_cast<size_t>(mb.n_blocks) * kVox, stream);
     if (e != cudaSuccess) return e;
-    mesh_classify_kernel<<<mb.n_blocks, kVox, 0, stream>>>(meta, mb);
+    mesh_classify_kernel<<<mb.n_blocks, kVox, 0, stream>>>(table, meta, mb);
     return cudaGetLastError();
 }
 
-cudaError_t launch_point_masks(const PoolMeta &meta, const MeshBuffers &mb, cudaStream_t stream) {
-    if (mb.n_blocks == 0) return cudaSuccess;
-    point_masks_kernel<<<mb.n_blocks, kVox, 0, stream>>>(meta, mb);
+cudaError_t launch_point_masks(const HashTable &table, const PoolMeta &meta, const MeshBuffers &mb,
+                               cudaStream_t stream) {
+    cudaError_t e = upload_tables_once();
+    if (e != cudaSuccess || mb.n_blocks == 0) return e;
+    point_masks_kernel<<<mb.n_blocks, kVox, 0, stream>>>(table, meta, mb);
     return cudaGetLastError();
 }
 

@@ -11,8 +11,12 @@ loop body (reference :326-461) maps one-to-one onto the C ABI:
     carve (no instance ids)                                                 ->  b2v_sgrid_carve
     get_voxels(min_count, min_confidence)                                   ->  b2v_sgrid_get_voxels / copy_voxels
 
-Outputs are the reference's single-point-cloud representation (:590-700): points, colours, class ids, object ids.
-The object-segment representation (`get_object_segments`, oriented boxes) is not part of this backend.
+    get_object_segments(min_count, min_confidence)                          ->  b2v_sgrid_get_voxels + grouping / PCA boxes
+
+Outputs: when 2-D instance ids are integrated, the reference's OBJECTS representation (:523-587:
+`get_object_segments` -> `VolumetricIntegrationObjectList`, one entry per object with its points, colours, class id,
+confidence range and oriented box); otherwise its single-point-cloud representation (:590-700): points, colours,
+class ids, object ids.
 """
 
 from __future__ import annotations
@@ -51,6 +55,7 @@ DEFAULT_PARAMETERS = {
     "kVolumetricSemanticIntegrationMinVotes": 3,
     "kVolumetricIntegrationB200CapacityBlocks": 1 << 15,
     "kVolumetricIntegrationB200Device": 0,
+    "kVolumetricIntegrationB200GenerateObjects": True,   # kGenerateObjectsDefault (reference :84)
 }
 
 
@@ -115,6 +120,7 @@ def make_semantic_integrator_class(Base, api):
                 return False
             depth = np.ascontiguousarray(depth, np.float32)
             flt = bool(p["kVolumetricIntegrationVoxelGridShadowPointsFilter"])
+            self.integrated_instance_ids = False
             use_instances = (bool(p["kVolumetricSemanticIntegrationUseInstanceIds"]) and instances is not None
                              and np.asarray(instances).size > 0 and classes is not None)
             self.camera_frustrum.set_T_cw(kd.pose)
@@ -130,6 +136,7 @@ def make_semantic_integrator_class(Base, api):
                         min_vote_ratio=float(p["kVolumetricSemanticIntegrationMinVoteRatio"]),
                         min_votes=int(p["kVolumetricSemanticIntegrationMinVotes"]))
                     object_image = remap_instance_ids(instances, self.last_instance_map)
+                    self.integrated_instance_ids = True
                 else:
                     self.volume.carve(self.camera_frustrum, depth_used, carve_thr)
             fx, fy, cx, cy = self._intrinsics()
@@ -143,6 +150,22 @@ def make_semantic_integrator_class(Base, api):
 
         def _make_output(self, task_type):
             p = self.b200_parameters
+            ObjList = getattr(api, "VolumetricIntegrationObjectList", None)
+            if (p["kVolumetricIntegrationB200GenerateObjects"] and getattr(self, "integrated_instance_ids", False)
+                    and ObjList is not None):
+                # reference :523-587: objects only when instance ids are available
+                grp = self.volume.get_object_segments(
+                    min_count=int(p["kVolumetricIntegrationVoxelGridMinCount"]),
+                    min_confidence=float(p["kVolumetricIntegrationVoxelGridMinConfidence"]))
+                sem_rgb = getattr(api, "sem_img_to_rgb", None)      # SemanticMappingShared.sem_img_to_rgb
+                ids_rgb = getattr(api, "ids_to_rgb_float", None)    # IdsColorTable.ids_to_rgb_float
+                n = len(grp.object_vector)
+                sem_cols = (np.ascontiguousarray(sem_rgb(np.asarray(grp.class_ids), bgr=True), np.float32) / 255.0
+                            if sem_rgb is not None and n else np.zeros((n, 3), np.float32))
+                obj_cols = (np.ascontiguousarray(ids_rgb(np.asarray(grp.object_ids), bgr=True), np.float32)
+                            if ids_rgb is not None and n else np.zeros((n, 3), np.float32))
+                objects = ObjList(grp, sem_cols, obj_cols, n)
+                return api.VolumetricIntegrationOutput(task_type, self.last_integrated_id, None, None, objects)
             v = self.volume.get_voxels(min_count=int(p["kVolumetricIntegrationVoxelGridMinCount"]),
                                        min_confidence=float(p["kVolumetricIntegrationVoxelGridMinConfidence"]))
             pc = api.VolumetricIntegrationPointCloud(points=np.ascontiguousarray(v.points, np.float32),
@@ -290,5 +313,13 @@ def load_pyslam_semantic_plugin():
         VolumetricIntegrationOutput=B.VolumetricIntegrationOutput,
         VolumetricIntegrationMesh=B.VolumetricIntegrationMesh,
         VolumetricIntegrationPointCloud=B.VolumetricIntegrationPointCloud,
+        VolumetricIntegrationObjectList=B.VolumetricIntegrationObjectList,
         DatasetEnvironmentType=DatasetEnvironmentType, Parameters=Parameters)
+    try:   # colours of the viewer: semantic palette and per-object id colours (reference :535-575)
+        from pyslam.semantics.semantic_mapping_shared import SemanticMappingShared
+        from pyslam.utilities.colors import IdsColorTable
+        api.sem_img_to_rgb = SemanticMappingShared.sem_img_to_rgb
+        api.ids_to_rgb_float = IdsColorTable().ids_to_rgb_float
+    except Exception:
+        pass
     return make_semantic_integrator_class(B.VolumetricIntegratorBase, api)

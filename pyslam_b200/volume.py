@@ -620,6 +620,122 @@ class VoxelBlockGrid:
         return self._collect(self._L.b2v_grid_get_voxels_in_bb(self._h, bb.ctypes.data, int(min_count)))
 
 
+class OrientedBoundingBox3D:
+    """`volumetric.OrientedBoundingBox3D` fields: center [3], size [3], orientation (unit quaternion w, x, y, z of the
+    box -> world rotation).  `compute_from_points` is the reference's PCA method (bounding_boxes_3d.cpp:373-556):
+    running centroid / covariance (Welford) in float64, eigenvectors sorted by descending eigenvalue, right-handed,
+    extents from the min / max of the points in that frame."""
+
+    def __init__(self, center=None, size=None, rotation=None):
+        self.center = np.zeros(3) if center is None else np.asarray(center, np.float64)
+        self.size = np.zeros(3) if size is None else np.asarray(size, np.float64)
+        self.R = np.eye(3) if rotation is None else np.asarray(rotation, np.float64)
+
+    @property
+    def orientation(self):
+        return _quat_wxyz(self.R)
+
+    def get_matrix(self):
+        M = np.eye(4)
+        M[:3, :3], M[:3, 3] = self.R, self.center
+        return M
+
+    def get_corners(self):
+        h = self.size / 2.0
+        sg = np.array([[1, 1, -1], [-1, 1, -1], [-1, -1, -1], [1, -1, -1], [1, 1, 1], [-1, 1, 1], [-1, -1, 1], [1, -1, 1]], float)
+        return self.center + (sg * h) @ self.R.T
+
+    @staticmethod
+    def compute_from_points(points):
+        P = np.asarray(points, np.float64).reshape(-1, 3)
+        n = len(P)
+        if n == 0:
+            return OrientedBoundingBox3D()
+        if n == 1:
+            return OrientedBoundingBox3D(P[0], np.zeros(3), np.eye(3))
+        if n == 2:
+            c, diff = 0.5 * (P[0] + P[1]), P[1] - P[0]
+            dn = np.linalg.norm(diff)
+            if dn < 1e-10:
+                return OrientedBoundingBox3D(c, np.zeros(3), np.eye(3))
+            a1 = diff / dn
+            ref = np.array([1.0, 0, 0]) if abs(a1[0]) < 0.9 else np.array([0, 1.0, 0])
+            a2 = np.cross(ref, a1)
+            a2 /= np.linalg.norm(a2)
+            a3 = np.cross(a1, a2)
+            a3 /= np.linalg.norm(a3)
+            R = np.stack([a1, a2, a3], axis=1)
+            if np.linalg.det(R) < 0:
+                R[:, 2] = -R[:, 2]
+            centroid = c
+        else:
+            # the reference's one-pass Welford update equals the two-pass centroid / covariance up to rounding
+            centroid = P.mean(axis=0)
+            d = P - centroid
+            cov = d.T @ d / n
+            w, V = np.linalg.eigh(cov)
+            R = V[:, np.argsort(-w, kind="stable")]
+            if np.dot(np.cross(R[:, 0], R[:, 1]), R[:, 2]) < 0:
+                R[:, 2] = -R[:, 2]
+        local = (P - centroid) @ R
+        lo, hi = local.min(axis=0), local.max(axis=0)
+        return OrientedBoundingBox3D(centroid + R @ (0.5 * (hi + lo)), hi - lo, R)
+
+
+def _quat_wxyz(R):
+    """Rotation matrix -> unit quaternion (w, x, y, z), Eigen's branch order."""
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = [0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s]
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+        q = [0.0] * 4
+        q[0] = (R[k, j] - R[j, k]) / s
+        q[1 + i] = 0.25 * s
+        q[1 + j] = (R[j, i] + R[i, j]) / s
+        q[1 + k] = (R[k, i] + R[i, k]) / s
+    return np.array(q)
+
+
+class ObjectData:
+    """`volumetric.ObjectData` (voxel_grid_data.h:64-79)."""
+
+    def __init__(self, object_id, class_id, points, colors, confidence_min, confidence_max):
+        self.object_id, self.class_id = int(object_id), int(class_id)
+        self.points, self.colors = points, colors
+        self.confidence_min, self.confidence_max = confidence_min, confidence_max
+        self.oriented_bounding_box = OrientedBoundingBox3D.compute_from_points(points)
+
+
+class ObjectDataGroup:
+    """`volumetric.ObjectDataGroup` (voxel_grid_data.h:87-96)."""
+
+    def __init__(self, objects):
+        self.object_vector = objects
+        self.class_ids = [o.class_id for o in objects]
+        self.object_ids = [o.object_id for o in objects]
+
+
+class ClassData:
+    """`volumetric.ClassData` (voxel_grid_data.h:110-125)."""
+
+    def __init__(self, class_id, points, colors, confidence_min, confidence_max):
+        self.class_id = int(class_id)
+        self.points, self.colors = points, colors
+        self.confidence_min, self.confidence_max = confidence_min, confidence_max
+
+
+class ClassDataGroup:
+    """`volumetric.ClassDataGroup` (voxel_grid_data.h:127-140)."""
+
+    def __init__(self, classes):
+        self.class_vector = classes
+        self.class_ids = [c.class_id for c in classes]
+
+
 class VoxelBlockSemanticGrid:
     """GPU drop-in for `volumetric.VoxelBlockSemanticGrid(voxel_size, block_size=8)` — per-voxel label
     *voting* (cpp/volumetric/voxel_block_semantic_grid.h:59-118; voxel_data_semantic.h:106-199).
@@ -707,6 +823,57 @@ class VoxelBlockSemanticGrid:
             raise RuntimeError("instance_ids but no class_ids is not supported")  # voxel_block_grid.hpp:43-46
         self._check(self._L.b2v_sgrid_integrate(self._h, n, pts.ctypes.data, 1 if pts.dtype == np.float64 else 0,
                                                 cp, cu8, ci, ii, di), "b2v_sgrid_integrate")
+
+    def integrate_segment(self, points, colors, class_id: int, object_id: int):
+        """`integrate_segment(points, colors, class_id, object_id)` (volumetric_grid_module.h:97-125, 564-590 ->
+        voxel_block_semantic_grid.hpp:52-99): every point carries the same (class, object) label; a negative id
+        skips the whole segment."""
+        pts = np.asarray(points)
+        cols = np.asarray(colors)
+        if pts.ndim != 2 or pts.shape[1] != 3:
+            raise RuntimeError("points must be a contiguous Nx3 array")
+        if cols.ndim != 2 or cols.shape[1] != 3:
+            raise RuntimeError("colors must be a contiguous Nx3 array")
+        if cols.shape[0] != pts.shape[0]:
+            raise RuntimeError("points and colors must have the same size")
+        if int(object_id) < 0 or int(class_id) < 0 or pts.shape[0] == 0:
+            return
+        n = pts.shape[0]
+        self.integrate(pts, cols, np.full(n, int(class_id), np.int32), np.full(n, int(object_id), np.int32))
+
+    # ---- segments (voxel_block_semantic_grid.hpp:204-316) ----
+    def _segments(self, by_class: bool, min_count: int, min_confidence: float):
+        # the reference keeps voxels with count > min_count (strict, unlike get_voxels' >=) and confidence >=
+        # min_confidence: the GPU read-out (count -> scan -> emit) does the scan and the compaction ...
+        v = self.get_voxels(int(min_count) + 1, float(min_confidence))
+        ids = np.asarray(v.class_ids if by_class else v.object_ids)
+        keep = ids >= 0                                   # negative = uninitialised label
+        pts, cols = np.asarray(v.points)[keep], np.asarray(v.colors)[keep]
+        cls, conf, ids = np.asarray(v.class_ids)[keep], np.asarray(v.confidences)[keep], ids[keep]
+        # ... and the host groups the survivors by id (stable: block order within a segment is kept)
+        order = np.argsort(ids, kind="stable")
+        uniq, start = np.unique(ids[order], return_index=True)
+        bounds = list(start) + [len(order)]
+        out = []
+        for k, seg_id in enumerate(uniq):
+            sel = order[bounds[k]:bounds[k + 1]]
+            out.append((int(seg_id), pts[sel], cols[sel], int(cls[sel[0]]), float(conf[sel].min()),
+                        float(conf[sel].max())))
+        return out
+
+    def get_object_segments(self, min_count: int = 1, min_confidence: float = 0.0):
+        """`get_object_segments(min_count, min_confidence)` -> ObjectDataGroup (voxel_grid_data.h:64-96): voxels grouped
+        by object id (ids < 0 dropped), each with its points / colours, the class id of its first voxel, the
+        confidence range and a PCA oriented bounding box (bounding_boxes_3d.cpp:373-556, the reference's default
+        OBBComputationMethod::PCA)."""
+        objs = [ObjectData(i, c, p, col, cmin, cmax) for i, p, col, c, cmin, cmax in
+                self._segments(False, min_count, min_confidence)]
+        return ObjectDataGroup(objs)
+
+    def get_class_segments(self, min_count: int = 1, min_confidence: float = 0.0):
+        """`get_class_segments(min_count, min_confidence)` -> ClassDataGroup (voxel_grid_data.h:110-140)."""
+        return ClassDataGroup([ClassData(i, p, col, cmin, cmax) for i, p, col, _c, cmin, cmax in
+                               self._segments(True, min_count, min_confidence)])
 
     def integrate_rgbd(self, depth, color, K, Twc, class_image=None, object_image=None, max_depth=np.inf,
                        min_depth=0.0, use_depths=True, filter_shadow_points=False):

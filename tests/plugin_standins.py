@@ -91,6 +91,28 @@ class VolumetricIntegrationOutput:
         self.timestamp = time.perf_counter()
 
 
+class VolumetricIntegrationObject:
+    """Fields of pyslam/dense/volumetric_integrator_base.py:262-282."""
+
+    def __init__(self, object_data):
+        self.points = np.ascontiguousarray(object_data.points, np.float32)
+        self.colors = np.ascontiguousarray(object_data.colors, np.float32)
+        self.class_id, self.object_id = object_data.class_id, object_data.object_id
+        self.confidence_min, self.confidence_max = object_data.confidence_min, object_data.confidence_max
+        self.box_matrix = np.ascontiguousarray(np.asarray(object_data.oriented_bounding_box.get_matrix()).T)
+        self.box_size = np.ascontiguousarray(object_data.oriented_bounding_box.size, np.float64)
+
+
+class VolumetricIntegrationObjectList:
+    """Fields of pyslam/dense/volumetric_integrator_base.py:285-305."""
+
+    def __init__(self, object_data_group, semantic_colors, object_colors, num_objects):
+        self.object_list = [VolumetricIntegrationObject(o) for o in object_data_group.object_vector]
+        self.semantic_colors = np.ascontiguousarray(semantic_colors, np.float32)
+        self.object_colors = np.ascontiguousarray(object_colors, np.float32)
+        self.num_objects = num_objects
+
+
 class _Value:
     def __init__(self, v):
         self.value = v
@@ -198,6 +220,7 @@ API = SimpleNamespace(
     VolumetricIntegrationOutput=VolumetricIntegrationOutput,
     VolumetricIntegrationMesh=VolumetricIntegrationMesh,
     VolumetricIntegrationPointCloud=VolumetricIntegrationPointCloud,
+    VolumetricIntegrationObjectList=VolumetricIntegrationObjectList,
     DatasetEnvironmentType=DatasetEnvironmentType, Parameters=None)
 
 

@@ -144,3 +144,41 @@ def test_compiled_reference_reproduces_the_semantic_goldens(tag):
     assert oracle.RefSemanticGrid.get_next_object_id() == int(a[f"{tag}_next_object_id"])
     d2 = sort_dump(r2.dump_blocks(1))
     assert np.array_equal(d2["count"], a[f"{tag}_count"]) and np.array_equal(d2["object_id"], a[f"{tag}_object_id"])
+
+
+def _blobs(rng):
+    out = []
+    for oid, (c, sc) in enumerate([((0, 0, 1), (0.5, 0.2, 0.1)), ((2, 1, 1), (0.1, 0.6, 0.3)), ((-1, 2, 0.5), (0.3, 0.3, 0.3))], 1):
+        Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        out.append((oid, oid + 10, (rng.normal(size=(4000, 3)) * np.array(sc)) @ Q.T + np.array(c),
+                    rng.random((4000, 3)).astype(np.float32)))
+    return out
+
+
+def test_pca_oriented_box_equals_the_compiled_reference():
+    """The product's OrientedBoundingBox3D.compute_from_points (numpy) against the boxes the UNMODIFIED reference
+    attaches to its object segments (bounding_boxes_3d.cpp:373-556 via voxel_block_semantic_grid.hpp:248-252):
+    centre and size to 1e-9; the axes up to the eigenvector sign the eigen-solver happens to return."""
+    from pyslam_b200.volume import OrientedBoundingBox3D
+    rng = np.random.default_rng(0)
+    g = oracle.RefSemanticGrid(0.05, "voting")
+    for oid, cid, p, col in _blobs(rng):
+        for _ in range(3):
+            g.integrate(p, col, np.full(len(p), cid, np.int32), np.full(len(p), oid, np.int32))
+    segs = g.get_object_segments(1, 0.0)
+    assert sorted(s["id"] for s in segs) == [1, 2, 3]
+    for s in segs:
+        b = OrientedBoundingBox3D.compute_from_points(s["points"])
+        assert np.abs(b.center - s["obb_center"]).max() < 1e-9 and np.abs(b.size - s["obb_size"]).max() < 1e-9
+        w, x, y, z = s["obb_quat_wxyz"]
+        Rr = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                       [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert np.abs(np.abs(np.sum(b.R * Rr, axis=0)) - 1.0).max() < 1e-9     # same axes, sign aside
+        assert s["class_id"] == s["id"] + 10 and len(s["points"]) > 1000
+    # degenerate inputs
+    assert np.array_equal(OrientedBoundingBox3D.compute_from_points(np.zeros((0, 3))).size, np.zeros(3))
+    b1 = OrientedBoundingBox3D.compute_from_points([[1.0, 2.0, 3.0]])
+    assert np.array_equal(b1.center, [1.0, 2.0, 3.0]) and np.array_equal(b1.size, np.zeros(3))
+    b2 = OrientedBoundingBox3D.compute_from_points([[0.0, 0, 0], [2.0, 0, 0]])
+    assert np.allclose(b2.center, [1.0, 0, 0]) and np.allclose(b2.size, [2.0, 0, 0])

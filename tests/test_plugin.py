@@ -290,6 +290,12 @@ class _FakeSemanticGrid:
                                class_ids=np.array([1, 2], np.int32), object_ids=np.array([3, -1], np.int32),
                                confidences=np.ones(2, np.float32))
 
+    def get_object_segments(self, min_count=1, min_confidence=0.0):
+        from pyslam_b200.volume import ObjectData, ObjectDataGroup
+        self.calls.append(("objects", min_count, min_confidence))
+        pts = np.array([[0.0, 0, 0], [1.0, 0, 0], [0, 2.0, 0], [0, 0, 3.0]])
+        return ObjectDataGroup([ObjectData(3, 1, pts, np.ones((4, 3), np.float32), 0.7, 0.9)])
+
     def reset(self):
         self.calls.append(("reset",))
 
@@ -321,9 +327,20 @@ def test_semantic_adapter_flow_with_fake_grid(monkeypatch, tmp_path):
     assert np.allclose(rgbd[2] @ T, np.eye(4), atol=1e-9)                    # Twc = inv(Tcw)
     assert set(np.unique(rgbd[3])) == {-1, 0, 3}                             # instance ids remapped to object ids
     assert rgbd[4]["filter_shadow_points"] is True and rgbd[4]["use_depths"] is True
+    # instance ids were integrated -> the reference's OBJECTS representation (semantic_grid.py:523-587)
     out = integ.pop_output()
+    assert out.point_cloud is None and out.objects.num_objects == 1 and ("objects", 3, 0.6) in integ.volume.calls
+    o = out.objects.object_list[0]
+    assert (o.object_id, o.class_id) == (3, 1) and o.points.shape == (4, 3) and o.box_size.shape == (3,)
+    assert o.box_matrix.shape == (4, 4) and np.all(np.sort(o.box_size) > 0)
+    # ... and with objects switched off the single point cloud with labels
+    integ1 = Cls(_camera(cfg), P.DatasetEnvironmentType.INDOOR, None, "B200_SEMANTIC",
+                 use_semantic_probabilistic=True, kVolumetricIntegrationB200GenerateObjects=False)
+    integ1.add_keyframe_data(kd)
+    integ1.step()
+    out = integ1.pop_output()
     assert out.point_cloud.semantics.tolist() == [1, 2] and out.point_cloud.object_ids.tolist() == [3, -1]
-    assert ("voxels", 3, 0.6) in integ.volume.calls
+    assert ("voxels", 3, 0.6) in integ1.volume.calls
     # no instance image: plain carve + integrate without object ids
     integ2 = Cls(_camera(cfg), P.DatasetEnvironmentType.OUTDOOR, None, "B200_SEMANTIC",
                  kVolumetricIntegrationVoxelGridUseCarving=True)
@@ -385,7 +402,10 @@ def test_semantic_adapter_end_to_end_on_gpu():
         if o is None:
             break
         out = o
-    assert out.point_cloud.points.shape[1] == 3 and len(out.point_cloud.semantics) == len(out.point_cloud.points)
+    assert out.objects.num_objects == len(out.objects.object_list) > 0     # instance ids -> objects representation
+    ids = sorted(o.object_id for o in out.objects.object_list)
+    dump_ids = a["object_id"][(a["count"] > 3) & (a["confidence"] >= 0.6)]
+    assert ids == sorted(set(int(i) for i in dump_ids if i >= 0))
     integ.quit()
 
 
