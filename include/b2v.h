@@ -275,6 +275,11 @@ int64_t b2v_sgrid_dump_blocks(b2v_sgrid *g, int32_t *keys, uint64_t *hashes, int
                               float *col_sum, int32_t *object_id, int32_t *class_id, float *confidence,
                               int32_t *aux, int32_t K, int32_t *lab_obj, int32_t *lab_cls, float *lab_logp);
 
+/* Self-test of the update kernels' IEEE division fast path (shared correctly rounded reciprocal + two residual
+ * corrections instead of the compiler's div.rn expansion): counts inputs whose result differs from __frcp_rn over all
+ * 2^23 significands (x3 exponents) and from __fdiv_rn over `pairs` pseudo-random operand pairs.  Both must be 0. */
+int b2v_selftest_division(int32_t device, uint64_t pairs, uint64_t *bad_reciprocals, uint64_t *bad_quotients);
+
 /* library / device info */
 int b2v_version(void);
 int b2v_device_sm_count(int32_t device);

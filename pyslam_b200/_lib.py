@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "b2v_grid_last_error", "b2v_grid_integrate", "b2v_grid_integrate_rgbd", "b2v_filter_shadow_points", "b2v_grid_synchronize", "b2v_grid_num_blocks",
     "b2v_grid_size", "b2v_grid_get_voxels", "b2v_grid_copy_voxels",
     "b2v_grid_remove_low_count_voxels", "b2v_grid_dump_blocks", "b2v_grid_carve",
-    "b2v_grid_get_voxels_in_frustum", "b2v_grid_get_voxels_in_bb", "b2v_version", "b2v_device_sm_count",
+    "b2v_grid_get_voxels_in_frustum", "b2v_grid_get_voxels_in_bb", "b2v_version", "b2v_device_sm_count", "b2v_selftest_division",
     "b2v_sgrid_create", "b2v_sgrid_destroy", "b2v_sgrid_last_error", "b2v_sgrid_clear",
     "b2v_sgrid_set_depth_threshold", "b2v_sgrid_set_depth_decay_rate", "b2v_sgrid_integrate",
     "b2v_sgrid_integrate_rgbd",
@@ -81,6 +81,8 @@ def load() -> C.CDLL:
     L.b2v_version.restype = C.c_int
     L.b2v_device_sm_count.restype = C.c_int
     L.b2v_device_sm_count.argtypes = [i32]
+    L.b2v_selftest_division.restype = C.c_int
+    L.b2v_selftest_division.argtypes = [i32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 
     L.b2v_create.restype = C.c_int
     L.b2v_create.argtypes = [C.POINTER(B2VConfig), C.POINTER(vp)]

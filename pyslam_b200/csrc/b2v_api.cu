@@ -181,6 +181,20 @@ static int volume_clear_device(b2v_volume *v) {
 
 extern "C" int b2v_version(void) { return 100; }
 
+extern "C" int b2v_selftest_division(int32_t device, uint64_t pairs, uint64_t *bad_reciprocals, uint64_t *bad_quotients) {
+    if (cudaSetDevice(device) != cudaSuccess) return B2V_ERR_CUDA;
+    unsigned long long *d = nullptr, h[2] = {0, 0};
+    if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) return B2V_ERR_CUDA;
+    cudaError_t e = cudaMemset(d, 0, sizeof(h));
+    if (e == cudaSuccess) e = launch_selftest_division(d, pairs, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return B2V_ERR_CUDA;
+    if (bad_reciprocals) *bad_reciprocals = h[0];
+    if (bad_quotients) *bad_quotients = h[1];
+    return B2V_OK;
+}
+
 extern "C" int b2v_device_sm_count(int32_t device) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;

@@ -158,6 +158,8 @@ static_assert(sizeof(GroupAllocArgs) < 32000, "kernel parameter space");
 cudaError_t launch_allocate_group(const GroupAllocArgs &args, const float *lam, const HashTable &table,
                                   const PoolMeta &meta, cudaStream_t stream);
 int integrate_max_resident_ctas_per_sm();
+// d_bad[0]: reciprocals (3 x 2^23 inputs), d_bad[1]: quotients (`pairs` inputs) whose fast path differs from IEEE
+cudaError_t launch_selftest_division(unsigned long long *d_bad, uint64_t pairs, cudaStream_t stream);
 // fused update of a group of frames (each block is read and written once per group)
 cudaError_t launch_integrate_group(const GroupArgs &args, const HashTable &table, const PoolMeta &meta,
                                    int group_buf, int grid_ctas, cudaStream_t stream);

@@ -11,6 +11,8 @@
 // Arithmetic contract: DESIGN.md §"Arithmetic contract".  Every floating-point operation that
 // decides a key, a pixel or a stored value is written with an explicit-rounding intrinsic so the
 // compiler can neither contract nor reorder it; the CPU oracle performs the same IEEE operations.
+#include <cuda_fp16.h>
+
 #include "b2v_internal.h"
 
 namespace b2v {
@@ -97,6 +99,14 @@ __device__ __forceinline__ uint32_t rel_key(int kx, int ky, int kz, const int *r
                    rz = static_cast<uint32_t>(kz - ref[2] + 512);
     if ((rx | ry | rz) >= 1024u) return kNoKey;
     return rx | (ry << 10) | (rz << 20);
+}
+
+// 16-byte texel of the update kernels: {valid depth | 0, lambda, half2(r, g), half2(b, 0)}; the colours are exact in
+// binary16 (integers 0..255) and widen to float32 with one instruction each
+__device__ __forceinline__ float4 make_texel(float d, float lam, uint8_t r, uint8_t g, uint8_t b) {
+    const __half2 rg = __halves2half2(__ushort2half_rn(r), __ushort2half_rn(g));
+    const __half2 bx = __halves2half2(__ushort2half_rn(b), __ushort2half_rn(0));
+    return make_float4(d, lam, *reinterpret_cast<const float *>(&rg), *reinterpret_cast<const float *>(&bx));
 }
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ----
@@ -249,10 +259,8 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const FrameP
             const int x = x0 + (q & (kTmaTile - 1)), y = y0 + q / kTmaTile;
             if (x < P.W && y < P.H) {
                 const float d = s_td[q];
-                const uint32_t rgbx = static_cast<uint32_t>(s_tc[3 * q]) | (static_cast<uint32_t>(s_tc[3 * q + 1]) << 8) |
-                                      (static_cast<uint32_t>(s_tc[3 * q + 2]) << 16);
-                tex[static_cast<size_t>(y) * P.W + x] =
-                    make_float4((d > 0.0f && d < P.depth_trunc) ? d : 0.0f, s_tl[q], __uint_as_float(rgbx), 0.0f);
+                tex[static_cast<size_t>(y) * P.W + x] = make_texel((d > 0.0f && d < P.depth_trunc) ? d : 0.0f, s_tl[q],
+                                                                   s_tc[3 * q], s_tc[3 * q + 1], s_tc[3 * q + 2]);
             }
         }
     } else {
@@ -260,7 +268,7 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const FrameP
         const int x0 = blockIdx.x * tile, y0 = blockIdx.y * tile;
         for (int q0 = 0; q0 < tile * tile; q0 += 4 * kAllocThreads) {
             float dv[4], lv[4];
-            uint32_t cv[4];
+            uint8_t cv[4][3];
             size_t pv[4];
             bool ok[4];
 #pragma unroll
@@ -272,14 +280,15 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const FrameP
                 dv[k] = __ldg(depth + pv[k]);
                 lv[k] = __ldg(lam + pv[k]);
                 const uint8_t *c = rgb + 3 * pv[k];
-                cv[k] = static_cast<uint32_t>(__ldg(c)) | (static_cast<uint32_t>(__ldg(c + 1)) << 8) |
-                        (static_cast<uint32_t>(__ldg(c + 2)) << 16);
+                cv[k][0] = __ldg(c);
+                cv[k][1] = __ldg(c + 1);
+                cv[k][2] = __ldg(c + 2);
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (ok[k])
-                    tex[pv[k]] = make_float4((dv[k] > 0.0f && dv[k] < P.depth_trunc) ? dv[k] : 0.0f, lv[k],
-                                             __uint_as_float(cv[k]), 0.0f);
+                    tex[pv[k]] = make_texel((dv[k] > 0.0f && dv[k] < P.depth_trunc) ? dv[k] : 0.0f, lv[k], cv[k][0],
+                                            cv[k][1], cv[k][2]);
         }
     }
     __syncthreads();  // reference key visible
@@ -540,12 +549,37 @@ __device__ __forceinline__ VoxelRun voxel_run(const uint4 e, const int t, const 
     return r;
 }
 
-// One frame applied to the kRun voxels of a thread.  F lives in kernel-parameter space.
-__device__ __forceinline__ bool apply_frame(const IntFrame &F, const VoxelRun &r, const float *s_rcp, float *ts,
-                                            float *w, float *cr, float *cg, float *cb) {
+// ---- IEEE division without the compiler's slow-path scaffolding ------------------------------------------------
+// div.rn.f32 expands to MUFU.RCP + a Newton chain + FCHK + a call to a slow path (denormal / huge operands), wrapped
+// in BSSY / BSYNC: ~14 issue slots and a dozen register moves per division, three divisions per voxel update.  Here
+// the operand range is known, so the fast path is written out: one correctly rounded reciprocal shared by the
+// quotients of one denominator, and per quotient two residual corrections (Markstein: with y = RN(1/b) and q
+// faithful, RN(q + (a - b q) y) = RN(a / b); the first correction makes q faithful).  Valid for normal operands with
+// 2^-100 <= |b| <= 2^100 and |a / b| >= 2^-100 (exact residuals); the callers route anything else to __fdiv_rn.
+// tests/test_gpu_tsdf.py::test_fast_division_is_ieee checks rcp_rn_fast over ALL 2^23 significands and div_rn_fast
+// against __fdiv_rn on 2^30 operand pairs; the parity tests compare the end results.
+constexpr float kDivLo = 7.8886090522101181e-31f;   // 2^-100
+constexpr float kDivHi = 1.2676506002282294e+30f;   // 2^100
+__device__ __noinline__ float div_rn_slow(const float a, const float b) { return __fdiv_rn(a, b); }  // rare operands
+__device__ __forceinline__ float rcp_rn_fast(const float b) {  // RN(1 / b), kDivLo <= |b| <= kDivHi
+    float y0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(b));
+    return __fmaf_rn(y0, __fmaf_rn(-b, y0, 1.0f), y0);
+}
+__device__ __forceinline__ float div_rn_fast(const float a, const float b, const float y /* = RN(1/b) */) {
+    float q = __fmul_rn(a, y);
+    q = __fmaf_rn(__fmaf_rn(-q, b, a), y, q);
+    return __fmaf_rn(__fmaf_rn(-q, b, a), y, q);
+}
+
+// One frame applied to the kRun voxels of a thread.  F lives in kernel-parameter space.  Everything up to the texel
+// gather is branch-free (predicated); the update itself is skipped by warps none of whose voxels is in the band.
+__device__ __forceinline__ bool apply_frame(const IntFrame &F, const VoxelRun &r, float *ts, float *w, float *cr,
+                                            float *cg, float *cb) {
     float p0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.E[0], r.h0), __fmul_rn(F.E[1], r.h1)), __fmul_rn(F.E[2], r.h2)), F.E[3]);
     float p1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.E[4], r.h0), __fmul_rn(F.E[5], r.h1)), __fmul_rn(F.E[6], r.h2)), F.E[7]);
     float p2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.E[8], r.h0), __fmul_rn(F.E[9], r.h1)), __fmul_rn(F.E[10], r.h2)), F.E[11]);
+#pragma unroll 1
     for (int s = 0; s < r.zskip; s += kRun) {  // zskip is a multiple of kRun, uniform across the warp
 #pragma unroll
         for (int k = 0; k < kRun; ++k) {
@@ -556,19 +590,41 @@ __device__ __forceinline__ bool apply_frame(const IntFrame &F, const VoxelRun &r
     }
     float pz[kRun];
     int pix[kRun];
+    bool rare = false;
 #pragma unroll
     for (int k = 0; k < kRun; ++k) {
         pz[k] = p2;
-        pix[k] = -1;
-        if (p2 > 0.0f) {
-            const float u_f = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(p0, F.fxf), p2), F.cxf), 0.5f);
-            const float v_f = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(p1, F.fyf), p2), F.cyf), 0.5f);
-            if (u_f >= 0.0001f && u_f < F.safe_w && v_f >= 0.0001f && v_f < F.safe_h)
-                pix[k] = __float2int_rz(v_f) * F.W + __float2int_rz(u_f);
-        }
+        // p2 <= 0 (or NaN): Open3D skips the voxel; outside [2^-100, 2^100] the fast quotient is not exact (`rare`)
+        const bool in_range = p2 >= kDivLo && p2 <= kDivHi;
+        rare |= p2 > 0.0f && !in_range;
+        const float y = rcp_rn_fast(p2);
+        // a quotient below 2^-100 in magnitude may be inexact, but then RN(q + c) = RN(c) either way
+        const float u_f = __fadd_rn(__fadd_rn(div_rn_fast(__fmul_rn(p0, F.fxf), p2, y), F.cxf), 0.5f);
+        const float v_f = __fadd_rn(__fadd_rn(div_rn_fast(__fmul_rn(p1, F.fyf), p2, y), F.cyf), 0.5f);
+        const bool inb = in_range && u_f >= 0.0001f && u_f < F.safe_w && v_f >= 0.0001f && v_f < F.safe_h;
+        pix[k] = inb ? __float2int_rz(v_f) * F.W + __float2int_rz(u_f) : -1;
         p0 = __fadd_rn(p0, F.Es[0]);
         p1 = __fadd_rn(p1, F.Es[1]);
         p2 = __fadd_rn(p2, F.Es[2]);
+    }
+    if (rare) {  // a voxel within 1e-30 m of the camera plane (impossible with a rigid pose): exact divisions
+#pragma unroll 1
+        for (int k = 0; k < kRun; ++k) {
+            const float q2 = pz[k];
+            if (q2 > 0.0f && !(q2 >= kDivLo && q2 <= kDivHi)) {
+                // p.x, p.y of this voxel: replay the chain from the column base (stepping back is not bit-exact)
+                float a0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.E[0], r.h0), __fmul_rn(F.E[1], r.h1)), __fmul_rn(F.E[2], r.h2)), F.E[3]);
+                float a1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F.E[4], r.h0), __fmul_rn(F.E[5], r.h1)), __fmul_rn(F.E[6], r.h2)), F.E[7]);
+                for (int s = 0; s < r.zskip + k; ++s) {
+                    a0 = __fadd_rn(a0, F.Es[0]);
+                    a1 = __fadd_rn(a1, F.Es[1]);
+                }
+                const float u_f = __fadd_rn(__fadd_rn(div_rn_slow(__fmul_rn(a0, F.fxf), q2), F.cxf), 0.5f);
+                const float v_f = __fadd_rn(__fadd_rn(div_rn_slow(__fmul_rn(a1, F.fyf), q2), F.cyf), 0.5f);
+                const bool inb = u_f >= 0.0001f && u_f < F.safe_w && v_f >= 0.0001f && v_f < F.safe_h;
+                pix[k] = inb ? __float2int_rz(v_f) * F.W + __float2int_rz(u_f) : -1;
+            }
+        }
     }
     float4 tx[kRun];
 #pragma unroll
@@ -580,15 +636,18 @@ __device__ __forceinline__ bool apply_frame(const IntFrame &F, const VoxelRun &r
         const float sdf = __fmul_rn(__fsub_rn(d, pz[k]), tx[k].y);
         if (d > 0.0f && sdf > -F.tau) {
             const float tv = fminf(1.0f, __fmul_rn(sdf, F.inv_tau));
-            const uint32_t rgbx = __float_as_uint(tx[k].z);
             const float w0 = w[k];
             const float wn = __fadd_rn(w0, 1.0f);
-            // colour: float32 running mean with the correctly rounded 1/wn (table for the small integer weights)
-            const float rc = wn < 256.0f ? s_rcp[__float2int_rz(wn)] : __frcp_rn(wn);
-            ts[k] = __fdiv_rn(__fadd_rn(__fmul_rn(ts[k], w0), tv), wn);
-            cr[k] = __fmul_rn(__fmaf_rn(cr[k], w0, static_cast<float>(rgbx & 0xFFu)), rc);
-            cg[k] = __fmul_rn(__fmaf_rn(cg[k], w0, static_cast<float>((rgbx >> 8) & 0xFFu)), rc);
-            cb[k] = __fmul_rn(__fmaf_rn(cb[k], w0, static_cast<float>((rgbx >> 16) & 0xFFu)), rc);
+            const float rc = rcp_rn_fast(wn);  // correctly rounded 1 / (w + 1): weights are integers < 2^24
+            const float num = __fadd_rn(__fmul_rn(ts[k], w0), tv);
+            // (tsdf*w + t) / (w + 1): exact residuals need |num| >= 2^-100 (num = 0 gives +-0 either way)
+            ts[k] = (fabsf(num) >= kDivLo || num == 0.0f) ? div_rn_fast(num, wn, rc) : div_rn_slow(num, wn);
+            // colour: float32 running mean; the texel carries r, g, b as binary16 (exact for 0..255)
+            const __half2 rg = *reinterpret_cast<const __half2 *>(&tx[k].z);
+            const __half2 bx = *reinterpret_cast<const __half2 *>(&tx[k].w);
+            cr[k] = __fmul_rn(__fmaf_rn(cr[k], w0, __low2float(rg)), rc);
+            cg[k] = __fmul_rn(__fmaf_rn(cg[k], w0, __high2float(rg)), rc);
+            cb[k] = __fmul_rn(__fmaf_rn(cb[k], w0, __low2float(bx)), rc);
             w[k] = wn;
             upd = true;
         }
@@ -612,26 +671,18 @@ __device__ __forceinline__ void store_block(float *blk, const float q[kPlanes][k
         for (int k = 0; k < kRun; ++k) blk[c * kVox + 64 * k] = q[c][k];
 }
 
-__device__ __forceinline__ void fill_rcp_table(float *s_rcp, int t) {
-    s_rcp[t] = __frcp_rn(static_cast<float>(t));
-    s_rcp[t + 128] = __frcp_rn(static_cast<float>(t + 128));
-}
-
 __global__ void __launch_bounds__(kIntThreads, 8)
 integrate_kernel(const __grid_constant__ IntFrame F, const __grid_constant__ VolumeConsts V, const HashTable T,
                  const PoolMeta M, const int ring) {
-    __shared__ float s_rcp[256];
     const uint32_t n = min(M.counters[kCtrActive0 + ring], M.capacity);
     const uint32_t *__restrict__ act = M.active_slots + static_cast<size_t>(ring) * M.capacity;
     const int t = threadIdx.x;
-    fill_rcp_table(s_rcp, t);
     if (blockIdx.x == 0 && t == 0) {
         atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrUpdatesLo),
                   static_cast<unsigned long long>(n));
         atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrVisitsLo),
                   static_cast<unsigned long long>(n));
     }
-    __syncthreads();
 
     uint32_t i = blockIdx.x;
     uint4 e = make_uint4(0u, 0u, 0u, kNoBlock);
@@ -646,7 +697,7 @@ integrate_kernel(const __grid_constant__ IntFrame F, const __grid_constant__ Vol
             float q[kPlanes][kRun];
             load_block(blk, q);
             const VoxelRun r = voxel_run(e, t, V);
-            if (apply_frame(F, r, s_rcp, q[0], q[1], q[2], q[3], q[4])) store_block(blk, q);
+            if (apply_frame(F, r, q[0], q[1], q[2], q[3], q[4])) store_block(blk, q);
         }
         e = e_next;
         i = i_next;
@@ -672,14 +723,12 @@ template <bool kUnrolled>
 __global__ void __launch_bounds__(kIntThreads, 8)
 integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, const PoolMeta M,
                        const int gbuf) {
-    __shared__ float s_rcp[256];          // correctly rounded 1/n for the small integer weights
     __shared__ uint32_t s_next;           // work-stealing: next list position of this CTA
     const uint32_t n = min(M.counters[group_ctr(gbuf, kGcUnion)], M.capacity);
     const uint32_t *__restrict__ list = M.union_slots + static_cast<size_t>(gbuf) * M.capacity;
     const uint32_t *__restrict__ mask = M.group_mask + static_cast<size_t>(gbuf) * (static_cast<size_t>(T.mask) + 1);
     uint32_t *cursor = M.counters + group_ctr(gbuf, kGcNext);
     const int t = threadIdx.x;
-    fill_rcp_table(s_rcp, t);
     if (blockIdx.x == 0 && t == 0)
         atomicAdd(reinterpret_cast<unsigned long long *>(M.counters + kCtrVisitsLo),
                   static_cast<unsigned long long>(n));
@@ -717,10 +766,10 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
             if constexpr (kUnrolled) {
 #pragma unroll
                 for (int k = 0; k < kUnrolledGroup; ++k)  // ascending bits = frame order
-                    if ((m >> k) & 1u) upd |= apply_frame(A.f[k], r, s_rcp, q[0], q[1], q[2], q[3], q[4]);
+                    if ((m >> k) & 1u) upd |= apply_frame(A.f[k], r, q[0], q[1], q[2], q[3], q[4]);
             } else {
                 for (uint32_t mm = m; mm; mm &= mm - 1u)  // ascending bits = frame order; constants via LDC
-                    upd |= apply_frame(A.f[__ffs(mm) - 1], r, s_rcp, q[0], q[1], q[2], q[3], q[4]);
+                    upd |= apply_frame(A.f[__ffs(mm) - 1], r, q[0], q[1], q[2], q[3], q[4]);
             }
             if (upd) store_block(blk, q);
         }
@@ -846,6 +895,49 @@ cudaError_t launch_upload_blocks(const int4 *keys, const float *vox, uint32_t n,
     if (n == 0) return cudaSuccess;
     upload_insert_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, n, table, meta, scratch_idx);
     upload_copy_kernel<<<n, 128, 0, stream>>>(vox, scratch_idx, meta);
+    return cudaGetLastError();
+}
+
+// ---- self-test of the division fast path (b2v_selftest_division) ------------------------------------------------
+__global__ void selftest_rcp_kernel(unsigned long long *bad) {
+    // every significand, at three exponents
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= (1u << 23)) return;
+    unsigned n = 0;
+    for (uint32_t e : {127u, 100u, 140u}) {
+        const float b = __uint_as_float((e << 23) | m);
+        n += __float_as_uint(rcp_rn_fast(b)) != __float_as_uint(__frcp_rn(b));
+    }
+    if (n) atomicAdd(bad, static_cast<unsigned long long>(n));
+}
+__global__ void selftest_div_kernel(unsigned long long *bad, const uint64_t seed, const uint32_t per_thread) {
+    uint64_t s = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x + 1);
+    unsigned n = 0;
+    for (uint32_t i = 0; i < per_thread; ++i) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;   // xorshift64
+        // denominators as the kernels see them: depths (0.01 .. 40 m), integer weights, plus any exponent in range
+        const uint32_t mode = static_cast<uint32_t>(s >> 60);
+        float b;
+        if (mode < 6) b = __uint_as_float(((120u + (static_cast<uint32_t>(s >> 50) % 12u)) << 23) | (static_cast<uint32_t>(s) & 0x7FFFFFu));
+        else if (mode < 10) b = static_cast<float>(1u + (static_cast<uint32_t>(s >> 32) % 70000u));
+        else b = __uint_as_float(((30u + (static_cast<uint32_t>(s >> 50) % 195u)) << 23) | (static_cast<uint32_t>(s) & 0x7FFFFFu));
+        const uint32_t ea = 60u + (static_cast<uint32_t>(s >> 40) % 120u);
+        float a = __uint_as_float((static_cast<uint32_t>(s >> 24) & 0x80000000u) | (ea << 23) | (static_cast<uint32_t>(s >> 17) & 0x7FFFFFu));
+        if ((s & 0xFFF00000000ull) == 0) a = 0.0f;
+        const float want = __fdiv_rn(a, b);
+        const float ab = fabsf(b);
+        const bool ok = ab >= kDivLo && ab <= kDivHi && (fabsf(want) >= kDivLo || a == 0.0f);
+        const float got = ok ? div_rn_fast(a, b, rcp_rn_fast(b)) : want;
+        n += __float_as_uint(want) != __float_as_uint(got);
+    }
+    if (n) atomicAdd(bad, static_cast<unsigned long long>(n));
+}
+
+cudaError_t launch_selftest_division(unsigned long long *d_bad, uint64_t pairs, cudaStream_t stream) {
+    selftest_rcp_kernel<<<(1u << 23) / 256, 256, 0, stream>>>(d_bad);
+    const uint32_t per_thread = 1024;
+    const uint64_t threads = (pairs + per_thread - 1) / per_thread;
+    selftest_div_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(d_bad + 1, 0x1234567ull, per_thread);
     return cudaGetLastError();
 }
 

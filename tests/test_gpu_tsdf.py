@@ -568,3 +568,15 @@ def test_raw_uint16_depth_equals_host_converted_float_depth():
     with pytest.raises(RuntimeError):
         ref.integrate_batch(raw, Cc, cfg.K, T, depth_scale=0.0)       # non-positive scale
     ref.close()
+
+
+def test_fast_division_is_ieee():
+    """The update kernels divide with a shared correctly rounded reciprocal + two residual corrections instead of the
+    compiler's div.rn expansion.  All 2^23 significands of the reciprocal and 2^30 operand pairs of the quotient
+    (depth-like and integer-weight denominators, plus random exponents) must equal __frcp_rn / __fdiv_rn bit for bit."""
+    import ctypes as C
+    from pyslam_b200 import _lib
+    L = _lib.load()
+    bad_r, bad_q = C.c_uint64(1), C.c_uint64(1)
+    assert L.b2v_selftest_division(0, 1 << 30, C.byref(bad_r), C.byref(bad_q)) == 0
+    assert bad_r.value == 0 and bad_q.value == 0, (bad_r.value, bad_q.value)
