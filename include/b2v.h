@@ -94,6 +94,11 @@ int b2v_integrate_u16(b2v_volume *v, const uint16_t *depth, float depth_scale, c
 int b2v_integrate_batch_u16(b2v_volume *v, int32_t n_frames, const uint16_t *depth, float depth_scale,
                             const uint8_t *color, int32_t height, int32_t width, const double K[4], const double *Tcw,
                             void *stream);
+/* Pipelined callers with DEVICE frames (pyslam_b200.sharding.FrameIngest): the next b2v_integrate_batch* call's inputs
+ * are ready when `event` (a cudaEvent_t recorded by the producer of the frames) fires.  Without it the batch waits
+ * for everything enqueued so far on the caller's stream - including the update kernels of the previous batch, which
+ * its allocate kernels could overlap.  One-shot: consumed by the next batch call. */
+int b2v_set_input_event(b2v_volume *v, void *event);
 /* wait for all enqueued work; returns B2V_ERR_CAPACITY if a frame overflowed the pool */
 int b2v_synchronize(b2v_volume *v);
 
@@ -155,6 +160,9 @@ const char *b2v_grid_last_error(const b2v_grid *g);
 /* integrate(points f32[n*3], colors f32[n*3] | NULL)  (volumetric_grid_module.h:131-467 ->
  * voxel_block_grid.hpp:115-136) */
 int b2v_grid_integrate(b2v_grid *g, const float *points, const float *colors, int64_t n_points);
+/* the float64-points overload (volumetric_grid_module.h:737-749): voxel keys from the float64 coordinates
+ * (floor(x * (double)inv_voxel_size), voxel_hashing.h:69-75), sums accumulate static_cast<float>(x) */
+int b2v_grid_integrate_f64(b2v_grid *g, const double *points, const float *colors, int64_t n_points);
 /* Fused front-end of VolumetricIntegratorVoxelGrid: depth2pointcloud (pyslam/utilities/depth.py:45-85) +
  * world transform + integrate (pyslam/dense/volumetric_integrator_voxel_grid.py:247-300) in one call, no
  * point cloud materialised.  depth float32 [H*W], color uint8 RGB [H*W*3] (host or device), K = {fx,fy,cx,cy}

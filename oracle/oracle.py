@@ -81,6 +81,8 @@ def _ref():
         L.refgrid_clear.argtypes = [C.c_void_p]
         L.refgrid_integrate.restype = C.c_double
         L.refgrid_integrate.argtypes = [C.c_void_p, _f32p, C.c_void_p, C.c_int64]
+        L.refgrid_integrate_f64.restype = C.c_double
+        L.refgrid_integrate_f64.argtypes = [C.c_void_p, _f64p, C.c_void_p, C.c_int64]
         L.refgrid_num_blocks.restype = C.c_int64
         L.refgrid_num_blocks.argtypes = [C.c_void_p]
         L.refgrid_block_size.argtypes = [C.c_void_p]
@@ -150,14 +152,16 @@ class RefGrid:
             self._h = None
 
     def integrate(self, points, colors=None) -> float:
-        pts = np.ascontiguousarray(points, dtype=np.float32)
+        f64 = np.asarray(points).dtype == np.float64        # the reference's float64-points overload
+        pts = np.ascontiguousarray(points, dtype=np.float64 if f64 else np.float32)
         assert pts.ndim == 2 and pts.shape[1] == 3
         cp = None
         if colors is not None:
             cols = np.ascontiguousarray(colors, dtype=np.float32)
             assert cols.shape == pts.shape
             cp = cols.ctypes.data
-        self.last_elapsed_s = self._L.refgrid_integrate(self._h, pts, cp, pts.shape[0])
+        fn = self._L.refgrid_integrate_f64 if f64 else self._L.refgrid_integrate
+        self.last_elapsed_s = fn(self._h, pts.reshape(-1) if f64 else pts, cp, pts.shape[0])
         return self.last_elapsed_s
 
     def num_blocks(self) -> int:

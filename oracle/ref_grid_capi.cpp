@@ -73,6 +73,19 @@ double refgrid_integrate(void *h, const float *pts, const float *cols, int64_t n
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// reference: the float64-points overload, VoxelBlockGridT::integrate_raw<double,float> (volumetric_grid_module.h:737-749)
+double refgrid_integrate_f64(void *h, const double *pts, const float *cols, int64_t n) {
+    auto *g = static_cast<DumpableGrid *>(h);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (cols != nullptr) {
+        g->integrate_raw<double, float>(pts, static_cast<size_t>(n), cols);
+    } else {
+        g->integrate_raw<double>(pts, static_cast<size_t>(n));
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 int64_t refgrid_num_blocks(void *h) {
     return static_cast<int64_t>(static_cast<DumpableGrid *>(h)->num_blocks());
 }

@@ -113,6 +113,7 @@ struct b2v_volume {
     int group_frames = 8;                // frames per fused group (1..kMaxGroup), b2v_set_group_size
     LambdaMap lam_map{};
     bool lam_map_ok = false;
+    cudaEvent_t input_event = nullptr;   // b2v_set_input_event: readiness of the next batch's device inputs
     bool rings_stale = false;            // a fused batch advanced frame_id: the per-frame ring counters must be re-armed
     float4 *d_gtex[kGroupBufs * kMaxGroup] = {};  // texel images of the group buffers
     size_t gtex_pixels = 0;
@@ -728,12 +729,21 @@ extern "C" int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float 
         ~FenceGuard() { v->inputs_fenced = false; }
     } fence_guard{v};
     if (v->overlap) {
-        // one fence for the whole batch: everything enqueued on the caller's stream so far (the inputs'
-        // producers, earlier per-frame work) happens before the batch's allocate kernels
-        B2V_CUDA(v, cudaEventRecord(v->ev_in, cs));
-        B2V_CUDA(v, cudaStreamWaitEvent(v->alloc, v->ev_in, 0));
+        // one fence for the whole batch: by default everything enqueued on the caller's stream so far (the inputs'
+        // producers, earlier per-frame work) happens before the batch's allocate kernels.  A caller that knows better
+        // (b2v_set_input_event: "the inputs are ready when this event fires") keeps the allocate kernels of this batch
+        // from also waiting for the update kernels of the previous one.
+        if (v->input_event && dev_hint == 1) {
+            B2V_CUDA(v, cudaStreamWaitEvent(v->alloc, v->input_event, 0));
+        } else {
+            B2V_CUDA(v, cudaEventRecord(v->ev_in, cs));
+            B2V_CUDA(v, cudaStreamWaitEvent(v->alloc, v->ev_in, 0));
+        }
         v->inputs_fenced = true;
+    } else if (v->input_event && dev_hint == 1) {
+        B2V_CUDA(v, cudaStreamWaitEvent(cs, v->input_event, 0));
     }
+    v->input_event = nullptr;
     int rc = B2V_OK;
     const bool u16 = v->in_u16_scale > 0.0f;  // `depth` is really const uint16_t *
     const uint16_t *depth16 = reinterpret_cast<const uint16_t *>(depth);
@@ -882,6 +892,12 @@ extern "C" int b2v_integrate_u16(b2v_volume *v, const uint16_t *depth, float dep
     const int rc = integrate_frame(v, reinterpret_cast<const float *>(depth), color, height, width, K, Tcw, stream);
     v->in_u16_scale = 0.0f;
     return rc;
+}
+
+extern "C" int b2v_set_input_event(b2v_volume *v, void *event) {
+    if (!v) return B2V_ERR_INVALID_ARGUMENT;
+    v->input_event = static_cast<cudaEvent_t>(event);
+    return B2V_OK;
 }
 
 extern "C" int b2v_set_group_size(b2v_volume *v, int32_t frames) {
@@ -1349,7 +1365,7 @@ extern "C" int b2v_grid_clear(b2v_grid *g) {
     return B2V_OK;
 }
 
-extern "C" int b2v_grid_integrate(b2v_grid *g, const float *points, const float *colors, int64_t n_points) {
+static int grid_integrate_any(b2v_grid *g, const void *points, bool f64, const float *colors, int64_t n_points) {
     if (!g) return B2V_ERR_INVALID_ARGUMENT;
     if (n_points < 0 || (n_points > 0 && !points)) {
         g->err = "b2v_grid_integrate: bad arguments";
@@ -1357,18 +1373,19 @@ extern "C" int b2v_grid_integrate(b2v_grid *g, const float *points, const float 
     }
     if (n_points == 0) return B2V_OK;  // voxel_block_grid.hpp:22-24,121-123
     B2V_CUDA(g, cudaSetDevice(g->device));
-    const float *d_p = points, *d_c = colors;
+    const void *d_p = points;
+    const float *d_c = colors;
     const bool dev_p = is_device_pointer(points);
     const bool dev_c = colors ? is_device_pointer(colors) : true;
     if (!dev_p || !dev_c) {
         if (static_cast<size_t>(n_points) > g->stage_points) {
             B2V_CUDA(g, cudaStreamSynchronize(g->stream));
-            B2V_CUDA(g, regrow(&g->d_pts, static_cast<size_t>(n_points) * 3));
+            B2V_CUDA(g, regrow(&g->d_pts, static_cast<size_t>(n_points) * 3 * 2));  // room for float64 points
             B2V_CUDA(g, regrow(&g->d_cols, static_cast<size_t>(n_points) * 3));
             g->stage_points = static_cast<size_t>(n_points);
         }
         if (!dev_p) {
-            B2V_CUDA(g, cudaMemcpyAsync(g->d_pts, points, static_cast<size_t>(n_points) * 3 * sizeof(float),
+            B2V_CUDA(g, cudaMemcpyAsync(g->d_pts, points, static_cast<size_t>(n_points) * 3 * (f64 ? sizeof(double) : sizeof(float)),
                                         cudaMemcpyHostToDevice, g->stream));
             d_p = g->d_pts;
         }
@@ -1378,8 +1395,16 @@ extern "C" int b2v_grid_integrate(b2v_grid *g, const float *points, const float 
             d_c = g->d_cols;
         }
     }
-    B2V_CUDA(g, launch_grid_integrate(d_p, d_c, n_points, g->inv_voxel_size, g->table, g->meta, g->stream));
+    B2V_CUDA(g, launch_grid_integrate(d_p, f64, d_c, n_points, g->inv_voxel_size, g->table, g->meta, g->stream));
     return B2V_OK;
+}
+
+extern "C" int b2v_grid_integrate(b2v_grid *g, const float *points, const float *colors, int64_t n_points) {
+    return grid_integrate_any(g, points, false, colors, n_points);
+}
+
+extern "C" int b2v_grid_integrate_f64(b2v_grid *g, const double *points, const float *colors, int64_t n_points) {
+    return grid_integrate_any(g, points, true, colors, n_points);
 }
 
 extern "C" int b2v_filter_shadow_points(const float *depth, int32_t height, int32_t width, int32_t delta_x,

@@ -16,17 +16,25 @@ constexpr int kGridPlanes = 7;  // count(int32), px, py, pz, cr, cg, cb
 constexpr int kGridBlockWords = kGridPlanes * kVox;
 
 // ---- pass 1: make sure every point's block exists -------------------------------------------
+// voxel coordinate of a point in its own precision: get_voxel_key_inv<Tpos, Tpos> (voxel_hashing.h:69-75) with the
+// float32 inverse voxel size widened for float64 points (voxel_block_grid.hpp:473)
+__device__ __forceinline__ int point_voxel_coord(float x, float inv_vs) { return voxel_coord(x, inv_vs); }
+__device__ __forceinline__ int point_voxel_coord(double x, float inv_vs) {
+    return __double2int_rd(__dmul_rn(x, static_cast<double>(inv_vs)));
+}
+
+template <typename Tp>
 __global__ void __launch_bounds__(256)
-grid_insert_kernel(const float *__restrict__ pts, const int64_t n, const float inv_vs,
+grid_insert_kernel(const Tp *__restrict__ pts, const int64_t n, const float inv_vs,
                    const HashTable T, const GridMeta G) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool have = i < n;
     int bx = 0, by = 0, bz = 0;
     if (have) {
-        bx = block_coord(voxel_coord(pts[3 * i + 0], inv_vs));
-        by = block_coord(voxel_coord(pts[3 * i + 1], inv_vs));
-        bz = block_coord(voxel_coord(pts[3 * i + 2], inv_vs));
+        bx = block_coord(point_voxel_coord(pts[3 * i + 0], inv_vs));
+        by = block_coord(point_voxel_coord(pts[3 * i + 1], inv_vs));
+        bz = block_coord(point_voxel_coord(pts[3 * i + 2], inv_vs));
     }
     // one probe per distinct block per warp (neighbouring pixels share blocks)
     const unsigned long long pk = have ? (static_cast<unsigned long long>(slot_hash(bx, by, bz)) << 32 |
@@ -59,13 +67,16 @@ grid_insert_kernel(const float *__restrict__ pts, const int64_t n, const float i
 }
 
 // ---- pass 2: accumulate ----------------------------------------------------------------------
+template <typename Tp>
 __global__ void __launch_bounds__(256)
-grid_accumulate_kernel(const float *__restrict__ pts, const float *__restrict__ cols, const int64_t n,
+grid_accumulate_kernel(const Tp *__restrict__ pts, const float *__restrict__ cols, const int64_t n,
                        const float inv_vs, const HashTable T, const GridMeta G) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float x = pts[3 * i + 0], y = pts[3 * i + 1], z = pts[3 * i + 2];
-    const int vx = voxel_coord(x, inv_vs), vy = voxel_coord(y, inv_vs), vz = voxel_coord(z, inv_vs);
+    const Tp xp = pts[3 * i + 0], yp = pts[3 * i + 1], zp = pts[3 * i + 2];
+    const int vx = point_voxel_coord(xp, inv_vs), vy = point_voxel_coord(yp, inv_vs), vz = point_voxel_coord(zp, inv_vs);
+    // position_sum += static_cast<float>(x) (voxel_data.h:53-57)
+    const float x = static_cast<float>(xp), y = static_cast<float>(yp), z = static_cast<float>(zp);
     const uint32_t slot = table_find(T, block_coord(vx), block_coord(vy), block_coord(vz));
     if (slot == kEmpty) return;
     const uint32_t idx = T.entries[slot].w;
@@ -364,12 +375,19 @@ cudaError_t launch_grid_carve(const GridMeta &meta, uint32_t n_blocks, const Gri
 }
 
 // ---- launchers -------------------------------------------------------------------------------
-cudaError_t launch_grid_integrate(const float *pts, const float *cols, int64_t n, float inv_vs,
+cudaError_t launch_grid_integrate(const void *pts, bool pts_f64, const float *cols, int64_t n, float inv_vs,
                                   const HashTable &table, const GridMeta &meta, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     const unsigned grid = static_cast<unsigned>((n + 255) / 256);
-    grid_insert_kernel<<<grid, 256, 0, stream>>>(pts, n, inv_vs, table, meta);
-    grid_accumulate_kernel<<<grid, 256, 0, stream>>>(pts, cols, n, inv_vs, table, meta);
+    if (pts_f64) {
+        const double *p = static_cast<const double *>(pts);
+        grid_insert_kernel<double><<<grid, 256, 0, stream>>>(p, n, inv_vs, table, meta);
+        grid_accumulate_kernel<double><<<grid, 256, 0, stream>>>(p, cols, n, inv_vs, table, meta);
+    } else {
+        const float *p = static_cast<const float *>(pts);
+        grid_insert_kernel<float><<<grid, 256, 0, stream>>>(p, n, inv_vs, table, meta);
+        grid_accumulate_kernel<float><<<grid, 256, 0, stream>>>(p, cols, n, inv_vs, table, meta);
+    }
     return cudaGetLastError();
 }
 

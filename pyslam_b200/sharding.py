@@ -134,7 +134,12 @@ class FrameIngest:
                 if self.cuda:
                     b["ready"].record(self.s_up)
             if self.cuda:
-                self.s_int.wait_event(b["ready"])
+                if hasattr(self.volume, "set_input_event"):
+                    # the allocate kernels of this chunk wait for the upload / all-gather only, not for the update
+                    # kernels of the previous chunk that are queued on the compute stream
+                    self.volume.set_input_event(b["ready"].cuda_event)
+                else:
+                    self.s_int.wait_event(b["ready"])
                 self.volume.integrate_batch(b["depth"][:cnt], b["color"][:cnt], K, T[c0:c0 + cnt],
                                             stream=self.s_int.cuda_stream, depth_scale=depth_scale)
                 b["free"].record(self.s_int)

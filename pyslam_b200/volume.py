@@ -253,6 +253,11 @@ class B200TsdfVolume:
         """integrate_batch: fuse groups of up to 8 frames per block visit (default) or go frame by frame."""
         self._check(self._L.b2v_set_fusion(self._h, 1 if enable else 0), "b2v_set_fusion")
 
+    def set_input_event(self, cuda_event):
+        """The next integrate_batch call's device frames are ready when `cuda_event` (a raw cudaEvent_t handle, e.g.
+        `torch.cuda.Event.cuda_event`) fires; see b2v_set_input_event."""
+        self._check(self._L.b2v_set_input_event(self._h, C.c_void_p(int(cuda_event))), "b2v_set_input_event")
+
     def set_group_size(self, frames: int):
         """Frames per fused group of integrate_batch (1..32, default 8); results do not depend on it."""
         self._check(self._L.b2v_set_group_size(self._h, int(frames)), "b2v_set_group_size")
@@ -478,8 +483,8 @@ class VoxelBlockGrid:
 
     def integrate(self, points, colors=None, class_ids=None, instance_ids=None, depths=None):
         """integrate(points [N,3] f32|f64, colors [N,3] u8|f32 | None)
-        (volumetric_grid_module.h:131-467).  float64 points are narrowed to float32 (the reference
-        front-end always passes float32, volumetric_integrator_voxel_grid.py:281); uint8 colours are
+        (volumetric_grid_module.h:131-467).  float64 points take the reference's float64 overload (:737-749): voxel
+        keys from the float64 coordinates, sums accumulate float32(x) (b2v_grid_integrate_f64); uint8 colours are
         scaled by the float32 constant 1/255 exactly as voxel_data.h:82-85 does."""
         if class_ids is not None or instance_ids is not None or depths is not None:
             raise NotImplementedError("semantic integration is a SURVEY.md §8(f) 'next' row")
@@ -488,7 +493,8 @@ class VoxelBlockGrid:
             raise RuntimeError("points must be a 2D array with shape (N, 3)")
         if pts.dtype not in (np.float32, np.float64):
             raise RuntimeError("points must be float32 or float64")
-        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        f64 = pts.dtype == np.float64
+        pts = np.ascontiguousarray(pts)
         cp = None
         cols = None
         if colors is not None and np.asarray(colors).size > 0:
@@ -503,8 +509,8 @@ class VoxelBlockGrid:
                 raise RuntimeError("colors must be uint8 or float32")
             cols = np.ascontiguousarray(cols, dtype=np.float32)
             cp = cols.ctypes.data
-        self._check(self._L.b2v_grid_integrate(self._h, pts.ctypes.data, cp, pts.shape[0]),
-                    "b2v_grid_integrate")
+        fn = self._L.b2v_grid_integrate_f64 if f64 else self._L.b2v_grid_integrate
+        self._check(fn(self._h, pts.ctypes.data, cp, pts.shape[0]), "b2v_grid_integrate")
         self._check(self._L.b2v_grid_synchronize(self._h), "b2v_grid_synchronize")
 
     def integrate_rgbd(self, depth, color, K, Twc, max_depth=np.inf, min_depth=0.0, filter_shadow_points=False):

@@ -193,3 +193,27 @@ def test_front_end_rows_match_the_reference_python_functions():
         same = d["count"] == g[f"{tag}_count"]
         assert _sum_close(d["pos_sum"][same], g[f"{tag}_pos_sum"][same], g[f"{tag}_count"][same])
         assert _sum_close(d["col_sum"][same], g[f"{tag}_col_sum"][same], g[f"{tag}_count"][same])
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="compiled reference (oracle/_ref) not built")
+def test_float64_points_take_the_double_precision_key_like_the_reference():
+    """integrate(points float64): the reference's float64 overload keys voxels with floor(x * (double)inv_vs) and
+    accumulates float32(x) (volumetric_grid_module.h:737-749, voxel_data.h:53-57).  Points are placed within float32
+    rounding of voxel boundaries, where narrowing first would pick the neighbouring voxel."""
+    rng = np.random.default_rng(7)
+    vs = 0.005
+    k = rng.integers(-400, 400, size=(20000, 3)).astype(np.float64)
+    pts = k * (1.0 / (np.float32(1.0) / np.float32(vs)).astype(np.float64)) + rng.choice([-1e-9, 1e-9, 3e-10], size=(20000, 3))
+    cols = rng.random((20000, 3)).astype(np.float32)
+    g = VoxelBlockGrid(vs, 8, capacity_blocks=1 << 15)
+    r = oracle.RefGrid(vs, 8)
+    g.integrate(pts, cols)
+    r.integrate(pts, cols)
+    a, b = sort_dump(g.dump_blocks()), sort_dump(r.dump_blocks())
+    assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["count"], b["count"])
+    narrow = VoxelBlockGrid(vs, 8, capacity_blocks=1 << 15)
+    narrow.integrate(pts.astype(np.float32), cols)
+    assert not np.array_equal(sort_dump(narrow.dump_blocks())["count"], b["count"])   # the case is not vacuous
+    one = b["count"] == 1
+    assert np.array_equal(a["pos_sum"][one], b["pos_sum"][one])
+    assert np.allclose(a["pos_sum"], b["pos_sum"], rtol=1e-5, atol=1e-5)

@@ -580,3 +580,50 @@ def test_fast_division_is_ieee():
     bad_r, bad_q = C.c_uint64(1), C.c_uint64(1)
     assert L.b2v_selftest_division(0, 1 << 30, C.byref(bad_r), C.byref(bad_q)) == 0
     assert bad_r.value == 0 and bad_q.value == 0, (bad_r.value, bad_q.value)
+
+
+def test_frame_ingest_single_gpu_equals_integrate_batch():
+    """FrameIngest without a process group: chunked, buffered uploads on a side stream + device-pointer batches;
+    float32 and raw uint16 depth.  Same volume as one integrate_batch call."""
+    import torch
+    from pyslam_b200.sharding import FrameIngest
+    cfg = S.CONFIGS["C1"]
+    n = 21
+    frames = [S.render_frame(cfg, i) for i in range(n)]
+    D, Cc, T = (np.stack([f[k] for f in frames]) for k in range(3))
+    ref, _ = _pair(cfg)
+    ref.integrate_batch(D, Cc, cfg.K, T)
+    vol, _ = _pair(cfg)
+    ing = FrameIngest(vol, chunk_frames=8, buffers=2)
+    ing.integrate_batch(torch.from_numpy(D).pin_memory(), torch.from_numpy(Cc).pin_memory(), cfg.K, T)
+    ing.synchronize()
+    a, b = sort_dump(ref.dump_blocks()), sort_dump(vol.dump_blocks())
+    for name in ("keys", "hashes", "vox"):
+        assert np.array_equal(a[name], b[name]), name
+    assert ing.h2d_bytes == n * cfg.height * cfg.width * 7 and ing.gather_bytes == 0
+    raw = np.round(D * 5000.0).astype(np.uint16)
+    ref16, _ = _pair(cfg)
+    ref16.integrate_batch(raw, Cc, cfg.K, T, depth_scale=np.float32(1 / 5000.0))
+    vol16, _ = _pair(cfg)
+    ing16 = FrameIngest(vol16, chunk_frames=8)
+    ing16.integrate_batch(raw, Cc, cfg.K, T, depth_scale=np.float32(1 / 5000.0))   # pageable numpy input
+    ing16.synchronize()
+    a, b = sort_dump(ref16.dump_blocks()), sort_dump(vol16.dump_blocks())
+    for name in ("keys", "hashes", "vox"):
+        assert np.array_equal(a[name], b[name]), name
+
+
+def test_degenerate_pose_takes_the_exact_division_path():
+    """A (non-rigid) world->camera matrix whose depth row is ~1e-33 puts every voxel within 2^-100 of the camera
+    plane: the update kernels leave their division fast path for __fdiv_rn.  Result == twin (which always divides
+    exactly), and a following regular frame is unaffected."""
+    cfg = S.CONFIGS["T0"]
+    vol, orc = _pair(cfg)
+    d, c, T = S.render_frame(cfg, 0)
+    Tdeg = T.copy()
+    Tdeg[2, :3] = 0.0
+    Tdeg[2, 3] = 1.0e-33
+    for pose in (T, Tdeg, S.render_frame(cfg, 1)[2]):
+        vol.integrate(d, c, cfg.K, pose)
+        orc.integrate(d, c, cfg.K, pose)
+    _assert_same_volume(vol, orc)
