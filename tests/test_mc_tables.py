@@ -4,7 +4,13 @@ self-validating; the product copy must equal the oracle copy."""
 import os
 import re
 
-from oracle import mc_tables as M
+import importlib.util
+import os
+
+_spec = importlib.util.spec_from_file_location(
+    "mc_tables", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "mc_tables.py"))
+M = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(M)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

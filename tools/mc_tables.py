@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE (oracle).  Marching-cubes case tables + structural self-validation.
+"""Generator of the marching-cubes case tables (build-time tool: emits `pyslam_b200/csrc/mc_tables.h` for the product
+and `oracle/mc_tables.h` for the oracles) + their structural self-validation.
 
 No marching-cubes table exists in /root/reference or anywhere on this box (SURVEY.md §7
 "hard parts"), so the classic Lorensen-Cline / Bourke 256-case table is typed in here and
@@ -408,7 +409,7 @@ def emit_c_header(guard, qual=""):
     lines = [
         f"#ifndef {guard}", f"#define {guard}",
         "/* Marching-cubes case tables (classic Lorensen-Cline / Bourke), corner/edge numbering of",
-        " * SURVEY.md Appendix A.4.  GENERATED by oracle/mc_tables.py emit_c_header(); the source",
+        " * SURVEY.md Appendix A.4.  GENERATED by tools/mc_tables.py emit_c_header(); the source",
         " * table is structurally validated by mc_tables.validate() (tests/test_mc_tables.py). */",
         f"{qual}static const unsigned short MC_EDGE_TABLE[256] = {{",
     ]
