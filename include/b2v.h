@@ -134,7 +134,9 @@ int b2v_upload_blocks(b2v_volume *v, int64_t n_blocks, const int32_t *keys, cons
  * d_voxels float32 [n][5][512].  export returns the block count (with both pointers NULL: just the count). */
 int64_t b2v_export_blocks_device(b2v_volume *v, int32_t *d_keys4, float *d_voxels, int64_t max_blocks);
 int b2v_import_blocks_device(b2v_volume *v, int64_t n_blocks, const int32_t *d_keys4, const float *d_voxels);
-/* keys int32[n*3] of the blocks touched by the most recent frame; returns n or <0 */
+/* keys int32[n*3] of the blocks touched by the most recent b2v_integrate frame - or, after b2v_integrate_batch, by
+ * the frames of the batch's last fused group (their union; b2v_last_frame_stats still counts the last frame alone);
+ * returns n or <0 */
 int64_t b2v_last_touched_keys(b2v_volume *v, int32_t *keys, int64_t max_keys);
 
 /* ---- mesh: replaces self.volume.extract_triangle_mesh() (tsdf.py:239,260) ----
