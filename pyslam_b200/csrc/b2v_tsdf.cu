@@ -20,37 +20,16 @@
 namespace b2v {
 
 // ------------------------------------------------------------------------------------------------
-// allocation: frame packing + voxel-block key generation
+// allocation
 // ------------------------------------------------------------------------------------------------
-//
-// Two independent kernels per frame (or per fused group: blockIdx.z = frame):
-//   pack_kernel     every CTA turns a 32x32-pixel tile - staged into shared memory by three 2-D TMA tile loads
-//                   (depth f32, colour u8x3, lambda f32) - into 16-byte {valid depth | 0, lambda, half2(r,g),
-//                   half2(b,0)} texels, the only image the update kernels gather from.  Pure streaming: 11 B in,
-//                   16 B out per pixel.
-//   keygen_kernel   one WARP per 8x4 depth samples (32x16 pixels at stride 4), no CTA-wide barrier until the final
-//                   flush: back-project (float64), block range of the +-tau box / the touched Open3D units; the
-//                   warp's DISTINCT boxes (__match_any_sync; typically 3-8, each 64 blocks) are expanded one
-//                   candidate block per lane into a per-warp shared-memory set of distinct keys (~100); every
-//                   distinct key then probes / inserts into the global table - one key per lane, all probes in
-//                   flight - and ORs the frame's membership bit (fused) or exchanges the frame stamp; new and
-//                   first-touched slots are queued per CTA and flushed with one global atomic per list.
-// Keys of blocks owned by another rank (BlockKeyHash % N) are dropped right after the expansion, before they cost
-// a set insert or a probe.
 
-constexpr int kKgWarps = 8;          // warps per CTA of the key generation kernel
-constexpr int kKgThreads = kKgWarps * 32;
-constexpr int kKgTileX = 8, kKgTileY = 4;   // depth samples per warp
-constexpr int kKeySet = 512;         // per-warp set of distinct block keys (power of two)
-constexpr int kKeyList = 384;        // ... compacted (beyond: straight to the table)
-constexpr int kNewCap = 1024;        // per-CTA queues of fresh / first-touched slots
-constexpr int kActCap = 2560;
+constexpr int kAllocTile = 8;       // 8 x 8 depth samples per CTA (32 x 32 pixels at stride 4)
+constexpr int kAllocThreads = 256;
+constexpr int kBoxSet = 128;        // distinct [lo, lo + n) boxes under one tile (power of two)
+constexpr int kBoxList = 64;        // ... compacted
+constexpr int kKeySet = 1024;       // distinct block keys under one tile (power of two)
+constexpr int kListCap = 512;       // CTA-local lists of fresh / first-touched slots
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
-
-struct FrameSlot {   // which frame this CTA works for
-    int group_bit;       // >= 0: fused group mode (bit of the membership mask); -1: per-frame mode
-    uint32_t frame_id;
-};
 
 __device__ __forceinline__ void assign_block(const HashTable &T, const PoolMeta &M, uint32_t slot,
                                              uint32_t idx) {
@@ -66,15 +45,19 @@ __device__ __forceinline__ void assign_block(const HashTable &T, const PoolMeta 
     }
 }
 
-// per-CTA queues of the keygen kernel
-struct KgQueues {
-    uint32_t *s_new, *s_n_new, *s_act, *s_n_act;
-};
-
 // Global find-or-insert of one block key + first-touch detection for this frame.  New slots and
 // first-touched slots are queued in shared-memory lists (flushed with one atomic per CTA).
+struct FrameSlot {   // which frame this CTA works for
+    int group_bit;       // >= 0: fused group mode (bit of the membership mask); -1: per-frame mode
+    uint32_t frame_id;
+};
+
 __device__ __forceinline__ void touch_key(const FrameParams &P, const FrameSlot &FS, const HashTable &T, const PoolMeta &M,
-                                          int ring, int kx, int ky, int kz, const KgQueues &Q) {
+                                          int ring, int kx, int ky, int kz, uint32_t *s_new,
+                                          uint32_t *s_n_new, uint32_t *s_act, uint32_t *s_n_act) {
+    if (P.shard_count > 1 &&
+        static_cast<int>(block_key_hash(kx, ky, kz) % static_cast<uint64_t>(P.shard_count)) != P.shard_rank)
+        return;
     bool is_new;
     const uint32_t slot = table_insert(T, kx, ky, kz, &is_new);
     if (slot == kEmpty) {
@@ -82,10 +65,10 @@ __device__ __forceinline__ void touch_key(const FrameParams &P, const FrameSlot 
         return;
     }
     if (is_new) {
-        const uint32_t pos = atomicAdd(Q.s_n_new, 1u);
-        if (pos < kNewCap) {
-            Q.s_new[pos] = slot;
-        } else {  // queue overflow: assign directly
+        const uint32_t pos = atomicAdd(s_n_new, 1u);
+        if (pos < kListCap) {
+            s_new[pos] = slot;
+        } else {  // list overflow: assign directly
             assign_block(T, M, slot, atomicAdd(M.counters + kCtrPool, 1u));
             atomicAdd(FS.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcNew) : M.counters + kCtrNew0 + ring, 1u);
         }
@@ -98,9 +81,9 @@ __device__ __forceinline__ void touch_key(const FrameParams &P, const FrameSlot 
         first = atomicExch(T.stamp + slot, FS.frame_id) != FS.frame_id;
     }
     if (first) {
-        const uint32_t pos = atomicAdd(Q.s_n_act, 1u);
-        if (pos < kActCap) {
-            Q.s_act[pos] = slot;
+        const uint32_t pos = atomicAdd(s_n_act, 1u);
+        if (pos < kListCap) {
+            s_act[pos] = slot;
         } else if (FS.group_bit >= 0) {
             const uint32_t g = atomicAdd(M.counters + group_ctr(P.group_buf, kGcUnion), 1u);
             if (g < M.capacity) M.union_slots[static_cast<size_t>(P.group_buf) * M.capacity + g] = slot;
@@ -111,182 +94,13 @@ __device__ __forceinline__ void touch_key(const FrameParams &P, const FrameSlot 
     }
 }
 
-__device__ __forceinline__ bool owned(const FrameParams &P, int kx, int ky, int kz) {
-    return P.shard_count <= 1 ||
-           static_cast<int>(block_key_hash(kx, ky, kz) % static_cast<uint64_t>(P.shard_count)) == P.shard_rank;
-}
-
-// block key -> 30-bit code relative to the warp's reference key (10 bits per axis); kNoKey if the
+// block key -> 30-bit code relative to the tile's reference key (10 bits per axis); kNoKey if the
 // key is further than 511 blocks from the reference on some axis (then it takes the direct path)
-__device__ __forceinline__ uint32_t rel_key(int kx, int ky, int kz, const int ref[3]) {
+__device__ __forceinline__ uint32_t rel_key(int kx, int ky, int kz, const int *ref) {
     const uint32_t rx = static_cast<uint32_t>(kx - ref[0] + 512), ry = static_cast<uint32_t>(ky - ref[1] + 512),
                    rz = static_cast<uint32_t>(kz - ref[2] + 512);
     if ((rx | ry | rz) >= 1024u) return kNoKey;
     return rx | (ry << 10) | (rz << 20);
-}
-
-__device__ __forceinline__ void keygen_body(const FrameParams &P, const FramePose &pose, const FrameSlot FS,
-                                            const float *__restrict__ depth, const HashTable &T, const PoolMeta &M,
-                                            const int ring) {
-    __shared__ uint32_t s_set[kKgWarps][kKeySet];
-    __shared__ uint32_t s_keys[kKgWarps][kKeyList];
-    __shared__ uint32_t s_nkeys[kKgWarps];
-    __shared__ uint32_t s_new[kNewCap];
-    __shared__ uint32_t s_act[kActCap];
-    __shared__ uint32_t s_n_new, s_n_act, s_base_new, s_base_act;
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const KgQueues Q{s_new, &s_n_new, s_act, &s_n_act};
-    if (tid == 0) {
-        s_n_new = 0;
-        s_n_act = 0;
-        if (blockIdx.x == 0 && FS.group_bit < 0) {
-            // the ring slot the NEXT frame will count into (its last user finished 3 frames ago)
-            const int nxt = (ring + 1) % kActiveRing;
-            M.counters[kCtrActive0 + nxt] = 0;
-            M.counters[kCtrNew0 + nxt] = 0;
-        }
-    }
-    for (int i = lane; i < kKeySet; i += 32) s_set[wid][i] = kNoKey;
-    if (lane == 0) s_nkeys[wid] = 0;
-    __syncthreads();  // queue counters initialised (the only barrier before the flush)
-
-    // ---- the warp's 8 x 4 depth samples ----
-    const int gw = (P.W + P.stride - 1) / P.stride, gh = (P.H + P.stride - 1) / P.stride;
-    const int tiles_x = (gw + kKgTileX - 1) / kKgTileX, tiles_y = (gh + kKgTileY - 1) / kKgTileY;
-    const int tile = blockIdx.x * kKgWarps + wid;
-    int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
-    bool have = false;
-    if (tile < tiles_x * tiles_y) {
-        const int j = ((tile % tiles_x) * kKgTileX + (lane & (kKgTileX - 1))) * P.stride;
-        const int i = ((tile / tiles_x) * kKgTileY + lane / kKgTileX) * P.stride;
-        if (j < P.W && i < P.H) {
-            const float d = __ldg(depth + static_cast<size_t>(i) * P.W + j);
-            if (d > 0.0f && d < P.depth_trunc) {
-                const double z = static_cast<double>(d);
-                const double x = __ddiv_rn(__dmul_rn(__dsub_rn(static_cast<double>(j), P.cx), z), P.fx);
-                const double y = __ddiv_rn(__dmul_rn(__dsub_rn(static_cast<double>(i), P.cy), z), P.fy);
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const double pw = __dadd_rn(
-                        __dadd_rn(__dadd_rn(__dmul_rn(pose.Rwc[3 * a + 0], x), __dmul_rn(pose.Rwc[3 * a + 1], y)),
-                                  __dmul_rn(pose.Rwc[3 * a + 2], z)),
-                        pose.twc[a]);
-                    if (P.unit_shift > 0) {
-                        // Open3D ScalableTSDFVolume::LocateVolumeUnit: floor(p / volume_unit_length) in float64;
-                        // every 8^3 block of a touched unit is touched
-                        const int ulo = __double2int_rd(__ddiv_rn(__dsub_rn(pw, P.tau_d), P.unit_len));
-                        const int uhi = __double2int_rd(__ddiv_rn(__dadd_rn(pw, P.tau_d), P.unit_len));
-                        lo[a] = ulo << P.unit_shift;
-                        n[a] = (uhi - ulo + 1) << P.unit_shift;
-                    } else {  // decision D1: pyslam float32 key arithmetic (voxel_hashing.h:69-75, 139-151)
-                        const int vlo = voxel_coord(__double2float_rn(__dsub_rn(pw, P.tau_d)), P.inv_vs);
-                        const int vhi = voxel_coord(__double2float_rn(__dadd_rn(pw, P.tau_d)), P.inv_vs);
-                        lo[a] = block_coord(vlo);
-                        n[a] = block_coord(vhi) - lo[a] + 1;
-                    }
-                }
-                have = true;
-            }
-        }
-    }
-    const unsigned hv = __ballot_sync(0xffffffffu, have);
-    if (hv != 0u) {  // (warp-uniform)
-        // reference key of the warp: the box origin of its first valid sample
-        const int first = __ffs(hv) - 1;
-        const int ref[3] = {__shfl_sync(0xffffffffu, lo[0], first), __shfl_sync(0xffffffffu, lo[1], first),
-                            __shfl_sync(0xffffffffu, lo[2], first)};
-        // ---- distinct boxes: neighbouring samples share theirs ----
-        const uint32_t r0 = static_cast<uint32_t>(lo[0] - ref[0] + 32768), r1 = static_cast<uint32_t>(lo[1] - ref[1] + 32768),
-                       r2 = static_cast<uint32_t>(lo[2] - ref[2] + 32768);
-        const bool packable = have && (r0 | r1 | r2) < 65536u && n[0] <= 15 && n[1] <= 15 && n[2] <= 15;
-        const uint32_t k_lo = packable ? (r0 | (r1 << 16)) : (0x80000000u | static_cast<uint32_t>(lane));
-        const uint32_t k_hi = packable ? (r2 | (static_cast<uint32_t>(n[0] | (n[1] << 4) | (n[2] << 8)) << 16)) : 0xFFFFFFFFu;
-        const unsigned same = __match_any_sync(0xffffffffu, k_lo) & __match_any_sync(0xffffffffu, k_hi);
-        const bool leader = packable && (__ffs(same) - 1) == lane;
-        if (have && !packable) {  // far-away or over-sized box: straight to the table
-            for (int dx = 0; dx < n[0]; ++dx)
-                for (int dy = 0; dy < n[1]; ++dy)
-                    for (int dz = 0; dz < n[2]; ++dz)
-                        if (owned(P, lo[0] + dx, lo[1] + dy, lo[2] + dz))
-                            touch_key(P, FS, T, M, ring, lo[0] + dx, lo[1] + dy, lo[2] + dz, Q);
-        }
-        // ---- distinct keys: expand every distinct box, one candidate block per lane ----
-        for (unsigned boxes = __ballot_sync(0xffffffffu, leader); boxes; boxes &= boxes - 1) {
-            const int b = __ffs(boxes) - 1;
-            const int bl[3] = {__shfl_sync(0xffffffffu, lo[0], b), __shfl_sync(0xffffffffu, lo[1], b),
-                               __shfl_sync(0xffffffffu, lo[2], b)};
-            const int bn1 = __shfl_sync(0xffffffffu, n[1], b), bn2 = __shfl_sync(0xffffffffu, n[2], b);
-            const int total = __shfl_sync(0xffffffffu, n[0], b) * bn1 * bn2;
-            for (int c = lane; c < total; c += 32) {
-                const int dz = c % bn2, r = c / bn2, dy = r % bn1, dx = r / bn1;
-                const int kx = bl[0] + dx, ky = bl[1] + dy, kz = bl[2] + dz;
-                // sharded volumes: keys of other ranks are dropped before they cost a set insert or a probe
-                if (!owned(P, kx, ky, kz)) continue;
-                const uint32_t rk = rel_key(kx, ky, kz, ref);
-                bool placed = false;
-                if (rk != kNoKey) {
-                    uint32_t h = mix32(rk) & (kKeySet - 1);
-                    for (int k = 0; k < 64 && !placed; ++k) {
-                        const uint32_t old = atomicCAS(&s_set[wid][h], kNoKey, rk);
-                        if (old == kNoKey) {  // first sighting under this warp: queue it for the probe phase
-                            const uint32_t pos = atomicAdd(&s_nkeys[wid], 1u);
-                            if (pos < kKeyList) {
-                                s_keys[wid][pos] = rk;
-                                placed = true;
-                            } else {
-                                break;  // list full: probe it right away (below)
-                            }
-                        } else if (old == rk) {
-                            placed = true;
-                        }
-                        h = (h + 1) & (kKeySet - 1);
-                    }
-                }
-                if (!placed) touch_key(P, FS, T, M, ring, kx, ky, kz, Q);
-            }
-        }
-        __syncwarp();
-        // ---- probe: every distinct key of the warp, one per lane, all probes in flight ----
-        const uint32_t nkeys = min(s_nkeys[wid], static_cast<uint32_t>(kKeyList));
-        for (uint32_t q = lane; q < nkeys; q += 32) {
-            const uint32_t rk = s_keys[wid][q];
-            touch_key(P, FS, T, M, ring, ref[0] + static_cast<int>(rk & 1023u) - 512,
-                      ref[1] + static_cast<int>((rk >> 10) & 1023u) - 512,
-                      ref[2] + static_cast<int>((rk >> 20) & 1023u) - 512, Q);
-        }
-    }
-    __syncthreads();
-
-    // ---- flush: one global atomic per list and CTA (three threads, three independent round trips) ----
-    const uint32_t n_new = min(s_n_new, static_cast<uint32_t>(kNewCap));
-    const uint32_t n_act = min(s_n_act, static_cast<uint32_t>(kActCap));
-    if (tid == 0) s_base_new = n_new ? atomicAdd(M.counters + kCtrPool, n_new) : 0u;
-    uint32_t *list_count = FS.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcUnion) : M.counters + kCtrActive0 + ring;
-    if (tid == 32) s_base_act = n_act ? atomicAdd(list_count, n_act) : 0u;
-    if (tid == 64 && n_new)
-        atomicAdd(FS.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcNew) : M.counters + kCtrNew0 + ring, n_new);
-    __syncthreads();
-    for (uint32_t k = tid; k < n_new; k += kKgThreads) assign_block(T, M, s_new[k], s_base_new + k);
-    uint32_t *active_out = FS.group_bit >= 0 ? M.union_slots + static_cast<size_t>(P.group_buf) * M.capacity
-                                             : M.active_slots + static_cast<size_t>(ring) * M.capacity;
-    for (uint32_t k = tid; k < n_act; k += kKgThreads) {
-        const uint32_t g = s_base_act + k;
-        if (g < M.capacity) active_out[g] = s_act[k];
-    }
-}
-
-__global__ void __launch_bounds__(kKgThreads, 4)
-keygen_kernel(const __grid_constant__ FrameParams P, const float *__restrict__ depth, const HashTable T,
-              const PoolMeta M, const int ring) {
-    keygen_body(P, P.pose, FrameSlot{-1, P.frame_id}, depth, T, M, ring);
-}
-
-// blockIdx.z = frame of the group: one launch generates the keys of up to kMaxGroup frames
-__global__ void __launch_bounds__(kKgThreads, 4)
-keygen_group_kernel(const __grid_constant__ GroupAllocArgs A, const HashTable T, const PoolMeta M) {
-    const int k = blockIdx.z;
-    keygen_body(A.P, A.pose[k], FrameSlot{k, A.frame_id0 + static_cast<uint32_t>(k)}, A.depth[k], T, M, 0);
 }
 
 // 16-byte texel of the update kernels: {valid depth | 0, lambda, half2(r, g), half2(b, 0)}; the colours are exact in
@@ -298,8 +112,7 @@ __device__ __forceinline__ float4 make_texel(float d, float lam, uint8_t r, uint
 }
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ----
-constexpr int kTmaTile = 32;  // pixels per tile side
-constexpr int kPackThreads = 256;
+constexpr int kTmaTile = 32;  // = kAllocTile * 4: the TMA path serves the default stride 4
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -334,33 +147,117 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         : "memory");
 }
 
-// Pack one 32x32-pixel tile of a frame into texels.  kTma: one thread arms an mbarrier with the tile's byte count and
-// issues three 2-D TMA tile loads (cp.async.bulk.tensor.2d, SASS UTMALDG.2D) into shared memory; everybody waits on
-// the mbarrier and converts.  Otherwise (ragged width, unaligned images): plain loads, four pixels per thread.
+// Per frame: pack the frame into texels, find the touched blocks, allocate the new ones.
+//   pack    every CTA packs its 32x32-pixel tile into 16-byte {valid depth | 0, lambda, rgbx} texels
+//   boxes   one thread per depth sample: back-project (float64), block range [lo, lo+n) of the
+//           [p - tau, p + tau] box; neighbouring samples share boxes, so the DISTINCT boxes of the
+//           tile (typically 10-20, each 27 blocks) are collected in a shared-memory set
+//   keys    the distinct boxes are expanded, one candidate block per thread, into a shared-memory set
+//           of distinct block keys (typically ~100 per tile)
+//   probe   every distinct key probes / inserts into the global table - one key per thread, all
+//           probes in flight - and exchanges the slot's frame stamp (first toucher queues the slot)
+//   flush   one atomic per CTA hands out contiguous pool indices and active-list positions
 template <bool kTma>
-__device__ __forceinline__ void pack_body(const FrameParams &P, const float *__restrict__ depth,
-                                          const uint8_t *__restrict__ rgb, const float *__restrict__ lam,
-                                          float4 *__restrict__ tex, const FrameMaps &maps, const LambdaMap &lmap) {
+__device__ __forceinline__ void allocate_body(const FrameParams &P, const FramePose &pose, const FrameSlot FS,
+                                              const float *__restrict__ depth,
+                                              const uint8_t *__restrict__ rgb, const float *__restrict__ lam,
+                                              float4 *__restrict__ tex, const HashTable &T, const PoolMeta &M,
+                                              const int ring, const FrameMaps &maps, const LambdaMap &lmap) {
+    // TMA staging buffers of the 32x32-pixel tile (kTma only): depth, lambda (f32) and colour (u8 x3)
+    __shared__ alignas(128) float s_td[kTmaTile * kTmaTile];
+    __shared__ alignas(128) float s_tl[kTmaTile * kTmaTile];
+    __shared__ alignas(128) uint8_t s_tc[kTmaTile * kTmaTile * 3];
+    __shared__ alignas(8) unsigned long long s_bar;
+    __shared__ unsigned long long s_boxset[kBoxSet];
+    __shared__ unsigned long long s_box[kBoxList];
+    __shared__ uint32_t s_keyset[kKeySet];
+    __shared__ uint32_t s_keys[kListCap];  // the distinct keys, compacted
+    __shared__ uint32_t s_new[kListCap];
+    __shared__ uint32_t s_act[kListCap];
+    __shared__ uint32_t s_n_box, s_n_keys, s_n_new, s_n_act, s_base_new, s_base_act;
+    __shared__ int s_ref[4];  // reference key of the tile; s_ref[3]: 0 = unset, 1 = set
+
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * kTmaTile, y0 = blockIdx.y * kTmaTile;
+    for (int i = tid; i < kKeySet; i += kAllocThreads) s_keyset[i] = kNoKey;
+    if (tid < kBoxSet) s_boxset[tid] = ~0ull;
+    if (tid == 0) {
+        s_n_box = 0;
+        s_n_keys = 0;
+        s_n_new = 0;
+        s_n_act = 0;
+        s_ref[3] = 0;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && FS.group_bit < 0) {
+            // the ring slot the NEXT frame will count into (its last user finished 3 frames ago)
+            const int nxt = (ring + 1) % kActiveRing;
+            M.counters[kCtrActive0 + nxt] = 0;
+            M.counters[kCtrNew0 + nxt] = 0;
+        }
+    }
+
     if constexpr (kTma) {
-        __shared__ alignas(128) float s_td[kTmaTile * kTmaTile];
-        __shared__ alignas(128) float s_tl[kTmaTile * kTmaTile];
-        __shared__ alignas(128) uint8_t s_tc[kTmaTile * kTmaTile * 3];
-        __shared__ alignas(8) unsigned long long s_bar;
+        // one thread arms an mbarrier with the tile's byte count and issues three 2-D TMA tile loads;
+        // they land in shared memory while the CTA back-projects its depth samples
         if (tid == 0) {
             mbar_init(&s_bar, 1);
             fence_mbar_init();
             mbar_expect_tx(&s_bar, kTmaTile * kTmaTile * (4 + 4 + 3));
+            const int x0 = blockIdx.x * kTmaTile, y0 = blockIdx.y * kTmaTile;
             tma_load_2d(s_td, &maps.depth, x0, y0, &s_bar);
             tma_load_2d(s_tl, &lmap.lam, x0, y0, &s_bar);
             tma_load_2d(s_tc, &maps.color, 3 * x0, y0, &s_bar);
         }
-        __syncthreads();  // the barrier object is initialised before anybody polls it
-        mbar_wait(&s_bar, 0);
+    }
+
+    // ---- boxes: thread s < 64 owns depth sample s of the tile ----
+    int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+    bool have = false;
+    if (tid < kAllocTile * kAllocTile) {
+        const int j = (blockIdx.x * kAllocTile + (tid & (kAllocTile - 1))) * P.stride;
+        const int i = (blockIdx.y * kAllocTile + (tid / kAllocTile)) * P.stride;
+        if (j < P.W && i < P.H) {
+            const float d = __ldg(depth + static_cast<size_t>(i) * P.W + j);
+            if (d > 0.0f && d < P.depth_trunc) {
+                const double z = static_cast<double>(d);
+                const double x = __ddiv_rn(__dmul_rn(__dsub_rn(static_cast<double>(j), P.cx), z), P.fx);
+                const double y = __ddiv_rn(__dmul_rn(__dsub_rn(static_cast<double>(i), P.cy), z), P.fy);
 #pragma unroll
-        for (int k = 0; k < kTmaTile * kTmaTile / kPackThreads; ++k) {
-            const int q = k * kPackThreads + tid;
+                for (int a = 0; a < 3; ++a) {
+                    const double pw = __dadd_rn(
+                        __dadd_rn(__dadd_rn(__dmul_rn(pose.Rwc[3 * a + 0], x), __dmul_rn(pose.Rwc[3 * a + 1], y)),
+                                  __dmul_rn(pose.Rwc[3 * a + 2], z)),
+                        pose.twc[a]);
+                    if (P.unit_shift > 0) {
+                        // Open3D ScalableTSDFVolume::LocateVolumeUnit: floor(p / volume_unit_length) in float64;
+                        // every 8^3 block of a touched unit is touched
+                        const int ulo = __double2int_rd(__ddiv_rn(__dsub_rn(pw, P.tau_d), P.unit_len));
+                        const int uhi = __double2int_rd(__ddiv_rn(__dadd_rn(pw, P.tau_d), P.unit_len));
+                        lo[a] = ulo << P.unit_shift;
+                        n[a] = (uhi - ulo + 1) << P.unit_shift;
+                    } else {  // decision D1: pyslam float32 key arithmetic (voxel_hashing.h:69-75, 139-151)
+                        const int vlo = voxel_coord(__double2float_rn(__dsub_rn(pw, P.tau_d)), P.inv_vs);
+                        const int vhi = voxel_coord(__double2float_rn(__dadd_rn(pw, P.tau_d)), P.inv_vs);
+                        lo[a] = block_coord(vlo);
+                        n[a] = block_coord(vhi) - lo[a] + 1;
+                    }
+                }
+                have = true;
+            }
+        }
+    }
+    __syncthreads();  // sets initialised
+    if (have && atomicCAS(&s_ref[3], 0, 1) == 0) {
+        s_ref[0] = lo[0];
+        s_ref[1] = lo[1];
+        s_ref[2] = lo[2];
+    }
+
+    // ---- pack this CTA's pixel tile into texels (independent of the allocation work) ----
+    if constexpr (kTma) {
+        mbar_wait(&s_bar, 0);  // s_bar was initialised before the first __syncthreads above
+        const int x0 = blockIdx.x * kTmaTile, y0 = blockIdx.y * kTmaTile;
+#pragma unroll
+        for (int k = 0; k < kTmaTile * kTmaTile / kAllocThreads; ++k) {
+            const int q = k * kAllocThreads + tid;
             const int x = x0 + (q & (kTmaTile - 1)), y = y0 + q / kTmaTile;
             if (x < P.W && y < P.H) {
                 const float d = s_td[q];
@@ -369,63 +266,173 @@ __device__ __forceinline__ void pack_body(const FrameParams &P, const float *__r
             }
         }
     } else {
-        float dv[4], lv[4];
-        uint8_t cv[4][3];
-        size_t pv[4];
-        bool ok[4];
+        const int tile = kAllocTile * P.stride;  // pixels per tile side
+        const int x0 = blockIdx.x * tile, y0 = blockIdx.y * tile;
+        for (int q0 = 0; q0 < tile * tile; q0 += 4 * kAllocThreads) {
+            float dv[4], lv[4];
+            uint8_t cv[4][3];
+            size_t pv[4];
+            bool ok[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // four independent pixels per thread: loads issued together
-            const int q = k * kPackThreads + tid;
-            const int x = x0 + (q & (kTmaTile - 1)), y = y0 + q / kTmaTile;
-            ok[k] = x < P.W && y < P.H;
-            pv[k] = ok[k] ? static_cast<size_t>(y) * P.W + x : 0;
-            dv[k] = __ldg(depth + pv[k]);
-            lv[k] = __ldg(lam + pv[k]);
-            const uint8_t *c = rgb + 3 * pv[k];
-            cv[k][0] = __ldg(c);
-            cv[k][1] = __ldg(c + 1);
-            cv[k][2] = __ldg(c + 2);
+            for (int k = 0; k < 4; ++k) {  // four independent pixels per thread: loads issued together
+                const int q = q0 + k * kAllocThreads + tid;
+                const int x = x0 + q % tile, y = y0 + q / tile;
+                ok[k] = q < tile * tile && x < P.W && y < P.H;
+                pv[k] = ok[k] ? static_cast<size_t>(y) * P.W + x : 0;
+                dv[k] = __ldg(depth + pv[k]);
+                lv[k] = __ldg(lam + pv[k]);
+                const uint8_t *c = rgb + 3 * pv[k];
+                cv[k][0] = __ldg(c);
+                cv[k][1] = __ldg(c + 1);
+                cv[k][2] = __ldg(c + 2);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (ok[k])
+                    tex[pv[k]] = make_texel((dv[k] > 0.0f && dv[k] < P.depth_trunc) ? dv[k] : 0.0f, lv[k], cv[k][0],
+                                            cv[k][1], cv[k][2]);
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (ok[k])
-                tex[pv[k]] = make_texel((dv[k] > 0.0f && dv[k] < P.depth_trunc) ? dv[k] : 0.0f, lv[k], cv[k][0],
-                                        cv[k][1], cv[k][2]);
+    }
+    __syncthreads();  // reference key visible
+
+    // ---- distinct boxes of the tile ----
+    if (have) {
+        const uint32_t r0 = static_cast<uint32_t>(lo[0] - s_ref[0] + 32768), r1 = static_cast<uint32_t>(lo[1] - s_ref[1] + 32768),
+                       r2 = static_cast<uint32_t>(lo[2] - s_ref[2] + 32768);
+        bool placed = false;
+        if ((r0 | r1 | r2) < 65536u && n[0] <= 15 && n[1] <= 15 && n[2] <= 15) {
+            const unsigned long long bk = static_cast<unsigned long long>(r0) | (static_cast<unsigned long long>(r1) << 16) |
+                                          (static_cast<unsigned long long>(r2) << 32) |
+                                          (static_cast<unsigned long long>(n[0] | (n[1] << 4) | (n[2] << 8)) << 48);
+            uint32_t h = mix32(static_cast<uint32_t>(bk) ^ static_cast<uint32_t>(bk >> 32)) & (kBoxSet - 1);
+            for (int k = 0; k < kBoxSet && !placed; ++k) {
+                const unsigned long long old = atomicCAS(s_boxset + h, ~0ull, bk);
+                if (old == ~0ull) {
+                    const uint32_t pos = atomicAdd(&s_n_box, 1u);
+                    if (pos < kBoxList) {
+                        s_box[pos] = bk;
+                        placed = true;
+                    } else {
+                        break;  // list full: handle this box directly below
+                    }
+                } else if (old == bk) {
+                    placed = true;
+                }
+                h = (h + 1) & (kBoxSet - 1);
+            }
+        }
+        if (!placed) {  // far-away or over-sized box, or > 64 distinct boxes: straight to the table
+            for (int dx = 0; dx < n[0]; ++dx)
+                for (int dy = 0; dy < n[1]; ++dy)
+                    for (int dz = 0; dz < n[2]; ++dz)
+                        touch_key(P, FS, T, M, ring, lo[0] + dx, lo[1] + dy, lo[2] + dz, s_new, &s_n_new, s_act, &s_n_act);
+        }
+    }
+    __syncthreads();
+
+    // ---- distinct keys: expand every distinct box, one candidate block per thread ----
+    {
+        const uint32_t nbox = min(s_n_box, static_cast<uint32_t>(kBoxList));
+        for (uint32_t item = tid; item < nbox * 32u; item += kAllocThreads) {  // 32 lanes per box (27 typical)
+            const unsigned long long bk = s_box[item >> 5];
+            const uint32_t c = item & 31u;
+            const uint32_t n0 = static_cast<uint32_t>(bk >> 48) & 15u, n1 = static_cast<uint32_t>(bk >> 52) & 15u,
+                           n2 = static_cast<uint32_t>(bk >> 56) & 15u;
+            // boxes with more than 32 blocks loop over the remainder (c, c + 32, ...)
+            for (uint32_t cc = c; cc < n0 * n1 * n2; cc += 32u) {
+                const uint32_t dz = cc % n2, r = cc / n2, dy = r % n1, dx = r / n1;
+                const int kx = s_ref[0] + static_cast<int>(static_cast<uint32_t>(bk) & 0xFFFFu) - 32768 + static_cast<int>(dx);
+                const int ky = s_ref[1] + static_cast<int>(static_cast<uint32_t>(bk >> 16) & 0xFFFFu) - 32768 + static_cast<int>(dy);
+                const int kz = s_ref[2] + static_cast<int>(static_cast<uint32_t>(bk >> 32) & 0xFFFFu) - 32768 + static_cast<int>(dz);
+                // sharded volumes: keys of other ranks are dropped before they cost a set insert or a probe
+                if (P.shard_count > 1 &&
+                    static_cast<int>(block_key_hash(kx, ky, kz) % static_cast<uint64_t>(P.shard_count)) != P.shard_rank)
+                    continue;
+                const uint32_t rk = rel_key(kx, ky, kz, s_ref);
+                bool placed = false;
+                if (rk != kNoKey) {
+                    uint32_t h = mix32(rk) & (kKeySet - 1);
+                    for (int k = 0; k < 96 && !placed; ++k) {
+                        const uint32_t old = atomicCAS(s_keyset + h, kNoKey, rk);
+                        if (old == kNoKey) {  // first sighting in this tile: queue it for the probe phase
+                            const uint32_t pos = atomicAdd(&s_n_keys, 1u);
+                            if (pos < kListCap) {
+                                s_keys[pos] = rk;
+                                placed = true;
+                            } else {
+                                break;  // list full: probe it right away (below)
+                            }
+                        } else if (old == rk) {
+                            placed = true;
+                        }
+                        h = (h + 1) & (kKeySet - 1);
+                    }
+                }
+                if (!placed) touch_key(P, FS, T, M, ring, kx, ky, kz, s_new, &s_n_new, s_act, &s_n_act);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- probe: every distinct key of the tile, one per thread, all probes in flight ----
+    {
+        const uint32_t nkeys = min(s_n_keys, static_cast<uint32_t>(kListCap));
+        for (uint32_t q = tid; q < nkeys; q += kAllocThreads) {
+            const uint32_t rk = s_keys[q];
+            touch_key(P, FS, T, M, ring, s_ref[0] + static_cast<int>(rk & 1023u) - 512,
+                      s_ref[1] + static_cast<int>((rk >> 10) & 1023u) - 512,
+                      s_ref[2] + static_cast<int>((rk >> 20) & 1023u) - 512, s_new, &s_n_new, s_act, &s_n_act);
+        }
+    }
+    __syncthreads();
+
+    // ---- flush: one global atomic per list and CTA (three threads, three independent round trips) ----
+    const uint32_t n_new = min(s_n_new, static_cast<uint32_t>(kListCap));
+    const uint32_t n_act = min(s_n_act, static_cast<uint32_t>(kListCap));
+    if (tid == 0) s_base_new = n_new ? atomicAdd(M.counters + kCtrPool, n_new) : 0u;
+    uint32_t *list_count = FS.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcUnion) : M.counters + kCtrActive0 + ring;
+    if (tid == 32) s_base_act = n_act ? atomicAdd(list_count, n_act) : 0u;
+    if (tid == 64 && n_new)
+        atomicAdd(FS.group_bit >= 0 ? M.counters + group_ctr(P.group_buf, kGcNew) : M.counters + kCtrNew0 + ring, n_new);
+    __syncthreads();
+    for (uint32_t k = tid; k < n_new; k += kAllocThreads) assign_block(T, M, s_new[k], s_base_new + k);
+    uint32_t *active_out = FS.group_bit >= 0 ? M.union_slots + static_cast<size_t>(P.group_buf) * M.capacity
+                                            : M.active_slots + static_cast<size_t>(ring) * M.capacity;
+    for (uint32_t k = tid; k < n_act; k += kAllocThreads) {
+        const uint32_t g = s_base_act + k;
+        if (g < M.capacity) active_out[g] = s_act[k];
     }
 }
 
 template <bool kTma>
-__global__ void __launch_bounds__(kPackThreads)
-pack_kernel(const __grid_constant__ FrameParams P, const float *__restrict__ depth, const uint8_t *__restrict__ rgb,
-            const float *__restrict__ lam, float4 *__restrict__ tex, const __grid_constant__ FrameMaps maps,
-            const __grid_constant__ LambdaMap lmap) {
-    pack_body<kTma>(P, depth, rgb, lam, tex, maps, lmap);
+__global__ void __launch_bounds__(kAllocThreads, 4)
+allocate_kernel(const FrameParams P, const float *__restrict__ depth, const uint8_t *__restrict__ rgb,
+                const float *__restrict__ lam, float4 *__restrict__ tex, const HashTable T,
+                const PoolMeta M, const int ring, const __grid_constant__ FrameMaps maps,
+                const __grid_constant__ LambdaMap lmap) {
+    allocate_body<kTma>(P, P.pose, FrameSlot{-1, P.frame_id}, depth, rgb, lam, tex, T, M, ring, maps, lmap);
 }
 
+// blockIdx.z = frame of the group: one launch allocates for up to kMaxGroup frames
 template <bool kTma>
-__global__ void __launch_bounds__(kPackThreads)
-pack_group_kernel(const __grid_constant__ GroupAllocArgs A, const float *__restrict__ lam) {
+__global__ void __launch_bounds__(kAllocThreads, 8)
+allocate_group_kernel(const __grid_constant__ GroupAllocArgs A, const float *__restrict__ lam,
+                      const HashTable T, const PoolMeta M) {
     const int k = blockIdx.z;
-    pack_body<kTma>(A.P, A.depth[k], A.color[k], lam, A.tex[k], A.maps[k], A.lmap);
-}
-
-static dim3 keygen_grid(const FrameParams &p, int frames) {
-    const int gw = (p.W + p.stride - 1) / p.stride, gh = (p.H + p.stride - 1) / p.stride;
-    const int tiles = ((gw + kKgTileX - 1) / kKgTileX) * ((gh + kKgTileY - 1) / kKgTileY);
-    return dim3((tiles + kKgWarps - 1) / kKgWarps, 1, frames);
-}
-static dim3 pack_grid(const FrameParams &p, int frames) {
-    return dim3((p.W + kTmaTile - 1) / kTmaTile, (p.H + kTmaTile - 1) / kTmaTile, frames);
+    allocate_body<kTma>(A.P, A.pose[k], FrameSlot{k, A.frame_id0 + static_cast<uint32_t>(k)}, A.depth[k], A.color[k], lam,
+                        A.tex[k], T, M, 0, A.maps[k], A.lmap);
 }
 
 cudaError_t launch_allocate_group(const GroupAllocArgs &args, const float *lam, const HashTable &table,
                                   const PoolMeta &meta, cudaStream_t stream) {
     const FrameParams &p = args.P;
-    if (args.use_tma)
-        pack_group_kernel<true><<<pack_grid(p, args.count), kPackThreads, 0, stream>>>(args, lam);
+    const int gw = (p.W + p.stride - 1) / p.stride;
+    const int gh = (p.H + p.stride - 1) / p.stride;
+    const dim3 grid((gw + kAllocTile - 1) / kAllocTile, (gh + kAllocTile - 1) / kAllocTile, args.count);
+    if (args.use_tma && p.stride * kAllocTile == kTmaTile)
+        allocate_group_kernel<true><<<grid, kAllocThreads, 0, stream>>>(args, lam, table, meta);
     else
-        pack_group_kernel<false><<<pack_grid(p, args.count), kPackThreads, 0, stream>>>(args, lam);
-    keygen_group_kernel<<<keygen_grid(p, args.count), kKgThreads, 0, stream>>>(args, table, meta);
+        allocate_group_kernel<false><<<grid, kAllocThreads, 0, stream>>>(args, lam, table, meta);
     return cudaGetLastError();
 }
 
@@ -433,21 +440,24 @@ cudaError_t launch_allocate(const FrameParams &p, const float *depth, const uint
                             const float *lam, float4 *texels, const HashTable &table,
                             const PoolMeta &meta, int ring, const FrameMaps *maps, const LambdaMap *lmap,
                             cudaStream_t stream) {
-    if (maps != nullptr && lmap != nullptr) {
-        pack_kernel<true><<<pack_grid(p, 1), kPackThreads, 0, stream>>>(p, depth, color, lam, texels, *maps, *lmap);
+    const int gw = (p.W + p.stride - 1) / p.stride;
+    const int gh = (p.H + p.stride - 1) / p.stride;
+    const dim3 grid((gw + kAllocTile - 1) / kAllocTile, (gh + kAllocTile - 1) / kAllocTile);
+    if (maps != nullptr && lmap != nullptr && p.stride * kAllocTile == kTmaTile) {
+        allocate_kernel<true><<<grid, kAllocThreads, 0, stream>>>(p, depth, color, lam, texels, table, meta,
+                                                                 ring, *maps, *lmap);
     } else {
         static const FrameMaps dummy{};
         static const LambdaMap ldummy{};
-        pack_kernel<false><<<pack_grid(p, 1), kPackThreads, 0, stream>>>(p, depth, color, lam, texels, dummy, ldummy);
+        allocate_kernel<false><<<grid, kAllocThreads, 0, stream>>>(p, depth, color, lam, texels, table, meta,
+                                                                  ring, dummy, ldummy);
     }
-    keygen_kernel<<<keygen_grid(p, 1), kKgThreads, 0, stream>>>(p, depth, table, meta, ring);
     return cudaGetLastError();
 }
 
 bool tma_tiles_usable(int W, int stride, const void *depth, const void *color, const void *lam) {
-    (void)stride;  // the pack tile is 32 x 32 pixels whatever the sampling stride of the key generation
     auto aligned = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    return (W % 16) == 0 && aligned(depth) && aligned(color) && aligned(lam);
+    return stride * kAllocTile == kTmaTile && (W % 16) == 0 && aligned(depth) && aligned(color) && aligned(lam);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -711,8 +721,9 @@ cudaError_t launch_integrate(const FrameParams &p, const VolumeConsts &vc, const
 // unrolled over the 8 slots of the group, so every constant is an immediate-offset uniform operand.
 // ------------------------------------------------------------------------------------------------
 constexpr int kUnrolledGroup = 8;   // groups up to this size use the fully unrolled frame loop
-template <bool kUnrolled>
-__global__ void __launch_bounds__(kIntThreads, 8)
+// kMinCtas: resident CTAs per SM the register allocation is capped for (8 -> 64 registers, 10 -> 48, 12 -> 40)
+template <bool kUnrolled, int kMinCtas>
+__global__ void __launch_bounds__(kIntThreads, kMinCtas)
 integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, const PoolMeta M,
                        const int gbuf) {
     __shared__ uint32_t s_next;           // work-stealing: next list position of this CTA
@@ -793,10 +804,15 @@ cudaError_t launch_integrate_group(const GroupArgs &args, const HashTable &table
         const char *e = std::getenv("B2V_UNROLL");
         return e != nullptr && std::atoi(e) != 0;
     }();
+    const int per_sm = grid_ctas / 148;   // B2V_INT_CTAS_PER_SM selects the occupancy variant (default 8)
     if (unroll && args.count <= kUnrolledGroup)
-        integrate_group_kernel<true><<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
+        integrate_group_kernel<true, 8><<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
+    else if (per_sm >= 11)
+        integrate_group_kernel<false, 12><<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
+    else if (per_sm >= 9)
+        integrate_group_kernel<false, 10><<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
     else
-        integrate_group_kernel<false><<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
+        integrate_group_kernel<false, 8><<<grid_ctas, kIntThreads, 0, stream>>>(args, table, meta, group_buf);
     group_clear_kernel<<<148, 256, 0, stream>>>(table, meta, group_buf);
     return cudaGetLastError();
 }

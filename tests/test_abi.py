@@ -38,11 +38,11 @@ def test_library_is_sm100a_and_uses_128bit_cas():
     out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    assert "keygen_kernel" in sass and "pack_kernel" in sass and "integrate_kernel" in sass
+    assert "allocate_kernel" in sass and "integrate_kernel" in sass
     assert "ATOMG.E.CAS.128" in sass  # 16-byte hash-table entries are inserted with one 128-bit CAS
-    assert "UTMALDG.2D" in sass       # depth / colour / lambda tiles are staged by TMA in the pack kernels
-    assert "MATCH.ANY" in sass        # warp-level de-duplication of boxes / blocks in the key generation kernels
-    for kernel in ("integrate_group_kernel", "keygen_group_kernel", "pack_group_kernel", "mesh_", "sem_runs_kernel", "sem_assoc_kernel",
+    assert "UTMALDG.2D" in sass       # depth / colour / lambda tiles are staged by TMA in the allocate kernels
+    assert "MATCH.ANY" in sass        # warp-level de-duplication of block inserts (point-average / semantic grids)
+    for kernel in ("integrate_group_kernel", "allocate_group_kernel", "mesh_", "sem_runs_kernel", "sem_assoc_kernel",
                    "remap_u8c3_linear_kernel", "shadow_hist_kernel", "depth_u16_to_f32_kernel"):
         assert kernel in sass, kernel
 
