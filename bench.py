@@ -311,7 +311,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # (NCCL_DEBUG is left to the caller: even WARN prints a version banner on stdout, and stdout is the JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

@@ -271,7 +271,7 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     B2V_CUDA(v, cudaMalloc(&v->meta.group_mask, static_cast<size_t>(tcap) * kGroupBufs * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMalloc(&v->meta.union_slots, static_cast<size_t>(cap) * kGroupBufs * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMallocHost(&v->h_counters, kNumCounters * sizeof(uint32_t)));
-    B2V_CUDA(v, cudaMallocHost(&v->h_totals, 2 * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMallocHost(&v->h_totals, 4 * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMemsetAsync(v->meta.pool, 0, static_cast<size_t>(cap) * kBlockFloats * sizeof(float),
                                 v->compute));
     int rc = volume_clear_device(v);
@@ -329,6 +329,7 @@ extern "C" int b2v_destroy(b2v_volume *v) {
     cudaFree(v->mb.vert_base);
     cudaFree(v->mb.sums);
     cudaFree(v->mb.offs);
+    cudaFree(v->mb.work);
     cudaFree(v->mb.totals);
     cudaFree(v->mb.vertices);
     cudaFree(v->mb.colors);
@@ -1176,7 +1177,7 @@ template <typename T> static cudaError_t regrow(T **p, size_t n) {
 }
 
 static int ensure_mesh_scratch(b2v_volume *v, uint32_t nb) {
-    if (!v->mb.totals) B2V_CUDA(v, cudaMalloc(&v->mb.totals, 2 * sizeof(uint32_t)));
+    if (!v->mb.totals) B2V_CUDA(v, cudaMalloc(&v->mb.totals, 4 * sizeof(uint32_t)));
     if (nb <= v->mesh_blocks_cap) return B2V_OK;
     const size_t n = nb;
     B2V_CUDA(v, regrow(&v->mb.nbr, n * 8));
@@ -1185,6 +1186,7 @@ static int ensure_mesh_scratch(b2v_volume *v, uint32_t nb) {
     B2V_CUDA(v, regrow(&v->mb.vert_base, n * kVox));
     B2V_CUDA(v, regrow(&v->mb.sums, n * 2));
     B2V_CUDA(v, regrow(&v->mb.offs, n * 2));
+    B2V_CUDA(v, regrow(&v->mb.work, n * 2));
     v->mesh_blocks_cap = nb;
     return B2V_OK;
 }
@@ -1203,7 +1205,7 @@ static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t
         B2V_CUDA(v, launch_point_masks(v->table, v->meta, v->mb, cs));
     }
     B2V_CUDA(v, launch_mesh_scan(v->mb, cs));
-    B2V_CUDA(v, cudaMemcpyAsync(v->h_totals, v->mb.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+    B2V_CUDA(v, cudaMemcpyAsync(v->h_totals, v->mb.totals, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
     B2V_CUDA(v, cudaStreamSynchronize(cs));
     const size_t nv = v->h_totals[0], nt = v->h_totals[1];
     if (nv > v->mesh_v_cap) {
@@ -1216,8 +1218,8 @@ static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t
         B2V_CUDA(v, regrow(&v->mb.triangles, nt * 3));
         v->mesh_t_cap = nt;
     }
-    B2V_CUDA(v, launch_mesh_vertices(v->meta, v->mb, v->geo.voxel_length, v->geo.unit_shift, !mesh, cs));
-    if (mesh) B2V_CUDA(v, launch_mesh_triangles(v->mb, cs));
+    B2V_CUDA(v, launch_mesh_vertices(v->meta, v->mb, v->geo.voxel_length, v->geo.unit_shift, !mesh, v->h_totals[2], cs));
+    if (mesh) B2V_CUDA(v, launch_mesh_triangles(v->mb, v->h_totals[3], cs));
     B2V_CUDA(v, cudaStreamSynchronize(cs));
     v->launches += mesh ? 5 : 4;
     v->last_nv = static_cast<int64_t>(nv);

@@ -184,7 +184,8 @@ struct MeshBuffers {
     uint32_t *vert_base;     // [n_blocks][512] index of the voxel's first vertex
     uint32_t *sums;          // [2][n_blocks] per-block vertex / triangle counts
     uint32_t *offs;          // [2][n_blocks] exclusive scans of sums
-    uint32_t *totals;        // [2] total vertices, triangles
+    uint32_t *totals;        // [4] total vertices, triangles; blocks with vertices, blocks with triangles
+    uint32_t *work;          // [2][n_blocks] the blocks with vertices / with triangles (what the emit kernels visit)
     double *vertices;        // [nv][3] float64, Open3D's formula
     double *colors;          // [nv][3] in [0,1]
     int32_t *edge_ids;       // [nv][4] canonical weld key (voxel x,y,z, axis)
@@ -200,8 +201,8 @@ cudaError_t launch_point_masks(const HashTable &table, const PoolMeta &meta, con
 // per-block sums + exclusive scans -> offs, totals
 cudaError_t launch_mesh_scan(const MeshBuffers &mb, cudaStream_t stream);
 cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, double voxel_length, int unit_shift,
-                                 bool points, cudaStream_t stream);
-cudaError_t launch_mesh_triangles(const MeshBuffers &mb, cudaStream_t stream);
+                                 bool points, uint32_t work_blocks, cudaStream_t stream);
+cudaError_t launch_mesh_triangles(const MeshBuffers &mb, uint32_t work_blocks, cudaStream_t stream);
 
 // ---- point-average grid (b2v_grid.cu) ----
 struct GridMeta {

@@ -20,6 +20,7 @@ __constant__ unsigned short c_edge_table[256];
 __constant__ signed char c_tri_table[256][16];
 __constant__ unsigned char c_num_tris[256];
 __constant__ signed char c_edge_shift[12][4];
+__constant__ unsigned short c_halo[217];   // the 9^3 - 8^3 tile cells outside the own block: x | y << 4 | z << 8
 
 static cudaError_t upload_tables_once() {
     static bool done = false;
@@ -32,6 +33,13 @@ static cudaError_t upload_tables_once() {
     if ((e = cudaMemcpyToSymbol(c_tri_table, MC_TRI_TABLE, sizeof(MC_TRI_TABLE))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_num_tris, MC_NUM_TRIS, sizeof(MC_NUM_TRIS))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_edge_shift, MC_EDGE_SHIFT, sizeof(MC_EDGE_SHIFT))) != cudaSuccess) return e;
+    unsigned short halo[217];
+    int nh = 0;
+    for (int z = 0; z < 9; ++z)
+        for (int y = 0; y < 9; ++y)
+            for (int x = 0; x < 9; ++x)
+                if (x == 8 || y == 8 || z == 8) halo[nh++] = static_cast<unsigned short>(x | (y << 4) | (z << 8));
+    if ((e = cudaMemcpyToSymbol(c_halo, halo, sizeof(halo))) != cudaSuccess) return e;
     done = true;
     done_device = dev;
     return cudaSuccess;
@@ -71,10 +79,18 @@ mesh_classify_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) 
     __shared__ int s_nbr[8];
     const uint32_t b = blockIdx.x;
     const int t = threadIdx.x;
+    const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
+    // own voxel first (coalesced, needs no neighbour), then the 217 halo cells of the 9^3 tile
+    const float *own = M.pool + static_cast<size_t>(b) * kBlockFloats;
+    const float f0 = own[t], w0 = own[kVox + t];
+    s_f[lx + ly * 9 + lz * 81] = f0;
+    s_w[lx + ly * 9 + lz * 81] = w0;
     if (t < 8) mb.nbr[b * 8 + t] = s_nbr[t] = neighbor_block(T, M, b, t);
     __syncthreads();
-    for (int i = t; i < 729; i += kVox) {
-        const int x = i % 9, y = (i / 9) % 9, z = i / 81;
+    bool neg = w0 != 0.0f && f0 < 0.0f, pos = w0 != 0.0f && !(f0 < 0.0f);
+    if (t < 217) {
+        const int h = c_halo[t];
+        const int x = h & 15, y = (h >> 4) & 15, z = h >> 8;
         const int pb = s_nbr[(x >> 3) | ((y >> 3) << 1) | ((z >> 3) << 2)];
         float f = 0.0f, w = 0.0f;
         if (pb >= 0) {
@@ -83,11 +99,16 @@ mesh_classify_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) 
             f = blk[v];
             w = blk[kVox + v];
         }
-        s_f[i] = f;
-        s_w[i] = w;
+        s_f[x + y * 9 + z * 81] = f;
+        s_w[x + y * 9 + z * 81] = w;
+        neg |= w != 0.0f && f < 0.0f;
+        pos |= w != 0.0f && !(f < 0.0f);
     }
-    __syncthreads();
-    const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
+    // a tile whose observed voxels all lie on one side of the surface has no cube to emit (most blocks: free space or
+    // behind the surface); mb.cube / mb.edge_mask were cleared by the launcher
+    const int has_neg = __syncthreads_or(neg);
+    const int has_pos = __syncthreads_or(pos);
+    if (!(has_neg && has_pos)) return;
     int cube = 0;
     bool ok = true;
 #pragma unroll
@@ -99,8 +120,8 @@ mesh_classify_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) 
         if (s_f[i] < 0.0f) cube |= (1 << c);
     }
     if (!ok || cube == 255) cube = 0;
-    mb.cube[static_cast<size_t>(b) * kVox + t] = static_cast<uint8_t>(cube);
     if (cube) {
+        mb.cube[static_cast<size_t>(b) * kVox + t] = static_cast<uint8_t>(cube);
         const unsigned em = c_edge_table[cube];
         for (int e = 0; e < 12; ++e) {
             if (!((em >> e) & 1u)) continue;
@@ -166,8 +187,13 @@ mesh_block_sums_kernel(const MeshBuffers mb) {
     }
     __syncthreads();
     if (t == 0) {
-        mb.sums[b] = s_v[0] + s_v[1] + s_v[2] + s_v[3];
-        mb.sums[mb.n_blocks + b] = s_t[0] + s_t[1] + s_t[2] + s_t[3];
+        const uint32_t sv = s_v[0] + s_v[1] + s_v[2] + s_v[3], st = s_t[0] + s_t[1] + s_t[2] + s_t[3];
+        mb.sums[b] = sv;
+        mb.sums[mb.n_blocks + b] = st;
+        // the emit kernels run over the blocks that have output only (list order does not matter: positions come
+        // from the scan of the sums)
+        if (sv) mb.work[atomicAdd(mb.totals + 2, 1u)] = b;
+        if (st) mb.work[mb.n_blocks + atomicAdd(mb.totals + 3, 1u)] = b;
     }
 }
 
@@ -183,8 +209,7 @@ __global__ void __launch_bounds__(kVox)
 mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const double vl, const int unit_shift) {
     __shared__ uint32_t s_warp[16];
     __shared__ int s_nbr[8];
-    const uint32_t b = blockIdx.x;
-    if (mb.sums[b] == 0u) return;  // no vertex lives in this block (most blocks: free space / behind the surface)
+    const uint32_t b = mb.work[blockIdx.x];  // blocks with at least one vertex
     const int t = threadIdx.x;
     if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
     const size_t flat = static_cast<size_t>(b) * kVox + t;
@@ -263,8 +288,7 @@ __global__ void __launch_bounds__(kVox)
 mesh_triangles_kernel(const MeshBuffers mb) {
     __shared__ uint32_t s_warp[16];
     __shared__ int s_nbr[8];
-    const uint32_t b = blockIdx.x;
-    if (mb.sums[mb.n_blocks + b] == 0u) return;  // no triangle rooted in this block
+    const uint32_t b = mb.work[mb.n_blocks + blockIdx.x];  // blocks with at least one triangle
     const int t = threadIdx.x;
     if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
     const int cube = mb.cube[static_cast<size_t>(b) * kVox + t];
@@ -298,6 +322,7 @@ cudaError_t launch_mesh_classify(const HashTable &table, const PoolMeta &meta, c
     cudaError_t e = upload_tables_once();
     if (e != cudaSuccess || mb.n_blocks == 0) return e;
     e = cudaMemsetAsync(mb.edge_mask, 0, static_cast<size_t>(mb.n_blocks) * kVox, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(mb.cube, 0, static_cast<size_t>(mb.n_blocks) * kVox, stream);
     if (e != cudaSuccess) return e;
     mesh_classify_kernel<<<mb.n_blocks, kVox, 0, stream>>>(table, meta, mb);
     return cudaGetLastError();
@@ -312,25 +337,26 @@ cudaError_t launch_point_masks(const HashTable &table, const PoolMeta &meta, con
 }
 
 cudaError_t launch_mesh_scan(const MeshBuffers &mb, cudaStream_t stream) {
-    if (mb.n_blocks == 0) return cudaMemsetAsync(mb.totals, 0, 2 * sizeof(uint32_t), stream);
+    cudaError_t e = cudaMemsetAsync(mb.totals, 0, 4 * sizeof(uint32_t), stream);
+    if (e != cudaSuccess || mb.n_blocks == 0) return e;
     mesh_block_sums_kernel<<<mb.n_blocks, 128, 0, stream>>>(mb);
     exclusive_scan_kernel<<<2, 1024, 0, stream>>>(mb.sums, mb.offs, mb.totals, mb.n_blocks);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, double voxel_length, int unit_shift,
-                                 bool points, cudaStream_t stream) {
-    if (mb.n_blocks == 0) return cudaSuccess;
+                                 bool points, uint32_t work_blocks, cudaStream_t stream) {
+    if (work_blocks == 0) return cudaSuccess;
     if (points)
-        mesh_vertices_kernel<true><<<mb.n_blocks, kVox, 0, stream>>>(meta, mb, voxel_length, unit_shift);
+        mesh_vertices_kernel<true><<<work_blocks, kVox, 0, stream>>>(meta, mb, voxel_length, unit_shift);
     else
-        mesh_vertices_kernel<false><<<mb.n_blocks, kVox, 0, stream>>>(meta, mb, voxel_length, unit_shift);
+        mesh_vertices_kernel<false><<<work_blocks, kVox, 0, stream>>>(meta, mb, voxel_length, unit_shift);
     return cudaGetLastError();
 }
 
-cudaError_t launch_mesh_triangles(const MeshBuffers &mb, cudaStream_t stream) {
-    if (mb.n_blocks == 0) return cudaSuccess;
-    mesh_triangles_kernel<<<mb.n_blocks, kVox, 0, stream>>>(mb);
+cudaError_t launch_mesh_triangles(const MeshBuffers &mb, uint32_t work_blocks, cudaStream_t stream) {
+    if (work_blocks == 0) return cudaSuccess;
+    mesh_triangles_kernel<<<work_blocks, kVox, 0, stream>>>(mb);
     return cudaGetLastError();
 }
 
