@@ -79,7 +79,7 @@ int b2v_set_rectification(b2v_volume *v, const float *map_x, const float *map_y,
 int b2v_remap(const void *src, int32_t kind, int32_t height, int32_t width, const float *map_x,
               const float *map_y, void *dst, int32_t swap_rb, int32_t device);
 /* n frames back to back (the rebuild(map) bulk path, base.py:1242-1318): depth [n*H*W],
- * color [n*H*W*3], Tcw [n*16]; same K for all.  By default groups of up to 8 frames are FUSED: a block
+ * color [n*H*W*3], Tcw [n*16]; same K for all.  By default groups of up to 16 frames are FUSED: a block
  * is read once, updated by the frames of the group in frame order, and written once - bit-identical
  * to frame-by-frame integration (b2v_set_fusion(v, 0) forces frame-by-frame). */
 int b2v_integrate_batch(b2v_volume *v, int32_t n_frames, const float *depth, const uint8_t *color,
@@ -114,7 +114,7 @@ int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches
  * Results are bit-identical either way.  Synchronises. */
 int b2v_set_overlap(b2v_volume *v, int32_t enable);
 int b2v_set_fusion(b2v_volume *v, int32_t enable);
-/* frames per fused group of b2v_integrate_batch: 1..32, default 8.  Larger groups amortise launch and latency costs
+/* frames per fused group of b2v_integrate_batch: 1..32, default 16.  Larger groups amortise launch and latency costs
  * (hash-sharded ranks with few blocks each); results do not depend on it.  Synchronises. */
 int b2v_set_group_size(b2v_volume *v, int32_t frames);
 /* Per-kernel device timing (CUDA events on the launching stream around each launch), for the

@@ -110,7 +110,7 @@ struct b2v_volume {
     bool use_tma = true;                 // stage image tiles with TMA when the layout allows it
     bool inputs_fenced = false;          // batch call: device inputs already ordered before the alloc stream
     bool fuse = true;                    // b2v_integrate_batch fuses groups of up to kMaxGroup frames
-    int group_frames = 8;                // frames per fused group (1..kMaxGroup), b2v_set_group_size
+    int group_frames = 16;               // frames per fused group (1..kMaxGroup), b2v_set_group_size
     LambdaMap lam_map{};
     bool lam_map_ok = false;
     cudaEvent_t input_event = nullptr;   // b2v_set_input_event: readiness of the next batch's device inputs

@@ -250,7 +250,7 @@ class B200TsdfVolume:
         return int(b.value)
 
     def set_fusion(self, enable: bool):
-        """integrate_batch: fuse groups of up to 8 frames per block visit (default) or go frame by frame."""
+        """integrate_batch: fuse groups of frames per block visit (default, see set_group_size) or go frame by frame."""
         self._check(self._L.b2v_set_fusion(self._h, 1 if enable else 0), "b2v_set_fusion")
 
     def set_input_event(self, cuda_event):
@@ -259,7 +259,7 @@ class B200TsdfVolume:
         self._check(self._L.b2v_set_input_event(self._h, C.c_void_p(int(cuda_event))), "b2v_set_input_event")
 
     def set_group_size(self, frames: int):
-        """Frames per fused group of integrate_batch (1..32, default 8); results do not depend on it."""
+        """Frames per fused group of integrate_batch (1..32, default 16); results do not depend on it."""
         self._check(self._L.b2v_set_group_size(self._h, int(frames)), "b2v_set_group_size")
 
     def set_rectification(self, map_x, map_y, swap_rb: bool = False):
