@@ -329,7 +329,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     cfg, depth, color, Tcw = load_frames(args.config, args.frames, rank, world, barrier)
     F, H, W = depth.shape
     shards = args.shard_of if (world == 1 and args.shard_of > 1) else world
-    group = args.group if args.group > 0 else (16 if shards <= 2 else 32)
+    group = args.group if args.group > 0 else 32
 
     def make_volume(shard_rank, shard_count):
         v = B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=args.capacity,
@@ -678,7 +678,7 @@ def main():
     ap.add_argument("--frames", type=int, default=300, help="frames per step (the sequence length)")
     ap.add_argument("--capacity", type=int, default=1 << 19, help="block-pool capacity (10 KiB each)")
     ap.add_argument("--cpu-frames", type=int, default=32, help="frames in the bounded CPU sample")
-    ap.add_argument("--group", type=int, default=0, help="frames per fused group (0: 16 for 1-2 shards, 32 beyond)")
+    ap.add_argument("--group", type=int, default=0, help="frames per fused group (0: 32; the library default is 16)")
     ap.add_argument("--chunk", type=int, default=64, help="frames per ingest chunk (upload + all-gather granularity)")
     ap.add_argument("--mesh", action="store_true", help="N > 1: also time the distributed mesh extraction")
     ap.add_argument("--no-cpu", action="store_true")

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Summarise ncu captures (gpurun_out/*.ncu-rep + launch list) into the tracked profiles/ files.
 
-    python profiles/summarize.py r1 gpurun_out/launches_r1.csv gpurun_out/prof_r1_group.ncu-rep gpurun_out/prof_r1_frame.ncu-rep
+    python profiles/summarize.py r2 C2x300 gpurun_out/r2_launches.csv gpurun_out/r2_prof_*.ncu-rep
+
+`C2x300` names the workload the captures ran (bench.py copies `traffic` only when it runs the same one).
 
 Writes profiles/<round>_launches_summary.csv, profiles/<round>_kernels.csv, profiles/<round>_summary.md and
 profiles/latest.json (dram bytes per launch of the dominant kernel: bench.py's roofline.traffic)."""
@@ -35,6 +37,9 @@ METRICS = [
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
     ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch"),
     ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe"),
 ]
 
 
@@ -50,7 +55,10 @@ def raw_rows(rep):
     idx = {h: i for i, h in enumerate(hdr)}
     res = []
     for r in rows[2:]:
-        d = {"kernel": r[idx["Kernel Name"]].split("(")[0]}
+        name = r[idx["Kernel Name"]].split("(")[0]
+        for junk in ("void ", "b2v::"):
+            name = name.replace(junk, "")
+        d = {"kernel": name.split("<")[0]}
         for m, name in METRICS:
             if m in idx:
                 d[name] = (r[idx[m]], units[idx[m]])
@@ -59,7 +67,7 @@ def raw_rows(rep):
 
 
 def main():
-    rnd, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
+    rnd, workload, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4:]
     # ---- launch list: per-kernel totals and shares (cold-cache, serialised: compare SHARES) ----
     rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
     hdr = rows[0]
@@ -67,7 +75,7 @@ def main():
     per = collections.defaultdict(list)
     for r in rows[1:]:
         try:
-            per[r[ki].split("(")[0]].append(float(r[vi].replace(",", "")))
+            per[r[ki].split("(")[0].replace("void ", "").replace("b2v::", "")].append(float(r[vi].replace(",", "")))
         except ValueError:
             pass
     total = sum(sum(v) for v in per.values())
@@ -93,7 +101,10 @@ def main():
         rd = statistics.mean(to_bytes(*d["dram read"]) for d in ds)
         wr = statistics.mean(to_bytes(*d["dram write"]) for d in ds)
         latest[k] = {"dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
-                     "duration_us": statistics.mean(float(d["duration"][0]) for d in ds), "captures": len(ds)}
+                     "duration_us": statistics.mean(float(d["duration"][0]) for d in ds), "captures": len(ds),
+                     "workload": workload, "source": "ncu --set full, profiles/" + rnd + "_kernels.csv"}
+        if "issue active %" in ds[0]:
+            latest[k]["issue_active_pct"] = statistics.mean(float(d["issue active %"][0]) for d in ds)
     latest["round"] = rnd
     latest["source"] = [os.path.basename(r) for r in reps]
     json.dump(latest, open(os.path.join(HERE, "latest.json"), "w"), indent=1)

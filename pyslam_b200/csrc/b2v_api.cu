@@ -1221,7 +1221,7 @@ static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t
     B2V_CUDA(v, launch_mesh_vertices(v->meta, v->mb, v->geo.voxel_length, v->geo.unit_shift, !mesh, v->h_totals[2], cs));
     if (mesh) B2V_CUDA(v, launch_mesh_triangles(v->mb, v->h_totals[3], cs));
     B2V_CUDA(v, cudaStreamSynchronize(cs));
-    v->launches += mesh ? 5 : 4;
+    v->launches += mesh ? 6 : 5;
     v->last_nv = static_cast<int64_t>(nv);
     v->last_nt = mesh ? static_cast<int64_t>(nt) : 0;
     if (n_vertices) *n_vertices = v->last_nv;

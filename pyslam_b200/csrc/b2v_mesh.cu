@@ -47,8 +47,7 @@ static cudaError_t upload_tables_once() {
 
 // ---- pass 0: neighbour block indices --------------------------------------------------------
 
-// pool index of the block at +(o&1, o>>1&1, o>>2&1) of block b, -1 if it does not exist; done by the first 8 threads
-// of the classify / point-mask CTAs (the result is kept in mb.nbr for the emit kernels)
+// pool index of the block at +(o&1, o>>1&1, o>>2&1) of block b, -1 if it does not exist
 __device__ __forceinline__ int32_t neighbor_block(const HashTable &T, const PoolMeta &M, uint32_t b, uint32_t o) {
     if (o == 0) return static_cast<int32_t>(b);
     const int4 k = M.block_keys[b];
@@ -56,6 +55,13 @@ __device__ __forceinline__ int32_t neighbor_block(const HashTable &T, const Pool
     if (s == kEmpty) return -1;
     const uint32_t w = T.entries[s].w;
     return w < M.capacity ? static_cast<int32_t>(w) : -1;
+}
+
+// pass 0: one thread per (block, neighbour) - a separate, massively parallel launch so that the two dependent memory
+// hops of a table probe are not on the critical path of every classify CTA
+__global__ void mesh_neighbors_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < mb.n_blocks * 8u) mb.nbr[i] = neighbor_block(T, M, i >> 3, i & 7u);
 }
 
 // owner voxel of cube edge e rooted at local (lx,ly,lz): returns flat index into per-voxel arrays
@@ -72,24 +78,38 @@ __device__ __forceinline__ bool edge_owner(const int *s_nbr, int lx, int ly, int
 
 // ---- pass 1a: marching-cubes case + vertex ownership (mesh) ---------------------------------
 
-__global__ void __launch_bounds__(kVox)
-mesh_classify_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) {
+constexpr int kClsThreads = 128;   // 4 voxels per thread: 16 resident CTAs per SM keep more tile loads in flight
+
+__global__ void __launch_bounds__(kClsThreads)
+mesh_classify_kernel(const PoolMeta M, const MeshBuffers mb) {
     __shared__ float s_f[729];
     __shared__ float s_w[729];
     __shared__ int s_nbr[8];
     const uint32_t b = blockIdx.x;
     const int t = threadIdx.x;
-    const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
-    // own voxel first (coalesced, needs no neighbour), then the 217 halo cells of the 9^3 tile
+    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
+    // own voxels first (coalesced, independent of the neighbours): voxel t + 128 k
     const float *own = M.pool + static_cast<size_t>(b) * kBlockFloats;
-    const float f0 = own[t], w0 = own[kVox + t];
-    s_f[lx + ly * 9 + lz * 81] = f0;
-    s_w[lx + ly * 9 + lz * 81] = w0;
-    if (t < 8) mb.nbr[b * 8 + t] = s_nbr[t] = neighbor_block(T, M, b, t);
+    float f0[4], w0[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        f0[k] = own[t + kClsThreads * k];
+        w0[k] = own[kVox + t + kClsThreads * k];
+    }
+    const int lx = t & 7, ly = (t >> 3) & 7, lz0 = t >> 6;   // voxel k: lz = lz0 + 2 k
+    bool neg = false, pos = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = lx + ly * 9 + (lz0 + 2 * k) * 81;
+        s_f[c] = f0[k];
+        s_w[c] = w0[k];
+        neg |= w0[k] != 0.0f && f0[k] < 0.0f;
+        pos |= w0[k] != 0.0f && !(f0[k] < 0.0f);
+    }
     __syncthreads();
-    bool neg = w0 != 0.0f && f0 < 0.0f, pos = w0 != 0.0f && !(f0 < 0.0f);
-    if (t < 217) {
-        const int h = c_halo[t];
+    // the 217 halo cells of the 9^3 tile
+    for (int i = t; i < 217; i += kClsThreads) {
+        const int h = c_halo[i];
         const int x = h & 15, y = (h >> 4) & 15, z = h >> 8;
         const int pb = s_nbr[(x >> 3) | ((y >> 3) << 1) | ((z >> 3) << 2)];
         float f = 0.0f, w = 0.0f;
@@ -109,26 +129,30 @@ mesh_classify_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) 
     const int has_neg = __syncthreads_or(neg);
     const int has_pos = __syncthreads_or(pos);
     if (!(has_neg && has_pos)) return;
-    int cube = 0;
-    bool ok = true;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        // corner offsets {000,100,110,010,001,101,111,011} (SURVEY.md A.4 `shift`)
-        const int sx = ((c + 1) >> 1) & 1, sy = (c >> 1) & 1, sz = c >> 2;
-        const int i = (lx + sx) + (ly + sy) * 9 + (lz + sz) * 81;
-        ok = ok && (s_w[i] != 0.0f);
-        if (s_f[i] < 0.0f) cube |= (1 << c);
-    }
-    if (!ok || cube == 255) cube = 0;
-    if (cube) {
-        mb.cube[static_cast<size_t>(b) * kVox + t] = static_cast<uint8_t>(cube);
-        const unsigned em = c_edge_table[cube];
-        for (int e = 0; e < 12; ++e) {
-            if (!((em >> e) & 1u)) continue;
-            size_t flat;
-            int axis;
-            if (edge_owner(s_nbr, lx, ly, lz, e, &flat, &axis))
-                atomicOr(mb.edge_mask + (flat >> 2), (1u << axis) << ((flat & 3) * 8));
+    for (int k = 0; k < 4; ++k) {
+        const int lz = lz0 + 2 * k;
+        int cube = 0;
+        bool ok = true;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            // corner offsets {000,100,110,010,001,101,111,011} (SURVEY.md A.4 `shift`)
+            const int sx = ((c + 1) >> 1) & 1, sy = (c >> 1) & 1, sz = c >> 2;
+            const int i = (lx + sx) + (ly + sy) * 9 + (lz + sz) * 81;
+            ok = ok && (s_w[i] != 0.0f);
+            if (s_f[i] < 0.0f) cube |= (1 << c);
+        }
+        if (!ok || cube == 255) cube = 0;
+        if (cube) {
+            mb.cube[static_cast<size_t>(b) * kVox + t + kClsThreads * k] = static_cast<uint8_t>(cube);
+            const unsigned em = c_edge_table[cube];
+            for (int e = 0; e < 12; ++e) {
+                if (!((em >> e) & 1u)) continue;
+                size_t flat;
+                int axis;
+                if (edge_owner(s_nbr, lx, ly, lz, e, &flat, &axis))
+                    atomicOr(mb.edge_mask + (flat >> 2), (1u << axis) << ((flat & 3) * 8));
+            }
         }
     }
 }
@@ -136,12 +160,12 @@ mesh_classify_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) 
 // ---- pass 1b: zero-crossing masks (point cloud) ---------------------------------------------
 
 __global__ void __launch_bounds__(kVox)
-point_masks_kernel(const HashTable T, const PoolMeta M, const MeshBuffers mb) {
+point_masks_kernel(const PoolMeta M, const MeshBuffers mb) {
     __shared__ int s_nbr[8];
     __shared__ uint8_t s_m[kVox];
     const uint32_t b = blockIdx.x;
     const int t = threadIdx.x;
-    if (t < 8) mb.nbr[b * 8 + t] = s_nbr[t] = neighbor_block(T, M, b, t);
+    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
     __syncthreads();
     const float *blk = M.pool + static_cast<size_t>(b) * kBlockFloats;
     const float f0 = blk[t], w0 = blk[kVox + t];
@@ -213,16 +237,19 @@ mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const double vl, co
     const int t = threadIdx.x;
     if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
     const size_t flat = static_cast<size_t>(b) * kVox + t;
-    const unsigned m = (mb.edge_mask[flat >> 2] >> ((flat & 3) * 8)) & 7u;
-    const uint32_t base = mb.offs[b] + block_excl_scan_512(__popc(m), s_warp);
-    mb.vert_base[flat] = base;
-    if (m == 0) return;
-    const int4 key = M.block_keys[b];
-    const int l[3] = {t & 7, (t >> 3) & 7, t >> 6};
-    const int g[3] = {key.x * kB + l[0], key.y * kB + l[1], key.z * kB + l[2]};
+    // everything that does not depend on the masks is requested up front (coalesced; one memory round trip
+    // instead of three dependent ones)
     const float *blk = M.pool + static_cast<size_t>(b) * kBlockFloats;
     const float r0 = fabsf(blk[t]);
     const float c0[3] = {blk[2 * kVox + t], blk[3 * kVox + t], blk[4 * kVox + t]};
+    const int4 key = M.block_keys[b];
+    const uint32_t off_b = mb.offs[b];
+    const unsigned m = (mb.edge_mask[flat >> 2] >> ((flat & 3) * 8)) & 7u;
+    const uint32_t base = off_b + block_excl_scan_512(__popc(m), s_warp);
+    mb.vert_base[flat] = base;
+    if (m == 0) return;
+    const int l[3] = {t & 7, (t >> 3) & 7, t >> 6};
+    const int g[3] = {key.x * kB + l[0], key.y * kB + l[1], key.z * kB + l[2]};
     const double half = __dmul_rn(vl, 0.5);
     double ctr[3];
     if (kPoints) {
@@ -324,7 +351,8 @@ cudaError_t launch_mesh_classify(const HashTable &table, const PoolMeta &meta, c
     e = cudaMemsetAsync(mb.edge_mask, 0, static_cast<size_t>(mb.n_blocks) * kVox, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(mb.cube, 0, static_cast<size_t>(mb.n_blocks) * kVox, stream);
     if (e != cudaSuccess) return e;
-    mesh_classify_kernel<<<mb.n_blocks, kVox, 0, stream>>>(table, meta, mb);
+    mesh_neighbors_kernel<<<(mb.n_blocks * 8u + 255u) / 256u, 256, 0, stream>>>(table, meta, mb);
+    mesh_classify_kernel<<<mb.n_blocks, kClsThreads, 0, stream>>>(meta, mb);
     return cudaGetLastError();
 }
 
@@ -332,7 +360,8 @@ cudaError_t launch_point_masks(const HashTable &table, const PoolMeta &meta, con
                                cudaStream_t stream) {
     cudaError_t e = upload_tables_once();
     if (e != cudaSuccess || mb.n_blocks == 0) return e;
-    point_masks_kernel<<<mb.n_blocks, kVox, 0, stream>>>(table, meta, mb);
+    mesh_neighbors_kernel<<<(mb.n_blocks * 8u + 255u) / 256u, 256, 0, stream>>>(table, meta, mb);
+    point_masks_kernel<<<mb.n_blocks, kVox, 0, stream>>>(meta, mb);
     return cudaGetLastError();
 }
 

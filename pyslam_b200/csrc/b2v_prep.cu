@@ -55,8 +55,14 @@ __device__ __forceinline__ void digit_layout(int pass, int *shift, uint32_t *nbi
     }
 }
 
-__global__ void shadow_hist_kernel(const float *__restrict__ depth, int H, int W, int dx, int dy, int pass,
-                                   const SelectState *__restrict__ st, uint32_t *__restrict__ hist) {
+__global__ void __launch_bounds__(256)
+shadow_hist_kernel(const float *__restrict__ depth, int H, int W, int dx, int dy, int pass,
+                   const SelectState *__restrict__ st, uint32_t *__restrict__ hist) {
+    // per-CTA histograms in shared memory (the positive deltas of an image crowd into a few bins: global atomics
+    // on them serialise), flushed once
+    __shared__ uint32_t s_h[4096];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_h[i] = 0u;
+    __syncthreads();
     int shift;
     uint32_t nbins, hi_mask;
     digit_layout(pass, &shift, &nbins, &hi_mask);
@@ -68,43 +74,81 @@ __global__ void shadow_hist_kernel(const float *__restrict__ depth, int H, int W
         if (!delta_at(depth, H, W, dx, dy, i, &v) || !(v > 0.0f)) continue;  // delta_values[delta_values > 0]
         const uint32_t bits = __float_as_uint(v);
         const uint32_t digit = (bits >> shift) & (nbins - 1);
-        if ((bits & hi_mask) == p0) atomicAdd(hist + digit, 1u);
-        if ((bits & hi_mask) == p1) atomicAdd(hist + 2048 + digit, 1u);
+        if ((bits & hi_mask) == p0) atomicAdd(s_h + digit, 1u);
+        if ((bits & hi_mask) == p1) atomicAdd(s_h + 2048 + digit, 1u);
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x)
+        if (s_h[i]) atomicAdd(hist + i, s_h[i]);
 }
 
-// one block: walk the two histograms, fix the next digit of both ranks, clear the histograms
-__global__ void shadow_pick_kernel(int pass, SelectState *st, uint32_t *hist) {
+// one block: walk the two histograms, fix the next digit of both ranks, clear the histograms.  The walk is a
+// block-wide scan: thread t owns 8 consecutive bins of each histogram.
+__global__ void __launch_bounds__(256)
+shadow_pick_kernel(int pass, SelectState *st, uint32_t *hist) {
+    __shared__ uint32_t s_part[2][256];
+    __shared__ uint32_t s_total;
     int shift;
     uint32_t nbins, hi_mask;
     digit_layout(pass, &shift, &nbins, &hi_mask);
-    if (threadIdx.x == 0) {
+    const int t = threadIdx.x;
+    uint32_t mine[2][8];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t b = static_cast<uint32_t>(t) * 8u + j;
+            mine[k][j] = b < nbins ? hist[2048 * k + b] : 0u;
+            sum += mine[k][j];
+        }
+        s_part[k][t] = sum;
+    }
+    __syncthreads();
+    if (t == 0) {  // 256 partial sums: exclusive prefixes in place (tiny, serial)
+        for (int k = 0; k < 2; ++k) {
+            uint32_t run = 0;
+            for (int i = 0; i < 256; ++i) {
+                const uint32_t v = s_part[k][i];
+                s_part[k][i] = run;
+                run += v;
+            }
+            if (k == 0) s_total = run;
+        }
         if (pass == 0) {
-            uint32_t total = 0;
-            for (uint32_t b = 0; b < nbins; ++b) total += hist[b];
+            const uint32_t total = s_total;
             st->total = total;
             st->rank[0] = total ? (total - 1) / 2 : 0;  // numpy median: mean of elements (n-1)//2 and n//2
             st->rank[1] = total / 2;
             st->prefix[0] = st->prefix[1] = 0;
         }
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t *h = hist + 2048 * k;
-            uint32_t r = st->rank[k], b = 0;
-            while (b + 1 < nbins && r >= h[b]) {
-                r -= h[b];
-                ++b;
+    }
+    __syncthreads();
+    // the bin b with  sum(h[0..b)) <= rank < sum(h[0..b]), or the last bin (the serial walk's stopping rule)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t r = st->rank[k];
+        uint32_t before = s_part[k][t];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t b = static_cast<uint32_t>(t) * 8u + j;
+            if (b < nbins) {
+                const bool last = b + 1 == nbins;
+                if (r >= before && (r < before + mine[k][j] || last)) {
+                    st->rank[k] = r - before;
+                    st->prefix[k] |= b << shift;
+                }
             }
-            st->rank[k] = r;
-            st->prefix[k] |= b << shift;
-        }
-        if (pass == 2) {
-            const float a = __uint_as_float(st->prefix[0]), b = __uint_as_float(st->prefix[1]);
-            // np.median -> mean of the two middle values in float32; then float32(1.4826) * mad; then 3 * sigma
-            const float mad = st->total ? __fmul_rn(__fadd_rn(a, b), 0.5f) : __uint_as_float(0x7FC00000u);
-            st->threshold = __fmul_rn(3.0f, __fmul_rn(1.4826f, mad));
+            before += mine[k][j];
         }
     }
     __syncthreads();
+    if (t == 0 && pass == 2) {
+        const float a = __uint_as_float(st->prefix[0]), b = __uint_as_float(st->prefix[1]);
+        // np.median -> mean of the two middle values in float32; then float32(1.4826) * mad; then 3 * sigma
+        const float mad = st->total ? __fmul_rn(__fadd_rn(a, b), 0.5f) : __uint_as_float(0x7FC00000u);
+        st->threshold = __fmul_rn(3.0f, __fmul_rn(1.4826f, mad));
+    }
     for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
 }
 
