@@ -124,10 +124,12 @@ shadow_pick_kernel(int pass, SelectState *st, uint32_t *hist) {
         }
     }
     __syncthreads();
+    const uint32_t ranks[2] = {st->rank[0], st->rank[1]};
+    __syncthreads();  // every thread has read the ranks before the owner of the crossing bin rewrites them
     // the bin b with  sum(h[0..b)) <= rank < sum(h[0..b]), or the last bin (the serial walk's stopping rule)
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        const uint32_t r = st->rank[k];
+        const uint32_t r = ranks[k];
         uint32_t before = s_part[k][t];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
