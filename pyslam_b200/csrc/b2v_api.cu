@@ -326,7 +326,7 @@ extern "C" int b2v_destroy(b2v_volume *v) {
     cudaFree(v->mb.nbr);
     cudaFree(v->mb.cube);
     cudaFree(v->mb.edge_mask);
-    cudaFree(v->mb.vert_base);
+    cudaFree(v->mb.local);
     cudaFree(v->mb.sums);
     cudaFree(v->mb.offs);
     cudaFree(v->mb.work);
@@ -1183,7 +1183,7 @@ static int ensure_mesh_scratch(b2v_volume *v, uint32_t nb) {
     B2V_CUDA(v, regrow(&v->mb.nbr, n * 8));
     B2V_CUDA(v, regrow(&v->mb.cube, n * kVox));
     B2V_CUDA(v, regrow(&v->mb.edge_mask, n * (kVox / 4)));
-    B2V_CUDA(v, regrow(&v->mb.vert_base, n * kVox));
+    B2V_CUDA(v, regrow(&v->mb.local, n * kVox));
     B2V_CUDA(v, regrow(&v->mb.sums, n * 2));
     B2V_CUDA(v, regrow(&v->mb.offs, n * 2));
     B2V_CUDA(v, regrow(&v->mb.work, n * 2));

@@ -181,7 +181,7 @@ struct MeshBuffers {
     int32_t *nbr;            // [n_blocks][8] pool index of the block at +(dx,dy,dz) (bit0=x), -1 if missing
     uint8_t *cube;           // [n_blocks][512] marching-cubes case of the cube rooted here (0 = none)
     uint32_t *edge_mask;     // [n_blocks][128] byte per voxel: bit a = a vertex lives on its +a edge
-    uint32_t *vert_base;     // [n_blocks][512] index of the voxel's first vertex
+    uint32_t *local;         // [n_blocks][512] position of the voxel's first vertex (low 16 bits) / triangle (high) in its block
     uint32_t *sums;          // [2][n_blocks] per-block vertex / triangle counts
     uint32_t *offs;          // [2][n_blocks] exclusive scans of sums
     uint32_t *totals;        // [4] total vertices, triangles; blocks with vertices, blocks with triangles

@@ -197,21 +197,48 @@ __global__ void __launch_bounds__(128)
 mesh_block_sums_kernel(const MeshBuffers mb) {
     __shared__ uint32_t s_v[4], s_t[4];
     const uint32_t b = blockIdx.x;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const uint32_t m4 = mb.edge_mask[static_cast<size_t>(b) * 128 + t];
     const uint32_t c4 = reinterpret_cast<const uint32_t *>(mb.cube)[static_cast<size_t>(b) * 128 + t];
-    uint32_t nv = __popc(m4 & 0x07070707u);
-    uint32_t nt = c_num_tris[c4 & 0xFF] + c_num_tris[(c4 >> 8) & 0xFF] + c_num_tris[(c4 >> 16) & 0xFF] +
-                  c_num_tris[c4 >> 24];
-    nv = __reduce_add_sync(0xffffffffu, nv);
-    nt = __reduce_add_sync(0xffffffffu, nt);
-    if ((t & 31) == 0) {
-        s_v[t >> 5] = nv;
-        s_t[t >> 5] = nt;
+    uint32_t pv[4], pt[4];   // vertices / triangles of the thread's four voxels
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pv[k] = __popc((m4 >> (8 * k)) & 7u);
+        pt[k] = c_num_tris[(c4 >> (8 * k)) & 0xFFu];
+    }
+    const uint32_t nv = pv[0] + pv[1] + pv[2] + pv[3], nt = pt[0] + pt[1] + pt[2] + pt[3];
+    // exclusive scan over the 128 threads (vertices in the low half, triangles in the high half: <= 1536 / 2560)
+    uint32_t x = nv | (nt << 16);
+    const uint32_t mine = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) {
+        s_v[wid] = x & 0xFFFFu;
+        s_t[wid] = x >> 16;
     }
     __syncthreads();
+    uint32_t ov = 0, ot = 0;
+    for (int w = 0; w < wid; ++w) {
+        ov += s_v[w];
+        ot += s_t[w];
+    }
+    const uint32_t sv = s_v[0] + s_v[1] + s_v[2] + s_v[3], st = s_t[0] + s_t[1] + s_t[2] + s_t[3];
+    if (sv | st) {  // per-voxel position inside the block: the emit kernels need no scan of their own
+        uint32_t bv = ov + ((x - mine) & 0xFFFFu), bt = ot + ((x - mine) >> 16);
+        uint4 out;
+        uint32_t *o = &out.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[k] = bv | (bt << 16);
+            bv += pv[k];
+            bt += pt[k];
+        }
+        reinterpret_cast<uint4 *>(mb.local)[static_cast<size_t>(b) * 128 + t] = out;
+    }
     if (t == 0) {
-        const uint32_t sv = s_v[0] + s_v[1] + s_v[2] + s_v[3], st = s_t[0] + s_t[1] + s_t[2] + s_t[3];
         mb.sums[b] = sv;
         mb.sums[mb.n_blocks + b] = st;
         // the emit kernels run over the blocks that have output only (list order does not matter: positions come
@@ -228,26 +255,22 @@ mesh_block_sums_kernel(const MeshBuffers mb) {
 // points = true: ExtractPointCloud: p0 = (vl/2 + vl * x_in_unit) + unit * L, p1 = p0 + vl on the axis,
 //     p = (p0 r1 + p1 r0) / (r0 + r1) with float32 r0 = |f0|, r1 = |f1| (their sum in float32), colour
 //     ((c0 r1 + c1 r0) / (r0 + r1)) / 255 in float32, widened
+constexpr int kEmitThreads = 128;   // four CTAs per block, no barrier: threads without output leave at once
+
 template <bool kPoints>
-__global__ void __launch_bounds__(kVox)
+__global__ void __launch_bounds__(kEmitThreads)
 mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const double vl, const int unit_shift) {
-    __shared__ uint32_t s_warp[16];
-    __shared__ int s_nbr[8];
-    const uint32_t b = mb.work[blockIdx.x];  // blocks with at least one vertex
-    const int t = threadIdx.x;
-    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
+    const uint32_t b = mb.work[blockIdx.x >> 2];  // blocks with at least one vertex
+    const int t = (blockIdx.x & 3) * kEmitThreads + threadIdx.x;
     const size_t flat = static_cast<size_t>(b) * kVox + t;
-    // everything that does not depend on the masks is requested up front (coalesced; one memory round trip
-    // instead of three dependent ones)
+    const unsigned m = (mb.edge_mask[flat >> 2] >> ((flat & 3) * 8)) & 7u;
+    if (m == 0) return;
+    const int *s_nbr = mb.nbr + static_cast<size_t>(b) * 8;
     const float *blk = M.pool + static_cast<size_t>(b) * kBlockFloats;
     const float r0 = fabsf(blk[t]);
     const float c0[3] = {blk[2 * kVox + t], blk[3 * kVox + t], blk[4 * kVox + t]};
     const int4 key = M.block_keys[b];
-    const uint32_t off_b = mb.offs[b];
-    const unsigned m = (mb.edge_mask[flat >> 2] >> ((flat & 3) * 8)) & 7u;
-    const uint32_t base = off_b + block_excl_scan_512(__popc(m), s_warp);
-    mb.vert_base[flat] = base;
-    if (m == 0) return;
+    const uint32_t base = mb.offs[b] + (mb.local[flat] & 0xFFFFu);
     const int l[3] = {t & 7, (t >> 3) & 7, t >> 6};
     const int g[3] = {key.x * kB + l[0], key.y * kB + l[1], key.z * kB + l[2]};
     const double half = __dmul_rn(vl, 0.5);
@@ -311,17 +334,16 @@ mesh_vertices_kernel(const PoolMeta M, const MeshBuffers mb, const double vl, co
 
 // ---- pass 3b: triangles ----------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kVox)
+__global__ void __launch_bounds__(kEmitThreads)
 mesh_triangles_kernel(const MeshBuffers mb) {
-    __shared__ uint32_t s_warp[16];
-    __shared__ int s_nbr[8];
-    const uint32_t b = mb.work[mb.n_blocks + blockIdx.x];  // blocks with at least one triangle
-    const int t = threadIdx.x;
-    if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
-    const int cube = mb.cube[static_cast<size_t>(b) * kVox + t];
+    const uint32_t b = mb.work[mb.n_blocks + (blockIdx.x >> 2)];  // blocks with at least one triangle
+    const int t = (blockIdx.x & 3) * kEmitThreads + threadIdx.x;
+    const size_t own = static_cast<size_t>(b) * kVox + t;
+    const int cube = mb.cube[own];
     const uint32_t nt = c_num_tris[cube];
-    const uint32_t tbase = mb.offs[mb.n_blocks + b] + block_excl_scan_512(nt, s_warp);
     if (nt == 0) return;
+    const uint32_t tbase = mb.offs[mb.n_blocks + b] + (mb.local[own] >> 16);
+    const int *s_nbr = mb.nbr + static_cast<size_t>(b) * 8;
     const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
     int vid[12];
     const unsigned em = c_edge_table[cube];
@@ -332,7 +354,7 @@ mesh_triangles_kernel(const MeshBuffers mb) {
         int axis;
         if (!edge_owner(s_nbr, lx, ly, lz, e, &flat, &axis)) continue;
         const unsigned m = (mb.edge_mask[flat >> 2] >> ((flat & 3) * 8)) & 7u;
-        vid[e] = static_cast<int>(mb.vert_base[flat] + __popc(m & ((1u << axis) - 1u)));
+        vid[e] = static_cast<int>(mb.offs[flat >> 9] + (mb.local[flat] & 0xFFFFu) + __popc(m & ((1u << axis) - 1u)));
     }
     for (uint32_t k = 0; k < nt; ++k) {
         int32_t *tri = mb.triangles + 3 * static_cast<size_t>(tbase + k);
@@ -377,15 +399,15 @@ cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, do
                                  bool points, uint32_t work_blocks, cudaStream_t stream) {
     if (work_blocks == 0) return cudaSuccess;
     if (points)
-        mesh_vertices_kernel<true><<<work_blocks, kVox, 0, stream>>>(meta, mb, voxel_length, unit_shift);
+        mesh_vertices_kernel<true><<<work_blocks * 4u, kEmitThreads, 0, stream>>>(meta, mb, voxel_length, unit_shift);
     else
-        mesh_vertices_kernel<false><<<work_blocks, kVox, 0, stream>>>(meta, mb, voxel_length, unit_shift);
+        mesh_vertices_kernel<false><<<work_blocks * 4u, kEmitThreads, 0, stream>>>(meta, mb, voxel_length, unit_shift);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mesh_triangles(const MeshBuffers &mb, uint32_t work_blocks, cudaStream_t stream) {
     if (work_blocks == 0) return cudaSuccess;
-    mesh_triangles_kernel<<<work_blocks, kVox, 0, stream>>>(mb);
+    mesh_triangles_kernel<<<work_blocks * 4u, kEmitThreads, 0, stream>>>(mb);
     return cudaGetLastError();
 }
 
