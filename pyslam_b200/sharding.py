@@ -54,15 +54,16 @@ class FrameIngest:
     (pinned numpy arrays or torch tensors; every rank passes the same batch) is, per chunk of `chunk_frames`:
 
         upload stream   H2D of this rank's 1/world share of the chunk (its own PCIe link)
-                        all-gather of the shares (NCCL over NVLink; in place in the chunk buffer)
+        gather stream   all-gather of the shares (NCCL over NVLink; in place in the chunk buffer)
         compute stream  volume.integrate_batch(chunk buffer, device pointers)   [allocate + fused update kernels]
 
-    with `buffers` chunk buffers in rotation, so upload + all-gather of chunk c+1 overlap the kernels of chunk c.
+    with `buffers` chunk buffers in rotation: the upload of chunk c+2, the all-gather of chunk c+1 and the kernels of
+    chunk c run concurrently (three streams, events between them).
     Frame order is unchanged, so the result is bit-identical to a single-GPU `integrate_batch` of the batch.
     world = 1 (or no process group) degenerates to a chunked, double-buffered upload.  `depth_scale`: the depths are
     raw uint16 (2 bytes per pixel over PCIe AND NVLink), widened on the GPU."""
 
-    def __init__(self, volume, group=None, chunk_frames: int = 64, buffers: int = 3, device=None):
+    def __init__(self, volume, group=None, chunk_frames: int = 64, buffers: int = 4, device=None):
         import torch
         import torch.distributed as dist
         self.volume = volume
@@ -78,6 +79,7 @@ class FrameIngest:
         self._shape = None
         if self.cuda:
             self.s_up = torch.cuda.Stream(self.device)
+            self.s_gather = torch.cuda.Stream(self.device)
             self.s_int = torch.cuda.Stream(self.device)
         self.h2d_bytes = 0       # bytes this rank uploaded (accounting for bench.py)
         self.gather_bytes = 0    # bytes this rank received from its peers
@@ -96,6 +98,7 @@ class FrameIngest:
                      color=torch.empty((cap, H, W, 3), dtype=torch.uint8, device=self.device))
             if self.cuda:
                 b["free"] = torch.cuda.Event()
+                b["uploaded"] = torch.cuda.Event()
                 b["ready"] = torch.cuda.Event()
             self._bufs.append(b)
         self._shape = shape
@@ -114,6 +117,7 @@ class FrameIngest:
         self._ensure(H, W, D.dtype)
         world, r = self.world, self.rank
         up = torch.cuda.stream(self.s_up) if self.cuda else contextlib.nullcontext()
+        ga = torch.cuda.stream(self.s_gather) if self.cuda else contextlib.nullcontext()
         for i, (c0, cnt, q) in enumerate(chunk_plan(n, world, self.chunk_frames)):
             b = self._bufs[i % self.n_buffers]
             lo, hi = min(r * q, cnt), min((r + 1) * q, cnt)
@@ -124,6 +128,11 @@ class FrameIngest:
                     b["depth"][lo:hi].copy_(D[c0 + lo:c0 + hi], non_blocking=True)
                     b["color"][lo:hi].copy_(Cc[c0 + lo:c0 + hi], non_blocking=True)
                     self.h2d_bytes += (hi - lo) * H * W * (D.element_size() + 3)
+                if self.cuda:
+                    b["uploaded"].record(self.s_up)
+            with ga:
+                if self.cuda:
+                    self.s_gather.wait_event(b["uploaded"])
                 if world > 1:
                     # in place: segment r of the buffer is this rank's contribution
                     for t in (b["depth"], b["color"]):
@@ -132,7 +141,7 @@ class FrameIngest:
                         self.dist.all_gather_into_tensor(t[:world * q], t[r * q:(r + 1) * q], group=self.group)
                     self.gather_bytes += (cnt - (hi - lo)) * H * W * (D.element_size() + 3)
                 if self.cuda:
-                    b["ready"].record(self.s_up)
+                    b["ready"].record(self.s_gather)
             if self.cuda:
                 if hasattr(self.volume, "set_input_event"):
                     # the allocate kernels of this chunk wait for the upload / all-gather only, not for the update
@@ -151,6 +160,7 @@ class FrameIngest:
         import torch
         if self.cuda:
             self.s_up.synchronize()
+            self.s_gather.synchronize()
             self.s_int.synchronize()
         self.volume.synchronize()
 
@@ -235,13 +245,18 @@ def extract_mesh_distributed(volume, dst: int = 0, group=None, device=None, capa
     if dist.get_rank(group) != dst:
         return None
     cap = capacity_blocks or max(2 * len(keys), 1024)
-    scratch = B200TsdfVolume(volume.voxel_length, volume.sdf_trunc, volume.depth_trunc,
-                             capacity_blocks=cap, device=volume.device,
-                             volume_unit_resolution=volume.volume_unit_resolution)
+    scratch = getattr(volume, "_mesh_scratch", None)   # kept between extractions (one per output tick)
+    if scratch is None or scratch.capacity_blocks < len(keys) + 1:
+        if scratch is not None:
+            scratch.close()
+        scratch = B200TsdfVolume(volume.voxel_length, volume.sdf_trunc, volume.depth_trunc,
+                                 capacity_blocks=cap, device=volume.device,
+                                 volume_unit_resolution=volume.volume_unit_resolution)
+        volume._mesh_scratch = scratch
+    else:
+        scratch.reset()
     if on_device:
         scratch.import_blocks_torch(keys, vox)
     else:
         scratch.upload_blocks(keys, vox)
-    mesh = scratch.extract_mesh()
-    scratch.close()
-    return mesh
+    return scratch.extract_mesh()
