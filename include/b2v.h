@@ -165,6 +165,10 @@ int b2v_grid_integrate(b2v_grid *g, const float *points, const float *colors, in
 /* the float64-points overload (volumetric_grid_module.h:737-749): voxel keys from the float64 coordinates
  * (floor(x * (double)inv_voxel_size), voxel_hashing.h:69-75), sums accumulate static_cast<float>(x) */
 int b2v_grid_integrate_f64(b2v_grid *g, const double *points, const float *colors, int64_t n_points);
+/* every dtype combination of the pybind overloads (volumetric_grid_module.h:737-802): points float32 | float64,
+ * colours float32 | uint8 (scaled on the device by the float32 constant 1/255, voxel_data.h:79-97) | NULL */
+int b2v_grid_integrate_ex(b2v_grid *g, const void *points, int32_t points_f64, const void *colors, int32_t colors_u8,
+                          int64_t n_points);
 /* Fused front-end of VolumetricIntegratorVoxelGrid: depth2pointcloud (pyslam/utilities/depth.py:45-85) +
  * world transform + integrate (pyslam/dense/volumetric_integrator_voxel_grid.py:247-300) in one call, no
  * point cloud materialised.  depth float32 [H*W], color uint8 RGB [H*W*3] (host or device), K = {fx,fy,cx,cy}

@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "b2v_integrate_batch", "b2v_integrate_u16", "b2v_integrate_batch_u16", "b2v_synchronize", "b2v_num_blocks", "b2v_last_frame_stats",
     "b2v_counters", "b2v_set_overlap", "b2v_set_fusion", "b2v_set_group_size", "b2v_set_input_event", "b2v_set_rectification", "b2v_remap", "b2v_profile_enable", "b2v_profile_read", "b2v_dump_blocks", "b2v_upload_blocks", "b2v_export_blocks_device", "b2v_import_blocks_device", "b2v_last_touched_keys", "b2v_extract_mesh", "b2v_copy_mesh",
     "b2v_extract_points", "b2v_copy_points", "b2v_grid_create", "b2v_grid_destroy", "b2v_grid_clear",
-    "b2v_grid_last_error", "b2v_grid_integrate", "b2v_grid_integrate_f64", "b2v_grid_integrate_rgbd", "b2v_filter_shadow_points", "b2v_grid_synchronize", "b2v_grid_num_blocks",
+    "b2v_grid_last_error", "b2v_grid_integrate", "b2v_grid_integrate_f64", "b2v_grid_integrate_ex", "b2v_grid_integrate_rgbd", "b2v_filter_shadow_points", "b2v_grid_synchronize", "b2v_grid_num_blocks",
     "b2v_grid_size", "b2v_grid_get_voxels", "b2v_grid_copy_voxels",
     "b2v_grid_remove_low_count_voxels", "b2v_grid_dump_blocks", "b2v_grid_carve",
     "b2v_grid_get_voxels_in_frustum", "b2v_grid_get_voxels_in_bb", "b2v_version", "b2v_device_sm_count", "b2v_selftest_division",
@@ -192,6 +192,8 @@ def load() -> C.CDLL:
     L.b2v_grid_integrate.argtypes = [vp, vp, vp, i64]
     L.b2v_grid_integrate_f64.restype = C.c_int
     L.b2v_grid_integrate_f64.argtypes = [vp, vp, vp, i64]
+    L.b2v_grid_integrate_ex.restype = C.c_int
+    L.b2v_grid_integrate_ex.argtypes = [vp, vp, i32, vp, i32, i64]
     L.b2v_grid_integrate_rgbd.restype = C.c_int
     L.b2v_grid_integrate_rgbd.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.c_float, C.c_float, i32]
     L.b2v_filter_shadow_points.restype = C.c_int

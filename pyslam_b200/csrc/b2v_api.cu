@@ -1367,7 +1367,7 @@ extern "C" int b2v_grid_clear(b2v_grid *g) {
     return B2V_OK;
 }
 
-static int grid_integrate_any(b2v_grid *g, const void *points, bool f64, const float *colors, int64_t n_points) {
+static int grid_integrate_any(b2v_grid *g, const void *points, bool f64, const void *colors, bool u8, int64_t n_points) {
     if (!g) return B2V_ERR_INVALID_ARGUMENT;
     if (n_points < 0 || (n_points > 0 && !points)) {
         g->err = "b2v_grid_integrate: bad arguments";
@@ -1376,7 +1376,7 @@ static int grid_integrate_any(b2v_grid *g, const void *points, bool f64, const f
     if (n_points == 0) return B2V_OK;  // voxel_block_grid.hpp:22-24,121-123
     B2V_CUDA(g, cudaSetDevice(g->device));
     const void *d_p = points;
-    const float *d_c = colors;
+    const void *d_c = colors;
     const bool dev_p = is_device_pointer(points);
     const bool dev_c = colors ? is_device_pointer(colors) : true;
     if (!dev_p || !dev_c) {
@@ -1392,21 +1392,26 @@ static int grid_integrate_any(b2v_grid *g, const void *points, bool f64, const f
             d_p = g->d_pts;
         }
         if (colors && !dev_c) {
-            B2V_CUDA(g, cudaMemcpyAsync(g->d_cols, colors, static_cast<size_t>(n_points) * 3 * sizeof(float),
+            B2V_CUDA(g, cudaMemcpyAsync(g->d_cols, colors, static_cast<size_t>(n_points) * 3 * (u8 ? 1 : sizeof(float)),
                                         cudaMemcpyHostToDevice, g->stream));
             d_c = g->d_cols;
         }
     }
-    B2V_CUDA(g, launch_grid_integrate(d_p, f64, d_c, n_points, g->inv_voxel_size, g->table, g->meta, g->stream));
+    B2V_CUDA(g, launch_grid_integrate(d_p, f64, d_c, u8, n_points, g->inv_voxel_size, g->table, g->meta, g->stream));
     return B2V_OK;
 }
 
 extern "C" int b2v_grid_integrate(b2v_grid *g, const float *points, const float *colors, int64_t n_points) {
-    return grid_integrate_any(g, points, false, colors, n_points);
+    return grid_integrate_any(g, points, false, colors, false, n_points);
 }
 
 extern "C" int b2v_grid_integrate_f64(b2v_grid *g, const double *points, const float *colors, int64_t n_points) {
-    return grid_integrate_any(g, points, true, colors, n_points);
+    return grid_integrate_any(g, points, true, colors, false, n_points);
+}
+
+extern "C" int b2v_grid_integrate_ex(b2v_grid *g, const void *points, int32_t points_f64, const void *colors,
+                                     int32_t colors_u8, int64_t n_points) {
+    return grid_integrate_any(g, points, points_f64 != 0, colors, colors_u8 != 0, n_points);
 }
 
 extern "C" int b2v_filter_shadow_points(const float *depth, int32_t height, int32_t width, int32_t delta_x,

@@ -67,9 +67,13 @@ grid_insert_kernel(const Tp *__restrict__ pts, const int64_t n, const float inv_
 }
 
 // ---- pass 2: accumulate ----------------------------------------------------------------------
-template <typename Tp>
+// colour of a point as the voxel accumulates it: float passthrough, uint8 * (1.0f / 255.0f) (voxel_data.h:79-97)
+__device__ __forceinline__ float color_value(float c) { return c; }
+__device__ __forceinline__ float color_value(uint8_t c) { return __fmul_rn(static_cast<float>(c), 1.0f / 255.0f); }
+
+template <typename Tp, typename Tc>
 __global__ void __launch_bounds__(256)
-grid_accumulate_kernel(const Tp *__restrict__ pts, const float *__restrict__ cols, const int64_t n,
+grid_accumulate_kernel(const Tp *__restrict__ pts, const Tc *__restrict__ cols, const int64_t n,
                        const float inv_vs, const HashTable T, const GridMeta G) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -88,9 +92,9 @@ grid_accumulate_kernel(const Tp *__restrict__ pts, const float *__restrict__ col
     atomicAdd(fb + 2 * kVox + l, y);
     atomicAdd(fb + 3 * kVox + l, z);
     if (cols != nullptr) {
-        atomicAdd(fb + 4 * kVox + l, cols[3 * i + 0]);
-        atomicAdd(fb + 5 * kVox + l, cols[3 * i + 1]);
-        atomicAdd(fb + 6 * kVox + l, cols[3 * i + 2]);
+        atomicAdd(fb + 4 * kVox + l, color_value(cols[3 * i + 0]));
+        atomicAdd(fb + 5 * kVox + l, color_value(cols[3 * i + 1]));
+        atomicAdd(fb + 6 * kVox + l, color_value(cols[3 * i + 2]));
     }
     atomicAdd(reinterpret_cast<int *>(blk) + l, 1);
 }
@@ -375,19 +379,24 @@ cudaError_t launch_grid_carve(const GridMeta &meta, uint32_t n_blocks, const Gri
 }
 
 // ---- launchers -------------------------------------------------------------------------------
-cudaError_t launch_grid_integrate(const void *pts, bool pts_f64, const float *cols, int64_t n, float inv_vs,
+template <typename Tp>
+static void launch_grid_integrate_t(const Tp *p, const void *cols, bool cols_u8, int64_t n, float inv_vs,
+                                    const HashTable &table, const GridMeta &meta, cudaStream_t stream) {
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    grid_insert_kernel<Tp><<<grid, 256, 0, stream>>>(p, n, inv_vs, table, meta);
+    if (cols_u8)
+        grid_accumulate_kernel<Tp, uint8_t><<<grid, 256, 0, stream>>>(p, static_cast<const uint8_t *>(cols), n, inv_vs, table, meta);
+    else
+        grid_accumulate_kernel<Tp, float><<<grid, 256, 0, stream>>>(p, static_cast<const float *>(cols), n, inv_vs, table, meta);
+}
+
+cudaError_t launch_grid_integrate(const void *pts, bool pts_f64, const void *cols, bool cols_u8, int64_t n, float inv_vs,
                                   const HashTable &table, const GridMeta &meta, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
-    if (pts_f64) {
-        const double *p = static_cast<const double *>(pts);
-        grid_insert_kernel<double><<<grid, 256, 0, stream>>>(p, n, inv_vs, table, meta);
-        grid_accumulate_kernel<double><<<grid, 256, 0, stream>>>(p, cols, n, inv_vs, table, meta);
-    } else {
-        const float *p = static_cast<const float *>(pts);
-        grid_insert_kernel<float><<<grid, 256, 0, stream>>>(p, n, inv_vs, table, meta);
-        grid_accumulate_kernel<float><<<grid, 256, 0, stream>>>(p, cols, n, inv_vs, table, meta);
-    }
+    if (pts_f64)
+        launch_grid_integrate_t(static_cast<const double *>(pts), cols, cols_u8, n, inv_vs, table, meta, stream);
+    else
+        launch_grid_integrate_t(static_cast<const float *>(pts), cols, cols_u8, n, inv_vs, table, meta, stream);
     return cudaGetLastError();
 }
 

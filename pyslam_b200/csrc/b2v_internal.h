@@ -211,7 +211,7 @@ struct GridMeta {
     uint32_t *counters;    // kCtrPool, kCtrError
     uint32_t capacity;
 };
-cudaError_t launch_grid_integrate(const void *pts, bool pts_f64, const float *cols, int64_t n, float inv_vs,
+cudaError_t launch_grid_integrate(const void *pts, bool pts_f64, const void *cols, bool cols_u8, int64_t n, float inv_vs,
                                   const HashTable &table, const GridMeta &meta, cudaStream_t stream);
 cudaError_t launch_grid_count(const GridMeta &meta, uint32_t n_blocks, int min_count, uint32_t *sums,
                               uint32_t *offs, uint32_t *total, cudaStream_t stream);

@@ -484,8 +484,8 @@ class VoxelBlockGrid:
     def integrate(self, points, colors=None, class_ids=None, instance_ids=None, depths=None):
         """integrate(points [N,3] f32|f64, colors [N,3] u8|f32 | None)
         (volumetric_grid_module.h:131-467).  float64 points take the reference's float64 overload (:737-749): voxel
-        keys from the float64 coordinates, sums accumulate float32(x) (b2v_grid_integrate_f64); uint8 colours are
-        scaled by the float32 constant 1/255 exactly as voxel_data.h:82-85 does."""
+        keys from the float64 coordinates, sums accumulate float32(x); uint8 colours are scaled on the device by the
+        float32 constant 1/255 exactly as voxel_data.h:82-85 does (b2v_grid_integrate_ex)."""
         if class_ids is not None or instance_ids is not None or depths is not None:
             raise NotImplementedError("semantic integration is a SURVEY.md §8(f) 'next' row")
         pts = np.asarray(points)
@@ -495,7 +495,7 @@ class VoxelBlockGrid:
             raise RuntimeError("points must be float32 or float64")
         f64 = pts.dtype == np.float64
         pts = np.ascontiguousarray(pts)
-        cp = None
+        cp, cu8 = None, 0
         cols = None
         if colors is not None and np.asarray(colors).size > 0:
             cols = np.asarray(colors)
@@ -504,13 +504,15 @@ class VoxelBlockGrid:
             if cols.shape[0] != pts.shape[0]:
                 raise RuntimeError("points and colors must have the same number of rows")
             if cols.dtype == np.uint8:
-                cols = cols.astype(np.float32) * (np.float32(1.0) / np.float32(255.0))
-            elif cols.dtype not in (np.float32, np.float64):
+                cu8 = 1
+                cols = np.ascontiguousarray(cols)
+            elif cols.dtype in (np.float32, np.float64):
+                cols = np.ascontiguousarray(cols, dtype=np.float32)
+            else:
                 raise RuntimeError("colors must be uint8 or float32")
-            cols = np.ascontiguousarray(cols, dtype=np.float32)
             cp = cols.ctypes.data
-        fn = self._L.b2v_grid_integrate_f64 if f64 else self._L.b2v_grid_integrate
-        self._check(fn(self._h, pts.ctypes.data, cp, pts.shape[0]), "b2v_grid_integrate")
+        self._check(self._L.b2v_grid_integrate_ex(self._h, pts.ctypes.data, 1 if f64 else 0, cp, cu8, pts.shape[0]),
+                    "b2v_grid_integrate")
         self._check(self._L.b2v_grid_synchronize(self._h), "b2v_grid_synchronize")
 
     def integrate_rgbd(self, depth, color, K, Twc, max_depth=np.inf, min_depth=0.0, filter_shadow_points=False):

@@ -109,6 +109,27 @@ def test_argument_checks_and_clear():
         VoxelBlockGrid(0.05, 4)
 
 
+def test_uint8_colors_scaled_on_device_like_voxel_data():
+    """uint8 colours go to the device as bytes and are scaled there by the float32 constant 1/255
+    (voxel_data.h:79-97): the result must be bit-identical to feeding float32(c) * float32(1/255)."""
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-1.0, 1.0, (20000, 3))
+    cols = rng.integers(0, 256, (20000, 3), dtype=np.uint8)
+    a = VoxelBlockGrid(0.05, 8, capacity_blocks=8192)
+    b = VoxelBlockGrid(0.05, 8, capacity_blocks=8192)
+    for dt in (np.float32, np.float64):
+        a.clear(); b.clear()
+        a.integrate(pts.astype(dt), cols)
+        b.integrate(pts.astype(dt), cols.astype(np.float32) * (np.float32(1.0) / np.float32(255.0)))
+        va, vb = a.get_voxels(), b.get_voxels()
+        oa = np.lexsort((va.points[:, 2], va.points[:, 1], va.points[:, 0]))
+        ob = np.lexsort((vb.points[:, 2], vb.points[:, 1], vb.points[:, 0]))
+        assert len(oa) == len(ob) > 1000
+        assert np.array_equal(va.points[oa], vb.points[ob])
+        # float atomics: the per-voxel summation order differs between two runs, not the addends
+        assert np.allclose(va.colors[oa], vb.colors[ob], rtol=0, atol=2e-6)
+
+
 def _sorted_pts(p):
     return p[np.lexsort((p[:, 2], p[:, 1], p[:, 0]))]
 
