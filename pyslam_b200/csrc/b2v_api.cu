@@ -147,6 +147,7 @@ struct b2v_volume {
     PoolMeta meta{};
     uint32_t frame_id = 0;  // frames integrated since reset (stamp = frame_id + 1)
     int grid_ctas = 0;
+    int sm_count = 0;
     int64_t launches = 0;
     uint32_t *h_counters = nullptr;  // pinned mirror
     std::string err;
@@ -270,8 +271,10 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     B2V_CUDA(v, cudaMalloc(&v->meta.active_slots, static_cast<size_t>(cap) * kActiveRing * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMalloc(&v->meta.group_mask, static_cast<size_t>(tcap) * kGroupBufs * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMalloc(&v->meta.union_slots, static_cast<size_t>(cap) * kGroupBufs * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMalloc(&v->meta.block_flags, static_cast<size_t>(cap) * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMemsetAsync(v->meta.block_flags, 0, static_cast<size_t>(cap) * sizeof(uint32_t), v->compute));
     B2V_CUDA(v, cudaMallocHost(&v->h_counters, kNumCounters * sizeof(uint32_t)));
-    B2V_CUDA(v, cudaMallocHost(&v->h_totals, 4 * sizeof(uint32_t)));
+    B2V_CUDA(v, cudaMallocHost(&v->h_totals, kNumMeshTotals * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMemsetAsync(v->meta.pool, 0, static_cast<size_t>(cap) * kBlockFloats * sizeof(float),
                                 v->compute));
     int rc = volume_clear_device(v);
@@ -284,6 +287,7 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
         if (n >= 1 && n <= 32) per_sm = n;
     }
     v->grid_ctas = (sms > 0 ? sms : 148) * per_sm;
+    v->sm_count = sms;
     B2V_CUDA(v, cudaStreamSynchronize(v->compute));
     return B2V_OK;
 }
@@ -317,6 +321,7 @@ extern "C" int b2v_destroy(b2v_volume *v) {
     }
     cudaFree(v->meta.group_mask);
     cudaFree(v->meta.union_slots);
+    cudaFree(v->meta.block_flags);
     cudaFree(v->table.entries);
     cudaFree(v->table.stamp);
     cudaFree(v->meta.pool);
@@ -374,6 +379,7 @@ extern "C" int b2v_reset(b2v_volume *v) {
     const uint32_t nb = block_count(v);
     B2V_CUDA(v, cudaMemsetAsync(v->meta.pool, 0, static_cast<size_t>(nb) * kBlockFloats * sizeof(float),
                                 v->compute));
+    B2V_CUDA(v, cudaMemsetAsync(v->meta.block_flags, 0, static_cast<size_t>(nb) * sizeof(uint32_t), v->compute));
     rc = volume_clear_device(v);
     if (rc != B2V_OK) return rc;
     v->frame_id = 0;
@@ -1177,7 +1183,7 @@ template <typename T> static cudaError_t regrow(T **p, size_t n) {
 }
 
 static int ensure_mesh_scratch(b2v_volume *v, uint32_t nb) {
-    if (!v->mb.totals) B2V_CUDA(v, cudaMalloc(&v->mb.totals, 4 * sizeof(uint32_t)));
+    if (!v->mb.totals) B2V_CUDA(v, cudaMalloc(&v->mb.totals, kNumMeshTotals * sizeof(uint32_t)));
     if (nb <= v->mesh_blocks_cap) return B2V_OK;
     const size_t n = nb;
     B2V_CUDA(v, regrow(&v->mb.nbr, n * 8));
@@ -1186,7 +1192,7 @@ static int ensure_mesh_scratch(b2v_volume *v, uint32_t nb) {
     B2V_CUDA(v, regrow(&v->mb.local, n * kVox));
     B2V_CUDA(v, regrow(&v->mb.sums, n * 2));
     B2V_CUDA(v, regrow(&v->mb.offs, n * 2));
-    B2V_CUDA(v, regrow(&v->mb.work, n * 2));
+    B2V_CUDA(v, regrow(&v->mb.work, n * 4));
     v->mesh_blocks_cap = nb;
     return B2V_OK;
 }
@@ -1199,15 +1205,16 @@ static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t
     if (rc != B2V_OK) return rc;
     v->mb.n_blocks = nb;
     cudaStream_t cs = v->compute;
+    const int sms = v->sm_count > 0 ? v->sm_count : 148;
     if (mesh) {
-        B2V_CUDA(v, launch_mesh_classify(v->table, v->meta, v->mb, cs));
+        B2V_CUDA(v, launch_mesh_classify(v->table, v->meta, v->mb, sms, cs));
     } else {
-        B2V_CUDA(v, launch_point_masks(v->table, v->meta, v->mb, cs));
+        B2V_CUDA(v, launch_point_masks(v->table, v->meta, v->mb, sms, cs));
     }
-    B2V_CUDA(v, launch_mesh_scan(v->mb, cs));
-    B2V_CUDA(v, cudaMemcpyAsync(v->h_totals, v->mb.totals, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+    B2V_CUDA(v, launch_mesh_scan(v->mb, sms, cs));
+    B2V_CUDA(v, cudaMemcpyAsync(v->h_totals, v->mb.totals, kNumMeshTotals * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
     B2V_CUDA(v, cudaStreamSynchronize(cs));
-    const size_t nv = v->h_totals[0], nt = v->h_totals[1];
+    const size_t nv = v->h_totals[kMtVertices], nt = v->h_totals[kMtTriangles];
     if (nv > v->mesh_v_cap) {
         B2V_CUDA(v, regrow(&v->mb.vertices, nv * 3));
         B2V_CUDA(v, regrow(&v->mb.colors, nv * 3));
@@ -1218,8 +1225,8 @@ static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t
         B2V_CUDA(v, regrow(&v->mb.triangles, nt * 3));
         v->mesh_t_cap = nt;
     }
-    B2V_CUDA(v, launch_mesh_vertices(v->meta, v->mb, v->geo.voxel_length, v->geo.unit_shift, !mesh, v->h_totals[2], cs));
-    if (mesh) B2V_CUDA(v, launch_mesh_triangles(v->mb, v->h_totals[3], cs));
+    B2V_CUDA(v, launch_mesh_vertices(v->meta, v->mb, v->geo.voxel_length, v->geo.unit_shift, !mesh, v->h_totals[kMtVertexBlocks], cs));
+    if (mesh) B2V_CUDA(v, launch_mesh_triangles(v->mb, v->h_totals[kMtTriangleBlocks], cs));
     B2V_CUDA(v, cudaStreamSynchronize(cs));
     v->launches += mesh ? 6 : 5;
     v->last_nv = static_cast<int64_t>(nv);

@@ -74,6 +74,9 @@ struct PoolMeta {
     uint32_t *active_slots;   // [kActiveRing][capacity] table slots touched by a frame
     uint32_t *group_mask;     // [kGroupBufs][table capacity] bit k: the slot is touched by frame k of the group
     uint32_t *union_slots;    // [kGroupBufs][capacity] slots touched by any frame of the group
+    uint32_t *block_flags;    // [capacity] sign summary for the mesh extraction's tile filter: bit 0 = some store left
+                              // an observed voxel (w != 0) with tsdf < 0, bit 1 = with tsdf >= 0; bits are only ever
+                              // set, so the union over a tile is a superset of the signs present now
     uint32_t capacity;
 };
 
@@ -184,22 +187,28 @@ struct MeshBuffers {
     uint32_t *local;         // [n_blocks][512] position of the voxel's first vertex (low 16 bits) / triangle (high) in its block
     uint32_t *sums;          // [2][n_blocks] per-block vertex / triangle counts
     uint32_t *offs;          // [2][n_blocks] exclusive scans of sums
-    uint32_t *totals;        // [4] total vertices, triangles; blocks with vertices, blocks with triangles
-    uint32_t *work;          // [2][n_blocks] the blocks with vertices / with triangles (what the emit kernels visit)
+    uint32_t *totals;        // [8] total vertices, triangles; blocks with vertices, blocks with triangles; candidate
+                             // tiles (sign-summary filter), classified tiles (see MeshTotal)
+    uint32_t *work;          // [4][n_blocks] the blocks with vertices / with triangles (what the emit kernels visit);
+                             // candidate tiles; tiles with a sign change (what classify / block sums visit)
     double *vertices;        // [nv][3] float64, Open3D's formula
     double *colors;          // [nv][3] in [0,1]
     int32_t *edge_ids;       // [nv][4] canonical weld key (voxel x,y,z, axis)
     int32_t *triangles;      // [nt][3]
 };
-// neighbour lookup (7 hash probes per block) + marching-cubes case per voxel + vertex ownership masks
-// (Open3D ExtractTriangleMesh semantics)
-cudaError_t launch_mesh_classify(const HashTable &table, const PoolMeta &meta, const MeshBuffers &mb,
+enum MeshTotal : int { kMtVertices = 0, kMtTriangles = 1, kMtVertexBlocks = 2, kMtTriangleBlocks = 3,
+                       kMtCandidates = 4, kMtTiles = 5, kNumMeshTotals = 8 };
+// neighbour lookup (7 hash probes per block) + candidate tiles from the blocks' sign summaries, then the
+// marching-cubes case per voxel + vertex ownership masks of the candidates (Open3D ExtractTriangleMesh semantics)
+cudaError_t launch_mesh_classify(const HashTable &table, const PoolMeta &meta, const MeshBuffers &mb, int grid_ctas,
                                  cudaStream_t stream);
-// neighbour lookup + zero-crossing masks of Open3D ExtractPointCloud (no cube validity requirement)
-cudaError_t launch_point_masks(const HashTable &table, const PoolMeta &meta, const MeshBuffers &mb,
+// the same front end + zero-crossing masks of Open3D ExtractPointCloud (no cube validity requirement)
+cudaError_t launch_point_masks(const HashTable &table, const PoolMeta &meta, const MeshBuffers &mb, int grid_ctas,
                                cudaStream_t stream);
 // per-block sums + exclusive scans -> offs, totals
-cudaError_t launch_mesh_scan(const MeshBuffers &mb, cudaStream_t stream);
+cudaError_t launch_mesh_scan(const MeshBuffers &mb, int grid_ctas, cudaStream_t stream);
+// recompute the sign summaries of blocks [0, n) from their voxels (after an import that bypassed the update kernels)
+cudaError_t launch_block_flags(const PoolMeta &meta, uint32_t n, cudaStream_t stream);
 cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, double voxel_length, int unit_shift,
                                  bool points, uint32_t work_blocks, cudaStream_t stream);
 cudaError_t launch_mesh_triangles(const MeshBuffers &mb, uint32_t work_blocks, cudaStream_t stream);

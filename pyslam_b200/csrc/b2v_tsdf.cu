@@ -673,6 +673,19 @@ __device__ __forceinline__ void store_block(float *blk, const float q[kPlanes][k
         for (int k = 0; k < kRun; ++k) blk[c * kVox + 64 * k] = q[c][k];
 }
 
+// sign summary of the block for the mesh extraction (PoolMeta::block_flags): one vote per warp, an atomic only when a
+// bit is missing (steady state: one 4-byte read per warp and block visit).  Called by converged warps.
+__device__ __forceinline__ void note_signs(uint32_t *flag, const float ts[kRun], const float w[kRun]) {
+    bool neg = false, pos = false;
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) {
+        neg |= w[k] != 0.0f && ts[k] < 0.0f;
+        pos |= w[k] != 0.0f && !(ts[k] < 0.0f);
+    }
+    const unsigned need = (__any_sync(0xffffffffu, neg) ? 1u : 0u) | (__any_sync(0xffffffffu, pos) ? 2u : 0u);
+    if ((threadIdx.x & 31) == 0 && (*flag & need) != need) atomicOr(flag, need);
+}
+
 __global__ void __launch_bounds__(kIntThreads, 8)
 integrate_kernel(const __grid_constant__ IntFrame F, const __grid_constant__ VolumeConsts V, const HashTable T,
                  const PoolMeta M, const int ring) {
@@ -699,7 +712,9 @@ integrate_kernel(const __grid_constant__ IntFrame F, const __grid_constant__ Vol
             float q[kPlanes][kRun];
             load_block(blk, q);
             const VoxelRun r = voxel_run(e, t, V);
-            if (apply_frame(F, r, q[0], q[1], q[2], q[3], q[4])) store_block(blk, q);
+            const bool upd = apply_frame(F, r, q[0], q[1], q[2], q[3], q[4]);
+            if (upd) store_block(blk, q);
+            if (__any_sync(0xffffffffu, upd)) note_signs(M.block_flags + e.w, q[0], q[1]);
         }
         e = e_next;
         i = i_next;
@@ -775,6 +790,7 @@ integrate_group_kernel(const __grid_constant__ GroupArgs A, const HashTable T, c
                     upd |= apply_frame(A.f[__ffs(mm) - 1], r, q[0], q[1], q[2], q[3], q[4]);
             }
             if (upd) store_block(blk, q);
+            if (__any_sync(0xffffffffu, upd)) note_signs(M.block_flags + e.w, q[0], q[1]);
         }
         e = e_next;
         m = m_next;
@@ -902,6 +918,40 @@ upload_copy_kernel(const float *__restrict__ vox, const uint32_t *__restrict__ i
     const float4 *src = reinterpret_cast<const float4 *>(vox + static_cast<size_t>(b) * kBlockFloats);
     float4 *out = reinterpret_cast<float4 *>(M.pool + static_cast<size_t>(dst) * kBlockFloats);
     for (int k = threadIdx.x; k < kBlockFloats / 4; k += 128) out[k] = src[k];
+    // the upload replaces the block: its sign summary is recomputed, not accumulated
+    const float4 f = src[threadIdx.x], w = src[128 + threadIdx.x];
+    const float fs[4] = {f.x, f.y, f.z, f.w}, ws[4] = {w.x, w.y, w.z, w.w};
+    bool neg = false, pos = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        neg |= ws[k] != 0.0f && fs[k] < 0.0f;
+        pos |= ws[k] != 0.0f && !(fs[k] < 0.0f);
+    }
+    const int any_neg = __syncthreads_or(neg), any_pos = __syncthreads_or(pos);
+    if (threadIdx.x == 0) M.block_flags[dst] = (any_neg ? 1u : 0u) | (any_pos ? 2u : 0u);
+}
+
+__global__ void __launch_bounds__(128)
+block_flags_kernel(const PoolMeta M, const uint32_t n) {
+    const uint32_t b = blockIdx.x;
+    if (b >= n) return;
+    const float4 *src = reinterpret_cast<const float4 *>(M.pool + static_cast<size_t>(b) * kBlockFloats);
+    const float4 f = src[threadIdx.x], w = src[128 + threadIdx.x];
+    const float fs[4] = {f.x, f.y, f.z, f.w}, ws[4] = {w.x, w.y, w.z, w.w};
+    bool neg = false, pos = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        neg |= ws[k] != 0.0f && fs[k] < 0.0f;
+        pos |= ws[k] != 0.0f && !(fs[k] < 0.0f);
+    }
+    const int any_neg = __syncthreads_or(neg), any_pos = __syncthreads_or(pos);
+    if (threadIdx.x == 0) M.block_flags[b] = (any_neg ? 1u : 0u) | (any_pos ? 2u : 0u);
+}
+
+cudaError_t launch_block_flags(const PoolMeta &meta, uint32_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    block_flags_kernel<<<n, 128, 0, stream>>>(meta, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_upload_blocks(const int4 *keys, const float *vox, uint32_t n, uint32_t *scratch_idx,
