@@ -336,6 +336,7 @@ extern "C" int b2v_destroy(b2v_volume *v) {
     cudaFree(v->mb.offs);
     cudaFree(v->mb.work);
     cudaFree(v->mb.totals);
+    cudaFree(v->mb.partials);
     cudaFree(v->mb.vertices);
     cudaFree(v->mb.colors);
     cudaFree(v->mb.edge_ids);
@@ -1192,6 +1193,7 @@ static int ensure_mesh_scratch(b2v_volume *v, uint32_t nb) {
     B2V_CUDA(v, regrow(&v->mb.local, n * kVox));
     B2V_CUDA(v, regrow(&v->mb.sums, n * 2));
     B2V_CUDA(v, regrow(&v->mb.offs, n * 2));
+    B2V_CUDA(v, regrow(&v->mb.partials, 2 * ((n + 1023) / 1024)));
     B2V_CUDA(v, regrow(&v->mb.work, n * 4));
     v->mesh_blocks_cap = nb;
     return B2V_OK;

@@ -187,6 +187,7 @@ struct MeshBuffers {
     uint32_t *local;         // [n_blocks][512] position of the voxel's first vertex (low 16 bits) / triangle (high) in its block
     uint32_t *sums;          // [2][n_blocks] per-block vertex / triangle counts
     uint32_t *offs;          // [2][n_blocks] exclusive scans of sums
+    uint32_t *partials;      // [2][ceil(n_blocks / 1024)] chunk sums of the two-level scan
     uint32_t *totals;        // [8] total vertices, triangles; blocks with vertices, blocks with triangles; candidate
                              // tiles (sign-summary filter), classified tiles (see MeshTotal)
     uint32_t *work;          // [4][n_blocks] the blocks with vertices / with triangles (what the emit kernels visit);

@@ -28,6 +28,11 @@ __device__ signed char g_tri_table[256][16];
 __device__ unsigned char g_num_tris[256];
 __device__ uchar4 g_edge_shift[12];
 
+// cube edge e -> owner voxel offset and axis: MC_EDGE_SHIFT as compile-time constants (checked at table upload)
+#define B2V_MC_EDGES(X) \
+    X(0, 0, 0, 0, 0) X(1, 1, 0, 0, 1) X(2, 0, 1, 0, 0) X(3, 0, 0, 0, 1) X(4, 0, 0, 1, 0) X(5, 1, 0, 1, 1) \
+    X(6, 0, 1, 1, 0) X(7, 0, 0, 1, 1) X(8, 0, 0, 0, 2) X(9, 1, 0, 0, 2) X(10, 1, 1, 0, 2) X(11, 0, 1, 0, 2)
+
 static cudaError_t upload_tables_once() {
     static bool done = false;
     static int done_device = -1;
@@ -43,6 +48,19 @@ static cudaError_t upload_tables_once() {
     if ((e = cudaMemcpyToSymbol(g_tri_table, MC_TRI_TABLE, sizeof(MC_TRI_TABLE))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(g_num_tris, MC_NUM_TRIS, sizeof(MC_NUM_TRIS))) != cudaSuccess) return e;
     static_assert(sizeof(MC_EDGE_SHIFT) == 12 * 4, "edge shift table is 12 x {dx, dy, dz, axis}");
+    {   // the classify kernel carries the same table as compile-time constants, and derives the edge mask of a case
+        // from its corner bits: both must agree with the generated tables
+#define B2V_CHECK(e, sx, sy, sz, ax)                                                                          \
+    if (MC_EDGE_SHIFT[e][0] != sx || MC_EDGE_SHIFT[e][1] != sy || MC_EDGE_SHIFT[e][2] != sz || MC_EDGE_SHIFT[e][3] != ax) \
+        return cudaErrorInvalidValue;
+        B2V_MC_EDGES(B2V_CHECK)
+#undef B2V_CHECK
+        for (unsigned cube = 0; cube < 256; ++cube) {
+            const unsigned lo = cube & 15u, hi = cube >> 4;
+            const unsigned em = (lo ^ ((lo >> 1) | ((lo & 1u) << 3))) | ((hi ^ ((hi >> 1) | ((hi & 1u) << 3))) << 4) | ((lo ^ hi) << 8);
+            if (em != MC_EDGE_TABLE[cube]) return cudaErrorInvalidValue;
+        }
+    }
     if ((e = cudaMemcpyToSymbol(g_edge_shift, MC_EDGE_SHIFT, sizeof(MC_EDGE_SHIFT))) != cudaSuccess) return e;
     unsigned short halo[217];
     int nh = 0;
@@ -118,35 +136,47 @@ __device__ __forceinline__ bool edge_owner(const int *nbr, int lx, int ly, int l
 
 // ---- pass 1a: marching-cubes case + vertex ownership (mesh) ---------------------------------
 
-constexpr int kClsThreads = 128;   // 4 voxels per thread: 16 resident CTAs per SM keep more tile loads in flight
+constexpr int kClsThreads = 128;   // 4 voxels per thread
+constexpr int kClsCtasPerSm = 10;  // 48 registers: the persistent grid is exactly one resident wave
 
 // Persistent over the candidate tiles.  The 9^3 tile is kept as two bit planes (row y + 9 z, bit x): "tsdf < 0" and
-// "observed"; a cube's case is assembled from four row words instead of sixteen shared-memory reads.
-__global__ void __launch_bounds__(kClsThreads)
+// "observed"; a cube's case is assembled from four row words instead of sixteen shared-memory reads.  Ownership bits
+// of voxels inside the block are collected in shared memory (the four cubes around an edge all set the same bit) and
+// merged into the global masks with one atomic per non-zero word; owners in a neighbouring block are set directly.
+// The own voxels of the CTA's next tile are loaded while the current one is classified.
+
+__global__ void __launch_bounds__(kClsThreads, kClsCtasPerSm)
 mesh_classify_kernel(const PoolMeta M, const MeshBuffers mb) {
     __shared__ uint32_t s_neg[81], s_val[81];
     __shared__ uint32_t s_cube[kVox / 4];
+    __shared__ uint32_t s_own[kVox / 4];
     __shared__ int s_nbr[8];
     const int t = threadIdx.x, lane = t & 31;
     const int lx = t & 7, ly = (t >> 3) & 7, lz0 = t >> 6;   // voxel k of the thread: index t + 128 k, lz = lz0 + 2 k
     const uint32_t n = mb.totals[kMtCandidates];
     const uint32_t *__restrict__ cand = mb.work + 2 * static_cast<size_t>(mb.n_blocks);
-    for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
-        const uint32_t b = cand[it];
-        if (t < 8) s_nbr[t] = mb.nbr[b * 8 + t];
-        if (t < 17) {   // the rows that hold halo cells only
-            const int row = t < 9 ? 72 + t : 8 + 9 * (t - 9);
-            s_neg[row] = 0;
-            s_val[row] = 0;
-        }
-        // own voxels first (coalesced, independent of the neighbours)
+    uint32_t it = blockIdx.x;
+    uint32_t b = 0;
+    int nbr_t = -1;
+    float f0[4], w0[4];
+    if (it < n) {
+        b = cand[it];
+        if (t < 8) nbr_t = mb.nbr[b * 8 + t];
         const float *own = M.pool + static_cast<size_t>(b) * kBlockFloats;
-        float f0[4], w0[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             f0[k] = own[t + kClsThreads * k];
             w0[k] = own[kVox + t + kClsThreads * k];
         }
+    }
+    while (it < n) {
+        if (t < 8) s_nbr[t] = nbr_t;
+        if (t < 17) {   // the rows that hold halo cells only
+            const int row = t < 9 ? 72 + t : 8 + 9 * (t - 9);
+            s_neg[row] = 0;
+            s_val[row] = 0;
+        }
+        s_own[t] = 0;
         bool neg = false, pos = false;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -159,6 +189,19 @@ mesh_classify_kernel(const PoolMeta M, const MeshBuffers mb) {
             }
             neg |= w0[k] != 0.0f && f0[k] < 0.0f;
             pos |= w0[k] != 0.0f && !(f0[k] < 0.0f);
+        }
+        // the next tile of this CTA: its own voxels are in flight while this one is classified
+        const uint32_t it_next = it + gridDim.x;
+        uint32_t b_next = 0;
+        if (it_next < n) {
+            b_next = cand[it_next];
+            if (t < 8) nbr_t = mb.nbr[b_next * 8 + t];
+            const float *own = M.pool + static_cast<size_t>(b_next) * kBlockFloats;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                f0[k] = own[t + kClsThreads * k];
+                w0[k] = own[kVox + t + kClsThreads * k];
+            }
         }
         __syncthreads();
         // the 217 halo cells of the 9^3 tile
@@ -180,7 +223,7 @@ mesh_classify_kernel(const PoolMeta M, const MeshBuffers mb) {
         const int has_neg = __syncthreads_or(neg);
         const int has_pos = __syncthreads_or(pos);
         if (has_neg && has_pos) {   // uniform over the CTA
-#pragma unroll
+#pragma unroll 1   // (twelve inlined edge cases per voxel: unrolled x4 the kernel needs 121 registers)
             for (int k = 0; k < 4; ++k) {
                 const int lz = lz0 + 2 * k;
                 const int r = ly + 9 * lz;
@@ -193,20 +236,37 @@ mesh_classify_kernel(const PoolMeta M, const MeshBuffers mb) {
                 if ((ok & 3u) != 3u || cube == 255u) cube = 0;   // an unobserved corner, or nothing to emit
                 reinterpret_cast<uint8_t *>(s_cube)[t + kClsThreads * k] = static_cast<uint8_t>(cube);
                 if (cube) {
-                    const unsigned em = c_edge_table[cube];
-                    for (int e = 0; e < 12; ++e) {
-                        if (!((em >> e) & 1u)) continue;
-                        size_t flat;
-                        if (edge_owner(s_nbr, lx, ly, lz, c_edge_shift[e][0], c_edge_shift[e][1], c_edge_shift[e][2], &flat))
-                            atomicOr(mb.edge_mask + (flat >> 2), (1u << c_edge_shift[e][3]) << ((flat & 3) * 8));
-                    }
+                    // edges with a sign change: e0..3 = corners i, i+1 of the bottom face, e4..7 the top face,
+                    // e8..11 the verticals (the classic edge table, tests/test_mc_tables.py)
+                    const uint32_t lo = cube & 15u, hi = cube >> 4;
+                    const uint32_t em = (lo ^ ((lo >> 1) | ((lo & 1u) << 3))) | ((hi ^ ((hi >> 1) | ((hi & 1u) << 3))) << 4) |
+                                        ((lo ^ hi) << 8);
+#define B2V_OWN(e, sx, sy, sz, ax)                                                                                   \
+    if (em & (1u << e)) {                                                                                            \
+        const int ox = lx + sx, oy = ly + sy, oz = lz + sz;                                                          \
+        const int ov = (ox & 7) + ((oy & 7) << 3) + ((oz & 7) << 6);                                                 \
+        if ((sx | sy | sz) && ((ox | oy | oz) & 8)) {                                                                \
+            const int ob = s_nbr[(ox >> 3) | ((oy >> 3) << 1) | ((oz >> 3) << 2)];                                   \
+            if (ob >= 0)                                                                                             \
+                atomicOr(mb.edge_mask + static_cast<size_t>(ob) * (kVox / 4) + (ov >> 2), (1u << ax) << ((ov & 3) * 8)); \
+        } else {                                                                                                     \
+            atomicOr(&s_own[ov >> 2], (1u << ax) << ((ov & 3) * 8));                                                 \
+        }                                                                                                            \
+    }
+                    B2V_MC_EDGES(B2V_OWN)
+#undef B2V_OWN
                 }
             }
             __syncthreads();
             reinterpret_cast<uint32_t *>(mb.cube)[static_cast<size_t>(b) * (kVox / 4) + t] = s_cube[t];
+            // other tiles set bits of this block's halo-side voxels concurrently: merge, do not store
+            const uint32_t own_bits = s_own[t];
+            if (own_bits) atomicOr(mb.edge_mask + static_cast<size_t>(b) * (kVox / 4) + t, own_bits);
             if (t == 0) mb.work[3 * static_cast<size_t>(mb.n_blocks) + atomicAdd(mb.totals + kMtTiles, 1u)] = b;
         }
         __syncthreads();   // the tile's shared arrays are rewritten by the next iteration
+        it = it_next;
+        b = b_next;
     }
 }
 
@@ -256,16 +316,26 @@ point_masks_kernel(const PoolMeta M, const MeshBuffers mb) {
 // ---- pass 2: per-block sums and their exclusive scans ---------------------------------------
 
 // persistent over the tiles pass 1 kept; the sums of every other block stay at the launcher's zero
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 16)
 mesh_block_sums_kernel(const MeshBuffers mb) {
     __shared__ uint32_t s_v[4], s_t[4];
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const uint32_t n = mb.totals[kMtTiles];
     const uint32_t *__restrict__ tiles = mb.work + 3 * static_cast<size_t>(mb.n_blocks);
+    uint32_t b = 0, m4 = 0, c4 = 0;
+    if (blockIdx.x < n) {
+        b = tiles[blockIdx.x];
+        m4 = mb.edge_mask[static_cast<size_t>(b) * 128 + t];
+        c4 = reinterpret_cast<const uint32_t *>(mb.cube)[static_cast<size_t>(b) * 128 + t];
+    }
     for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
-        const uint32_t b = tiles[it];
-        const uint32_t m4 = mb.edge_mask[static_cast<size_t>(b) * 128 + t];
-        const uint32_t c4 = reinterpret_cast<const uint32_t *>(mb.cube)[static_cast<size_t>(b) * 128 + t];
+        // the next tile's words are in flight during this one
+        uint32_t b_next = 0, m4_next = 0, c4_next = 0;
+        if (it + gridDim.x < n) {
+            b_next = tiles[it + gridDim.x];
+            m4_next = mb.edge_mask[static_cast<size_t>(b_next) * 128 + t];
+            c4_next = reinterpret_cast<const uint32_t *>(mb.cube)[static_cast<size_t>(b_next) * 128 + t];
+        }
         uint32_t pv[4], pt[4];   // vertices / triangles of the thread's four voxels
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -314,6 +384,9 @@ mesh_block_sums_kernel(const MeshBuffers mb) {
             if (st) mb.work[mb.n_blocks + atomicAdd(mb.totals + kMtTriangleBlocks, 1u)] = b;
         }
         __syncthreads();   // s_v / s_t are rewritten by the next iteration
+        b = b_next;
+        m4 = m4_next;
+        c4 = c4_next;
     }
 }
 
@@ -487,7 +560,7 @@ cudaError_t launch_mesh_classify(const HashTable &table, const PoolMeta &meta, c
                                  cudaStream_t stream) {
     cudaError_t e = launch_mesh_front(table, meta, mb, stream);
     if (e != cudaSuccess || mb.n_blocks == 0) return e;
-    const unsigned grid = min(mb.n_blocks, static_cast<unsigned>(sms) * (2048u / kClsThreads));
+    const unsigned grid = min(mb.n_blocks, static_cast<unsigned>(sms) * kClsCtasPerSm);
     mesh_classify_kernel<<<grid, kClsThreads, 0, stream>>>(meta, mb);
     return cudaGetLastError();
 }
@@ -505,7 +578,9 @@ cudaError_t launch_mesh_scan(const MeshBuffers &mb, int sms, cudaStream_t stream
     if (mb.n_blocks == 0) return cudaSuccess;
     const unsigned grid = min(mb.n_blocks, static_cast<unsigned>(sms) * 16u);
     mesh_block_sums_kernel<<<grid, 128, 0, stream>>>(mb);
-    exclusive_scan_kernel<<<2, 1024, 0, stream>>>(mb.sums, mb.offs, mb.totals, mb.n_blocks);
+    const dim3 chunks((mb.n_blocks + 1023u) / 1024u, 2);
+    scan_reduce_kernel<<<chunks, 1024, 0, stream>>>(mb.sums, mb.partials, mb.n_blocks);
+    scan_apply_kernel<<<chunks, 1024, 0, stream>>>(mb.sums, mb.offs, mb.partials, mb.totals, mb.n_blocks);
     return cudaGetLastError();
 }
 
