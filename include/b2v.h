@@ -109,6 +109,10 @@ int b2v_last_frame_stats(b2v_volume *v, int64_t *touched_blocks, int64_t *new_bl
 /* bench accounting since create/reset: (block, frame) updates applied; kernel launches; block visits
  * (a visit = one block read + written; equals the updates frame by frame, fewer in fused batches) */
 int b2v_counters(b2v_volume *v, int64_t *block_updates, int64_t *kernel_launches, int64_t *block_visits);
+/* how the most recent b2v_extract_mesh / b2v_extract_points narrowed its work: stats[0] = blocks of the map, [1] = tiles
+ * (a block + its +1 halo) whose blocks' sign summaries admit a surface crossing, [2] = tiles that hold both signs,
+ * [3] = blocks with vertices, [4] = blocks with triangles */
+int b2v_last_mesh_stats(b2v_volume *v, int64_t stats[5]);
 /* Scheduling option: 1 (default) runs allocate(f+1) on its own stream concurrently with integrate(f)
  * (it has no data dependency on it); 0 serialises both kernels on one stream (clean per-kernel timing).
  * Results are bit-identical either way.  Synchronises. */

@@ -275,6 +275,7 @@ extern "C" int b2v_create(const b2v_config *cfg, b2v_volume **out) {
     B2V_CUDA(v, cudaMemsetAsync(v->meta.block_flags, 0, static_cast<size_t>(cap) * sizeof(uint32_t), v->compute));
     B2V_CUDA(v, cudaMallocHost(&v->h_counters, kNumCounters * sizeof(uint32_t)));
     B2V_CUDA(v, cudaMallocHost(&v->h_totals, kNumMeshTotals * sizeof(uint32_t)));
+    std::memset(v->h_totals, 0, kNumMeshTotals * sizeof(uint32_t));
     B2V_CUDA(v, cudaMemsetAsync(v->meta.pool, 0, static_cast<size_t>(cap) * kBlockFloats * sizeof(float),
                                 v->compute));
     int rc = volume_clear_device(v);
@@ -1236,6 +1237,16 @@ static int extract_common(b2v_volume *v, bool mesh, int64_t *n_vertices, int64_t
     if (n_vertices) *n_vertices = v->last_nv;
     if (n_triangles) *n_triangles = v->last_nt;
     return rc;
+}
+
+extern "C" int b2v_last_mesh_stats(b2v_volume *v, int64_t stats[5]) {
+    if (!v || !stats) return B2V_ERR_INVALID_ARGUMENT;
+    stats[0] = v->mb.n_blocks;
+    stats[1] = v->h_totals[kMtCandidates];
+    stats[2] = v->h_totals[kMtTiles];
+    stats[3] = v->h_totals[kMtVertexBlocks];
+    stats[4] = v->h_totals[kMtTriangleBlocks];
+    return B2V_OK;
 }
 
 extern "C" int b2v_extract_mesh(b2v_volume *v, int64_t *n_vertices, int64_t *n_triangles) {

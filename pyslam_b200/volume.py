@@ -232,6 +232,13 @@ class B200TsdfVolume:
             raise RuntimeError(self._L.b2v_last_error(self._h).decode())
         return int(n)
 
+    def last_mesh_stats(self) -> dict:
+        """How the most recent mesh / point extraction narrowed its work (b2v_last_mesh_stats)."""
+        st = (C.c_int64 * 5)()
+        self._check(self._L.b2v_last_mesh_stats(self._h, st), "b2v_last_mesh_stats")
+        return dict(zip(("blocks", "candidate_tiles", "tiles_with_both_signs", "vertex_blocks", "triangle_blocks"),
+                        (int(x) for x in st)))
+
     def last_frame_stats(self):
         t, n = C.c_int64(0), C.c_int64(0)
         self._check(self._L.b2v_last_frame_stats(self._h, C.byref(t), C.byref(n)), "b2v_last_frame_stats")

@@ -24,6 +24,8 @@ for r in range(a.reps):
     t0 = time.perf_counter()
     vol._L.b2v_extract_mesh(vol._h, C.byref(nv), C.byref(nt))
     print(f"extract_mesh {1e3 * (time.perf_counter() - t0):.3f} ms: {vol.num_blocks()} blocks, {nv.value} vertices, {nt.value} triangles")
+print("mesh stats", vol.last_mesh_stats())
 t0 = time.perf_counter()
 vol._L.b2v_extract_points(vol._h, C.byref(nv))
 print(f"extract_points {1e3 * (time.perf_counter() - t0):.3f} ms: {nv.value} points")
+print("point stats", vol.last_mesh_stats())
