@@ -226,7 +226,35 @@ def cpu_ref_grid_fps(cfg, depth, color, Tcw, n_sample):
         p, col = frontend_points(cfg, depth[i], color[i], Tcw[i])
         total += g.integrate(p, col)
         pts += len(p)
-    return n / total, pts / n
+    return n / total, pts / n, g.dump_blocks()
+
+
+def grid_parity(cfg, depth, color, Tcw, n, ref_dump, device):
+    """Full-size check of the point-average grid: the same n frames through b2v_grid_integrate_rgbd vs the unmodified
+    compiled reference fed the reference front-end's points.  Keys and hashes must be equal; per-voxel counts may
+    differ where a point lies within float rounding of a voxel face (the reference front-end's numpy arithmetic vs the
+    fused kernel's: tests/test_gpu_grid.py), so the differing count is reported."""
+    from pyslam_b200 import VoxelBlockGrid
+    g = VoxelBlockGrid(cfg.voxel_size, 8, capacity_blocks=1 << 17, device=device)
+    for i in range(n):
+        g.integrate_rgbd(depth[i], color[i], cfg.K, S.inv_T(Tcw[i]), max_depth=cfg.depth_trunc)
+    d = g.dump_blocks()
+    g.close()
+
+    def order(k):
+        return np.lexsort((k[:, 2], k[:, 1], k[:, 0]))
+    og, orf = order(d["keys"]), order(ref_dump["keys"])
+    same_keys = len(og) == len(orf) and bool(np.array_equal(d["keys"][og], ref_dump["keys"][orf]))
+    out = {"frames": n, "blocks_gpu": int(len(og)), "blocks_reference": int(len(orf)), "block_keys_equal": same_keys}
+    if same_keys:
+        out["hashes_equal"] = bool(np.array_equal(d["hashes"][og], ref_dump["hashes"][orf]))
+        cg, cr = d["count"][og], ref_dump["count"][orf]
+        out["voxels_gpu"] = int((cg > 0).sum())
+        out["voxels_reference"] = int((cr > 0).sum())
+        out["points_gpu"] = int(cg.sum())
+        out["points_reference"] = int(cr.sum())
+        out["voxels_with_a_different_count"] = int((cg != cr).sum())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -655,6 +683,7 @@ def grid_leg(cfg, depth, color, Tcw, d_dev, c_dev, peak, device):
                                           "(sequential branch: oneTBB is not installed; g++ -O3 -march=x86-64-v3), fed "
                                           "the front-end's world points (not timed)"}
         out["speedup_vs_reference_1core"] = out["gpu"]["value"] / ref[0]
+        out["parity"] = grid_parity(cfg, depth, color, Tcw, 6, ref[2], device)
     return out
 
 
