@@ -52,12 +52,20 @@ struct FrameSlot {   // which frame this CTA works for
     uint32_t frame_id;
 };
 
+// owner rank of a block: BlockKeyHash % N.  64-bit division is emulated (~60 instructions); the
+// allocate kernels test ~1000 candidate keys per tile, so a power-of-two rank count takes the mask instead
+__device__ __forceinline__ bool owned_by_this_rank(const FrameParams &P, int kx, int ky, int kz) {
+    const uint64_t h = block_key_hash(kx, ky, kz);
+    const uint32_t n = static_cast<uint32_t>(P.shard_count);
+    const uint32_t owner = (n & (n - 1u)) == 0u ? static_cast<uint32_t>(h) & (n - 1u)
+                                                : static_cast<uint32_t>(h % static_cast<uint64_t>(n));
+    return owner == static_cast<uint32_t>(P.shard_rank);
+}
+
 __device__ __forceinline__ void touch_key(const FrameParams &P, const FrameSlot &FS, const HashTable &T, const PoolMeta &M,
                                           int ring, int kx, int ky, int kz, uint32_t *s_new,
                                           uint32_t *s_n_new, uint32_t *s_act, uint32_t *s_n_act) {
-    if (P.shard_count > 1 &&
-        static_cast<int>(block_key_hash(kx, ky, kz) % static_cast<uint64_t>(P.shard_count)) != P.shard_rank)
-        return;
+    if (P.shard_count > 1 && !owned_by_this_rank(P, kx, ky, kz)) return;
     bool is_new;
     const uint32_t slot = table_insert(T, kx, ky, kz, &is_new);
     if (slot == kEmpty) {
@@ -345,9 +353,7 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const FrameP
                 const int ky = s_ref[1] + static_cast<int>(static_cast<uint32_t>(bk >> 16) & 0xFFFFu) - 32768 + static_cast<int>(dy);
                 const int kz = s_ref[2] + static_cast<int>(static_cast<uint32_t>(bk >> 32) & 0xFFFFu) - 32768 + static_cast<int>(dz);
                 // sharded volumes: keys of other ranks are dropped before they cost a set insert or a probe
-                if (P.shard_count > 1 &&
-                    static_cast<int>(block_key_hash(kx, ky, kz) % static_cast<uint64_t>(P.shard_count)) != P.shard_rank)
-                    continue;
+                if (P.shard_count > 1 && !owned_by_this_rank(P, kx, ky, kz)) continue;
                 const uint32_t rk = rel_key(kx, ky, kz, s_ref);
                 bool placed = false;
                 if (rk != kNoKey) {

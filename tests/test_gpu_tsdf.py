@@ -238,13 +238,13 @@ def test_device_pointer_inputs_and_batch_equal_host_path():
         assert np.array_equal(a[name], b[name]) and np.array_equal(a[name], c_[name])
 
 
-def test_sharded_volumes_partition_the_blocks():
+@pytest.mark.parametrize("n", [4, 3, 8])   # power-of-two rank counts take a mask, the others the 64-bit modulo
+def test_sharded_volumes_partition_the_blocks(n):
     """Hash-bucket sharding: shard r owns BlockKeyHash % n == r; the union of the
     shards equals the unsharded volume bit for bit and no block is owned twice."""
     cfg = S.CONFIGS["T0"]
     frames = [S.render_frame(cfg, i) for i in range(3)]
     full, _ = _pair(cfg)
-    n = 4
     shards = [B200TsdfVolume(cfg.voxel_size, cfg.sdf_trunc, cfg.depth_trunc, capacity_blocks=4096,
                              shard_rank=r, shard_count=n) for r in range(n)]
     for d, c, T in frames:
