@@ -208,8 +208,6 @@ cudaError_t launch_point_masks(const HashTable &table, const PoolMeta &meta, con
                                cudaStream_t stream);
 // per-block sums + exclusive scans -> offs, totals
 cudaError_t launch_mesh_scan(const MeshBuffers &mb, int grid_ctas, cudaStream_t stream);
-// recompute the sign summaries of blocks [0, n) from their voxels (after an import that bypassed the update kernels)
-cudaError_t launch_block_flags(const PoolMeta &meta, uint32_t n, cudaStream_t stream);
 cudaError_t launch_mesh_vertices(const PoolMeta &meta, const MeshBuffers &mb, double voxel_length, int unit_shift,
                                  bool points, uint32_t work_blocks, cudaStream_t stream);
 cudaError_t launch_mesh_triangles(const MeshBuffers &mb, uint32_t work_blocks, cudaStream_t stream);

@@ -937,29 +937,6 @@ upload_copy_kernel(const float *__restrict__ vox, const uint32_t *__restrict__ i
     if (threadIdx.x == 0) M.block_flags[dst] = (any_neg ? 1u : 0u) | (any_pos ? 2u : 0u);
 }
 
-__global__ void __launch_bounds__(128)
-block_flags_kernel(const PoolMeta M, const uint32_t n) {
-    const uint32_t b = blockIdx.x;
-    if (b >= n) return;
-    const float4 *src = reinterpret_cast<const float4 *>(M.pool + static_cast<size_t>(b) * kBlockFloats);
-    const float4 f = src[threadIdx.x], w = src[128 + threadIdx.x];
-    const float fs[4] = {f.x, f.y, f.z, f.w}, ws[4] = {w.x, w.y, w.z, w.w};
-    bool neg = false, pos = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        neg |= ws[k] != 0.0f && fs[k] < 0.0f;
-        pos |= ws[k] != 0.0f && !(fs[k] < 0.0f);
-    }
-    const int any_neg = __syncthreads_or(neg), any_pos = __syncthreads_or(pos);
-    if (threadIdx.x == 0) M.block_flags[b] = (any_neg ? 1u : 0u) | (any_pos ? 2u : 0u);
-}
-
-cudaError_t launch_block_flags(const PoolMeta &meta, uint32_t n, cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
-    block_flags_kernel<<<n, 128, 0, stream>>>(meta, n);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_upload_blocks(const int4 *keys, const float *vox, uint32_t n, uint32_t *scratch_idx,
                                  const HashTable &table, const PoolMeta &meta, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
