@@ -111,6 +111,16 @@ __device__ __forceinline__ uint32_t rel_key(int kx, int ky, int kz, const int *r
     return rx | (ry << 10) | (rz << 20);
 }
 
+// every 8^3 block of one allocation unit (Open3D volume unit = 2^3 blocks; decision D1: the unit is the block)
+__device__ __forceinline__ void touch_unit(const FrameParams &P, const FrameSlot &FS, const HashTable &T, const PoolMeta &M,
+                                           int ring, int ux, int uy, int uz, uint32_t *s_new, uint32_t *s_n_new,
+                                           uint32_t *s_act, uint32_t *s_n_act) {
+    const int S = P.unit_shift, side = (1 << S) - 1;
+    for (int sub = 0; sub < (1 << (3 * S)); ++sub)
+        touch_key(P, FS, T, M, ring, (ux << S) + (sub & side), (uy << S) + ((sub >> S) & side), (uz << S) + (sub >> (2 * S)),
+                  s_new, s_n_new, s_act, s_n_act);
+}
+
 // 16-byte texel of the update kernels: {valid depth | 0, lambda, half2(r, g), half2(b, 0)}; the colours are exact in
 // binary16 (integers 0..255) and widen to float32 with one instruction each
 __device__ __forceinline__ float4 make_texel(float d, float lam, uint8_t r, uint8_t g, uint8_t b) {
@@ -157,13 +167,14 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 
 // Per frame: pack the frame into texels, find the touched blocks, allocate the new ones.
 //   pack    every CTA packs its 32x32-pixel tile into 16-byte {valid depth | 0, lambda, rgbx} texels
-//   boxes   one thread per depth sample: back-project (float64), block range [lo, lo+n) of the
-//           [p - tau, p + tau] box; neighbouring samples share boxes, so the DISTINCT boxes of the
-//           tile (typically 10-20, each 27 blocks) are collected in a shared-memory set
-//   keys    the distinct boxes are expanded, one candidate block per thread, into a shared-memory set
-//           of distinct block keys (typically ~100 per tile)
-//   probe   every distinct key probes / inserts into the global table - one key per thread, all
-//           probes in flight - and exchanges the slot's frame stamp (first toucher queues the slot)
+//   boxes   one thread per depth sample: back-project (float64), range [lo, lo+n) of allocation UNITS (Open3D volume
+//           units of 2^3 blocks; decision D1: blocks) of the [p - tau, p + tau] box; neighbouring samples share
+//           boxes, so the DISTINCT boxes of the tile (typically 10-20) are collected in a shared-memory set
+//   keys    the distinct boxes are expanded, one candidate unit per thread, into a shared-memory set of distinct
+//           unit keys (typically ~30 units = ~240 blocks per tile)
+//   probe   every block of every distinct unit probes / inserts into the global table - one block per thread, all
+//           probes in flight - and exchanges the slot's frame stamp (first toucher queues the slot); blocks of
+//           another rank are dropped here
 //   flush   one atomic per CTA hands out contiguous pool indices and active-list positions
 template <bool kTma>
 __device__ __forceinline__ void allocate_body(const FrameParams &P, const FramePose &pose, const FrameSlot FS,
@@ -184,8 +195,10 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const FrameP
     __shared__ uint32_t s_act[kListCap];
     __shared__ uint32_t s_n_box, s_n_keys, s_n_new, s_n_act, s_base_new, s_base_act;
     __shared__ int s_ref[4];  // reference key of the tile; s_ref[3]: 0 = unset, 1 = set
+    __shared__ uint32_t s_magic[16];   // ceil(2^16 / d): floor(x / d) = (x * magic) >> 16 for x < 4096, d <= 15
 
     const int tid = threadIdx.x;
+    if (tid < 16) s_magic[tid] = tid ? (65536u + tid - 1u) / static_cast<uint32_t>(tid) : 0u;
     for (int i = tid; i < kKeySet; i += kAllocThreads) s_keyset[i] = kNoKey;
     if (tid < kBoxSet) s_boxset[tid] = ~0ull;
     if (tid == 0) {
@@ -239,8 +252,8 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const FrameP
                         // every 8^3 block of a touched unit is touched
                         const int ulo = __double2int_rd(__ddiv_rn(__dsub_rn(pw, P.tau_d), P.unit_len));
                         const int uhi = __double2int_rd(__ddiv_rn(__dadd_rn(pw, P.tau_d), P.unit_len));
-                        lo[a] = ulo << P.unit_shift;
-                        n[a] = (uhi - ulo + 1) << P.unit_shift;
+                        lo[a] = ulo;
+                        n[a] = uhi - ulo + 1;
                     } else {  // decision D1: pyslam float32 key arithmetic (voxel_hashing.h:69-75, 139-151)
                         const int vlo = voxel_coord(__double2float_rn(__dsub_rn(pw, P.tau_d)), P.inv_vs);
                         const int vhi = voxel_coord(__double2float_rn(__dadd_rn(pw, P.tau_d)), P.inv_vs);
@@ -333,12 +346,12 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const FrameP
             for (int dx = 0; dx < n[0]; ++dx)
                 for (int dy = 0; dy < n[1]; ++dy)
                     for (int dz = 0; dz < n[2]; ++dz)
-                        touch_key(P, FS, T, M, ring, lo[0] + dx, lo[1] + dy, lo[2] + dz, s_new, &s_n_new, s_act, &s_n_act);
+                        touch_unit(P, FS, T, M, ring, lo[0] + dx, lo[1] + dy, lo[2] + dz, s_new, &s_n_new, s_act, &s_n_act);
         }
     }
     __syncthreads();
 
-    // ---- distinct keys: expand every distinct box, one candidate block per thread ----
+    // ---- distinct keys: expand every distinct box, one candidate unit per thread ----
     {
         const uint32_t nbox = min(s_n_box, static_cast<uint32_t>(kBoxList));
         for (uint32_t item = tid; item < nbox * 32u; item += kAllocThreads) {  // 32 lanes per box (27 typical)
@@ -346,14 +359,15 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const FrameP
             const uint32_t c = item & 31u;
             const uint32_t n0 = static_cast<uint32_t>(bk >> 48) & 15u, n1 = static_cast<uint32_t>(bk >> 52) & 15u,
                            n2 = static_cast<uint32_t>(bk >> 56) & 15u;
-            // boxes with more than 32 blocks loop over the remainder (c, c + 32, ...)
-            for (uint32_t cc = c; cc < n0 * n1 * n2; cc += 32u) {
-                const uint32_t dz = cc % n2, r = cc / n2, dy = r % n1, dx = r / n1;
-                const int kx = s_ref[0] + static_cast<int>(static_cast<uint32_t>(bk) & 0xFFFFu) - 32768 + static_cast<int>(dx);
-                const int ky = s_ref[1] + static_cast<int>(static_cast<uint32_t>(bk >> 16) & 0xFFFFu) - 32768 + static_cast<int>(dy);
-                const int kz = s_ref[2] + static_cast<int>(static_cast<uint32_t>(bk >> 32) & 0xFFFFu) - 32768 + static_cast<int>(dz);
-                // sharded volumes: keys of other ranks are dropped before they cost a set insert or a probe
-                if (P.shard_count > 1 && !owned_by_this_rank(P, kx, ky, kz)) continue;
+            // boxes with more than 32 blocks loop over the remainder (c, c + 32, ...); the candidate index is split
+            // with multiply-shift divisions (a 32-bit division costs ~20 instructions, and a tile has ~1000 candidates)
+            const int bx = s_ref[0] + static_cast<int>(static_cast<uint32_t>(bk) & 0xFFFFu) - 32768;
+            const int by = s_ref[1] + static_cast<int>(static_cast<uint32_t>(bk >> 16) & 0xFFFFu) - 32768;
+            const int bz = s_ref[2] + static_cast<int>(static_cast<uint32_t>(bk >> 32) & 0xFFFFu) - 32768;
+            const uint32_t m2 = s_magic[n2], m1 = s_magic[n1], total = n0 * n1 * n2;
+            for (uint32_t cc = c; cc < total; cc += 32u) {
+                const uint32_t r = (cc * m2) >> 16, dz = cc - r * n2, dx = (r * m1) >> 16, dy = r - dx * n1;
+                const int kx = bx + static_cast<int>(dx), ky = by + static_cast<int>(dy), kz = bz + static_cast<int>(dz);
                 const uint32_t rk = rel_key(kx, ky, kz, s_ref);
                 bool placed = false;
                 if (rk != kNoKey) {
@@ -374,20 +388,23 @@ __device__ __forceinline__ void allocate_body(const FrameParams &P, const FrameP
                         h = (h + 1) & (kKeySet - 1);
                     }
                 }
-                if (!placed) touch_key(P, FS, T, M, ring, kx, ky, kz, s_new, &s_n_new, s_act, &s_n_act);
+                if (!placed) touch_unit(P, FS, T, M, ring, kx, ky, kz, s_new, &s_n_new, s_act, &s_n_act);
             }
         }
     }
     __syncthreads();
 
-    // ---- probe: every distinct key of the tile, one per thread, all probes in flight ----
+    // ---- probe: every block of every distinct unit of the tile, one per thread, all probes in flight ----
     {
         const uint32_t nkeys = min(s_n_keys, static_cast<uint32_t>(kListCap));
-        for (uint32_t q = tid; q < nkeys; q += kAllocThreads) {
-            const uint32_t rk = s_keys[q];
-            touch_key(P, FS, T, M, ring, s_ref[0] + static_cast<int>(rk & 1023u) - 512,
-                      s_ref[1] + static_cast<int>((rk >> 10) & 1023u) - 512,
-                      s_ref[2] + static_cast<int>((rk >> 20) & 1023u) - 512, s_new, &s_n_new, s_act, &s_n_act);
+        const int S = P.unit_shift, side = (1 << S) - 1;
+        for (uint32_t q = tid; q < (nkeys << (3 * S)); q += kAllocThreads) {
+            const uint32_t rk = s_keys[q >> (3 * S)];
+            const int sub = static_cast<int>(q & ((1u << (3 * S)) - 1u));
+            const int ux = s_ref[0] + static_cast<int>(rk & 1023u) - 512, uy = s_ref[1] + static_cast<int>((rk >> 10) & 1023u) - 512,
+                      uz = s_ref[2] + static_cast<int>((rk >> 20) & 1023u) - 512;
+            touch_key(P, FS, T, M, ring, (ux << S) + (sub & side), (uy << S) + ((sub >> S) & side), (uz << S) + (sub >> (2 * S)),
+                      s_new, &s_n_new, s_act, &s_n_act);
         }
     }
     __syncthreads();
