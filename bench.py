@@ -179,16 +179,17 @@ def cpu_port_fps(cfg, depth, color, Tcw, n_sample, threads, passes=1):
 
 def best_thread_count(cfg, depth, color, Tcw) -> int:
     """The port's per-frame allocation pass is serial (as Open3D's is) and the box may be shared: pick the OpenMP
-    team size with the best steady-state throughput on 4 frames (explicit num_threads: OMP_NUM_THREADS is ignored)."""
+    team size with the best steady-state throughput on 8 frames, best of 3 rounds per candidate so that a burst of
+    foreign load on the host does not pick a poor size (explicit num_threads: OMP_NUM_THREADS is ignored)."""
     import oracle
     hi = host_threads()
-    cands = sorted({c for c in (8, 16, 32, 64, 96, hi) if c <= hi} | {hi})
+    cands = sorted({c for c in (8, 16, 32, 48, 64, 96, hi) if c <= hi} | {hi})
     orc = oracle.Open3DOrderVolume(cfg.voxel_size, cfg.sdf_trunc, 16, 4)
-    n = min(4, len(depth))
+    n = min(8, len(depth))
     for i in range(n):
         orc.integrate(depth[i], color[i], cfg.K, Tcw[i], cfg.depth_trunc, nthreads=hi)
     best, best_t = hi, float("inf")
-    for _ in range(2):
+    for _ in range(3):
         for c in cands:
             t0 = time.perf_counter()
             for i in range(n):
