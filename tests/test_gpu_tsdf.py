@@ -129,6 +129,10 @@ def test_mesh_matches_oracle_in_float64():
     # a second extraction of the same volume is identical (deterministic count -> scan -> emit)
     m2 = vol.extract_mesh()
     assert np.array_equal(m.triangles, m2.triangles) and np.array_equal(m.vertices, m2.vertices)
+    # the extraction narrows its work through the blocks' sign summaries without losing a tile (the equalities above)
+    st = vol.last_mesh_stats()
+    assert st["blocks"] == vol.num_blocks()
+    assert 0 < st["triangle_blocks"] <= st["vertex_blocks"] <= st["tiles_with_both_signs"] <= st["candidate_tiles"] <= st["blocks"]
 
 
 def test_upload_dump_round_trip_and_sphere_mesh():
