@@ -132,7 +132,8 @@ def test_mesh_matches_oracle_in_float64():
     # the extraction narrows its work through the blocks' sign summaries without losing a tile (the equalities above)
     st = vol.last_mesh_stats()
     assert st["blocks"] == vol.num_blocks()
-    assert 0 < st["triangle_blocks"] <= st["vertex_blocks"] <= st["tiles_with_both_signs"] <= st["candidate_tiles"] <= st["blocks"]
+    assert 0 < st["vertex_blocks"] <= st["tiles_with_both_signs"] <= st["candidate_tiles"] <= st["blocks"]
+    assert 0 < st["triangle_blocks"] <= st["tiles_with_both_signs"]
 
 
 def test_upload_dump_round_trip_and_sphere_mesh():
