@@ -17,8 +17,8 @@ legs may import this package; the product (`pyslam_b200/`) never does.
 * `numpy_tsdf`  - a second, independent numpy restatement of A.3 used to pin the C oracle.
 """
 
-from .oracle import (Open3DOrderVolume, RefGrid, RefSemanticGrid, TsdfOracle, build, canonical_mesh, have_ref, have_ref_semantic, numpy_integrate_block,
+from .oracle import (EigenOps, Open3DOrderVolume, have_eigen_ops, open3d_order_inverse4, RefGrid, RefSemanticGrid, TsdfOracle, build, canonical_mesh, have_ref, have_ref_semantic, numpy_integrate_block,
                      numpy_touched_blocks, ref_block_key_hash, ref_floor_div, ref_keys)
 
-__all__ = ["Open3DOrderVolume", "RefGrid", "RefSemanticGrid", "TsdfOracle", "build", "canonical_mesh", "have_ref", "have_ref_semantic", "numpy_integrate_block",
+__all__ = ["EigenOps", "have_eigen_ops", "open3d_order_inverse4", "Open3DOrderVolume", "RefGrid", "RefSemanticGrid", "TsdfOracle", "build", "canonical_mesh", "have_ref", "have_ref_semantic", "numpy_integrate_block",
            "numpy_touched_blocks", "ref_block_key_hash", "ref_floor_div", "ref_keys"]

@@ -498,6 +498,53 @@ def numpy_integrate_block(vox, key, depth, color, K, Tcw, voxel_size, sdf_trunc,
 # ---------------------------------------------------------------------------------------------
 # compiled reference: semantic voxel-block grids
 # ---------------------------------------------------------------------------------------------
+_EIGEN_SO = os.path.join(_DIR, "_ref", "libeigen_ops.so")
+
+
+def have_eigen_ops() -> bool:
+    return os.path.exists(_EIGEN_SO)
+
+
+class EigenOps:
+    """The three Eigen expressions of Open3D's TSDF path, evaluated by the Eigen vendored in the reference tree
+    (oracle/eigen_ops.cpp; x86-64 baseline like Open3D's wheels).  Row-major numpy in and out."""
+
+    def __init__(self):
+        if not have_eigen_ops():
+            raise RuntimeError("oracle/_ref/libeigen_ops.so missing (needs /root/reference to build)")
+        self._L = C.CDLL(_EIGEN_SO)
+        self.version = int(self._L.eig_version())
+
+    def mat4f_times_vec4f(self, M, v):
+        M = np.ascontiguousarray(M, np.float32).reshape(4, 4)
+        v = np.ascontiguousarray(v, np.float32).reshape(4)
+        out = np.zeros(4, np.float32)
+        self._L.eig_mat4f_times_vec4f(C.c_void_p(M.ctypes.data), C.c_void_p(v.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out
+
+    def mat4d_times_vec4d(self, M, v):
+        M = np.ascontiguousarray(M, np.float64).reshape(4, 4)
+        v = np.ascontiguousarray(v, np.float64).reshape(4)
+        out = np.zeros(4, np.float64)
+        self._L.eig_mat4d_times_vec4d(C.c_void_p(M.ctypes.data), C.c_void_p(v.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out
+
+    def mat4d_inverse(self, M):
+        M = np.ascontiguousarray(M, np.float64).reshape(4, 4)
+        out = np.zeros((4, 4), np.float64)
+        self._L.eig_mat4d_inverse(C.c_void_p(M.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out
+
+
+def open3d_order_inverse4(M):
+    """The float64 cofactor inverse oracle/open3d_order.c uses for camera_pose = extrinsic.inverse()."""
+    L = _o3d()
+    M = np.ascontiguousarray(M, np.float64).reshape(4, 4)
+    out = np.zeros((4, 4), np.float64)
+    L.o3d_inverse4(C.c_void_p(M.ctypes.data), C.c_void_p(out.ctypes.data))
+    return out
+
+
 _SEM_SO = os.path.join(_DIR, "_ref", "libref_semantic.so")
 _sem_lib = None
 
