@@ -5,12 +5,12 @@ update, per-block marching cubes, and the point-average compat grid).  `csrc/` h
 CUDA kernels and the C ABI (include/b2v.h); the Python modules mirror the reference's interface.
 """
 
-from .volume import (B200TsdfVolume, BoundingBox3D, CameraFrustrum, PointCloud, TriangleMesh,
+from .volume import (B200TsdfVolume, BoundingBox3D, CameraFrustrum, PointCloud, TBBUtils, TriangleMesh,
                      VoxelBlockGrid, VoxelBlockSemanticGrid, VoxelBlockSemanticProbabilisticGrid, VoxelGridData,
                      VoxelSemanticGrid, VoxelSemanticGridProbabilistic, filter_shadow_points, remap,
                      remap_instance_ids)
 
-__all__ = ["B200TsdfVolume", "BoundingBox3D", "CameraFrustrum", "PointCloud", "TriangleMesh",
+__all__ = ["B200TsdfVolume", "BoundingBox3D", "CameraFrustrum", "PointCloud", "TBBUtils", "TriangleMesh",
            "VoxelBlockGrid", "VoxelBlockSemanticGrid", "VoxelBlockSemanticProbabilisticGrid", "VoxelGridData",
            "VoxelSemanticGrid", "VoxelSemanticGridProbabilistic", "filter_shadow_points", "remap",
            "remap_instance_ids"]

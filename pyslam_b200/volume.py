@@ -445,6 +445,22 @@ class BoundingBox3D:
         self.bounds = np.array([min_x, min_y, min_z, max_x, max_y, max_z], np.float64)
 
 
+class TBBUtils:
+    """`volumetric.TBBUtils` of the reference module (cpp/volumetric/volumetric_module.cpp:43-50): the integrators call
+    `TBBUtils.set_max_threads(n)` to size the CPU thread pool of the voxel grids.  The B200 grids have no CPU pool; the
+    value is kept so that `get_max_threads()` answers what was set."""
+    _max_threads = 0
+
+    @staticmethod
+    def set_max_threads(num_threads: int) -> None:
+        TBBUtils._max_threads = int(num_threads)
+
+    @staticmethod
+    def get_max_threads() -> int:
+        import os
+        return TBBUtils._max_threads if TBBUtils._max_threads > 0 else (os.cpu_count() or 1)
+
+
 class VoxelGridData:
     """`VoxelGridDataT` (cpp/volumetric/voxel_grid_data.h:36-50): points / colors SoA."""
 

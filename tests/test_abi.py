@@ -113,3 +113,21 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and int(out.stdout.split()[0]) >= 100
+
+
+def test_voxel_block_grid_duck_type_is_complete():
+    """SURVEY.md 8b duck-type B: every method the reference binds on `volumetric.VoxelBlockGrid`
+    (cpp/volumetric/volumetric_grid_module.h:732-935, 977-978) exists on the mirror, plus `TBBUtils`
+    (volumetric_module.cpp:43-50)."""
+    import pyslam_b200 as P
+    for name in ("integrate", "get_voxels", "get_points", "get_colors", "clear", "reset", "size", "empty", "num_blocks",
+                 "get_block_size", "get_total_voxel_count", "get_voxels_in_bb", "get_voxels_in_camera_frustrum", "carve",
+                 "remove_low_count_voxels", "remove_low_confidence_voxels"):
+        assert callable(getattr(P.VoxelBlockGrid, name)), name
+    for cls in (P.VoxelBlockSemanticGrid, P.VoxelBlockSemanticProbabilisticGrid):
+        for name in ("integrate", "integrate_segment", "get_voxels", "get_object_segments", "get_class_segments",
+                     "merge_segments", "remove_segment", "remove_low_confidence_segments", "get_ids", "carve",
+                     "assign_object_ids_to_instance_ids", "set_depth_threshold", "clear", "reset"):
+            assert callable(getattr(cls, name)), (cls.__name__, name)
+    P.TBBUtils.set_max_threads(6)
+    assert P.TBBUtils.get_max_threads() == 6
