@@ -16,14 +16,9 @@
 
 namespace b2v {
 
-__constant__ unsigned short c_edge_table[256];
-__constant__ signed char c_tri_table[256][16];
-__constant__ unsigned char c_num_tris[256];
-__constant__ signed char c_edge_shift[12][4];
 __constant__ unsigned short c_halo[217];   // the 9^3 - 8^3 tile cells outside the own block: x | y << 4 | z << 8
-// the same tables in global memory for lookups whose index differs per lane (a divergent constant-bank read is
-// serialised per distinct address; these go through the L1 instead)
-__device__ unsigned short g_edge_table[256];
+// the marching-cubes tables live in global memory: their index differs per lane, and a divergent constant-bank read
+// is serialised per distinct address, while these go through the L1
 __device__ signed char g_tri_table[256][16];
 __device__ unsigned char g_num_tris[256];
 __device__ uchar4 g_edge_shift[12];
@@ -40,11 +35,6 @@ static cudaError_t upload_tables_once() {
     cudaGetDevice(&dev);
     if (done && done_device == dev) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaMemcpyToSymbol(c_edge_table, MC_EDGE_TABLE, sizeof(MC_EDGE_TABLE))) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_tri_table, MC_TRI_TABLE, sizeof(MC_TRI_TABLE))) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_num_tris, MC_NUM_TRIS, sizeof(MC_NUM_TRIS))) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_edge_shift, MC_EDGE_SHIFT, sizeof(MC_EDGE_SHIFT))) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(g_edge_table, MC_EDGE_TABLE, sizeof(MC_EDGE_TABLE))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(g_tri_table, MC_TRI_TABLE, sizeof(MC_TRI_TABLE))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(g_num_tris, MC_NUM_TRIS, sizeof(MC_NUM_TRIS))) != cudaSuccess) return e;
     static_assert(sizeof(MC_EDGE_SHIFT) == 12 * 4, "edge shift table is 12 x {dx, dy, dz, axis}");
