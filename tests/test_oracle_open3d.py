@@ -46,6 +46,21 @@ def test_twin_equals_open3d_order_restatement(cfg_name, frames):
     assert (a["vox"][:, 1] > 0).sum() > 10000
 
 
+def test_twin_equals_open3d_order_at_bench_scale_weights():
+    """320 integrations of the T0 frames (weights to 320, beyond the 256 the bench's steady state passes): tsdf and
+    weight stay bit-identical; the float32 colour mean stays within 1e-3 of Open3D's float64 one on the 0..255 scale.
+    Together with tests/test_gpu_open3d.py::test_bench_scale_fused_batches_equal_frame_by_frame_and_the_twin this ties
+    the kernels to the Open3D-order restatement at the weights the bench reaches."""
+    cfg = S.CONFIGS["T0"]
+    o3, tw = _both(cfg, [0, 1, 2, 3] * 80)
+    a, b = sort_dump(o3.dump_blocks()), sort_dump(tw.dump_blocks())
+    assert np.array_equal(a["keys"], b["keys"])
+    assert a["vox"][:, 1].max() == 320.0
+    assert np.array_equal(a["vox"][:, 1], b["vox"][:, 1].astype(np.float64))
+    assert np.array_equal(a["vox"][:, 0], b["vox"][:, 0].astype(np.float64))
+    assert np.abs(a["vox"][:, 2:] - b["vox"][:, 2:]).max() < 1e-3
+
+
 def test_twin_mesh_equals_open3d_order_mesh():
     cfg = S.CONFIGS["T0"]
     o3, tw = _both(cfg, [0, 1, 2, 3])
