@@ -19,8 +19,9 @@ configuration (16^3 volume units, stride 4): results are bit-identical to the Op
             MEASURED_PEAKS.json; `per_frame_equivalent` is SURVEY.md 8d's formula (2*S*512*A_f + 7*W*H per frame,
             what frame-by-frame integration must move) over the same time.  `per_frame_kernel` gives the un-fused
             HBM-bound `integrate_kernel` warm (consecutive frames share L2-resident blocks) and cold (L2 flushed).
-  cpu_baseline / --impl reference   the Open3D-order CPU port (oracle/open3d_order.c, OpenMP over volume units, all
-            host threads) on the same frames; Open3D itself is not installable here.
+  cpu_baseline / --impl reference   the Open3D-order CPU port (oracle/open3d_order.c, OpenMP over volume units, the
+            team size that a short probe finds fastest among 8 .. all host threads) on the same frames; Open3D
+            itself is not installable here.
 
 N > 1 (torchrun): the voxel-block hash space is sharded by BlockKeyHash % N; every rank integrates every frame into
 the blocks it owns.  Total work is fixed ("strong" scaling).  The union of the shards is checked against an
